@@ -1,0 +1,85 @@
+// Host-side building blocks shared by planner.cu / idm.cu / vae.cu: device allocation arena, canonical
+// weight-blob walker, weight packing for the tcgen05 path, and the DDPM coefficient table.
+#pragma once
+#include <map>
+#include <memory>
+#include <utility>
+#include <vector>
+
+#include "kernels.h"
+
+namespace ldp {
+
+// Owns device allocations; freed together at handle destruction.
+class Arena {
+ public:
+  ~Arena() { release(); }
+  int alloc(void** out, size_t bytes, bool zero = true) {
+    void* p = nullptr;
+    if (bytes == 0) bytes = 16;
+    cudaError_t e = cudaMalloc(&p, bytes);
+    if (e != cudaSuccess) {
+      set_last_error(std::string("cudaMalloc(") + std::to_string(bytes) + ") failed: " + cudaGetErrorString(e));
+      return LDP_ERR_CUDA;
+    }
+    if (zero) {
+      e = cudaMemset(p, 0, bytes);
+      if (e != cudaSuccess) {
+        set_last_error(std::string("cudaMemset failed: ") + cudaGetErrorString(e));
+        return LDP_ERR_CUDA;
+      }
+    }
+    ptrs_.push_back(p);
+    total_ += bytes;
+    *out = p;
+    return LDP_OK;
+  }
+  template <typename T>
+  int alloc_t(T** out, size_t count, bool zero = true) {
+    return alloc(reinterpret_cast<void**>(out), count * sizeof(T), zero);
+  }
+  void release() {
+    for (void* p : ptrs_) cudaFree(p);
+    ptrs_.clear();
+    total_ = 0;
+  }
+  size_t total() const { return total_; }
+
+ private:
+  std::vector<void*> ptrs_;
+  size_t total_ = 0;
+};
+
+// Walks the canonical float32 blob (params.py spec order): take(n) returns the device pointer of the next tensor.
+struct BlobWalker {
+  const float* base = nullptr;
+  uint64_t pos = 0;
+  const float* take(uint64_t n) {
+    const float* p = base ? base + pos : nullptr;
+    pos += n;
+    return p;
+  }
+};
+
+// A bf16 activation tensor, channels-last, viewed as (items, rows_per_item, channels) with row pitch ld.
+struct ActBf16 {
+  __nv_bfloat16* p = nullptr;
+  int c = 0;    // channels
+  int ld = 0;   // row pitch in elements (multiple of 8)
+};
+
+// One source of the K dimension of a packed weight: `taps` kernel taps over `c` channels that live at rows
+// [row0 + tap*tap_stride, +c) of the Flax kernel viewed as [K][N].
+struct PackedW {
+  __nv_bfloat16* wt = nullptr;   // [n_pad][kp]
+  int kp = 0, n_pad = 0;
+  TcKBlock* kb_dev = nullptr;
+  int num_kb = 0;
+};
+
+// DDPM coefficient table [n][8] (see kernels.h DdpmStep), fp32 arithmetic in the reference's op order
+// (diffusers FlaxDDPMScheduler.step / _get_variance).
+void ddpm_schedule_host(int n, std::vector<float>& betas, std::vector<float>& alphas, std::vector<float>& acp);
+void ddpm_coef_host(int n, std::vector<float>& coef);
+
+}  // namespace ldp

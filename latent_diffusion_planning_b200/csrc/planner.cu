@@ -1,0 +1,868 @@
+// Planner handle: ConditionalUnet1D score network (reference networks/diffusion_nets_v2.py:104-169) and the
+// reverse-diffusion loop around it (reference agent/ldp_agent.py:459-476), in two precisions:
+//   fp32  - SIMT implicit GEMM + separate GroupNorm/FiLM kernels (parity gate 1e-5),
+//   bf16  - one tcgen05 GEMM launch per convolution with GroupNorm/Mish/FiLM/residual fused into its epilogue and
+//           the scheduler step fused into the last 1x1 convolution; a whole denoising step is one CUDA graph.
+// Step- and batch-invariant work is hoisted out of the loop: the FiLM Dense of every block is split into a
+// time part (table over the N timesteps, built once at create) and an observation part (one GEMM per act()).
+#include <algorithm>
+#include <cmath>
+
+#include "net_common.h"
+
+namespace ldp {
+
+// ---------------------------------------------------------------------------------------------
+// schedule (host)
+// ---------------------------------------------------------------------------------------------
+void ddpm_schedule_host(int n, std::vector<float>& betas, std::vector<float>& alphas, std::vector<float>& acp) {
+  betas.resize(n);
+  alphas.resize(n);
+  acp.resize(n);
+  auto alpha_bar = [](double s) {
+    double c = std::cos((s + 0.008) / 1.008 * M_PI / 2.0);
+    return c * c;
+  };
+  float run = 1.0f;
+  for (int i = 0; i < n; ++i) {
+    double b = 1.0 - alpha_bar((double)(i + 1) / n) / alpha_bar((double)i / n);
+    betas[i] = (float)std::min(b, 0.999);
+    alphas[i] = 1.0f - betas[i];
+    run = run * alphas[i];                 // sequential fp32 cumprod (jnp.cumprod on f32)
+    acp[i] = run;
+  }
+}
+
+void ddpm_coef_host(int n, std::vector<float>& coef) {
+  std::vector<float> betas, alphas, acp;
+  ddpm_schedule_host(n, betas, alphas, acp);
+  coef.assign((size_t)n * 8, 0.f);
+  for (int t = 0; t < n; ++t) {
+    // fp32 throughout, in the op order of FlaxDDPMScheduler.step
+    float a_t = acp[t];
+    float a_prev = t > 0 ? acp[t - 1] : 1.0f;      // the `t > 0` select of alpha_prod_t_prev
+    float b_t = 1.0f - a_t, b_prev = 1.0f - a_prev;
+    float c0 = (std::sqrt(a_prev) * betas[t]) / b_t;
+    float ct = std::sqrt(alphas[t]) * b_prev / b_t;
+    float var = (1.0f - a_prev) / (1.0f - a_t) * betas[t];
+    var = std::max(var, 1e-20f);
+    float* c = &coef[(size_t)t * 8];
+    c[0] = 1.0f / std::sqrt(a_t);
+    c[1] = std::sqrt(b_t);
+    c[2] = c0;
+    c[3] = ct;
+    c[4] = t > 0 ? std::sqrt(var) : 0.f;            // the `t > 0` select of the noise term
+    c[5] = std::sqrt(a_prev);
+    c[6] = std::sqrt(b_prev);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// handle
+// ---------------------------------------------------------------------------------------------
+enum ConvKind { CONV_K = 0, CONV_DOWN = 1, CONV_UP = 2 };
+
+struct CrbW {
+  int cin = 0, cout = 0;
+  bool proj = false;
+  int film_off = 0;
+  const float *c1w, *c1b, *g1s, *g1b, *fw, *fb, *c2w, *c2b, *g2s, *g2b, *rw, *rb;
+};
+
+struct PlanWs {
+  int B = 0, T = 0;
+  Arena arena;
+  float* otab = nullptr;
+  float* x_state = nullptr;
+  float* eps_buf = nullptr;
+  int32_t* step_dev = nullptr;
+  DdpmCall* call_dev = nullptr;
+  // fp32 path
+  bool f32_ready = false;
+  float *f_tmp = nullptr, *f_h1 = nullptr, *f_res = nullptr, *f_final = nullptr;
+  std::vector<float*> f_out;       // one per CRB
+  std::vector<float*> f_down, f_up;
+  // bf16 path
+  bool bf16_ready = false;
+  __nv_bfloat16* x_bf16 = nullptr;
+  int ld_xb = 0;
+  std::vector<TcGemm> ops;         // one denoising step; last op = final 1x1 with the DDPM epilogue
+  cudaGraphExec_t graph = nullptr;
+  cudaGraph_t graph_src = nullptr;
+  ~PlanWs() {
+    if (graph) cudaGraphExecDestroy(graph);
+    if (graph_src) cudaGraphDestroy(graph_src);
+  }
+};
+
+}  // namespace ldp
+
+using namespace ldp;
+
+struct LdpPlanner {
+  LdpUnetConfig cfg;
+  Arena arena;
+  float* blob = nullptr;
+  const float *t0w, *t0b, *t1w, *t1b;
+  std::vector<CrbW> crb;
+  std::vector<const float*> down_w, down_b, up_w, up_b;
+  std::vector<float*> up_bias2;     // [b|b] for the two output phases of the transposed conv
+  const float *fcw, *fcb, *fgs, *fgb, *ow, *ob;
+  int sum_c2 = 0;
+  float* ttab = nullptr;     // [n_train][sum_c2]  time part of every FiLM Dense (+ its bias)
+  float* wc_all = nullptr;   // [Dc][sum_c2]       observation part of every FiLM Dense
+  float* coef = nullptr;     // [n_train][8]
+  std::map<std::pair<int, int>, std::unique_ptr<PlanWs>> ws;
+  std::map<std::pair<int, int>, PackedW> packed;   // (op id, T_in)
+  bool use_graph = true;
+};
+
+namespace ldp {
+
+static std::vector<std::tuple<int, int, bool>> block_plan(const LdpUnetConfig& c) {
+  std::vector<std::tuple<int, int, bool>> b;
+  int ch = c.input_dim;
+  for (int i = 0; i < c.n_levels; ++i) {
+    b.emplace_back(ch, c.down_dims[i], true);
+    b.emplace_back(c.down_dims[i], c.down_dims[i], false);
+    ch = c.down_dims[i];
+  }
+  int mid = c.down_dims[c.n_levels - 1];
+  b.emplace_back(mid, mid, false);
+  b.emplace_back(mid, mid, false);
+  ch = mid;
+  for (int i = c.n_levels - 2; i >= 0; --i) {
+    int skip = c.down_dims[i + 1];           // h.pop(): deepest remaining skip
+    b.emplace_back(ch + skip, c.down_dims[i], true);
+    b.emplace_back(c.down_dims[i], c.down_dims[i], false);
+    ch = c.down_dims[i];
+  }
+  return b;
+}
+
+static int64_t unet_param_count(const LdpUnetConfig& c) {
+  int64_t n = 0;
+  const int64_t ds = c.step_embed_dim, cond = ds + c.global_cond_dim, k = c.kernel_size;
+  n += ds * ds * 4 + ds * 4 + ds * 4 * ds + ds;
+  for (auto& [cin, cout, proj] : block_plan(c)) {
+    n += k * cin * cout + cout + 2 * cout;
+    n += cond * 2 * cout + 2 * cout;
+    n += k * (int64_t)cout * cout + cout + 2 * cout;
+    if (proj) n += (int64_t)cin * cout + cout;
+  }
+  for (int i = 0; i < c.n_levels - 1; ++i) n += 3 * (int64_t)c.down_dims[i] * c.down_dims[i] + c.down_dims[i];
+  for (int i = 0; i < c.n_levels - 1; ++i) n += 4 * (int64_t)c.down_dims[i] * c.down_dims[i] + c.down_dims[i];
+  const int64_t d0 = c.down_dims[0];
+  n += k * d0 * d0 + d0 + 2 * d0 + d0 * c.input_dim + c.input_dim;
+  return n;
+}
+
+static int validate_cfg(const LdpUnetConfig* c) {
+  LDP_CHECK(c != nullptr, LDP_ERR_INVALID_ARG, "null config");
+  LDP_CHECK(c->input_dim > 0 && c->global_cond_dim > 0 && c->step_embed_dim >= 4 && (c->step_embed_dim % 2) == 0,
+            LDP_ERR_INVALID_ARG, "bad dims");
+  LDP_CHECK(c->n_levels >= 1 && c->n_levels <= 6, LDP_ERR_INVALID_ARG, "n_levels must be 1..6");
+  LDP_CHECK(c->kernel_size == 5, LDP_ERR_UNSUPPORTED, "kernel_size must be 5 (reference agent/ldp_agent.yaml:13)");
+  LDP_CHECK(c->n_groups > 0 && c->n_train_steps > 0, LDP_ERR_INVALID_ARG, "bad n_groups / n_train_steps");
+  for (int i = 0; i < c->n_levels; ++i)
+    LDP_CHECK(c->down_dims[i] > 0 && c->down_dims[i] % c->n_groups == 0 && c->down_dims[i] % 8 == 0, LDP_ERR_INVALID_ARG,
+              "down_dims must be positive multiples of n_groups and 8");
+  return LDP_OK;
+}
+
+// ------------------------------- create -------------------------------------------------------
+static int planner_build_tables(LdpPlanner* h) {
+  const LdpUnetConfig& c = h->cfg;
+  cudaStream_t s = 0;
+  const int ds = c.step_embed_dim, n = c.n_train_steps, dc = c.global_cond_dim;
+  float *sinus, *hid, *temb, *wt_all, *bias_all;
+  Arena tmp;
+  LDP_TRY(tmp.alloc_t(&sinus, (size_t)n * ds));
+  LDP_TRY(tmp.alloc_t(&hid, (size_t)n * ds * 4));
+  LDP_TRY(tmp.alloc_t(&temb, (size_t)n * ds));
+  LDP_TRY(tmp.alloc_t(&wt_all, (size_t)ds * h->sum_c2));
+  LDP_TRY(tmp.alloc_t(&bias_all, (size_t)h->sum_c2));
+  LDP_TRY(h->arena.alloc_t(&h->wc_all, (size_t)dc * h->sum_c2));
+  LDP_TRY(h->arena.alloc_t(&h->ttab, (size_t)n * h->sum_c2));
+  // diffusion_step_encoder: sinusoid -> Dense(4d) -> Mish -> Dense(d)   (diffusion_nets_v2.py:120-127)
+  LDP_TRY(launch_sinusoid_table(sinus, n, ds, /*cos_first=*/0, s));
+  GemmF32 g;
+  g.x1 = sinus; g.c1 = ds; g.ld1 = ds; g.w = h->t0w; g.ldw = ds * 4; g.bias = h->t0b; g.out = hid; g.ldo = ds * 4;
+  g.m = n; g.n = ds * 4;
+  LDP_TRY(launch_gemm_f32(g, s));
+  g = GemmF32();
+  g.x1 = hid; g.c1 = ds * 4; g.ld1 = ds * 4; g.a_act = 1; g.w = h->t1w; g.ldw = ds; g.bias = h->t1b; g.out = temb;
+  g.ldo = ds; g.m = n; g.n = ds;
+  LDP_TRY(launch_gemm_f32(g, s));
+  // split every FiLM Dense (K = ds + Dc) into its time rows and observation rows, side by side over all blocks
+  for (auto& b : h->crb) {
+    const int n2 = 2 * b.cout;
+    LDP_CUDA_OK(cudaMemcpy2DAsync(wt_all + b.film_off, (size_t)h->sum_c2 * 4, b.fw, (size_t)n2 * 4, (size_t)n2 * 4, ds,
+                                  cudaMemcpyDeviceToDevice, s));
+    LDP_CUDA_OK(cudaMemcpy2DAsync(h->wc_all + b.film_off, (size_t)h->sum_c2 * 4, b.fw + (size_t)ds * n2, (size_t)n2 * 4,
+                                  (size_t)n2 * 4, dc, cudaMemcpyDeviceToDevice, s));
+    LDP_CUDA_OK(cudaMemcpyAsync(bias_all + b.film_off, b.fb, (size_t)n2 * 4, cudaMemcpyDeviceToDevice, s));
+  }
+  // ttab[k] = Mish(temb_k) Wt + bias   (Mish is elementwise, so Dense(Mish([temb|cond])) separates exactly)
+  g = GemmF32();
+  g.x1 = temb; g.c1 = ds; g.ld1 = ds; g.a_act = 1; g.w = wt_all; g.ldw = h->sum_c2; g.bias = bias_all; g.out = h->ttab;
+  g.ldo = h->sum_c2; g.m = n; g.n = h->sum_c2;
+  LDP_TRY(launch_gemm_f32(g, s));
+  std::vector<float> coef;
+  ddpm_coef_host(n, coef);
+  LDP_TRY(h->arena.alloc_t(&h->coef, coef.size()));
+  LDP_CUDA_OK(cudaMemcpy(h->coef, coef.data(), coef.size() * 4, cudaMemcpyHostToDevice));
+  for (size_t i = 0; i < h->up_w.size(); ++i) {
+    const int d = c.down_dims[c.n_levels - 2 - (int)i];
+    float* b2;
+    LDP_TRY(h->arena.alloc_t(&b2, (size_t)2 * d));
+    LDP_CUDA_OK(cudaMemcpy(b2, h->up_b[i], (size_t)d * 4, cudaMemcpyDeviceToDevice));
+    LDP_CUDA_OK(cudaMemcpy(b2 + d, h->up_b[i], (size_t)d * 4, cudaMemcpyDeviceToDevice));
+    h->up_bias2.push_back(b2);
+  }
+  LDP_CUDA_OK(cudaStreamSynchronize(s));
+  return LDP_OK;
+}
+
+static int planner_create_impl(const LdpUnetConfig* cfg, const float* params_host, uint64_t n_params, LdpPlanner* h) {
+  h->cfg = *cfg;
+  const LdpUnetConfig& c = h->cfg;
+  const int64_t expect = unet_param_count(c);
+  LDP_CHECK((int64_t)n_params == expect, LDP_ERR_PARAM_COUNT,
+            "planner weight blob has " + std::to_string(n_params) + " floats, config needs " + std::to_string(expect));
+  LDP_TRY(h->arena.alloc_t(&h->blob, n_params, false));
+  LDP_CUDA_OK(cudaMemcpy(h->blob, params_host, n_params * 4, cudaMemcpyHostToDevice));
+  BlobWalker w{h->blob, 0};
+  const int64_t ds = c.step_embed_dim, cond = ds + c.global_cond_dim, k = c.kernel_size;
+  h->t0w = w.take(ds * ds * 4); h->t0b = w.take(ds * 4);
+  h->t1w = w.take(ds * 4 * ds); h->t1b = w.take(ds);
+  int film_off = 0;
+  for (auto& [cin, cout, proj] : block_plan(c)) {
+    CrbW b;
+    b.cin = cin; b.cout = cout; b.proj = proj; b.film_off = film_off;
+    film_off += 2 * cout;
+    b.c1w = w.take(k * cin * cout); b.c1b = w.take(cout); b.g1s = w.take(cout); b.g1b = w.take(cout);
+    b.fw = w.take(cond * 2 * cout); b.fb = w.take(2 * cout);
+    b.c2w = w.take(k * (int64_t)cout * cout); b.c2b = w.take(cout); b.g2s = w.take(cout); b.g2b = w.take(cout);
+    b.rw = proj ? w.take((int64_t)cin * cout) : nullptr;
+    b.rb = proj ? w.take(cout) : nullptr;
+    h->crb.push_back(b);
+  }
+  h->sum_c2 = film_off;
+  for (int i = 0; i < c.n_levels - 1; ++i) {
+    int64_t d = c.down_dims[i];
+    h->down_w.push_back(w.take(3 * d * d));
+    h->down_b.push_back(w.take(d));
+  }
+  for (int i = 0; i < c.n_levels - 1; ++i) {
+    int64_t d = c.down_dims[c.n_levels - 2 - i];
+    h->up_w.push_back(w.take(4 * d * d));
+    h->up_b.push_back(w.take(d));
+  }
+  const int64_t d0 = c.down_dims[0];
+  h->fcw = w.take(k * d0 * d0); h->fcb = w.take(d0); h->fgs = w.take(d0); h->fgb = w.take(d0);
+  h->ow = w.take(d0 * c.input_dim); h->ob = w.take(c.input_dim);
+  LDP_CHECK((int64_t)w.pos == expect, LDP_ERR_PARAM_COUNT, "internal: blob walk mismatch");
+  const char* env = getenv("LDP_NO_GRAPH");
+  h->use_graph = !(env && env[0] == '1');
+  return planner_build_tables(h);
+}
+
+// ------------------------------- workspace -------------------------------------------------------
+static int level_len(int T, int level) { return T >> level; }
+
+static int get_ws(LdpPlanner* h, int B, int T, PlanWs** out) {
+  const LdpUnetConfig& c = h->cfg;
+  LDP_CHECK(B > 0 && T > 0, LDP_ERR_BAD_SHAPE, "B and T must be positive");
+  LDP_CHECK(T % (1 << (c.n_levels - 1)) == 0, LDP_ERR_BAD_SHAPE,
+            "T must be divisible by 2^(n_levels-1): the reference UNet's up path otherwise mismatches its skips");
+  auto key = std::make_pair(B, T);
+  auto it = h->ws.find(key);
+  if (it != h->ws.end()) {
+    *out = it->second.get();
+    return LDP_OK;
+  }
+  std::unique_ptr<PlanWs> w(new PlanWs());
+  w->B = B; w->T = T;
+  LDP_TRY(w->arena.alloc_t(&w->otab, (size_t)B * h->sum_c2));
+  LDP_TRY(w->arena.alloc_t(&w->x_state, (size_t)B * T * c.input_dim));
+  LDP_TRY(w->arena.alloc_t(&w->eps_buf, (size_t)B * T * c.input_dim));
+  LDP_TRY(w->arena.alloc_t(&w->step_dev, 4));
+  LDP_TRY(w->arena.alloc_t(&w->call_dev, 1));
+  *out = w.get();
+  h->ws[key] = std::move(w);
+  return LDP_OK;
+}
+
+static int compute_otab(LdpPlanner* h, PlanWs* w, const float* cond, cudaStream_t s) {
+  GemmF32 g;
+  g.x1 = cond; g.c1 = h->cfg.global_cond_dim; g.ld1 = h->cfg.global_cond_dim; g.a_act = 1;
+  g.w = h->wc_all; g.ldw = h->sum_c2; g.out = w->otab; g.ldo = h->sum_c2; g.m = w->B; g.n = h->sum_c2;
+  return launch_gemm_f32(g, s);
+}
+
+// ------------------------------- fp32 program -------------------------------------------------------
+static int prepare_f32(LdpPlanner* h, PlanWs* w) {
+  if (w->f32_ready) return LDP_OK;
+  const LdpUnetConfig& c = h->cfg;
+  size_t max_act = 0;
+  {
+    int lvl = 0;
+    for (size_t i = 0; i < h->crb.size(); ++i) {
+      // level of block i: down blocks 2l,2l+1 at level l; mid at last; up blocks mirror
+      int nl = c.n_levels;
+      if ((int)i < 2 * nl) lvl = (int)i / 2;
+      else if ((int)i < 2 * nl + 2) lvl = nl - 1;
+      else lvl = nl - 1 - ((int)i - 2 * nl - 2) / 2;
+      size_t a = (size_t)w->B * level_len(w->T, lvl) * std::max(h->crb[i].cout, h->crb[i].cin);
+      max_act = std::max(max_act, a);
+      float* o;
+      LDP_TRY(w->arena.alloc_t(&o, (size_t)w->B * level_len(w->T, lvl) * h->crb[i].cout));
+      w->f_out.push_back(o);
+    }
+  }
+  max_act = std::max(max_act, (size_t)w->B * w->T * c.down_dims[0]);
+  LDP_TRY(w->arena.alloc_t(&w->f_tmp, max_act));
+  LDP_TRY(w->arena.alloc_t(&w->f_h1, max_act));
+  LDP_TRY(w->arena.alloc_t(&w->f_res, max_act));
+  LDP_TRY(w->arena.alloc_t(&w->f_final, (size_t)w->B * w->T * c.down_dims[0]));
+  for (int i = 0; i < c.n_levels - 1; ++i) {
+    float* d;
+    LDP_TRY(w->arena.alloc_t(&d, (size_t)w->B * level_len(w->T, i + 1) * c.down_dims[i]));
+    w->f_down.push_back(d);
+  }
+  for (int i = 0; i < c.n_levels - 1; ++i) {
+    int lvl = c.n_levels - 1 - i;               // input level of Upsample1d_i
+    float* u;
+    LDP_TRY(w->arena.alloc_t(&u, (size_t)w->B * level_len(w->T, lvl - 1) * c.down_dims[lvl - 1]));
+    w->f_up.push_back(u);
+  }
+  w->f32_ready = true;
+  return LDP_OK;
+}
+
+struct SrcF32 { const float* p; int c; int ld; };
+
+static int conv_f32(const SrcF32& a, const SrcF32* b, int B, int t_in, int t_out, int taps, int stride, int pad, int dil,
+                    const float* wgt, const float* bias, int cout, float* out, cudaStream_t s) {
+  GemmF32 g;
+  g.x1 = a.p; g.c1 = a.c; g.ld1 = a.ld;
+  if (b) { g.x2 = b->p; g.c2 = b->c; g.ld2 = b->ld; }
+  g.t_in = t_in; g.t_out = t_out; g.taps = taps; g.stride = stride; g.pad = pad; g.dil = dil;
+  g.w = wgt; g.ldw = cout; g.bias = bias; g.out = out; g.ldo = cout; g.m = B * t_out; g.n = cout;
+  return launch_gemm_f32(g, s);
+}
+
+static int crb_f32(LdpPlanner* h, PlanWs* w, int bi, const SrcF32& a, const SrcF32* b2, int Tl, StepRef step, float* out,
+                   cudaStream_t s) {
+  const CrbW& b = h->crb[bi];
+  const int B = w->B, G = h->cfg.n_groups;
+  LDP_TRY(conv_f32(a, b2, B, Tl, Tl, 5, 1, 2, 1, b.c1w, b.c1b, b.cout, w->f_tmp, s));
+  GroupNormF32 n;
+  n.x = w->f_tmp; n.ldx = b.cout; n.y = w->f_h1; n.ldy = b.cout; n.B = B; n.P = Tl; n.C = b.cout; n.G = G;
+  n.gamma = b.g1s; n.beta = b.g1b; n.act = 1; n.film = 1; n.ttab = h->ttab; n.ld_ttab = h->sum_c2; n.step = step;
+  n.otab = w->otab; n.ld_otab = h->sum_c2; n.film_off = b.film_off;
+  LDP_TRY(launch_groupnorm_f32(n, s));
+  SrcF32 h1{w->f_h1, b.cout, b.cout};
+  LDP_TRY(conv_f32(h1, nullptr, B, Tl, Tl, 5, 1, 2, 1, b.c2w, b.c2b, b.cout, w->f_tmp, s));
+  const float* res = a.p;
+  int ldres = a.ld;
+  if (b.proj) {
+    LDP_TRY(conv_f32(a, b2, B, Tl, Tl, 1, 1, 0, 1, b.rw, b.rb, b.cout, w->f_res, s));
+    res = w->f_res;
+    ldres = b.cout;
+  }
+  n = GroupNormF32();
+  n.x = w->f_tmp; n.ldx = b.cout; n.y = out; n.ldy = b.cout; n.B = B; n.P = Tl; n.C = b.cout; n.G = G;
+  n.gamma = b.g2s; n.beta = b.g2b; n.act = 1; n.res = res; n.ldres = ldres;
+  return launch_groupnorm_f32(n, s);
+}
+
+// eps = UNet(x, step, cond);  otab must already hold the observation part of the FiLM embeddings.
+static int forward_f32(LdpPlanner* h, PlanWs* w, const float* x, StepRef step, float* eps, cudaStream_t s) {
+  const LdpUnetConfig& c = h->cfg;
+  LDP_TRY(prepare_f32(h, w));
+  const int B = w->B, nl = c.n_levels;
+  SrcF32 cur{x, c.input_dim, c.input_dim};
+  int bi = 0;
+  std::vector<SrcF32> skips;
+  for (int l = 0; l < nl; ++l) {
+    const int Tl = level_len(w->T, l);
+    LDP_TRY(crb_f32(h, w, bi, cur, nullptr, Tl, step, w->f_out[bi], s));
+    cur = SrcF32{w->f_out[bi], h->crb[bi].cout, h->crb[bi].cout}; ++bi;
+    LDP_TRY(crb_f32(h, w, bi, cur, nullptr, Tl, step, w->f_out[bi], s));
+    cur = SrcF32{w->f_out[bi], h->crb[bi].cout, h->crb[bi].cout}; ++bi;
+    skips.push_back(cur);
+    if (l < nl - 1) {
+      // Downsample1d: Conv(k3, stride 2, 'SAME') -> pad_lo = 0 for even lengths
+      const int d = c.down_dims[l];
+      LDP_TRY(conv_f32(cur, nullptr, B, Tl, Tl / 2, 3, 2, 0, 1, h->down_w[l], h->down_b[l], d, w->f_down[l], s));
+      cur = SrcF32{w->f_down[l], d, d};
+    }
+  }
+  {
+    const int Tl = level_len(w->T, nl - 1);
+    for (int r = 0; r < 2; ++r) {
+      LDP_TRY(crb_f32(h, w, bi, cur, nullptr, Tl, step, w->f_out[bi], s));
+      cur = SrcF32{w->f_out[bi], h->crb[bi].cout, h->crb[bi].cout}; ++bi;
+    }
+  }
+  for (int u = 0; u < nl - 1; ++u) {
+    const int lvl = nl - 1 - u;
+    const int Tl = level_len(w->T, lvl);
+    SrcF32 skip = skips.back();
+    skips.pop_back();
+    LDP_TRY(crb_f32(h, w, bi, cur, &skip, Tl, step, w->f_out[bi], s));
+    cur = SrcF32{w->f_out[bi], h->crb[bi].cout, h->crb[bi].cout}; ++bi;
+    LDP_TRY(crb_f32(h, w, bi, cur, nullptr, Tl, step, w->f_out[bi], s));
+    cur = SrcF32{w->f_out[bi], h->crb[bi].cout, h->crb[bi].cout}; ++bi;
+    // Upsample1d: Flax ConvTranspose(k4, s2, 'SAME'), kernel not flipped
+    const int d = c.down_dims[lvl - 1];
+    LDP_TRY(conv_f32(cur, nullptr, B, Tl, 2 * Tl, 4, 1, 2, 2, h->up_w[u], h->up_b[u], d, w->f_up[u], s));
+    cur = SrcF32{w->f_up[u], d, d};
+  }
+  const int d0 = c.down_dims[0];
+  LDP_TRY(conv_f32(cur, nullptr, B, w->T, w->T, 5, 1, 2, 1, h->fcw, h->fcb, d0, w->f_tmp, s));
+  GroupNormF32 n;
+  n.x = w->f_tmp; n.ldx = d0; n.y = w->f_final; n.ldy = d0; n.B = B; n.P = w->T; n.C = d0; n.G = 8;
+  n.gamma = h->fgs; n.beta = h->fgb; n.act = 1;
+  LDP_CHECK(d0 % 8 == 0, LDP_ERR_UNSUPPORTED, "final Conv1dBlock uses 8 groups");
+  LDP_TRY(launch_groupnorm_f32(n, s));
+  SrcF32 f{w->f_final, d0, d0};
+  return conv_f32(f, nullptr, B, w->T, w->T, 1, 1, 0, 1, h->ow, h->ob, c.input_dim, eps, s);
+}
+
+// ------------------------------- bf16 / tcgen05 program -------------------------------------------------------
+struct TcSrc { ActBf16 a; };
+
+// Build (or fetch) the packed weights + K-block table of one convolution at input length t_in.
+static int get_packed(LdpPlanner* h, int op_id, int kind, int taps_k, const ActBf16* srcs, int nsrc, int t_in,
+                      const float* wgt, int cout, int block_n, PackedW** out) {
+  auto key = std::make_pair(op_id, t_in);
+  auto it = h->packed.find(key);
+  if (it != h->packed.end()) {
+    *out = &it->second;
+    return LDP_OK;
+  }
+  int ctot = 0;
+  for (int i = 0; i < nsrc; ++i) ctot += srcs[i].c;
+  std::vector<TcKBlock> kb;
+  std::vector<int32_t> kmap, kmap2;     // kmap2: odd output phase of the transposed conv
+  auto push_sources = [&](int d1, int d2, int tap_row, int tap_row2) {
+    int coff = 0;
+    for (int sidx = 0; sidx < nsrc; ++sidx) {
+      for (int c0 = 0; c0 < srcs[sidx].c; c0 += 64) {
+        TcKBlock e;
+        e.src_acc = sidx;
+        e.c0 = c0; e.d1 = d1; e.d2 = d2;
+        kb.push_back(e);
+        for (int i = 0; i < 64; ++i) {
+          bool ok = c0 + i < srcs[sidx].c;
+          kmap.push_back(ok && tap_row >= 0 ? tap_row * ctot + coff + c0 + i : -1);
+          kmap2.push_back(ok && tap_row2 >= 0 ? tap_row2 * ctot + coff + c0 + i : -1);
+        }
+      }
+      coff += srcs[sidx].c;
+    }
+  };
+  if (kind == CONV_K) {
+    const int pad = taps_k / 2;
+    for (int j = 0; j < taps_k; ++j)
+      if (std::abs(j - pad) < t_in) push_sources(j - pad, 0, j, -1);     // taps that only ever see padding are dropped
+  } else if (kind == CONV_DOWN) {
+    // y[t] = sum_j W[j] x[2t+j] (pad_lo = 0 for even t_in); x viewed as (parity, t/2): tap j -> (j%2, t + j/2)
+    const int t_out = t_in / 2;
+    for (int j = 0; j < 3; ++j)
+      if (j < 2 || t_out >= 2) push_sources(j % 2, j / 2, j, -1);
+  } else {
+    // y[2u] = W0 x[u-1] + W2 x[u];  y[2u+1] = W1 x[u] + W3 x[u+1]
+    if (t_in >= 2) push_sources(-1, 0, 0, -1);
+    push_sources(0, 0, 2, 1);
+    if (t_in >= 2) push_sources(1, 0, -1, 3);
+  }
+  const int kp_main = (int)kmap.size();
+  const int kp = kp_main;
+  const int n_out = kind == CONV_UP ? 2 * cout : cout;
+  PackedW pw;
+  pw.kp = kp;
+  pw.n_pad = round_up(n_out, block_n);
+  pw.num_kb = (int)kb.size();
+  LDP_TRY(h->arena.alloc_t(&pw.wt, (size_t)pw.n_pad * kp));
+  LDP_TRY(h->arena.alloc_t(&pw.kb_dev, kb.size()));
+  LDP_CUDA_OK(cudaMemcpy(pw.kb_dev, kb.data(), kb.size() * sizeof(TcKBlock), cudaMemcpyHostToDevice));
+  int32_t* map_dev;
+  Arena tmp;
+  LDP_TRY(tmp.alloc_t(&map_dev, (size_t)kp * 2 + 16));
+  LDP_CUDA_OK(cudaMemcpy(map_dev, kmap.data(), (size_t)kp_main * 4, cudaMemcpyHostToDevice));
+  if (kind == CONV_UP) {
+    LDP_CUDA_OK(cudaMemcpy(map_dev + kp, kmap2.data(), (size_t)kp_main * 4, cudaMemcpyHostToDevice));
+    LDP_TRY(launch_pack_wt_bf16(wgt, cout, cout, map_dev, kp_main, pw.wt, kp, 0, cout, 0));
+    LDP_TRY(launch_pack_wt_bf16(wgt, cout, cout, map_dev + kp, kp_main, pw.wt + (size_t)cout * kp, kp, 0,
+                                pw.n_pad - cout, 0));
+  } else {
+    LDP_TRY(launch_pack_wt_bf16(wgt, cout, cout, map_dev, kp_main, pw.wt, kp, 0, pw.n_pad, 0));
+  }
+  LDP_CUDA_OK(cudaDeviceSynchronize());
+  h->packed[key] = pw;
+  *out = &h->packed[key];
+  return LDP_OK;
+}
+
+static int act_map(CUtensorMap* m, const ActBf16& a, int kind, int t_in, int B) {
+  if (kind == CONV_DOWN) {
+    const int t_out = t_in / 2;
+    uint64_t dims[4] = {(uint64_t)a.c, 2, (uint64_t)t_out, (uint64_t)B};
+    uint64_t str[3] = {(uint64_t)a.ld * 2, (uint64_t)a.ld * 4, (uint64_t)t_in * a.ld * 2};
+    uint32_t box[4] = {64, 1, (uint32_t)t_out, (uint32_t)(128 / t_out)};
+    return make_tmap_bf16(m, a.p, 4, dims, str, box);
+  }
+  uint64_t dims[4] = {(uint64_t)a.c, (uint64_t)t_in, 1, (uint64_t)B};
+  uint64_t str[3] = {(uint64_t)a.ld * 2, (uint64_t)t_in * a.ld * 2, (uint64_t)t_in * a.ld * 2};
+  uint32_t box[4] = {64, (uint32_t)t_in, 1, (uint32_t)(128 / t_in)};
+  return make_tmap_bf16(m, a.p, 4, dims, str, box);
+}
+
+// Generic convolution op on the tcgen05 path; the caller fills in the epilogue afterwards.
+static int conv_tc(LdpPlanner* h, PlanWs* w, int op_id, int kind, int taps_k, const ActBf16* srcs, int nsrc, int t_in,
+                   const float* wgt, int cout, TcGemm* op) {
+  const int rows = kind == CONV_DOWN ? t_in / 2 : t_in;
+  LDP_CHECK(rows >= 1 && rows <= 32 && (rows & (rows - 1)) == 0, LDP_ERR_UNSUPPORTED,
+            "bf16 path needs power-of-two level lengths <= 32 (use LDP_PREC_FP32 for other horizons)");
+  for (int i = 0; i < nsrc; ++i)
+    LDP_CHECK(srcs[i].ld % 8 == 0, LDP_ERR_INVALID_ARG, "activation pitch must be a multiple of 8 elements");
+  PackedW* pw;
+  LDP_TRY(get_packed(h, op_id, kind, taps_k, srcs, nsrc, t_in, wgt, cout, 128, &pw));
+  *op = TcGemm();
+  for (int i = 0; i < nsrc; ++i) LDP_TRY(act_map(&op->map_a[i], srcs[i], kind, t_in, w->B));
+  for (int i = nsrc; i < 4; ++i) op->map_a[i] = op->map_a[0];
+  uint64_t bd[2] = {(uint64_t)pw->kp, (uint64_t)pw->n_pad};
+  uint64_t bs[1] = {(uint64_t)pw->kp * 2};
+  uint32_t bb[2] = {64, 128};
+  LDP_TRY(make_tmap_bf16(&op->map_b, pw->wt, 2, bd, bs, bb));
+  op->kb = pw->kb_dev;
+  op->num_kb = pw->num_kb;
+  op->M = w->B * rows;
+  op->N = kind == CONV_UP ? 2 * cout : cout;
+  op->block_n = 128;
+  op->use_aux = 0;
+  op->tiles_per_item = 1;
+  op->rows_step = 0;
+  op->items_per_tile = 128 / rows;
+  op->rows_per_item = rows;
+  return LDP_OK;
+}
+
+static void set_gn(TcGemm* op, const float* bias, const float* gamma, const float* beta, int cout, int groups,
+                   __nv_bfloat16* out) {
+  op->mode = TC_EPI_GN;
+  op->bias = bias; op->gamma = gamma; op->beta = beta; op->eps = 1e-6f;
+  op->group_width = cout / groups;
+  op->out_bf16 = out; op->ld_out_bf16 = cout;
+}
+
+static int crb_tc(LdpPlanner* h, PlanWs* w, int bi, const ActBf16* srcs, int nsrc, int Tl, __nv_bfloat16* h1buf,
+                  __nv_bfloat16* outbuf) {
+  const CrbW& b = h->crb[bi];
+  LDP_CHECK((b.cout / h->cfg.n_groups) % 32 == 0, LDP_ERR_UNSUPPORTED,
+            "bf16 path needs GroupNorm group widths that are multiples of 32 channels");
+  TcGemm op;
+  LDP_TRY(conv_tc(h, w, 4 * bi + 0, CONV_K, 5, srcs, nsrc, Tl, b.c1w, b.cout, &op));
+  set_gn(&op, b.c1b, b.g1s, b.g1b, b.cout, h->cfg.n_groups, h1buf);
+  op.film = 1; op.ttab = h->ttab; op.ld_ttab = h->sum_c2; op.otab = w->otab; op.ld_otab = h->sum_c2;
+  op.film_off = b.film_off; op.film_c = b.cout;
+  w->ops.push_back(op);
+  ActBf16 h1{h1buf, b.cout, b.cout};
+  if (b.proj) {
+    // conv2 on h1 (accumulator 0) + the 1x1 residual projection of the block input (accumulator 1) in ONE launch
+    ActBf16 both[3] = {h1, srcs[0], nsrc > 1 ? srcs[1] : srcs[0]};
+    // pack: main K blocks from h1, aux K blocks from the block input(s)
+    PackedW* pw;
+    auto key = std::make_pair(4 * bi + 1, Tl);
+    if (h->packed.find(key) == h->packed.end()) {
+      // main part
+      std::vector<TcKBlock> kb;
+      std::vector<int32_t> kmap, kmap_aux;
+      for (int j = 0; j < 5; ++j) {
+        if (std::abs(j - 2) >= Tl) continue;
+        for (int c0 = 0; c0 < b.cout; c0 += 64) {
+          kb.push_back(TcKBlock{0, c0, j - 2, 0});
+          for (int i = 0; i < 64; ++i) kmap.push_back(c0 + i < b.cout ? j * b.cout + c0 + i : -1);
+        }
+      }
+      int coff = 0;
+      for (int sidx = 0; sidx < nsrc; ++sidx) {
+        for (int c0 = 0; c0 < srcs[sidx].c; c0 += 64) {
+          kb.push_back(TcKBlock{(1 + sidx) | (1 << 8), c0, 0, 0});
+          for (int i = 0; i < 64; ++i) kmap_aux.push_back(c0 + i < srcs[sidx].c ? coff + c0 + i : -1);
+        }
+        coff += srcs[sidx].c;
+      }
+      PackedW p2;
+      const int kp_main = (int)kmap.size();
+      p2.kp = kp_main + (int)kmap_aux.size();
+      p2.n_pad = round_up(b.cout, 128);
+      p2.num_kb = (int)kb.size();
+      LDP_TRY(h->arena.alloc_t(&p2.wt, (size_t)p2.n_pad * p2.kp));
+      LDP_TRY(h->arena.alloc_t(&p2.kb_dev, kb.size()));
+      LDP_CUDA_OK(cudaMemcpy(p2.kb_dev, kb.data(), kb.size() * sizeof(TcKBlock), cudaMemcpyHostToDevice));
+      Arena tmp;
+      int32_t* map_dev;
+      LDP_TRY(tmp.alloc_t(&map_dev, (size_t)p2.kp + 16));
+      LDP_CUDA_OK(cudaMemcpy(map_dev, kmap.data(), kmap.size() * 4, cudaMemcpyHostToDevice));
+      LDP_CUDA_OK(cudaMemcpy(map_dev + kp_main, kmap_aux.data(), kmap_aux.size() * 4, cudaMemcpyHostToDevice));
+      LDP_TRY(launch_pack_wt_bf16(b.c2w, b.cout, b.cout, map_dev, kp_main, p2.wt, p2.kp, 0, p2.n_pad, 0));
+      LDP_TRY(launch_pack_wt_bf16(b.rw, b.cout, b.cout, map_dev + kp_main, (int)kmap_aux.size(), p2.wt, p2.kp, kp_main,
+                                  p2.n_pad, 0));
+      LDP_CUDA_OK(cudaDeviceSynchronize());
+      h->packed[key] = p2;
+    }
+    pw = &h->packed[key];
+    op = TcGemm();
+    LDP_TRY(act_map(&op.map_a[0], both[0], CONV_K, Tl, w->B));
+    LDP_TRY(act_map(&op.map_a[1], both[1], CONV_K, Tl, w->B));
+    LDP_TRY(act_map(&op.map_a[2], both[2], CONV_K, Tl, w->B));
+    op.map_a[3] = op.map_a[2];
+    uint64_t bd[2] = {(uint64_t)pw->kp, (uint64_t)pw->n_pad};
+    uint64_t bs[1] = {(uint64_t)pw->kp * 2};
+    uint32_t bb[2] = {64, 128};
+    LDP_TRY(make_tmap_bf16(&op.map_b, pw->wt, 2, bd, bs, bb));
+    op.kb = pw->kb_dev; op.num_kb = pw->num_kb;
+    op.M = w->B * Tl; op.N = b.cout; op.block_n = 128; op.use_aux = 1;
+    op.items_per_tile = 128 / Tl; op.rows_per_item = Tl;
+    set_gn(&op, b.c2b, b.g2s, b.g2b, b.cout, h->cfg.n_groups, outbuf);
+    op.bias_aux = b.rb;
+  } else {
+    LDP_TRY(conv_tc(h, w, 4 * bi + 1, CONV_K, 5, &h1, 1, Tl, b.c2w, b.cout, &op));
+    set_gn(&op, b.c2b, b.g2s, b.g2b, b.cout, h->cfg.n_groups, outbuf);
+    op.res_bf16 = srcs[0].p; op.ld_res_bf16 = srcs[0].ld;
+  }
+  w->ops.push_back(op);
+  return LDP_OK;
+}
+
+static int prepare_bf16(LdpPlanner* h, PlanWs* w) {
+  if (w->bf16_ready) return LDP_OK;
+  LDP_TRY(tc_driver_check());
+  LDP_TRY(tc_gemm_init());
+  const LdpUnetConfig& c = h->cfg;
+  const int B = w->B, T = w->T, nl = c.n_levels;
+  w->ld_xb = round_up(c.input_dim, 8);
+  LDP_TRY(w->arena.alloc_t(&w->x_bf16, (size_t)B * T * w->ld_xb));
+  size_t max_act = 0;
+  for (int l = 0; l < nl; ++l) max_act = std::max(max_act, (size_t)B * level_len(T, l) * c.down_dims[l]);
+  __nv_bfloat16* h1buf;
+  LDP_TRY(w->arena.alloc_t(&h1buf, max_act));
+  auto new_act = [&](int Tl, int ch, ActBf16* a) -> int {
+    a->c = ch; a->ld = ch;
+    return w->arena.alloc_t(&a->p, (size_t)B * Tl * ch);
+  };
+  w->ops.clear();
+  ActBf16 cur{w->x_bf16, c.input_dim, w->ld_xb};
+  std::vector<ActBf16> skips;
+  int bi = 0;
+  for (int l = 0; l < nl; ++l) {
+    const int Tl = level_len(T, l);
+    for (int r = 0; r < 2; ++r) {
+      ActBf16 o;
+      LDP_TRY(new_act(Tl, h->crb[bi].cout, &o));
+      LDP_TRY(crb_tc(h, w, bi, &cur, 1, Tl, h1buf, o.p));
+      cur = o; ++bi;
+    }
+    skips.push_back(cur);
+    if (l < nl - 1) {
+      const int d = c.down_dims[l];
+      ActBf16 o;
+      LDP_TRY(new_act(Tl / 2, d, &o));
+      TcGemm op;
+      LDP_TRY(conv_tc(h, w, 1000 + l, CONV_DOWN, 3, &cur, 1, Tl, h->down_w[l], d, &op));
+      op.mode = TC_EPI_PLAIN; op.bias = h->down_b[l]; op.out_bf16 = o.p; op.ld_out_bf16 = d;
+      w->ops.push_back(op);
+      cur = o;
+    }
+  }
+  {
+    const int Tl = level_len(T, nl - 1);
+    for (int r = 0; r < 2; ++r) {
+      ActBf16 o;
+      LDP_TRY(new_act(Tl, h->crb[bi].cout, &o));
+      LDP_TRY(crb_tc(h, w, bi, &cur, 1, Tl, h1buf, o.p));
+      cur = o; ++bi;
+    }
+  }
+  for (int u = 0; u < nl - 1; ++u) {
+    const int lvl = nl - 1 - u;
+    const int Tl = level_len(T, lvl);
+    ActBf16 srcs[2] = {cur, skips.back()};
+    skips.pop_back();
+    ActBf16 o;
+    LDP_TRY(new_act(Tl, h->crb[bi].cout, &o));
+    LDP_TRY(crb_tc(h, w, bi, srcs, 2, Tl, h1buf, o.p));
+    cur = o; ++bi;
+    LDP_TRY(new_act(Tl, h->crb[bi].cout, &o));
+    LDP_TRY(crb_tc(h, w, bi, &cur, 1, Tl, h1buf, o.p));
+    cur = o; ++bi;
+    const int d = c.down_dims[lvl - 1];
+    LDP_TRY(new_act(2 * Tl, d, &o));
+    TcGemm op;
+    LDP_TRY(conv_tc(h, w, 2000 + u, CONV_UP, 4, &cur, 1, Tl, h->up_w[u], d, &op));
+    op.mode = TC_EPI_PLAIN; op.bias = h->up_bias2[u]; op.out_bf16 = o.p; op.ld_out_bf16 = 2 * d;
+    w->ops.push_back(op);
+    cur = o;
+  }
+  const int d0 = c.down_dims[0];
+  LDP_CHECK((d0 / 8) % 32 == 0, LDP_ERR_UNSUPPORTED, "bf16 path: final block group width must be a multiple of 32");
+  ActBf16 f;
+  LDP_TRY(new_act(T, d0, &f));
+  TcGemm op;
+  LDP_TRY(conv_tc(h, w, 3000, CONV_K, 5, &cur, 1, T, h->fcw, d0, &op));
+  set_gn(&op, h->fcb, h->fgs, h->fgb, d0, 8, f.p);
+  w->ops.push_back(op);
+  LDP_TRY(conv_tc(h, w, 3001, CONV_K, 1, &f, 1, T, h->ow, c.input_dim, &op));
+  op.mode = TC_EPI_DDPM;
+  op.bias = h->ob;
+  op.coef = h->coef;
+  op.call_dev = w->call_dev;
+  op.x_io = w->x_state; op.ld_x = c.input_dim;
+  op.out_bf16 = w->x_bf16; op.ld_out_bf16 = w->ld_xb;
+  w->ops.push_back(op);
+  w->bf16_ready = true;
+  return LDP_OK;
+}
+
+static int run_ops_bf16(PlanWs* w, StepRef step, bool final_plain, float* eps_out, int D, cudaStream_t s) {
+  for (size_t i = 0; i < w->ops.size(); ++i) {
+    TcGemm op = w->ops[i];
+    op.step = step;
+    op.step.rows_per_t = step.rows ? op.rows_per_item : 1;
+    if (i + 1 == w->ops.size() && final_plain) {
+      op.mode = TC_EPI_PLAIN;
+      op.out_f32 = eps_out; op.ld_out_f32 = D;
+      op.out_bf16 = nullptr;
+      op.x_io = nullptr;
+    }
+    LDP_TRY(launch_tc_gemm(op, s));
+  }
+  return LDP_OK;
+}
+
+}  // namespace ldp
+
+// ------------------------------- C ABI -------------------------------------------------------
+extern "C" {
+
+int64_t ldp_unet_param_count(const LdpUnetConfig* cfg) {
+  if (validate_cfg(cfg) != LDP_OK) return -1;
+  return unet_param_count(*cfg);
+}
+
+int ldp_planner_create(const LdpUnetConfig* cfg, const float* params_host, uint64_t n_params, LdpPlanner** out) {
+  LDP_CHECK(out != nullptr && params_host != nullptr, LDP_ERR_INVALID_ARG, "null pointer");
+  LDP_TRY(validate_cfg(cfg));
+  LdpPlanner* h = new LdpPlanner();
+  int st = planner_create_impl(cfg, params_host, n_params, h);
+  if (st != LDP_OK) {
+    delete h;
+    return st;
+  }
+  *out = h;
+  return LDP_OK;
+}
+
+int ldp_planner_destroy(LdpPlanner* h) {
+  if (!h) return LDP_OK;
+  cudaDeviceSynchronize();
+  delete h;
+  return LDP_OK;
+}
+
+int ldp_unet_forward(LdpPlanner* h, int precision, const float* sample_dev, const int32_t* timesteps_dev, int timestep,
+                     const float* cond_dev, int B, int T, float* eps_dev, void* cuda_stream) {
+  LDP_CHECK(h && sample_dev && cond_dev && eps_dev, LDP_ERR_INVALID_ARG, "null pointer");
+  LDP_CHECK(timesteps_dev || (timestep >= 0 && timestep < h->cfg.n_train_steps), LDP_ERR_INVALID_ARG,
+            "timestep outside [0, n_train_steps)");
+  cudaStream_t s = (cudaStream_t)cuda_stream;
+  PlanWs* w;
+  LDP_TRY(get_ws(h, B, T, &w));
+  LDP_TRY(compute_otab(h, w, cond_dev, s));
+  StepRef step;
+  step.rows = timesteps_dev;
+  step.scalar = timestep;
+  step.rows_per_t = 1;
+  if (precision == LDP_PREC_FP32) return forward_f32(h, w, sample_dev, step, eps_dev, s);
+  LDP_CHECK(precision == LDP_PREC_BF16, LDP_ERR_INVALID_ARG, "unknown precision");
+  LDP_TRY(prepare_bf16(h, w));
+  LDP_TRY(launch_cast_bf16(sample_dev, h->cfg.input_dim, w->x_bf16, w->ld_xb, (long long)B * T, h->cfg.input_dim, 0, s));
+  return run_ops_bf16(w, step, /*final_plain=*/true, eps_dev, h->cfg.input_dim, s);
+}
+
+int ldp_planner_sample(LdpPlanner* h, int precision, int sampler, const float* x_T_dev, const float* cond_dev,
+                       const float* noise_dev, uint64_t seed, int64_t row_offset, int B, int T, int n_steps,
+                       float* x0_dev, void* cuda_stream) {
+  LDP_CHECK(h && x_T_dev && cond_dev && x0_dev, LDP_ERR_INVALID_ARG, "null pointer");
+  LDP_CHECK(n_steps > 0 && n_steps <= h->cfg.n_train_steps, LDP_ERR_INVALID_ARG, "n_steps must be in [1, n_train_steps]");
+  LDP_CHECK(sampler == LDP_SAMPLER_DDPM || sampler == LDP_SAMPLER_DDIM, LDP_ERR_INVALID_ARG, "unknown sampler");
+  LDP_CHECK(precision == LDP_PREC_FP32 || precision == LDP_PREC_BF16, LDP_ERR_INVALID_ARG, "unknown precision");
+  cudaStream_t s = (cudaStream_t)cuda_stream;
+  const int D = h->cfg.input_dim;
+  PlanWs* w;
+  LDP_TRY(get_ws(h, B, T, &w));
+  const size_t n = (size_t)B * T * D;
+  LDP_TRY(compute_otab(h, w, cond_dev, s));
+  LDP_CUDA_OK(cudaMemcpyAsync(w->x_state, x_T_dev, n * 4, cudaMemcpyDeviceToDevice, s));
+  DdpmCall call;
+  call.noise = noise_dev;
+  call.noise_step_stride = (long long)n;
+  call.n_steps = n_steps;
+  call.sampler = sampler;
+  call.seed = seed;
+  call.elem_offset = (long long)row_offset * T * D;
+  call.stream_id = 0;
+  LDP_CUDA_OK(cudaMemcpyAsync(w->call_dev, &call, sizeof(call), cudaMemcpyHostToDevice, s));
+  LDP_TRY(launch_set_i32(w->step_dev, n_steps - 1, s));
+  StepRef step;
+  step.dev = w->step_dev;
+  if (precision == LDP_PREC_FP32) {
+    for (int i = 0; i < n_steps; ++i) {
+      LDP_TRY(forward_f32(h, w, w->x_state, step, w->eps_buf, s));
+      DdpmStep d;
+      d.coef = h->coef; d.step = step; d.eps = w->eps_buf; d.x = w->x_state; d.out = w->x_state;
+      d.call_dev = w->call_dev; d.n = (long long)n;
+      LDP_TRY(launch_ddpm_step(d, s));
+      LDP_TRY(launch_add_i32(w->step_dev, -1, s));
+    }
+  } else {
+    LDP_TRY(prepare_bf16(h, w));
+    LDP_TRY(launch_cast_bf16(w->x_state, D, w->x_bf16, w->ld_xb, (long long)B * T, D, 0, s));
+    if (h->use_graph && !w->graph) {
+      // capture one denoising step (all GEMMs + the step-counter decrement) once per (B,T)
+      cudaStream_t cs;
+      LDP_CUDA_OK(cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));
+      long long before = launch_count_get();
+      cudaError_t e = cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal);
+      int st = LDP_OK;
+      if (e == cudaSuccess) {
+        st = run_ops_bf16(w, step, false, nullptr, D, cs);
+        if (st == LDP_OK) st = launch_add_i32(w->step_dev, -1, cs);
+        e = cudaStreamEndCapture(cs, &w->graph_src);
+      }
+      count_launch((int)(before - launch_count_get()));  // captured launches did not execute
+      if (st != LDP_OK) { cudaStreamDestroy(cs); return st; }
+      LDP_CUDA_OK(e);
+      LDP_CUDA_OK(cudaGraphInstantiate(&w->graph, w->graph_src, 0));
+      LDP_CUDA_OK(cudaStreamDestroy(cs));
+    }
+    for (int i = 0; i < n_steps; ++i) {
+      if (w->graph) {
+        LDP_CUDA_OK(cudaGraphLaunch(w->graph, s));
+        count_launch((int)w->ops.size() + 1);
+      } else {
+        LDP_TRY(run_ops_bf16(w, step, false, nullptr, D, s));
+        LDP_TRY(launch_add_i32(w->step_dev, -1, s));
+      }
+    }
+  }
+  LDP_CUDA_OK(cudaMemcpyAsync(x0_dev, w->x_state, n * 4, cudaMemcpyDeviceToDevice, s));
+  return LDP_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,377 @@
+// fp32 SIMT kernels: the exact-arithmetic path (parity gate 1e-5 vs the fp64 oracle) and the small
+// elementwise / table / packing kernels both precisions share.
+#include "kernels.h"
+
+namespace ldp {
+
+static thread_local long long g_launches = 0;
+void count_launch(int n) { g_launches += n; }
+long long launch_count_get() { return g_launches; }
+void launch_count_reset() { g_launches = 0; }
+
+#define LDP_LAUNCH_OK()                                                                                     \
+  do {                                                                                                      \
+    cudaError_t _e = cudaGetLastError();                                                                    \
+    if (_e != cudaSuccess) {                                                                                \
+      set_last_error(std::string("kernel launch failed: ") + cudaGetErrorString(_e) + " (" + __FILE__ + ":" + \
+                     std::to_string(__LINE__) + ")");                                                       \
+      return LDP_ERR_CUDA;                                                                                  \
+    }                                                                                                       \
+    count_launch();                                                                                         \
+  } while (0)
+
+// ------------------------------------------------------------------------------------------------
+// implicit-GEMM, fp32 FFMA.  64x64 tile, K step 16, 256 threads, 4x4 register tile per thread.
+// ------------------------------------------------------------------------------------------------
+constexpr int GM = 64, GN = 64, GK = 16;
+
+__global__ void __launch_bounds__(256) gemm_f32_kernel(const GemmF32 p) {
+  __shared__ float As[GK][GM + 4];
+  __shared__ float Bs[GK][GN + 4];
+  const int tid = threadIdx.x;
+  const int m0 = blockIdx.y * GM, n0 = blockIdx.x * GN;
+  const int ctot = p.c1 + p.c2;
+  const int K = p.taps * ctot;
+  const int ty = tid / 16, tx = tid % 16;
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+  for (int k0 = 0; k0 < K; k0 += GK) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      int idx = tid + i * 256;
+      int r = idx / GK, kk = idx % GK;
+      int m = m0 + r, k = k0 + kk;
+      float v = 0.f;
+      if (m < p.m && k < K) {
+        int j = k / ctot, c = k - j * ctot;
+        int b = m / p.t_out, t = m - b * p.t_out;
+        int num = t * p.stride + j - p.pad;
+        if (num >= 0 && (num % p.dil) == 0) {
+          int ti = num / p.dil;
+          if (ti < p.t_in) {
+            long long row = (long long)b * p.t_in + ti;
+            v = (c < p.c1) ? p.x1[row * p.ld1 + c] : p.x2[row * p.ld2 + (c - p.c1)];
+            if (p.a_act == 1) v = mish_f<false>(v);
+          }
+        }
+      }
+      As[kk][r] = v;
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      int idx = tid + i * 256;
+      int kk = idx / GN, nn = idx % GN;
+      int k = k0 + kk, n = n0 + nn;
+      Bs[kk][nn] = (k < K && n < p.n) ? p.w[(long long)k * p.ldw + n] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < GK; ++kk) {
+      float a[4], b[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) a[i] = As[kk][ty * 4 + i];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) b[j] = Bs[kk][tx * 4 + j];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    int m = m0 + ty * 4 + i;
+    if (m >= p.m) continue;
+    const float* tabrow = p.tab ? p.tab + (long long)step_of(p.step, m) * p.ld_tab : nullptr;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      int n = n0 + tx * 4 + j;
+      if (n >= p.n) continue;
+      float v = acc[i][j];
+      if (p.bias) v += p.bias[n];
+      if (tabrow) v += tabrow[n];
+      if (p.act == 1) v = fmaxf(v, 0.f);
+      if (p.res) v += p.res[(long long)m * p.ldres + n];
+      p.out[(long long)m * p.ldo + n] = v;
+    }
+  }
+}
+
+int launch_gemm_f32(const GemmF32& p, cudaStream_t s) {
+  LDP_CHECK(p.x1 && p.w && p.out && p.m > 0 && p.n > 0, LDP_ERR_INVALID_ARG, "gemm_f32: bad arguments");
+  dim3 grid(ceil_div(p.n, GN), ceil_div(p.m, GM));
+  gemm_f32_kernel<<<grid, 256, 0, s>>>(p);
+  LDP_LAUNCH_OK();
+  return LDP_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// GroupNorm (+Mish/SiLU) (+FiLM) (+residual), fp32.  One block per (sample, group).
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float block_sum(float v, float* sh) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  __syncthreads();
+  if (l == 0) sh[w] = v;
+  __syncthreads();
+  float t = (threadIdx.x < (blockDim.x >> 5)) ? sh[threadIdx.x] : 0.f;
+  if (w == 0) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+    if (l == 0) sh[0] = t;
+  }
+  __syncthreads();
+  return sh[0];
+}
+
+__global__ void __launch_bounds__(256) groupnorm_f32_kernel(const GroupNormF32 p) {
+  __shared__ float sh[32];
+  const int b = blockIdx.x / p.G, g = blockIdx.x % p.G;
+  const int gw = p.C / p.G;
+  const int cnt = p.P * gw;
+  const float* xb = p.x + (long long)b * p.P * p.ldx + g * gw;
+  float s = 0.f, ss = 0.f;
+  for (int i = threadIdx.x; i < cnt; i += blockDim.x) {
+    int pos = i / gw, c = i - pos * gw;
+    float v = xb[(long long)pos * p.ldx + c];
+    s += v;
+    ss += v * v;
+  }
+  s = block_sum(s, sh);
+  ss = block_sum(ss, sh);
+  const float mean = s / cnt;
+  const float var = fmaxf(ss / cnt - mean * mean, 0.f);
+  const float rstd = rsqrtf(var + p.eps);
+  const float* trow = nullptr;
+  const float* orow = nullptr;
+  if (p.film) {
+    trow = p.ttab + (long long)step_of(p.step, b) * p.ld_ttab + p.film_off;
+    orow = p.otab + (long long)b * p.ld_otab + p.film_off;
+  }
+  float* yb = p.y + (long long)b * p.P * p.ldy + g * gw;
+  const float* rb = p.res ? p.res + (long long)b * p.P * p.ldres + g * gw : nullptr;
+  for (int i = threadIdx.x; i < cnt; i += blockDim.x) {
+    int pos = i / gw, c = i - pos * gw;
+    int ch = g * gw + c;
+    float v = (xb[(long long)pos * p.ldx + c] - mean) * rstd * p.gamma[ch] + p.beta[ch];
+    if (p.act == 1) v = mish_f<false>(v);
+    else if (p.act == 2) v = v / (1.f + expf(-v));
+    if (p.film) v = (trow[ch] + orow[ch]) * v + (trow[p.C + ch] + orow[p.C + ch]);
+    if (rb) v += rb[(long long)pos * p.ldres + c];
+    yb[(long long)pos * p.ldy + c] = v;
+  }
+}
+
+int launch_groupnorm_f32(const GroupNormF32& p, cudaStream_t s) {
+  LDP_CHECK(p.x && p.y && p.B > 0 && p.G > 0 && p.C % p.G == 0, LDP_ERR_INVALID_ARG, "groupnorm_f32: bad arguments");
+  groupnorm_f32_kernel<<<p.B * p.G, 256, 0, s>>>(p);
+  LDP_LAUNCH_OK();
+  return LDP_OK;
+}
+
+// LayerNorm over the last dim, one warp per row (Flax nn.LayerNorm: eps 1e-6, fast variance).
+__global__ void layernorm_f32_kernel(const float* x, float* y, int rows, int C, const float* gamma, const float* beta,
+                                     float eps, int relu_instead) {
+  int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const float* xr = x + (long long)row * C;
+  float* yr = y + (long long)row * C;
+  if (relu_instead) {
+    for (int c = lane; c < C; c += 32) yr[c] = fmaxf(xr[c], 0.f);
+    return;
+  }
+  float s = 0.f, ss = 0.f;
+  for (int c = lane; c < C; c += 32) {
+    float v = xr[c];
+    s += v;
+    ss += v * v;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    s += __shfl_xor_sync(0xffffffffu, s, o);
+    ss += __shfl_xor_sync(0xffffffffu, ss, o);
+  }
+  float mean = s / C, var = fmaxf(ss / C - mean * mean, 0.f), rstd = rsqrtf(var + eps);
+  for (int c = lane; c < C; c += 32) yr[c] = (xr[c] - mean) * rstd * gamma[c] + beta[c];
+}
+
+int launch_layernorm_f32(const float* x, float* y, int rows, int C, const float* gamma, const float* beta, float eps,
+                         int relu_instead, cudaStream_t s) {
+  layernorm_f32_kernel<<<ceil_div(rows, 8), 256, 0, s>>>(x, y, rows, C, gamma, beta, eps, relu_instead);
+  LDP_LAUNCH_OK();
+  return LDP_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// sinusoid tables: f_j = exp(-j ln(10000)/(half-1)) in fp32 as the reference does
+// (networks/diffusion_nets_v2.py:25-30, networks/diffusion.py:17-22)
+// ------------------------------------------------------------------------------------------------
+__global__ void sinusoid_table_kernel(float* out, int n_steps, int dim, int cos_first) {
+  int half = dim / 2;
+  int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n_steps * half) return;
+  int k = idx / half, j = idx % half;
+  float scale = -(logf(10000.f) / (float)(half - 1));
+  float f = expf((float)j * scale);
+  float arg = (float)k * f;
+  float sv = sinf(arg), cv = cosf(arg);
+  float* row = out + (long long)k * dim;
+  if (cos_first) { row[j] = cv; row[half + j] = sv; }
+  else           { row[j] = sv; row[half + j] = cv; }
+}
+
+int launch_sinusoid_table(float* out, int n_steps, int dim, int cos_first, cudaStream_t s) {
+  int n = n_steps * (dim / 2);
+  sinusoid_table_kernel<<<ceil_div(n, 256), 256, 0, s>>>(out, n_steps, dim, cos_first);
+  LDP_LAUNCH_OK();
+  return LDP_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// scheduler kernels
+// ------------------------------------------------------------------------------------------------
+__global__ void ddpm_step_kernel(const DdpmStep p) {
+  const int t = step_of(p.step, 0);
+  const float* cf = p.coef + t * 8;
+  const float inv_sa = cf[0], s1a = cf[1], c0 = cf[2], ct = cf[3], sigma = cf[4], sap = cf[5], s1ap = cf[6];
+  const DdpmCall call = p.call_dev ? *p.call_dev : p.call;
+  const float* noise = call.noise ? call.noise + (long long)(call.n_steps - 1 - t) * call.noise_step_stride : nullptr;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < p.n; i += (long long)gridDim.x * blockDim.x) {
+    float e = p.eps[i], x = p.x[i];
+    float x0 = fminf(fmaxf((x - s1a * e) * inv_sa, -1.f), 1.f);
+    float o;
+    if (call.sampler == LDP_SAMPLER_DDIM) {
+      o = sap * x0 + s1ap * e;
+    } else {
+      o = c0 * x0 + ct * x;
+      if (t > 0) {
+        float z = noise ? noise[i] : philox_normal(call.seed, call.stream_id, (uint32_t)t, (unsigned long long)(call.elem_offset + i));
+        o += sigma * z;
+      }
+    }
+    p.out[i] = o;
+  }
+}
+
+int launch_ddpm_step(const DdpmStep& p, cudaStream_t s) {
+  LDP_CHECK(p.coef && p.eps && p.x && p.out && p.n > 0, LDP_ERR_INVALID_ARG, "ddpm_step: bad arguments");
+  int blocks = (int)((p.n + 255) / 256);
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  ddpm_step_kernel<<<blocks, 256, 0, s>>>(p);
+  LDP_LAUNCH_OK();
+  return LDP_OK;
+}
+
+__global__ void add_noise_kernel(const float* acp, const float* x0, const float* noise, const int32_t* t, float* out,
+                                 long long rows, long long row_len) {
+  long long n = rows * row_len;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    long long r = i / row_len;
+    float a = acp[t[r]];
+    out[i] = sqrtf(a) * x0[i] + sqrtf(1.f - a) * noise[i];
+  }
+}
+
+int launch_add_noise(const float* acp, const float* x0, const float* noise, const int32_t* t, float* out, long long rows,
+                     long long row_len, cudaStream_t s) {
+  long long n = rows * row_len;
+  int blocks = (int)((n + 255) / 256);
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  add_noise_kernel<<<blocks, 256, 0, s>>>(acp, x0, noise, t, out, rows, row_len);
+  LDP_LAUNCH_OK();
+  return LDP_OK;
+}
+
+__global__ void philox_normal_kernel(unsigned long long seed, uint32_t stream_id, uint32_t step, float* out, long long n) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    out[i] = philox_normal(seed, stream_id, step, (unsigned long long)i);
+}
+
+int launch_philox_normal(unsigned long long seed, uint32_t stream_id, uint32_t step, float* out, long long n,
+                         cudaStream_t s) {
+  int blocks = (int)((n + 255) / 256);
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  philox_normal_kernel<<<blocks, 256, 0, s>>>(seed, stream_id, step, out, n);
+  LDP_LAUNCH_OK();
+  return LDP_OK;
+}
+
+__global__ void add_i32_kernel(int32_t* p, int delta) { *p += delta; }
+__global__ void set_i32_kernel(int32_t* p, int v) { *p = v; }
+int launch_add_i32(int32_t* p, int delta, cudaStream_t s) {
+  add_i32_kernel<<<1, 1, 0, s>>>(p, delta);
+  LDP_LAUNCH_OK();
+  return LDP_OK;
+}
+int launch_set_i32(int32_t* p, int v, cudaStream_t s) {
+  set_i32_kernel<<<1, 1, 0, s>>>(p, v);
+  LDP_LAUNCH_OK();
+  return LDP_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// casts / packing
+// ------------------------------------------------------------------------------------------------
+__global__ void cast_bf16_kernel(const float* in, int ld_in, __nv_bfloat16* out, int ld_out, long long rows, int cols,
+                                 int mish) {
+  long long n = rows * ld_out;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    long long r = i / ld_out;
+    int c = (int)(i - r * ld_out);
+    float v = 0.f;
+    if (c < cols) {
+      v = in[r * ld_in + c];
+      if (mish) v = mish_f<false>(v);
+    }
+    out[i] = __float2bfloat16(v);
+  }
+}
+
+int launch_cast_bf16(const float* in, int ld_in, __nv_bfloat16* out, int ld_out, long long rows, int cols, int mish,
+                     cudaStream_t s) {
+  long long n = rows * ld_out;
+  int blocks = (int)((n + 255) / 256);
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  cast_bf16_kernel<<<blocks, 256, 0, s>>>(in, ld_in, out, ld_out, rows, cols, mish);
+  LDP_LAUNCH_OK();
+  return LDP_OK;
+}
+
+// Weight packing for the tcgen05 path: W^T as [n_pad][kp] bf16 (K contiguous), K gathered through `map`.
+__global__ void pack_wt_bf16_kernel(const float* src, int ld_src, int n_src, const int32_t* map, int kp,
+                                    __nv_bfloat16* dst, int ld_dst, int k_off, int n_pad) {
+  __shared__ float tile[32][33];
+  int k0 = blockIdx.x * 32, n0 = blockIdx.y * 32;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {   // i: k within tile; threadIdx.x: n (coalesced reads)
+    int k = k0 + i, n = n0 + threadIdx.x;
+    float v = 0.f;
+    if (k < kp && n < n_src) {
+      int sk = map[k];
+      if (sk >= 0) v = src[(long long)sk * ld_src + n];
+    }
+    tile[i][threadIdx.x] = v;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {   // i: n within tile; threadIdx.x: k (coalesced writes)
+    int n = n0 + i, k = k0 + threadIdx.x;
+    if (n < n_pad && k < kp) dst[(long long)n * ld_dst + k_off + k] = __float2bfloat16(tile[threadIdx.x][i]);
+  }
+}
+
+int launch_pack_wt_bf16(const float* src, int ld_src, int n_src, const int32_t* map, int kp, __nv_bfloat16* dst,
+                        int ld_dst, int k_off, int n_pad, cudaStream_t s) {
+  dim3 grid(ceil_div(kp, 32), ceil_div(n_pad, 32));
+  pack_wt_bf16_kernel<<<grid, dim3(32, 8), 0, s>>>(src, ld_src, n_src, map, kp, dst, ld_dst, k_off, n_pad);
+  LDP_LAUNCH_OK();
+  return LDP_OK;
+}
+
+}  // namespace ldp

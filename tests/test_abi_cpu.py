@@ -1,0 +1,69 @@
+"""CPU-side checks of the drop-in boundary: the C-ABI library builds, loads, and exports every symbol that
+include/ldp_b200.h declares; host-only entry points (schedule) match the oracle bit for bit; argument errors are
+reported through status codes, not crashes.  No GPU compute is attempted here."""
+import ctypes as C
+import re
+from pathlib import Path
+
+import numpy as np
+
+from oracle import ldp_oracle as O
+from latent_diffusion_planning_b200 import _native as N
+from latent_diffusion_planning_b200 import params as P
+
+HEADER = Path(__file__).resolve().parents[1] / "include" / "ldp_b200.h"
+
+
+def _declared():
+    text = re.sub(r"/\*.*?\*/", "", HEADER.read_text(), flags=re.S)
+    return re.findall(r"LDP_API\s+[\w\s\*]+?\b(ldp_\w+)\s*\(", text)
+
+
+def test_header_symbols_are_exported(lib):
+    names = _declared()
+    assert len(names) >= 20
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in include/ldp_b200.h but not exported by libldp_b200.so"
+    assert set(N.EXPORTS) == set(names)
+
+
+def test_schedule_host_matches_oracle(lib):
+    for n in (100, 10, 1000):
+        b, a, c = (np.empty(n, np.float32) for _ in range(3))
+        assert lib.ldp_ddpm_schedule(n, b.ctypes.data, a.ctypes.data, c.ctypes.data) == 0
+        ob, oa, oc = O.ddpm_schedule(n)
+        assert np.array_equal(b, ob) and np.array_equal(a, oa) and np.array_equal(c, oc)
+
+
+def test_param_counts_match_specs(lib):
+    cfg = N.unet_config(265, 265)
+    assert lib.ldp_unet_param_count(C.byref(cfg)) == P.spec_size(P.unet_spec(265, 265)) == 69480457
+    cfg = N.unet_config(25, 50, (64, 128))
+    assert lib.ldp_unet_param_count(C.byref(cfg)) == P.spec_size(P.unet_spec(25, 50, (64, 128)))
+    icfg = N.idm_config(265, 7)
+    assert lib.ldp_idm_param_count(C.byref(icfg)) == P.spec_size(P.idm_spec(265, 7)) == 1914887
+    icfg = N.idm_config(30, 14)
+    assert lib.ldp_idm_param_count(C.byref(icfg)) == P.spec_size(P.idm_spec(30, 14))
+
+
+def test_argument_errors_are_status_codes(lib):
+    assert lib.ldp_ddpm_schedule(0, None, None, None) == -1
+    assert b"bad arguments" in lib.ldp_last_error()
+    bad = N.unet_config(265, 265, kernel_size=3)
+    assert lib.ldp_unet_param_count(C.byref(bad)) == -1
+    h = C.c_void_p()
+    assert lib.ldp_planner_create(C.byref(N.unet_config(265, 265)), None, 0, C.byref(h)) == -1
+    assert lib.ldp_version() >= 100
+
+
+def test_flatten_roundtrip():
+    spec = P.idm_spec(25, 7)
+    p = P.init_params(spec, 3)
+    blob = P.flatten_params(spec, p)
+    assert blob.dtype == np.float32 and blob.size == P.spec_size(spec)
+    off = 0
+    for k, shp in spec.items():
+        n = int(np.prod(shp))
+        assert np.array_equal(blob[off:off + n].reshape(shp), p[k])
+        off += n
+    assert P.unnest(P.nest(p)).keys() == p.keys()

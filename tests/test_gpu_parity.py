@@ -1,0 +1,297 @@
+"""GPU parity tests: every call goes through the C ABI (ctypes) and is compared with the CPU oracle on the same
+seeded inputs.  Tolerances are the ones BASELINE.json's north_star states: 1e-5 for the fp32 path, 1e-2 for the
+bf16 tensor-core path (max-abs on O(1) tensors), bit-exact for schedule indexing / integer facts."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import ldp_oracle as O
+from latent_diffusion_planning_b200 import params as P
+
+pytestmark = pytest.mark.gpu
+
+TOL_FP32 = 1e-5
+TOL_BF16 = 1e-2
+D_RM = 265          # rm_lift: 8*8*4 latent + 9 low-dim  
+
+
+def _maxerr(a, b):
+    return float((torch.as_tensor(a, dtype=torch.float64).cpu() - torch.as_tensor(b, dtype=torch.float64).cpu()).abs().max())
+
+
+@pytest.fixture(scope="module")
+def H(cuda):
+    from latent_diffusion_planning_b200 import handles
+    return handles
+
+
+@pytest.fixture(scope="module")
+def unet_small(H):
+    """Narrow UNet (fp32 path only - GroupNorm groups of 8 channels)."""
+    D = 25
+    dims = (64, 128, 256)
+    p = P.init_params(P.unet_spec(D, D, dims), seed=0)
+    return D, dims, p, H.Planner(p, D, D, dims)
+
+
+@pytest.fixture(scope="module")
+def unet_full(H):
+    p = P.init_params(P.unet_spec(D_RM, D_RM), seed=0)
+    return p, H.Planner(p, D_RM, D_RM)
+
+
+@pytest.fixture(scope="module")
+def idm_full(H):
+    p = P.init_params(P.idm_spec(D_RM, 7), seed=1)
+    return p, H.Idm(p, D_RM, 7)
+
+
+def _inputs(B, T, D, seed=1):
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn(B, T, D, generator=g)
+    c = torch.rand(B, D, generator=g) * 2 - 1
+    return x, c
+
+
+# ------------------------------------------------------------------------------------------------
+# scheduler / RNG
+# ------------------------------------------------------------------------------------------------
+def test_schedule_tables_bit_exact(lib):
+    n = 100
+    b, a, c = (np.empty(n, np.float32) for _ in range(3))
+    assert lib.ldp_ddpm_schedule(n, b.ctypes.data, a.ctypes.data, c.ctypes.data) == 0
+    ob, oa, oc = O.ddpm_schedule(n)
+    assert np.array_equal(b, ob) and np.array_equal(a, oa) and np.array_equal(c, oc)
+
+
+def test_philox_normal_matches_oracle(H, cuda):
+    z = H.philox_normal(0x1234ABCD5678, 1, 37, 10001).cpu().numpy()
+    ref = O.philox_normal(0x1234ABCD5678, 1, 37, 10001)
+    assert np.abs(z - ref).max() < 2e-5
+
+
+@pytest.mark.parametrize("t", [99, 98, 50, 1, 0])
+@pytest.mark.parametrize("sampler", ["ddpm", "ddim"])
+def test_ddpm_step(H, cuda, t, sampler):
+    sched = O.ddpm_schedule(100)
+    g = torch.Generator().manual_seed(t)
+    x, eps, z = (torch.randn(7, 8, 33, generator=g) for _ in range(3))
+    x = x * 3      # exercise the clip
+    s = H.DDPMScheduler(100)
+    out = s.step(None, eps.cuda(), t, x.cuda(), noise=z.cuda(), sampler=sampler)
+    ref = O.ddpm_step(sched, eps, t, x, z) if sampler == "ddpm" else O.ddim_step(sched, eps, t, x)
+    assert _maxerr(out, ref) < TOL_FP32 * max(1.0, float(ref.abs().max()))
+
+
+def test_ddpm_step_philox_noise(H, cuda):
+    sched = O.ddpm_schedule(100)
+    g = torch.Generator().manual_seed(3)
+    x, eps = torch.randn(1000, generator=g), torch.randn(1000, generator=g)
+    s = H.DDPMScheduler(100)
+    out = s.step(None, eps.cuda(), 42, x.cuda(), noise=None, seed=99, stream_id=0)
+    z = torch.tensor(O.philox_normal(99, 0, 42, 1000))
+    assert _maxerr(out, O.ddpm_step(sched, eps, 42, x, z)) < 3e-5
+
+
+def test_add_noise(H, cuda):
+    sched = O.ddpm_schedule(100)
+    g = torch.Generator().manual_seed(0)
+    x0, nz = torch.randn(6, 8, 25, generator=g), torch.randn(6, 8, 25, generator=g)
+    t = torch.tensor([0, 1, 50, 98, 99, 7])
+    out = H.DDPMScheduler(100).add_noise(None, x0.cuda(), nz.cuda(), t.cuda())
+    assert _maxerr(out, O.add_noise(sched, x0, nz, t.numpy())) < TOL_FP32
+
+
+# ------------------------------------------------------------------------------------------------
+# tcgen05 GEMM in isolation
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("M,K,N", [(128, 64, 128), (300, 200, 150), (1024, 1325, 256), (4096, 256, 7)])
+def test_tc_dense(H, cuda, M, K, N):
+    rng = np.random.default_rng(M + K + N)
+    a = rng.standard_normal((M, K)).astype(np.float32)
+    w = (rng.standard_normal((K, N)) / np.sqrt(K)).astype(np.float32)
+    b = rng.standard_normal(N).astype(np.float32)
+    out = H.tc_dense(torch.tensor(a).cuda(), w, b)
+    a16 = torch.tensor(a).bfloat16().double()
+    w16 = torch.tensor(w).bfloat16().double()
+    ref = a16 @ w16 + torch.tensor(b).double()
+    assert _maxerr(out, ref) < 2e-4          # bf16-rounded operands, fp32 accumulate
+
+
+# ------------------------------------------------------------------------------------------------
+# planner score net
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("B,T", [(3, 8), (2, 16), (5, 4)])
+def test_unet_forward_fp32_small(unet_small, B, T):
+    D, dims, p, planner = unet_small
+    x, c = _inputs(B, T, D)
+    for k in (0, 50, 99):
+        out = planner.forward(x.cuda(), k, c.cuda(), precision="fp32")
+        ref = O.unet_forward(p, x, k, c, down_dims=dims)
+        assert _maxerr(out, ref) < TOL_FP32
+
+
+def test_unet_forward_fp32_per_row_timesteps(unet_small):
+    D, dims, p, planner = unet_small
+    x, c = _inputs(4, 8, D, seed=5)
+    t = torch.tensor([0, 13, 50, 99])
+    out = planner.forward(x.cuda(), t.cuda(), c.cuda(), precision="fp32")
+    ref = O.unet_forward(p, x, t.numpy(), c, down_dims=dims)
+    assert _maxerr(out, ref) < TOL_FP32
+
+
+def test_unet_forward_fp32_full_width(unet_full):
+    """BASELINE config #1: batch 4, horizon 9 (T=8), latent 8x8x4 (+9 low-dim) -> one eps prediction at k=50."""
+    p, planner = unet_full
+    x, c = _inputs(4, 8, D_RM)
+    out = planner.forward(x.cuda(), 50, c.cuda(), precision="fp32")
+    ref = O.unet_forward(p, x, 50, c)
+    assert _maxerr(out, ref) < TOL_FP32
+
+
+@pytest.mark.parametrize("B,T,k", [(4, 8, 50), (16, 8, 99), (33, 8, 0), (8, 16, 50), (6, 4, 7)])
+def test_unet_forward_bf16(unet_full, B, T, k):
+    p, planner = unet_full
+    x, c = _inputs(B, T, D_RM, seed=B)
+    out = planner.forward(x.cuda(), k, c.cuda(), precision="bf16")
+    ref = O.unet_forward(p, x, k, c)
+    assert _maxerr(out, ref) < TOL_BF16 * max(1.0, float(ref.abs().max()))
+
+
+def test_unet_bf16_per_row_timesteps(unet_full):
+    p, planner = unet_full
+    x, c = _inputs(4, 8, D_RM, seed=9)
+    t = torch.tensor([0, 13, 50, 99])
+    out = planner.forward(x.cuda(), t.cuda(), c.cuda(), precision="bf16")
+    ref = O.unet_forward(p, x, t.numpy(), c)
+    assert _maxerr(out, ref) < TOL_BF16 * max(1.0, float(ref.abs().max()))
+
+
+def test_single_reverse_step_config1(unet_full, H):
+    """Config #1 as a whole: one DDPM reverse step at k=50 with teacher forcing (oracle x_k in, x_{k-1} out)."""
+    p, planner = unet_full
+    sched = O.ddpm_schedule(100)
+    x, c = _inputs(4, 8, D_RM, seed=11)
+    z = torch.randn(4, 8, D_RM, generator=torch.Generator().manual_seed(150))
+    ref = O.ddpm_step(sched, O.unet_forward(p, x, 50, c), 50, x, z)
+    s = H.DDPMScheduler(100)
+    for prec, tol in (("fp32", TOL_FP32), ("bf16", TOL_BF16)):
+        eps = planner.forward(x.cuda(), 50, c.cuda(), precision=prec)
+        out = s.step(None, eps, 50, x.cuda(), noise=z.cuda())
+        assert _maxerr(out, ref) < tol
+
+
+# ------------------------------------------------------------------------------------------------
+# planner loop
+# ------------------------------------------------------------------------------------------------
+def test_planner_loop_fp32_matches_oracle(unet_small):
+    """Full 100-step DDPM loop with identical injected noise, fp32 path vs fp64 oracle."""
+    D, dims, p, planner = unet_small
+    B, T, n = 2, 8, 100
+    x, c = _inputs(B, T, D, seed=21)
+    z = torch.randn(n, B, T, D, generator=torch.Generator().manual_seed(100))
+    out = planner.sample(x.cuda(), c.cuda(), noise=z.cuda(), precision="fp32")
+    ref = O.planner_sample(p, O.ddpm_schedule(100), x, c, z, n, down_dims=dims)
+    assert _maxerr(out, ref) < 1e-4       # 100 chained steps; per-step gate is TOL_FP32
+
+
+def test_planner_loop_bf16_fused_equals_unfused(unet_full, H):
+    """The fused loop (DDPM update in the last GEMM's epilogue, device step counter, CUDA graph) must equal the same
+    kernels driven step by step through unet_forward + ldp_ddpm_step."""
+    p, planner = unet_full
+    B, T, n = 8, 8, 4
+    x, c = _inputs(B, T, D_RM, seed=31)
+    z = torch.randn(n, B, T, D_RM, generator=torch.Generator().manual_seed(7)).cuda()
+    fused = planner.sample(x.cuda(), c.cuda(), noise=z, n_steps=n, precision="bf16")
+    s = H.DDPMScheduler(100)
+    cur = x.cuda()
+    for i in range(n):
+        k = n - 1 - i
+        cur = s.step(None, planner.forward(cur, k, c.cuda(), precision="bf16"), k, cur, noise=z[i])
+    assert _maxerr(fused, cur) < 1e-5
+
+
+def test_planner_loop_ddim_and_philox_are_deterministic(unet_full):
+    p, planner = unet_full
+    x, c = _inputs(8, 8, D_RM, seed=41)
+    a = planner.sample(x.cuda(), c.cuda(), seed=5, n_steps=6, precision="bf16")
+    b = planner.sample(x.cuda(), c.cuda(), seed=5, n_steps=6, precision="bf16")
+    assert torch.equal(a, b)
+    # sharding invariance of the counter-based noise: rows [4:8) with row_offset 4 reproduce the unsharded result
+    half = planner.sample(x[4:].cuda(), c[4:].cuda(), seed=5, row_offset=4, n_steps=6, precision="bf16")
+    assert _maxerr(half, a[4:]) < 1e-5
+    d = planner.sample(x.cuda(), c.cuda(), n_steps=6, sampler="ddim", precision="bf16")
+    assert torch.isfinite(d).all() and float(d.abs().max()) <= 1.0 + 1e-5     # DDIM ends on the clipped x0
+
+
+def test_planner_loop_bf16_statistics(unet_full):
+    """bf16 trajectories diverge chaotically from fp64 over 100 steps (the t=99 step multiplies eps error by ~2029
+    before the clip), so end to end we compare distributions: x0 moments of bf16 vs fp32 over the same inputs."""
+    p, planner = unet_full
+    B, T, n = 16, 8, 100
+    x, c = _inputs(B, T, D_RM, seed=51)
+    z = torch.randn(n, B, T, D_RM, generator=torch.Generator().manual_seed(3)).cuda()
+    a = planner.sample(x.cuda(), c.cuda(), noise=z, precision="bf16")
+    b = planner.sample(x.cuda(), c.cuda(), noise=z, precision="fp32")
+    assert torch.isfinite(a).all()
+    assert abs(float(a.mean() - b.mean())) < 0.02 and abs(float(a.std() - b.std())) < 0.02
+    assert float((a - b).abs().mean()) < 0.05
+
+
+# ------------------------------------------------------------------------------------------------
+# IDM
+# ------------------------------------------------------------------------------------------------
+def _idm_inputs(N, seed=2):
+    g = torch.Generator().manual_seed(seed)
+    return torch.rand(N, 2 * D_RM, generator=g) * 2 - 1, torch.randn(N, 7, generator=g)
+
+
+@pytest.mark.parametrize("N", [5, 128, 300])
+def test_idm_forward(idm_full, N):
+    p, idm = idm_full
+    s, a = _idm_inputs(N)
+    for k in (0, 50, 99):
+        ref = O.idm_forward(p, s, a, k)
+        assert _maxerr(idm.forward(s.cuda(), a.cuda(), k, precision="fp32"), ref) < TOL_FP32 * max(1.0, float(ref.abs().max()))
+        assert _maxerr(idm.forward(s.cuda(), a.cuda(), k, precision="bf16"), ref) < TOL_BF16 * max(1.0, float(ref.abs().max()))
+
+
+def test_idm_forward_per_row_time(idm_full):
+    p, idm = idm_full
+    s, a = _idm_inputs(6)
+    t = torch.tensor([0, 1, 50, 98, 99, 7])
+    ref = O.idm_forward(p, s, a, t.numpy())
+    assert _maxerr(idm.forward(s.cuda(), a.cuda(), t.cuda(), precision="fp32"), ref) < TOL_FP32 * max(1.0, float(ref.abs().max()))
+
+
+def test_idm_loop(idm_full):
+    p, idm = idm_full
+    N, n = 12, 100
+    s, a = _idm_inputs(N, seed=8)
+    z = torch.randn(n, N, 7, generator=torch.Generator().manual_seed(4))
+    ref = O.idm_sample(p, O.ddpm_schedule(100), s, a, z, n)
+    out = idm.sample(s.cuda(), a.cuda(), noise=z.cuda(), precision="fp32")
+    assert _maxerr(out, ref) < 1e-4
+    out16 = idm.sample(s.cuda(), a.cuda(), noise=z.cuda(), precision="bf16")
+    assert torch.isfinite(out16).all() and float((out16.cpu() - ref.float()).abs().mean()) < 0.05
+
+
+# ------------------------------------------------------------------------------------------------
+# error behaviour of the ABI
+# ------------------------------------------------------------------------------------------------
+def test_abi_errors(unet_small, H):
+    from latent_diffusion_planning_b200 import _native as N
+    D, dims, p, planner = unet_small
+    x, c = _inputs(2, 6, D)           # T=6 is invalid for a 3-level UNet (skip lengths would mismatch)
+    with pytest.raises(N.LdpError) as e:
+        planner.forward(x.cuda(), 3, c.cuda(), precision="fp32")
+    assert e.value.code == -2
+    with pytest.raises(N.LdpError):
+        planner.forward(_inputs(2, 8, D)[0].cuda(), 100, c.cuda(), precision="fp32")     # timestep out of range
+    import ctypes as C
+    lib = N.load()
+    blob = P.flatten_params(P.unet_spec(D, D, dims), p)
+    h = C.c_void_p()
+    cfg = N.unet_config(D + 1, D, dims)                                                  # wrong blob length for this config
+    assert lib.ldp_planner_create(C.byref(cfg), blob.ctypes.data, blob.size, C.byref(h)) == -5
+    assert b"floats" in lib.ldp_last_error()
