@@ -9,8 +9,10 @@
 // * W^T tiles come from weights pre-packed K-major ([N_pad][K_pad] bf16) at handle creation.
 // * Both land in 128B-swizzled shared memory; one elected thread issues tcgen05.mma (M=128, N=BN, K=16)
 //   with the fp32 accumulator in TMEM; a 4-stage mbarrier ring overlaps TMA with MMA.
-// * Warp roles: warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2-5 = epilogue
-//   (each owns one 32-lane quarter of TMEM; thread i owns output row 32*quarter+i).
+// * Warp roles: warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2-9 = epilogue
+//   (two warps per 32-lane TMEM quarter, each taking half of the tile's columns; thread i owns output row
+//   32*quarter+i).  Per-column vectors (bias, norm affine, FiLM time part) are staged in shared memory while
+//   the main loop runs.
 // * Fused epilogues (all fp32 math on the accumulator, read with tcgen05.ld):
 //     PLAIN  bias (+ReLU) (+residual) -> f32 and/or bf16
 //     GN     bias -> GroupNorm over (rows of one sample x group channels) -> Mish -> [FiLM] -> [+residual] -> bf16
@@ -26,8 +28,10 @@ constexpr int TC_BM = 128;
 constexpr int TC_BK = 64;
 constexpr int TC_STAGES = 4;
 constexpr int TC_A_BYTES = TC_BM * TC_BK * 2;   // 16 KB
-constexpr int TC_THREADS = 192;
-constexpr int TC_MAX_KB_SMEM = 320;
+constexpr int TC_EPI_WARPS = 8;                 // two warps per TMEM lane quarter, each takes half of the columns
+constexpr int TC_EPI_THREADS = TC_EPI_WARPS * 32;
+constexpr int TC_THREADS = 64 + TC_EPI_THREADS; // warp 0: TMA, warp 1: MMA, warps 2..9: epilogue
+constexpr int TC_MAX_KB_SMEM = 256;
 
 template <int BN>
 struct TcSmem {
@@ -36,7 +40,27 @@ struct TcSmem {
   static constexpr int TOTAL = TC_STAGES * STAGE_BYTES + 1024;   // + alignment slack
 };
 
-// ---- epilogue helpers ---------------------------------------------------------------------------
+// Per-CTA staging of everything the epilogue needs per output column (filled while the main loop runs).
+template <int BN>
+struct EpiSmem {
+  float bias[BN];
+  float gamma[BN];
+  float beta[BN];
+  float fscale[BN];     // FiLM scale / shift, time part (valid when the whole launch shares one timestep)
+  float fshift[BN];
+  float2 part[TC_BM][BN / 32];   // per-row, per-32-column-chunk (sum, sum of squares)
+};
+
+__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, %0;" ::"n"(TC_EPI_THREADS) : "memory"); }
+
+__device__ __forceinline__ float mish_fast(float y) {
+  // y * n/(n+2), n = e^y (e^y + 2); the exponent is clamped so that n stays finite (ratio is 1 to fp32 there)
+  float e = exp2f(fminf(y, 20.f) * 1.4426950408889634f);
+  float n = e * (e + 2.f);
+  return y * __fdividef(n, n + 2.f);
+}
+
+// ---- vector load/store helpers (32 consecutive columns of one row) -------------------------------------
 __device__ __forceinline__ void store_bf16x32(__nv_bfloat16* dst, const float (&v)[32], bool vec_ok, int nvalid) {
   if (vec_ok && nvalid == 32) {
     uint4* d4 = reinterpret_cast<uint4*>(dst);
@@ -68,166 +92,259 @@ __device__ __forceinline__ void store_f32x32(float* dst, const float (&v)[32], b
   }
 }
 
+__device__ __forceinline__ void add_f32x32(float (&v)[32], const float* src, bool vec_ok, int nvalid) {
+  if (vec_ok && nvalid == 32) {
+    const float4* s4 = reinterpret_cast<const float4*>(src);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float4 f = s4[j];
+      v[4 * j] += f.x; v[4 * j + 1] += f.y; v[4 * j + 2] += f.z; v[4 * j + 3] += f.w;
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < 32; ++i)
+      if (i < nvalid) v[i] += src[i];
+  }
+}
+
+__device__ __forceinline__ void add_bf16x32(float (&v)[32], const __nv_bfloat16* src, bool vec_ok, int nvalid) {
+  if (vec_ok && nvalid == 32) {
+    const uint4* rp = reinterpret_cast<const uint4*>(src);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      uint4 u = rp[j];
+      const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        float2 f = __bfloat1622float2(h[q]);
+        v[8 * j + 2 * q] += f.x;
+        v[8 * j + 2 * q + 1] += f.y;
+      }
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < 32; ++i)
+      if (i < nvalid) v[i] += __bfloat162float(src[i]);
+  }
+}
+
+// v[i] += s[i] for 32 consecutive floats of a shared-memory vector (LDS.128, broadcast across the warp)
+__device__ __forceinline__ void add_smem32(float (&v)[32], const float* s) {
+  const float4* s4 = reinterpret_cast<const float4*>(s);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    float4 f = s4[j];
+    v[4 * j] += f.x; v[4 * j + 1] += f.y; v[4 * j + 2] += f.z; v[4 * j + 3] += f.w;
+  }
+}
+
+// ---- epilogues: thread owns row `m`; this warp covers chunks [c_begin, c_begin + CPP) of the N tile ------------
 template <int BN>
-__device__ __forceinline__ void epilogue_plain(const TcGemm& p, uint32_t taddr, int m, int n0) {
+__device__ __forceinline__ void epilogue_plain(const TcGemm& p, EpiSmem<BN>& es, uint32_t taddr, int m, int n0,
+                                               int c_begin) {
+  constexpr int CPP = BN / 32 / 2;
   const bool row_ok = m < p.M;
-#pragma unroll 1
-  for (int c = 0; c < BN / 32; ++c) {
-    float v[32];
-    tmem_ld_32x32(taddr + c * 32, v);
+  const bool vf = (p.ld_out_f32 & 3) == 0, vb = (p.ld_out_bf16 & 7) == 0;
+  const bool vrf = (p.ld_res_f32 & 3) == 0, vrb = (p.ld_res_bf16 & 7) == 0;
+#pragma unroll
+  for (int cc = 0; cc < CPP; ++cc) {
+    const int c = c_begin + cc;
     const int nb = n0 + c * 32;
     const int nvalid = min(32, p.N - nb);
     if (nvalid <= 0) continue;           // uniform across the warp
+    float v[32];
+    tmem_ld_32x32(taddr + c * 32, v);
+    add_smem32(v, es.bias + c * 32);
+    if (p.relu) {
 #pragma unroll
-    for (int i = 0; i < 32; ++i) {
-      int n = nb + i;
-      float x = v[i];
-      if (i < nvalid) {
-        if (p.bias) x += __ldg(p.bias + n);
-        if (p.relu) x = fmaxf(x, 0.f);
-        if (row_ok) {
-          if (p.res_f32) x += p.res_f32[(long long)m * p.ld_res_f32 + n];
-          if (p.res_bf16) x += __bfloat162float(p.res_bf16[(long long)m * p.ld_res_bf16 + n]);
-        }
-      }
-      v[i] = x;
+      for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
     }
     if (row_ok) {
-      if (p.out_f32) store_f32x32(p.out_f32 + (long long)m * p.ld_out_f32 + nb, v, (p.ld_out_f32 & 3) == 0, nvalid);
-      if (p.out_bf16) store_bf16x32(p.out_bf16 + (long long)m * p.ld_out_bf16 + nb, v, (p.ld_out_bf16 & 7) == 0, nvalid);
+      if (p.res_f32) add_f32x32(v, p.res_f32 + (long long)m * p.ld_res_f32 + nb, vrf, nvalid);
+      if (p.res_bf16) add_bf16x32(v, p.res_bf16 + (long long)m * p.ld_res_bf16 + nb, vrb, nvalid);
+      if (p.out_f32) store_f32x32(p.out_f32 + (long long)m * p.ld_out_f32 + nb, v, vf, nvalid);
+      if (p.out_bf16) store_bf16x32(p.out_bf16 + (long long)m * p.ld_out_bf16 + nb, v, vb, nvalid);
     }
   }
 }
 
 template <int BN>
-__device__ __forceinline__ void epilogue_gn(const TcGemm& p, uint32_t taddr, int m, int n0) {
-  constexpr int NC = BN / 32;
+__device__ __forceinline__ void epilogue_gn(const TcGemm& p, EpiSmem<BN>& es, uint32_t taddr, int m, int n0, int c_begin,
+                                            int row) {
+  constexpr int NC = BN / 32, CPP = NC / 2;
   const int T = p.rows_per_item;
-  const int cpg = p.group_width >> 5;                    // 32-column chunks per group: 1, 2, 4 (or 8)
-  const int nchunks = min(NC, (p.N - n0) >> 5);          // N and group widths are multiples of 32 here
+  const int cpg = p.group_width >> 5;                    // chunks per group: 1, 2, 4 or 8
+  const int nchunks = min(NC, (p.N - n0) >> 5);          // N and the group widths are multiples of 32 here
   const bool row_ok = m < p.M;
-  float cs[NC], css[NC];
-  // pass 1: per-chunk sums of (acc + bias) and its square over this thread's row
+  // pass 1: (sum, sum sq) of (acc + bias) per 32-column chunk of this thread's row
 #pragma unroll
-  for (int c = 0; c < NC; ++c) {
-    cs[c] = 0.f;
-    css[c] = 0.f;
+  for (int cc = 0; cc < CPP; ++cc) {
+    const int c = c_begin + cc;
+    float s = 0.f, ss = 0.f;
     if (c < nchunks) {
       float v[32];
       tmem_ld_32x32(taddr + c * 32, v);
-      const float* bp = p.bias + n0 + c * 32;
+      add_smem32(v, es.bias + c * 32);
 #pragma unroll
       for (int i = 0; i < 32; ++i) {
-        float x = v[i] + __ldg(bp + i);
-        cs[c] += x;
-        css[c] += x * x;
+        s += v[i];
+        ss = fmaf(v[i], v[i], ss);
       }
     }
+    es.part[row][c] = make_float2(s, ss);
   }
-  // group totals (same value replicated on every chunk of the group), then across the T rows of the sample
-  float mean[NC], rstd[NC];
+  epi_bar();
+  // group statistics: chunks of the group (from smem) x the T rows of the sample (adjacent lanes)
+  float mean[CPP], rstd[CPP];
   const float inv_cnt = 1.f / (float)(T * p.group_width);
 #pragma unroll
-  for (int c = 0; c < NC; ++c) {
+  for (int cc = 0; cc < CPP; ++cc) {
+    const int c = c_begin + cc;
+    const int g0 = (c / cpg) * cpg;
     float s = 0.f, ss = 0.f;
-#pragma unroll
-    for (int c2 = 0; c2 < NC; ++c2) {
-      bool same = (c2 / cpg) == (c / cpg);
-      s += same ? cs[c2] : 0.f;
-      ss += same ? css[c2] : 0.f;
+    for (int c2 = g0; c2 < g0 + cpg; ++c2) {
+      float2 q = es.part[row][c2];
+      s += q.x;
+      ss += q.y;
     }
     for (int off = 1; off < T; off <<= 1) {
       s += __shfl_xor_sync(0xffffffffu, s, off);
       ss += __shfl_xor_sync(0xffffffffu, ss, off);
     }
-    float mu = s * inv_cnt;
-    float var = fmaxf(ss * inv_cnt - mu * mu, 0.f);
-    mean[c] = mu;
-    rstd[c] = rsqrtf(var + p.eps);
+    const float mu = s * inv_cnt;
+    mean[cc] = mu;
+    rstd[cc] = rsqrtf(fmaxf(ss * inv_cnt - mu * mu, 0.f) + p.eps);
   }
-  // pass 2: normalise -> Mish -> FiLM -> residual -> bf16
-  const int b = m / T;
-  const float* trow = nullptr;
-  const float* orow = nullptr;
-  if (p.film) {
-    trow = p.ttab + (long long)step_of(p.step, row_ok ? m : 0) * p.ld_ttab + p.film_off;
-    orow = p.otab + (long long)(row_ok ? b : 0) * p.ld_otab + p.film_off;
-  }
+  // pass 2: normalise -> Mish -> FiLM -> residual -> store
+  const int b = (row_ok ? m : 0) / T;
+  const float* orow = p.film ? p.otab + (long long)b * p.ld_otab + p.film_off : nullptr;
+  const float* trow = (p.film && p.step.rows) ? p.ttab + (long long)step_of(p.step, row_ok ? m : 0) * p.ld_ttab + p.film_off
+                                              : nullptr;        // per-row timesteps (training-style call)
 #pragma unroll
-  for (int c = 0; c < NC; ++c) {
-    if (c < nchunks) {
-      float v[32];
-      tmem_ld_32x32(taddr + c * 32, v);
-      const int nb = n0 + c * 32;
+  for (int cc = 0; cc < CPP; ++cc) {
+    const int c = c_begin + cc;
+    if (c >= nchunks) continue;
+    const int nb = n0 + c * 32;
+    float v[32];
+    tmem_ld_32x32(taddr + c * 32, v);
+    const float4* b4 = reinterpret_cast<const float4*>(es.bias + c * 32);
+    const float4* g4 = reinterpret_cast<const float4*>(es.gamma + c * 32);
+    const float4* be4 = reinterpret_cast<const float4*>(es.beta + c * 32);
+    const float mu = mean[cc], rs = rstd[cc];
 #pragma unroll
-      for (int i = 0; i < 32; ++i) {
-        int n = nb + i;
-        float x = v[i] + __ldg(p.bias + n);
-        x = (x - mean[c]) * rstd[c] * __ldg(p.gamma + n) + __ldg(p.beta + n);
-        x = mish_f<true>(x);
-        if (p.film) x = (__ldg(trow + n) + orow[n]) * x + (__ldg(trow + p.film_c + n) + orow[p.film_c + n]);
-        v[i] = x;
-      }
-      if (p.use_aux) {
-        float r[32];
-        tmem_ld_32x32(taddr + BN + c * 32, r);
+    for (int j = 0; j < 8; ++j) {
+      const float4 bb = b4[j], gg = g4[j], be = be4[j];
+      v[4 * j + 0] = mish_fast(fmaf(v[4 * j + 0] + bb.x - mu, rs * gg.x, be.x));
+      v[4 * j + 1] = mish_fast(fmaf(v[4 * j + 1] + bb.y - mu, rs * gg.y, be.y));
+      v[4 * j + 2] = mish_fast(fmaf(v[4 * j + 2] + bb.z - mu, rs * gg.z, be.z));
+      v[4 * j + 3] = mish_fast(fmaf(v[4 * j + 3] + bb.w - mu, rs * gg.w, be.w));
+    }
+    if (p.film) {
+      const float4* fs4 = reinterpret_cast<const float4*>(es.fscale + c * 32);
+      const float4* fb4 = reinterpret_cast<const float4*>(es.fshift + c * 32);
+      const float4* os4 = reinterpret_cast<const float4*>(orow + nb);
+      const float4* ob4 = reinterpret_cast<const float4*>(orow + p.film_c + nb);
 #pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] += r[i] + __ldg(p.bias_aux + nb + i);
-      } else if (p.res_bf16 && row_ok) {
-        const uint4* rp = reinterpret_cast<const uint4*>(p.res_bf16 + (long long)m * p.ld_res_bf16 + nb);
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          uint4 u = rp[j];
-          const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            float2 f = __bfloat1622float2(h[q]);
-            v[8 * j + 2 * q] += f.x;
-            v[8 * j + 2 * q + 1] += f.y;
-          }
+      for (int j = 0; j < 8; ++j) {
+        float4 sc = fs4[j], sh = fb4[j];
+        const float4 o1 = __ldg(os4 + j), o2 = __ldg(ob4 + j);
+        sc.x += o1.x; sc.y += o1.y; sc.z += o1.z; sc.w += o1.w;
+        sh.x += o2.x; sh.y += o2.y; sh.z += o2.z; sh.w += o2.w;
+        if (trow) {
+          const float4 t1 = __ldg(reinterpret_cast<const float4*>(trow + nb) + j);
+          const float4 t2 = __ldg(reinterpret_cast<const float4*>(trow + p.film_c + nb) + j);
+          sc.x += t1.x; sc.y += t1.y; sc.z += t1.z; sc.w += t1.w;
+          sh.x += t2.x; sh.y += t2.y; sh.z += t2.z; sh.w += t2.w;
         }
+        v[4 * j + 0] = fmaf(sc.x, v[4 * j + 0], sh.x);
+        v[4 * j + 1] = fmaf(sc.y, v[4 * j + 1], sh.y);
+        v[4 * j + 2] = fmaf(sc.z, v[4 * j + 2], sh.z);
+        v[4 * j + 3] = fmaf(sc.w, v[4 * j + 3], sh.w);
       }
-      if (row_ok) {
-        if (p.out_bf16) store_bf16x32(p.out_bf16 + (long long)m * p.ld_out_bf16 + nb, v, true, 32);
-        if (p.out_f32) store_f32x32(p.out_f32 + (long long)m * p.ld_out_f32 + nb, v, true, 32);
-      }
+    }
+    if (p.use_aux) {
+      float r[32];
+      tmem_ld_32x32(taddr + BN + c * 32, r);
+      const float* ba = p.bias_aux + nb;
+#pragma unroll
+      for (int i = 0; i < 32; ++i) v[i] += r[i] + __ldg(ba + i);
+    } else if (p.res_bf16 && row_ok) {
+      add_bf16x32(v, p.res_bf16 + (long long)m * p.ld_res_bf16 + nb, true, 32);
+    }
+    if (row_ok) {
+      if (p.out_bf16) store_bf16x32(p.out_bf16 + (long long)m * p.ld_out_bf16 + nb, v, true, 32);
+      if (p.out_f32) store_f32x32(p.out_f32 + (long long)m * p.ld_out_f32 + nb, v, true, 32);
     }
   }
 }
 
+// Four standard normals of Philox quad q (elements 4q..4q+3): two Box-Muller pairs.
+__device__ __forceinline__ void philox_normal4(unsigned long long seed, uint32_t stream, uint32_t step,
+                                               unsigned long long q, float (&z)[4]) {
+  uint4 r = philox4x32_10(make_uint4((uint32_t)q, (uint32_t)(q >> 32), step, stream),
+                          make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+  const float k = 2.3283064365386963e-10f;
+  float u0 = ((float)r.x + 0.5f) * k, u1 = ((float)r.y + 0.5f) * k;
+  float u2 = ((float)r.z + 0.5f) * k, u3 = ((float)r.w + 0.5f) * k;
+  float ra = sqrtf(-2.f * logf(u0)), rb = sqrtf(-2.f * logf(u2));
+  float s, c;
+  sincospif(2.f * u1, &s, &c);
+  z[0] = ra * c; z[1] = ra * s;
+  sincospif(2.f * u3, &s, &c);
+  z[2] = rb * c; z[3] = rb * s;
+}
+
 template <int BN>
-__device__ __forceinline__ void epilogue_ddpm(const TcGemm& p, uint32_t taddr, int m, int n0) {
+__device__ __forceinline__ void epilogue_ddpm(const TcGemm& p, EpiSmem<BN>& es, uint32_t taddr, int m, int n0,
+                                              int c_begin) {
+  constexpr int CPP = BN / 32 / 2;
   const bool row_ok = m < p.M;
   const int t = step_of(p.step, 0);
   const float* cf = p.coef + t * 8;
   const float inv_sa = cf[0], s1a = cf[1], c0 = cf[2], ct = cf[3], sigma = cf[4], sap = cf[5], s1ap = cf[6];
   const DdpmCall call = p.call_dev ? *p.call_dev : p.call;
   const float* noise = call.noise ? call.noise + (long long)(call.n_steps - 1 - t) * call.noise_step_stride : nullptr;
+  const bool ddim = call.sampler == LDP_SAMPLER_DDIM;
+  const bool add_noise = !ddim && t > 0;
 #pragma unroll 1
-  for (int c = 0; c < BN / 32; ++c) {
-    float v[32];
-    tmem_ld_32x32(taddr + c * 32, v);
+  for (int cc = 0; cc < CPP; ++cc) {
+    const int c = c_begin + cc;
     const int nb = n0 + c * 32;
     const int nvalid = min(32, p.N - nb);
-    if (nvalid <= 0 || !row_ok) continue;
+    if (nvalid <= 0) continue;                 // uniform
+    float v[32];
+    tmem_ld_32x32(taddr + c * 32, v);
+    if (!row_ok) continue;
+    add_smem32(v, es.bias + c * 32);
     float* xr = p.x_io + (long long)m * p.ld_x + nb;
     const long long e0 = (long long)m * p.N + nb;
+    float z4[4];
+    unsigned long long cur_q = ~0ull;
 #pragma unroll
     for (int i = 0; i < 32; ++i) {
       if (i < nvalid) {
-        float e = v[i] + __ldg(p.bias + nb + i);
-        float x = xr[i];
-        float x0 = fminf(fmaxf((x - s1a * e) * inv_sa, -1.f), 1.f);
+        const float e = v[i];
+        const float x = xr[i];
+        const float x0 = fminf(fmaxf((x - s1a * e) * inv_sa, -1.f), 1.f);
         float o;
-        if (call.sampler == LDP_SAMPLER_DDIM) {
+        if (ddim) {
           o = sap * x0 + s1ap * e;
         } else {
           o = c0 * x0 + ct * x;
-          if (t > 0) {
-            float z = noise ? noise[e0 + i]
-                            : philox_normal(call.seed, call.stream_id, (uint32_t)t,
-                                            (unsigned long long)(call.elem_offset + e0 + i));
-            o += sigma * z;
+          if (add_noise) {
+            float z;
+            if (noise) {
+              z = noise[e0 + i];
+            } else {
+              const unsigned long long ge = (unsigned long long)(call.elem_offset + e0 + i);
+              if ((ge >> 2) != cur_q) {
+                cur_q = ge >> 2;
+                philox_normal4(call.seed, call.stream_id, (uint32_t)t, cur_q, z4);
+              }
+              const uint32_t ln = (uint32_t)ge & 3u;
+              z = ln == 0 ? z4[0] : (ln == 1 ? z4[1] : (ln == 2 ? z4[2] : z4[3]));
+            }
+            o = fmaf(sigma, z, o);
           }
         }
         xr[i] = o;
@@ -239,43 +356,49 @@ __device__ __forceinline__ void epilogue_ddpm(const TcGemm& p, uint32_t taddr, i
 }
 
 template <int BN>
-__device__ __forceinline__ void epilogue_ln(const TcGemm& p, uint32_t taddr, int m, int n0) {
-  // requires N == BN (the whole feature row lives in this tile)
+__device__ __forceinline__ void epilogue_ln(const TcGemm& p, EpiSmem<BN>& es, uint32_t taddr, int m, int n0, int c_begin,
+                                            int row, int part) {
+  // requires N == BN: the whole feature row lives in this tile, split over the two warps of the lane quarter
+  constexpr int CPP = BN / 32 / 2;
   const bool row_ok = m < p.M;
   float s = 0.f, ss = 0.f;
   float* hrow = p.out_f32 + (long long)(row_ok ? m : 0) * p.ld_out_f32;
+  const bool vf = (p.ld_out_f32 & 3) == 0, vr = (p.ld_res_f32 & 3) == 0;
 #pragma unroll 1
-  for (int c = 0; c < BN / 32; ++c) {
+  for (int cc = 0; cc < CPP; ++cc) {
+    const int c = c_begin + cc;
+    const int nb = n0 + c * 32;
     float v[32];
     tmem_ld_32x32(taddr + c * 32, v);
-    const int nb = n0 + c * 32;
+    add_smem32(v, es.bias + c * 32);
+    if (p.res_f32 && row_ok) add_f32x32(v, p.res_f32 + (long long)m * p.ld_res_f32 + nb, vr, 32);
 #pragma unroll
     for (int i = 0; i < 32; ++i) {
-      float x = v[i] + __ldg(p.bias + nb + i);
-      if (p.res_f32 && row_ok) x += p.res_f32[(long long)m * p.ld_res_f32 + nb + i];
-      s += x;
-      ss += x * x;
-      v[i] = x;
+      s += v[i];
+      ss = fmaf(v[i], v[i], ss);
     }
-    if (row_ok) store_f32x32(hrow + nb, v, (p.ld_out_f32 & 3) == 0, 32);
+    if (row_ok) store_f32x32(hrow + nb, v, vf, 32);
   }
-  const float mu = s / (float)BN;
-  const float rs = rsqrtf(fmaxf(ss / (float)BN - mu * mu, 0.f) + p.eps);
+  es.part[row][part] = make_float2(s, ss);
+  epi_bar();
+  const float2 q0 = es.part[row][0], q1 = es.part[row][1];
+  const float mu = (q0.x + q1.x) / (float)BN;
+  const float rs = rsqrtf(fmaxf((q0.y + q1.y) / (float)BN - mu * mu, 0.f) + p.eps);
   if (!row_ok || !p.out_bf16) return;
 #pragma unroll 1
-  for (int c = 0; c < BN / 32; ++c) {
-    float v[32];
+  for (int cc = 0; cc < CPP; ++cc) {
+    const int c = c_begin + cc;
     const int nb = n0 + c * 32;
-    const float4* h4 = reinterpret_cast<const float4*>(hrow + nb);   // written above by this same thread
+    float v[32];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      float4 f = h4[j];
-      v[4 * j] = f.x; v[4 * j + 1] = f.y; v[4 * j + 2] = f.z; v[4 * j + 3] = f.w;
-    }
+    for (int i = 0; i < 32; ++i) v[i] = 0.f;
+    add_f32x32(v, hrow + nb, vf, 32);                     // h written above by this same thread
+    if (p.relu) {
 #pragma unroll
-    for (int i = 0; i < 32; ++i) {
-      float x = v[i];
-      v[i] = p.relu ? fmaxf(x, 0.f) : (x - mu) * rs * __ldg(p.gamma + nb + i) + __ldg(p.beta + nb + i);
+      for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
+    } else {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) v[i] = fmaf((v[i] - mu) * rs, es.gamma[c * 32 + i], es.beta[c * 32 + i]);
     }
     store_bf16x32(p.out_bf16 + (long long)m * p.ld_out_bf16 + nb, v, (p.ld_out_bf16 & 7) == 0, 32);
   }
@@ -290,6 +413,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
   __shared__ __align__(8) uint64_t bar_accum;
   __shared__ uint32_t tmem_holder;
   __shared__ __align__(16) TcKBlock kb_s[TC_MAX_KB_SMEM];     // K-block table staged once per CTA
+  __shared__ __align__(16) EpiSmem<BN> es;
 
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const int warp = threadIdx.x >> 5;
@@ -367,17 +491,37 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
       umma_commit(smem_u32(&bar_accum));                // accumulator(s) complete
     }
   } else {
-    // ===================== epilogue warps (2..5) =====================
+    // ===================== epilogue warps (2..9) =====================
+    const int ew = warp - 2;
     const int quarter = warp & 3;                        // TMEM lane quarter this warp may access
-    const int m = tile_m * TC_BM + quarter * 32 + lane;
+    const int part = ew >> 2;                            // which half of the tile's columns
+    const int row = quarter * 32 + lane;
+    const int m = tile_m * TC_BM + row;
+    // stage the per-column vectors while the main loop runs
+    {
+      const int et = threadIdx.x - 64;
+      const bool uniform_step = p.film && p.step.rows == nullptr;
+      const float* trow = uniform_step ? p.ttab + (long long)step_of(p.step, 0) * p.ld_ttab + p.film_off : nullptr;
+      for (int i = et; i < BN; i += TC_EPI_THREADS) {
+        const int n = n0 + i;
+        const bool ok = n < p.N;
+        es.bias[i] = (ok && p.bias) ? __ldg(p.bias + n) : 0.f;
+        es.gamma[i] = (ok && p.gamma) ? __ldg(p.gamma + n) : 0.f;
+        es.beta[i] = (ok && p.beta) ? __ldg(p.beta + n) : 0.f;
+        es.fscale[i] = (ok && trow) ? __ldg(trow + n) : 0.f;
+        es.fshift[i] = (ok && trow) ? __ldg(trow + p.film_c + n) : 0.f;
+      }
+      epi_bar();
+    }
     mbar_wait(smem_u32(&bar_accum), 0);
     tc_fence_after();
     const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16);
+    const int c_begin = part * (BN / 64);
     switch (p.mode) {
-      case TC_EPI_PLAIN: epilogue_plain<BN>(p, taddr, m, n0); break;
-      case TC_EPI_GN:    epilogue_gn<BN>(p, taddr, m, n0); break;
-      case TC_EPI_DDPM:  epilogue_ddpm<BN>(p, taddr, m, n0); break;
-      default:           epilogue_ln<BN>(p, taddr, m, n0); break;
+      case TC_EPI_PLAIN: epilogue_plain<BN>(p, es, taddr, m, n0, c_begin); break;
+      case TC_EPI_GN:    epilogue_gn<BN>(p, es, taddr, m, n0, c_begin, row); break;
+      case TC_EPI_DDPM:  epilogue_ddpm<BN>(p, es, taddr, m, n0, c_begin); break;
+      default:           epilogue_ln<BN>(p, es, taddr, m, n0, c_begin, row, part); break;
     }
   }
 
