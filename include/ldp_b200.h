@@ -122,6 +122,12 @@ LDP_API int ldp_planner_sample(LdpPlanner* h, int precision, int sampler, const 
                                const float* noise_dev, uint64_t seed, int64_t row_offset, int B, int T, int n_steps,
                                float* x0_dev, void* cuda_stream);
 
+/* Diagnostics (no reference counterpart): times every kernel of one bf16 denoising step in isolation - `reps`
+ * back-to-back launches between two CUDA events per kernel.  us_host[i] = microseconds per launch of kernel i;
+ * meta_host[4i..4i+3] = {M, N, K/64, block_n | epilogue << 16 | aux << 24}.  *n_ops = number of kernels. */
+LDP_API int ldp_planner_profile_step(LdpPlanner* h, int B, int T, int reps, float* us_host, int32_t* meta_host,
+                                     int max_ops, int* n_ops, void* cuda_stream);
+
 /* ---------------------------------------------------------------------------------------------------------
  * Inverse-dynamics score network  -  MLPDiffusion(FourierFeatures -> MLP -> MLPResNet)
  * (reference networks/mlp_diffusion_nets.py:8-68, networks/diffusion.py:7-22, networks/mlp_nets.py:49-97)

@@ -119,7 +119,7 @@ struct TcGemm {
   const TcKBlock* kb = nullptr;     // device table
   int num_kb = 0;
   int M = 0, N = 0;                 // logical output size
-  int block_n = 128;                // 128 or 256
+  int block_n = 128;                // 64, 128 or 256
   int use_aux = 0;                  // second accumulator present (columns [BN, 2BN) of TMEM)
   // tile -> TMA coordinates: (q, r) = divmod(tile_m, tiles_per_item); c2 = r*rows_step + kb.d2; c3 = q*items_per_tile
   int tiles_per_item = 1, rows_step = 0, items_per_tile = 1;
@@ -128,6 +128,7 @@ struct TcGemm {
   const float* bias = nullptr;      // [N]
   const float* bias_aux = nullptr;  // [N] for the aux accumulator
   int relu = 0;
+  int gn_act = 0;                   // GN epilogue activation: 0 Mish, 1 swish
   float* out_f32 = nullptr; int ld_out_f32 = 0;
   __nv_bfloat16* out_bf16 = nullptr; int ld_out_bf16 = 0;
   const float* res_f32 = nullptr; int ld_res_f32 = 0;
@@ -151,6 +152,9 @@ int launch_tc_gemm(const TcGemm& p, cudaStream_t s);
 // bf16 tensor, up to 4-D, dims/strides innermost-first (strides in BYTES for dims 1..rank-1), SWIZZLE_128B.
 int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
                    const uint32_t* box);
+// same, with per-dimension traversal strides (elementStrides; stride-2 convolutions read every other pixel)
+int make_tmap_bf16_strided(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
+                           const uint64_t* strides_bytes, const uint32_t* box, const uint32_t* elem_strides);
 int tc_driver_check();
 int tc_gemm_init();   // opt the kernels into their dynamic shared memory size (call outside stream capture)
 

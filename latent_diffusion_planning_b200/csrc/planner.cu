@@ -438,12 +438,13 @@ struct TcSrc { ActBf16 a; };
 // Build (or fetch) the packed weights + K-block table of one convolution at input length t_in.
 static int get_packed(LdpPlanner* h, int op_id, int kind, int taps_k, const ActBf16* srcs, int nsrc, int t_in,
                       const float* wgt, int cout, int block_n, PackedW** out) {
-  auto key = std::make_pair(op_id, t_in);
+  auto key = std::make_pair(op_id, t_in);   // n_pad is rounded to 128 below, so one packing serves both tile widths
   auto it = h->packed.find(key);
   if (it != h->packed.end()) {
     *out = &it->second;
     return LDP_OK;
   }
+  (void)block_n;
   int ctot = 0;
   for (int i = 0; i < nsrc; ++i) ctot += srcs[i].c;
   std::vector<TcKBlock> kb;
@@ -485,7 +486,7 @@ static int get_packed(LdpPlanner* h, int op_id, int kind, int taps_k, const ActB
   const int n_out = kind == CONV_UP ? 2 * cout : cout;
   PackedW pw;
   pw.kp = kp;
-  pw.n_pad = round_up(n_out, block_n);
+  pw.n_pad = round_up(n_out, 128);
   pw.num_kb = (int)kb.size();
   LDP_TRY(h->arena.alloc_t(&pw.wt, (size_t)pw.n_pad * kp));
   LDP_TRY(h->arena.alloc_t(&pw.kb_dev, kb.size()));
@@ -523,27 +524,38 @@ static int act_map(CUtensorMap* m, const ActBf16& a, int kind, int t_in, int B) 
 }
 
 // Generic convolution op on the tcgen05 path; the caller fills in the epilogue afterwards.
+// N-tile width: 64-wide tiles double the CTA count of the layers whose 128-wide grid would fill under half of the
+// 148 SMs (up path, stride-2 convolutions); GroupNorm groups must still fit inside one tile.
+static int pick_block_n(int M, int N, int group_width) {
+  const char* env = getenv("LDP_BN64");
+  if (env && env[0] == '0') return 128;
+  const int ctas128 = ceil_div(M, 128) * ceil_div(N, 128);
+  if (ctas128 <= 74 && N % 64 == 0 && group_width <= 64) return 64;
+  return 128;
+}
+
 static int conv_tc(LdpPlanner* h, PlanWs* w, int op_id, int kind, int taps_k, const ActBf16* srcs, int nsrc, int t_in,
-                   const float* wgt, int cout, TcGemm* op) {
+                   const float* wgt, int cout, int group_width, TcGemm* op) {
   const int rows = kind == CONV_DOWN ? t_in / 2 : t_in;
+  const int bn = pick_block_n(w->B * rows, kind == CONV_UP ? 2 * cout : cout, group_width);
   LDP_CHECK(rows >= 1 && rows <= 32 && (rows & (rows - 1)) == 0, LDP_ERR_UNSUPPORTED,
             "bf16 path needs power-of-two level lengths <= 32 (use LDP_PREC_FP32 for other horizons)");
   for (int i = 0; i < nsrc; ++i)
     LDP_CHECK(srcs[i].ld % 8 == 0, LDP_ERR_INVALID_ARG, "activation pitch must be a multiple of 8 elements");
   PackedW* pw;
-  LDP_TRY(get_packed(h, op_id, kind, taps_k, srcs, nsrc, t_in, wgt, cout, 128, &pw));
+  LDP_TRY(get_packed(h, op_id, kind, taps_k, srcs, nsrc, t_in, wgt, cout, bn, &pw));
   *op = TcGemm();
   for (int i = 0; i < nsrc; ++i) LDP_TRY(act_map(&op->map_a[i], srcs[i], kind, t_in, w->B));
   for (int i = nsrc; i < 4; ++i) op->map_a[i] = op->map_a[0];
   uint64_t bd[2] = {(uint64_t)pw->kp, (uint64_t)pw->n_pad};
   uint64_t bs[1] = {(uint64_t)pw->kp * 2};
-  uint32_t bb[2] = {64, 128};
+  uint32_t bb[2] = {64, (uint32_t)bn};
   LDP_TRY(make_tmap_bf16(&op->map_b, pw->wt, 2, bd, bs, bb));
   op->kb = pw->kb_dev;
   op->num_kb = pw->num_kb;
   op->M = w->B * rows;
   op->N = kind == CONV_UP ? 2 * cout : cout;
-  op->block_n = 128;
+  op->block_n = bn;
   op->use_aux = 0;
   op->tiles_per_item = 1;
   op->rows_step = 0;
@@ -566,7 +578,8 @@ static int crb_tc(LdpPlanner* h, PlanWs* w, int bi, const ActBf16* srcs, int nsr
   LDP_CHECK((b.cout / h->cfg.n_groups) % 32 == 0, LDP_ERR_UNSUPPORTED,
             "bf16 path needs GroupNorm group widths that are multiples of 32 channels");
   TcGemm op;
-  LDP_TRY(conv_tc(h, w, 4 * bi + 0, CONV_K, 5, srcs, nsrc, Tl, b.c1w, b.cout, &op));
+  const int gw = b.cout / h->cfg.n_groups;
+  LDP_TRY(conv_tc(h, w, 4 * bi + 0, CONV_K, 5, srcs, nsrc, Tl, b.c1w, b.cout, gw, &op));
   set_gn(&op, b.c1b, b.g1s, b.g1b, b.cout, h->cfg.n_groups, h1buf);
   op.film = 1; op.ttab = h->ttab; op.ld_ttab = h->sum_c2; op.otab = w->otab; op.ld_otab = h->sum_c2;
   op.film_off = b.film_off; op.film_c = b.cout;
@@ -624,15 +637,16 @@ static int crb_tc(LdpPlanner* h, PlanWs* w, int bi, const ActBf16* srcs, int nsr
     op.map_a[3] = op.map_a[2];
     uint64_t bd[2] = {(uint64_t)pw->kp, (uint64_t)pw->n_pad};
     uint64_t bs[1] = {(uint64_t)pw->kp * 2};
-    uint32_t bb[2] = {64, 128};
+    const int bn = pick_block_n(w->B * Tl, b.cout, gw);
+    uint32_t bb[2] = {64, (uint32_t)bn};
     LDP_TRY(make_tmap_bf16(&op.map_b, pw->wt, 2, bd, bs, bb));
     op.kb = pw->kb_dev; op.num_kb = pw->num_kb;
-    op.M = w->B * Tl; op.N = b.cout; op.block_n = 128; op.use_aux = 1;
+    op.M = w->B * Tl; op.N = b.cout; op.block_n = bn; op.use_aux = 1;
     op.items_per_tile = 128 / Tl; op.rows_per_item = Tl;
     set_gn(&op, b.c2b, b.g2s, b.g2b, b.cout, h->cfg.n_groups, outbuf);
     op.bias_aux = b.rb;
   } else {
-    LDP_TRY(conv_tc(h, w, 4 * bi + 1, CONV_K, 5, &h1, 1, Tl, b.c2w, b.cout, &op));
+    LDP_TRY(conv_tc(h, w, 4 * bi + 1, CONV_K, 5, &h1, 1, Tl, b.c2w, b.cout, gw, &op));
     set_gn(&op, b.c2b, b.g2s, b.g2b, b.cout, h->cfg.n_groups, outbuf);
     op.res_bf16 = srcs[0].p; op.ld_res_bf16 = srcs[0].ld;
   }
@@ -674,7 +688,7 @@ static int prepare_bf16(LdpPlanner* h, PlanWs* w) {
       ActBf16 o;
       LDP_TRY(new_act(Tl / 2, d, &o));
       TcGemm op;
-      LDP_TRY(conv_tc(h, w, 1000 + l, CONV_DOWN, 3, &cur, 1, Tl, h->down_w[l], d, &op));
+      LDP_TRY(conv_tc(h, w, 1000 + l, CONV_DOWN, 3, &cur, 1, Tl, h->down_w[l], d, 32, &op));
       op.mode = TC_EPI_PLAIN; op.bias = h->down_b[l]; op.out_bf16 = o.p; op.ld_out_bf16 = d;
       w->ops.push_back(op);
       cur = o;
@@ -704,7 +718,7 @@ static int prepare_bf16(LdpPlanner* h, PlanWs* w) {
     const int d = c.down_dims[lvl - 1];
     LDP_TRY(new_act(2 * Tl, d, &o));
     TcGemm op;
-    LDP_TRY(conv_tc(h, w, 2000 + u, CONV_UP, 4, &cur, 1, Tl, h->up_w[u], d, &op));
+    LDP_TRY(conv_tc(h, w, 2000 + u, CONV_UP, 4, &cur, 1, Tl, h->up_w[u], d, 32, &op));
     op.mode = TC_EPI_PLAIN; op.bias = h->up_bias2[u]; op.out_bf16 = o.p; op.ld_out_bf16 = 2 * d;
     w->ops.push_back(op);
     cur = o;
@@ -714,10 +728,10 @@ static int prepare_bf16(LdpPlanner* h, PlanWs* w) {
   ActBf16 f;
   LDP_TRY(new_act(T, d0, &f));
   TcGemm op;
-  LDP_TRY(conv_tc(h, w, 3000, CONV_K, 5, &cur, 1, T, h->fcw, d0, &op));
+  LDP_TRY(conv_tc(h, w, 3000, CONV_K, 5, &cur, 1, T, h->fcw, d0, d0 / 8, &op));
   set_gn(&op, h->fcb, h->fgs, h->fgb, d0, 8, f.p);
   w->ops.push_back(op);
-  LDP_TRY(conv_tc(h, w, 3001, CONV_K, 1, &f, 1, T, h->ow, c.input_dim, &op));
+  LDP_TRY(conv_tc(h, w, 3001, CONV_K, 1, &f, 1, T, h->ow, c.input_dim, 1 << 30, &op));
   op.mode = TC_EPI_DDPM;
   op.bias = h->ob;
   op.coef = h->coef;
@@ -862,6 +876,48 @@ int ldp_planner_sample(LdpPlanner* h, int precision, int sampler, const float* x
     }
   }
   LDP_CUDA_OK(cudaMemcpyAsync(x0_dev, w->x_state, n * 4, cudaMemcpyDeviceToDevice, s));
+  return LDP_OK;
+}
+
+
+// Diagnostics: time every kernel of one bf16 denoising step in isolation (reps back-to-back launches, CUDA events).
+int ldp_planner_profile_step(LdpPlanner* h, int B, int T, int reps, float* us_host, int32_t* meta_host, int max_ops,
+                             int* n_ops, void* cuda_stream) {
+  LDP_CHECK(h && us_host && meta_host && n_ops && reps > 0, LDP_ERR_INVALID_ARG, "bad arguments");
+  cudaStream_t s = (cudaStream_t)cuda_stream;
+  PlanWs* w;
+  LDP_TRY(get_ws(h, B, T, &w));
+  LDP_TRY(prepare_bf16(h, w));
+  LDP_CHECK((int)w->ops.size() <= max_ops, LDP_ERR_INVALID_ARG, "output arrays too small");
+  DdpmCall call;
+  call.n_steps = 1;
+  call.seed = 1;
+  LDP_CUDA_OK(cudaMemcpyAsync(w->call_dev, &call, sizeof(call), cudaMemcpyHostToDevice, s));
+  LDP_TRY(launch_set_i32(w->step_dev, h->cfg.n_train_steps / 2, s));
+  StepRef step;
+  step.dev = w->step_dev;
+  cudaEvent_t e0, e1;
+  LDP_CUDA_OK(cudaEventCreate(&e0));
+  LDP_CUDA_OK(cudaEventCreate(&e1));
+  for (size_t i = 0; i < w->ops.size(); ++i) {
+    TcGemm op = w->ops[i];
+    op.step = step;
+    for (int r = 0; r < 3; ++r) LDP_TRY(launch_tc_gemm(op, s));
+    LDP_CUDA_OK(cudaEventRecord(e0, s));
+    for (int r = 0; r < reps; ++r) LDP_TRY(launch_tc_gemm(op, s));
+    LDP_CUDA_OK(cudaEventRecord(e1, s));
+    LDP_CUDA_OK(cudaEventSynchronize(e1));
+    float ms = 0.f;
+    LDP_CUDA_OK(cudaEventElapsedTime(&ms, e0, e1));
+    us_host[i] = ms * 1000.f / reps;
+    meta_host[4 * i + 0] = op.M;
+    meta_host[4 * i + 1] = op.N;
+    meta_host[4 * i + 2] = op.num_kb;
+    meta_host[4 * i + 3] = op.block_n | (op.mode << 16) | (op.use_aux << 24);
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  *n_ops = (int)w->ops.size();
   return LDP_OK;
 }
 

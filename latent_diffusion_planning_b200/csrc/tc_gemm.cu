@@ -8,42 +8,51 @@
 //   convolution is TMA's out-of-bounds zero fill - no im2col buffer, no halo copies.
 // * W^T tiles come from weights pre-packed K-major ([N_pad][K_pad] bf16) at handle creation.
 // * Both land in 128B-swizzled shared memory; one elected thread issues tcgen05.mma (M=128, N=BN, K=16)
-//   with the fp32 accumulator in TMEM; a 4-stage mbarrier ring overlaps TMA with MMA.
+//   with the fp32 accumulator in TMEM; an mbarrier ring (6 stages at BN=128) overlaps TMA with MMA.
 // * Warp roles: warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2-9 = epilogue
 //   (two warps per 32-lane TMEM quarter, each taking half of the tile's columns; thread i owns output row
 //   32*quarter+i).  Per-column vectors (bias, norm affine, FiLM time part) are staged in shared memory while
 //   the main loop runs.
+// * One template instantiation per (BN, epilogue): each kernel carries only its own epilogue, written as compact
+//   loops over 32-column chunks (an earlier all-in-one, fully unrolled kernel was 16.6k SASS instructions and
+//   spent 85 % of its cycles in instruction-fetch stalls; see profiles/).
 // * Fused epilogues (all fp32 math on the accumulator, read with tcgen05.ld):
 //     PLAIN  bias (+ReLU) (+residual) -> f32 and/or bf16
-//     GN     bias -> GroupNorm over (rows of one sample x group channels) -> Mish -> [FiLM] -> [+residual] -> bf16
-//            (the tile owns whole samples and whole groups, so the statistics never leave the CTA)
+//     GN     bias -> GroupNorm over (rows of one sample x group channels) -> Mish|swish -> [FiLM] -> [+residual] -> bf16
+//            (the tile owns whole samples and whole groups, so the statistics never leave the CTA; one TMEM
+//            pass, the thread's 64 accumulator values stay in registers between statistics and normalisation)
 //     DDPM   bias -> eps; x0 = clip((x - s eps)/a); x <- c0 x0 + ct x + sigma z   (the scheduler step of the
-//            reverse-diffusion loop, reference agent/ldp_agent.py:470-471, fused around the score-net's last GEMM)
+//            reverse-diffusion loop, reference agent/ldp_agent.py:470-471, fused around the score-net's last GEMM;
+//            the tile is transposed through shared memory so that x / z / x_bf16 are accessed coalesced)
 //     LN     h = acc + bias + residual -> f32;  LayerNorm(h) (or ReLU(h)) -> bf16   (IDM MLPResNet block)
+// * Programmatic dependent launch: the prologue (barrier init, TMEM allocation, descriptor prefetch) runs before
+//   griddepcontrol.wait, i.e. it overlaps the tail of the previous layer's kernel inside the captured graph.
 #include "kernels.h"
 
 namespace ldp {
 
 constexpr int TC_BM = 128;
 constexpr int TC_BK = 64;
-constexpr int TC_STAGES = 4;
 constexpr int TC_A_BYTES = TC_BM * TC_BK * 2;   // 16 KB
 constexpr int TC_EPI_WARPS = 8;                 // two warps per TMEM lane quarter, each takes half of the columns
 constexpr int TC_EPI_THREADS = TC_EPI_WARPS * 32;
 constexpr int TC_THREADS = 64 + TC_EPI_THREADS; // warp 0: TMA, warp 1: MMA, warps 2..9: epilogue
 constexpr int TC_MAX_KB_SMEM = 256;
+constexpr int TC_MAX_STAGES = 8;
 
 template <int BN>
 struct TcSmem {
+  static constexpr int STAGES = BN == 64 ? 8 : (BN == 128 ? 6 : 4);
   static constexpr int B_BYTES = BN * TC_BK * 2;
   static constexpr int STAGE_BYTES = TC_A_BYTES + B_BYTES;
-  static constexpr int TOTAL = TC_STAGES * STAGE_BYTES + 1024;   // + alignment slack
+  static constexpr int TOTAL = STAGES * STAGE_BYTES + 1024;   // + alignment slack
 };
 
 // Per-CTA staging of everything the epilogue needs per output column (filled while the main loop runs).
 template <int BN>
 struct EpiSmem {
   float bias[BN];
+  float bias2[BN];      // bias of the aux accumulator (residual 1x1 projection)
   float gamma[BN];
   float beta[BN];
   float fscale[BN];     // FiLM scale / shift, time part (valid when the whole launch shares one timestep)
@@ -52,12 +61,30 @@ struct EpiSmem {
 };
 
 __device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, %0;" ::"n"(TC_EPI_THREADS) : "memory"); }
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void griddep_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float rcp_approx(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// Mish(y) = y tanh(softplus(y)) = y n/(n+2), n = e^y (e^y + 2); the exponent is clamped so that n stays finite
+// (the ratio is 1 to fp32 there).  Two MUFU ops per element.
 __device__ __forceinline__ float mish_fast(float y) {
-  // y * n/(n+2), n = e^y (e^y + 2); the exponent is clamped so that n stays finite (ratio is 1 to fp32 there)
-  float e = exp2f(fminf(y, 20.f) * 1.4426950408889634f);
-  float n = e * (e + 2.f);
-  return y * __fdividef(n, n + 2.f);
+  const float e = ex2_approx(fminf(y, 20.f) * 1.4426950408889634f);
+  const float n = e * (e + 2.f);
+  return y * (n * rcp_approx(n + 2.f));
+}
+// swish(y) = y / (1 + e^-y)
+__device__ __forceinline__ float swish_fast(float y) {
+  const float e = ex2_approx(fminf(-y, 80.f) * 1.4426950408889634f);
+  return y * rcp_approx(1.f + e);
 }
 
 // ---- vector load/store helpers (32 consecutive columns of one row) -------------------------------------
@@ -142,11 +169,11 @@ __device__ __forceinline__ void add_smem32(float (&v)[32], const float* s) {
 template <int BN>
 __device__ __forceinline__ void epilogue_plain(const TcGemm& p, EpiSmem<BN>& es, uint32_t taddr, int m, int n0,
                                                int c_begin) {
-  constexpr int CPP = BN / 32 / 2;
+  constexpr int CPP = BN / 64;
   const bool row_ok = m < p.M;
   const bool vf = (p.ld_out_f32 & 3) == 0, vb = (p.ld_out_bf16 & 7) == 0;
   const bool vrf = (p.ld_res_f32 & 3) == 0, vrb = (p.ld_res_bf16 & 7) == 0;
-#pragma unroll
+#pragma unroll 1
   for (int cc = 0; cc < CPP; ++cc) {
     const int c = c_begin + cc;
     const int nb = n0 + c * 32;
@@ -171,24 +198,24 @@ __device__ __forceinline__ void epilogue_plain(const TcGemm& p, EpiSmem<BN>& es,
 template <int BN>
 __device__ __forceinline__ void epilogue_gn(const TcGemm& p, EpiSmem<BN>& es, uint32_t taddr, int m, int n0, int c_begin,
                                             int row) {
-  constexpr int NC = BN / 32, CPP = NC / 2;
+  constexpr int NC = BN / 32, CPP = BN / 64;
   const int T = p.rows_per_item;
-  const int cpg = p.group_width >> 5;                    // chunks per group: 1, 2, 4 or 8
+  const int cpg = p.group_width >> 5;                    // chunks per group: 1, 2 or 4
   const int nchunks = min(NC, (p.N - n0) >> 5);          // N and the group widths are multiples of 32 here
   const bool row_ok = m < p.M;
-  // pass 1: (sum, sum sq) of (acc + bias) per 32-column chunk of this thread's row
+  // one TMEM pass: acc + bias stays in registers; (sum, sum sq) per 32-column chunk goes to shared memory
+  float v[CPP][32];
 #pragma unroll
   for (int cc = 0; cc < CPP; ++cc) {
     const int c = c_begin + cc;
     float s = 0.f, ss = 0.f;
     if (c < nchunks) {
-      float v[32];
-      tmem_ld_32x32(taddr + c * 32, v);
-      add_smem32(v, es.bias + c * 32);
+      tmem_ld_32x32(taddr + c * 32, v[cc]);
+      add_smem32(v[cc], es.bias + c * 32);
 #pragma unroll
       for (int i = 0; i < 32; ++i) {
-        s += v[i];
-        ss = fmaf(v[i], v[i], ss);
+        s += v[cc][i];
+        ss = fmaf(v[cc][i], v[cc][i], ss);
       }
     }
     es.part[row][c] = make_float2(s, ss);
@@ -215,7 +242,7 @@ __device__ __forceinline__ void epilogue_gn(const TcGemm& p, EpiSmem<BN>& es, ui
     mean[cc] = mu;
     rstd[cc] = rsqrtf(fmaxf(ss * inv_cnt - mu * mu, 0.f) + p.eps);
   }
-  // pass 2: normalise -> Mish -> FiLM -> residual -> store
+  // normalise -> activation -> FiLM -> residual -> store
   const int b = (row_ok ? m : 0) / T;
   const float* orow = p.film ? p.otab + (long long)b * p.ld_otab + p.film_off : nullptr;
   const float* trow = (p.film && p.step.rows) ? p.ttab + (long long)step_of(p.step, row_ok ? m : 0) * p.ld_ttab + p.film_off
@@ -225,19 +252,24 @@ __device__ __forceinline__ void epilogue_gn(const TcGemm& p, EpiSmem<BN>& es, ui
     const int c = c_begin + cc;
     if (c >= nchunks) continue;
     const int nb = n0 + c * 32;
-    float v[32];
-    tmem_ld_32x32(taddr + c * 32, v);
-    const float4* b4 = reinterpret_cast<const float4*>(es.bias + c * 32);
     const float4* g4 = reinterpret_cast<const float4*>(es.gamma + c * 32);
     const float4* be4 = reinterpret_cast<const float4*>(es.beta + c * 32);
     const float mu = mean[cc], rs = rstd[cc];
+    float(&w)[32] = v[cc];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      const float4 bb = b4[j], gg = g4[j], be = be4[j];
-      v[4 * j + 0] = mish_fast(fmaf(v[4 * j + 0] + bb.x - mu, rs * gg.x, be.x));
-      v[4 * j + 1] = mish_fast(fmaf(v[4 * j + 1] + bb.y - mu, rs * gg.y, be.y));
-      v[4 * j + 2] = mish_fast(fmaf(v[4 * j + 2] + bb.z - mu, rs * gg.z, be.z));
-      v[4 * j + 3] = mish_fast(fmaf(v[4 * j + 3] + bb.w - mu, rs * gg.w, be.w));
+      const float4 gg = g4[j], be = be4[j];
+      w[4 * j + 0] = fmaf(w[4 * j + 0] - mu, rs * gg.x, be.x);
+      w[4 * j + 1] = fmaf(w[4 * j + 1] - mu, rs * gg.y, be.y);
+      w[4 * j + 2] = fmaf(w[4 * j + 2] - mu, rs * gg.z, be.z);
+      w[4 * j + 3] = fmaf(w[4 * j + 3] - mu, rs * gg.w, be.w);
+    }
+    if (p.gn_act == 1) {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) w[i] = swish_fast(w[i]);
+    } else {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) w[i] = mish_fast(w[i]);
     }
     if (p.film) {
       const float4* fs4 = reinterpret_cast<const float4*>(es.fscale + c * 32);
@@ -256,31 +288,31 @@ __device__ __forceinline__ void epilogue_gn(const TcGemm& p, EpiSmem<BN>& es, ui
           sc.x += t1.x; sc.y += t1.y; sc.z += t1.z; sc.w += t1.w;
           sh.x += t2.x; sh.y += t2.y; sh.z += t2.z; sh.w += t2.w;
         }
-        v[4 * j + 0] = fmaf(sc.x, v[4 * j + 0], sh.x);
-        v[4 * j + 1] = fmaf(sc.y, v[4 * j + 1], sh.y);
-        v[4 * j + 2] = fmaf(sc.z, v[4 * j + 2], sh.z);
-        v[4 * j + 3] = fmaf(sc.w, v[4 * j + 3], sh.w);
+        w[4 * j + 0] = fmaf(sc.x, w[4 * j + 0], sh.x);
+        w[4 * j + 1] = fmaf(sc.y, w[4 * j + 1], sh.y);
+        w[4 * j + 2] = fmaf(sc.z, w[4 * j + 2], sh.z);
+        w[4 * j + 3] = fmaf(sc.w, w[4 * j + 3], sh.w);
       }
     }
     if (p.use_aux) {
       float r[32];
       tmem_ld_32x32(taddr + BN + c * 32, r);
-      const float* ba = p.bias_aux + nb;
+      add_smem32(r, es.bias2 + c * 32);
 #pragma unroll
-      for (int i = 0; i < 32; ++i) v[i] += r[i] + __ldg(ba + i);
+      for (int i = 0; i < 32; ++i) w[i] += r[i];
     } else if (p.res_bf16 && row_ok) {
-      add_bf16x32(v, p.res_bf16 + (long long)m * p.ld_res_bf16 + nb, true, 32);
+      add_bf16x32(w, p.res_bf16 + (long long)m * p.ld_res_bf16 + nb, true, 32);
     }
     if (row_ok) {
-      if (p.out_bf16) store_bf16x32(p.out_bf16 + (long long)m * p.ld_out_bf16 + nb, v, true, 32);
-      if (p.out_f32) store_f32x32(p.out_f32 + (long long)m * p.ld_out_f32 + nb, v, true, 32);
+      if (p.out_bf16) store_bf16x32(p.out_bf16 + (long long)m * p.ld_out_bf16 + nb, w, true, 32);
+      if (p.out_f32) store_f32x32(p.out_f32 + (long long)m * p.ld_out_f32 + nb, w, true, 32);
     }
   }
 }
 
 // Four standard normals of Philox quad q (elements 4q..4q+3): two Box-Muller pairs.
 __device__ __forceinline__ void philox_normal4(unsigned long long seed, uint32_t stream, uint32_t step,
-                                               unsigned long long q, float (&z)[4]) {
+                                               unsigned long long q, float* z) {
   uint4 r = philox4x32_10(make_uint4((uint32_t)q, (uint32_t)(q >> 32), step, stream),
                           make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
   const float k = 2.3283064365386963e-10f;
@@ -294,11 +326,27 @@ __device__ __forceinline__ void philox_normal4(unsigned long long seed, uint32_t
   z[2] = rb * c; z[3] = rb * s;
 }
 
+// DDPM / DDIM update fused behind the score net's last GEMM.  Phase 1: every epilogue thread drops its row of
+// eps = acc + bias into a padded shared-memory tile (the pipeline buffers, idle by now).  Phase 2: the tile is
+// walked row-major, a lane per group of 4 consecutive columns, so x, the injected noise and the bf16 copy of x
+// are accessed coalesced and one or two Philox calls serve four elements.
 template <int BN>
-__device__ __forceinline__ void epilogue_ddpm(const TcGemm& p, EpiSmem<BN>& es, uint32_t taddr, int m, int n0,
-                                              int c_begin) {
-  constexpr int CPP = BN / 32 / 2;
-  const bool row_ok = m < p.M;
+__device__ __forceinline__ void epilogue_ddpm(const TcGemm& p, EpiSmem<BN>& es, uint32_t taddr, float* tile, int tile_m,
+                                              int n0, int c_begin, int row, int ewarp, int lane) {
+  constexpr int CPP = BN / 64;
+  constexpr int TS = BN + 1;
+#pragma unroll 1
+  for (int cc = 0; cc < CPP; ++cc) {
+    const int c = c_begin + cc;
+    if (n0 + c * 32 >= p.N) continue;          // uniform
+    float v[32];
+    tmem_ld_32x32(taddr + c * 32, v);
+    add_smem32(v, es.bias + c * 32);
+    float* trow = tile + row * TS + c * 32;
+#pragma unroll
+    for (int i = 0; i < 32; ++i) trow[i] = v[i];
+  }
+  epi_bar();
   const int t = step_of(p.step, 0);
   const float* cf = p.coef + t * 8;
   const float inv_sa = cf[0], s1a = cf[1], c0 = cf[2], ct = cf[3], sigma = cf[4], sap = cf[5], s1ap = cf[6];
@@ -306,52 +354,69 @@ __device__ __forceinline__ void epilogue_ddpm(const TcGemm& p, EpiSmem<BN>& es, 
   const float* noise = call.noise ? call.noise + (long long)(call.n_steps - 1 - t) * call.noise_step_stride : nullptr;
   const bool ddim = call.sampler == LDP_SAMPLER_DDIM;
   const bool add_noise = !ddim && t > 0;
+  const int nv = min(BN, p.N - n0);
+  const bool vb = p.out_bf16 != nullptr && (p.ld_out_bf16 & 3) == 0;
 #pragma unroll 1
-  for (int cc = 0; cc < CPP; ++cc) {
-    const int c = c_begin + cc;
-    const int nb = n0 + c * 32;
-    const int nvalid = min(32, p.N - nb);
-    if (nvalid <= 0) continue;                 // uniform
-    float v[32];
-    tmem_ld_32x32(taddr + c * 32, v);
-    if (!row_ok) continue;
-    add_smem32(v, es.bias + c * 32);
-    float* xr = p.x_io + (long long)m * p.ld_x + nb;
-    const long long e0 = (long long)m * p.N + nb;
-    float z4[4];
-    unsigned long long cur_q = ~0ull;
+  for (int r = ewarp; r < TC_BM; r += TC_EPI_WARPS) {
+    const int m = tile_m * TC_BM + r;
+    if (m >= p.M) break;                        // uniform
+#pragma unroll 1
+    for (int g = lane; g * 4 < nv; g += 32) {
+      const int cb = g * 4;
+      const int cnt = min(4, nv - cb);
+      const long long e0 = (long long)m * p.N + n0 + cb;
+      float* xr = p.x_io + (long long)m * p.ld_x + n0 + cb;
+      float z[4] = {0.f, 0.f, 0.f, 0.f};
+      if (add_noise) {
+        if (noise) {
 #pragma unroll
-    for (int i = 0; i < 32; ++i) {
-      if (i < nvalid) {
-        const float e = v[i];
-        const float x = xr[i];
-        const float x0 = fminf(fmaxf((x - s1a * e) * inv_sa, -1.f), 1.f);
-        float o;
-        if (ddim) {
-          o = sap * x0 + s1ap * e;
+          for (int i = 0; i < 4; ++i)
+            if (i < cnt) z[i] = noise[e0 + i];
         } else {
-          o = c0 * x0 + ct * x;
-          if (add_noise) {
-            float z;
-            if (noise) {
-              z = noise[e0 + i];
-            } else {
-              const unsigned long long ge = (unsigned long long)(call.elem_offset + e0 + i);
-              if ((ge >> 2) != cur_q) {
-                cur_q = ge >> 2;
-                philox_normal4(call.seed, call.stream_id, (uint32_t)t, cur_q, z4);
-              }
-              const uint32_t ln = (uint32_t)ge & 3u;
-              z = ln == 0 ? z4[0] : (ln == 1 ? z4[1] : (ln == 2 ? z4[2] : z4[3]));
-            }
-            o = fmaf(sigma, z, o);
-          }
+          const unsigned long long ge = (unsigned long long)(call.elem_offset + e0);
+          const uint32_t off = (uint32_t)ge & 3u;
+          float zz[8];
+          philox_normal4(call.seed, call.stream_id, (uint32_t)t, ge >> 2, zz);
+          if (off != 0) philox_normal4(call.seed, call.stream_id, (uint32_t)t, (ge >> 2) + 1, zz + 4);
+          else { zz[4] = zz[5] = zz[6] = zz[7] = 0.f; }
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            z[i] = off == 0 ? zz[i] : (off == 1 ? zz[i + 1] : (off == 2 ? zz[i + 2] : zz[i + 3]));
         }
-        xr[i] = o;
-        v[i] = o;
+      }
+      float o[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        o[i] = 0.f;
+        if (i < cnt) {
+          const float e = tile[r * TS + cb + i];
+          const float x = xr[i];
+          const float x0 = fminf(fmaxf((x - s1a * e) * inv_sa, -1.f), 1.f);
+          float y;
+          if (ddim) {
+            y = sap * x0 + s1ap * e;
+          } else {
+            y = c0 * x0 + ct * x;
+            if (add_noise) y = fmaf(sigma, z[i], y);
+          }
+          xr[i] = y;
+          o[i] = y;
+        }
+      }
+      if (p.out_bf16) {
+        __nv_bfloat16* ob = p.out_bf16 + (long long)m * p.ld_out_bf16 + n0 + cb;
+        if (vb && cnt == 4) {
+          uint2 u;
+          u.x = pack_bf16x2(o[0], o[1]);
+          u.y = pack_bf16x2(o[2], o[3]);
+          *reinterpret_cast<uint2*>(ob) = u;
+        } else {
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            if (i < cnt) ob[i] = __float2bfloat16(o[i]);
+        }
       }
     }
-    if (p.out_bf16) store_bf16x32(p.out_bf16 + (long long)m * p.ld_out_bf16 + nb, v, false, nvalid);
   }
 }
 
@@ -359,7 +424,7 @@ template <int BN>
 __device__ __forceinline__ void epilogue_ln(const TcGemm& p, EpiSmem<BN>& es, uint32_t taddr, int m, int n0, int c_begin,
                                             int row, int part) {
   // requires N == BN: the whole feature row lives in this tile, split over the two warps of the lane quarter
-  constexpr int CPP = BN / 32 / 2;
+  constexpr int CPP = BN / 64;
   const bool row_ok = m < p.M;
   float s = 0.f, ss = 0.f;
   float* hrow = p.out_f32 + (long long)(row_ok ? m : 0) * p.ld_out_f32;
@@ -405,11 +470,12 @@ __device__ __forceinline__ void epilogue_ln(const TcGemm& p, EpiSmem<BN>& es, ui
 }
 
 // ---- the kernel --------------------------------------------------------------------------------
-template <int BN>
+template <int BN, int MODE>
 __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_constant__ TcGemm p) {
   extern __shared__ uint8_t smem_raw[];
-  __shared__ __align__(8) uint64_t bar_full[TC_STAGES];
-  __shared__ __align__(8) uint64_t bar_empty[TC_STAGES];
+  constexpr int STAGES = TcSmem<BN>::STAGES;
+  __shared__ __align__(8) uint64_t bar_full[TC_MAX_STAGES];
+  __shared__ __align__(8) uint64_t bar_empty[TC_MAX_STAGES];
   __shared__ __align__(8) uint64_t bar_accum;
   __shared__ uint32_t tmem_holder;
   __shared__ __align__(16) TcKBlock kb_s[TC_MAX_KB_SMEM];     // K-block table staged once per CTA
@@ -421,11 +487,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
   const int tile_m = blockIdx.x, tile_n = blockIdx.y;
   const int n0 = tile_n * BN;
   constexpr uint32_t NCOLS_MAIN = BN;
-  const uint32_t ncols = p.use_aux ? 2 * BN : BN;     // 128 / 256 / 512: powers of two >= 32
+  const uint32_t ncols = p.use_aux ? 2 * BN : BN;     // 64 .. 512: powers of two >= 32
 
+  // ---- prologue: touches only constants, shared memory and TMEM -> may overlap the previous kernel (PDL) ----
   if (threadIdx.x == 0) {
 #pragma unroll
-    for (int s = 0; s < TC_STAGES; ++s) {
+    for (int s = 0; s < STAGES; ++s) {
       mbar_init(smem_u32(&bar_full[s]), 1);
       mbar_init(smem_u32(&bar_empty[s]), 1);
     }
@@ -446,6 +513,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_holder;
+  griddep_launch();
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -453,6 +521,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
       const int q = tile_m / p.tiles_per_item, r = tile_m - q * p.tiles_per_item;
       const int c2_base = r * p.rows_step, c3 = q * p.items_per_tile;
       uint32_t stage = 0, phase = 0;
+      griddep_wait();                                   // activations of the previous layer are complete from here on
       for (int kb = 0; kb < p.num_kb; ++kb) {
         const TcKBlock e = kbt[kb];
         mbar_wait(smem_u32(&bar_empty[stage]), phase ^ 1u);
@@ -462,7 +531,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
         mbar_arrive_expect_tx(bar, TcSmem<BN>::STAGE_BYTES);
         tma_load_4d(sa, &p.map_a[e.src_acc & 0xff], bar, e.c0, e.d1, c2_base + e.d2, c3);
         tma_load_2d(sb, &p.map_b, bar, kb * TC_BK, n0);
-        if (++stage == TC_STAGES) { stage = 0; phase ^= 1u; }
+        if (++stage == STAGES) { stage = 0; phase ^= 1u; }
       }
     }
   } else if (warp == 1) {
@@ -486,7 +555,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
         }
         started |= 1u << acc;
         umma_commit(smem_u32(&bar_empty[stage]));       // frees the smem stage when these MMAs retire
-        if (++stage == TC_STAGES) { stage = 0; phase ^= 1u; }
+        if (++stage == STAGES) { stage = 0; phase ^= 1u; }
       }
       umma_commit(smem_u32(&bar_accum));                // accumulator(s) complete
     }
@@ -497,6 +566,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
     const int part = ew >> 2;                            // which half of the tile's columns
     const int row = quarter * 32 + lane;
     const int m = tile_m * TC_BM + row;
+    griddep_wait();                                      // the step counter / residuals / x belong to earlier kernels
     // stage the per-column vectors while the main loop runs
     {
       const int et = threadIdx.x - 64;
@@ -506,10 +576,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
         const int n = n0 + i;
         const bool ok = n < p.N;
         es.bias[i] = (ok && p.bias) ? __ldg(p.bias + n) : 0.f;
-        es.gamma[i] = (ok && p.gamma) ? __ldg(p.gamma + n) : 0.f;
-        es.beta[i] = (ok && p.beta) ? __ldg(p.beta + n) : 0.f;
-        es.fscale[i] = (ok && trow) ? __ldg(trow + n) : 0.f;
-        es.fshift[i] = (ok && trow) ? __ldg(trow + p.film_c + n) : 0.f;
+        if (MODE == TC_EPI_GN || MODE == TC_EPI_LN) {
+          es.bias2[i] = (ok && p.bias_aux) ? __ldg(p.bias_aux + n) : 0.f;
+          es.gamma[i] = (ok && p.gamma) ? __ldg(p.gamma + n) : 0.f;
+          es.beta[i] = (ok && p.beta) ? __ldg(p.beta + n) : 0.f;
+          es.fscale[i] = (ok && trow) ? __ldg(trow + n) : 0.f;
+          es.fshift[i] = (ok && trow) ? __ldg(trow + p.film_c + n) : 0.f;
+        }
       }
       epi_bar();
     }
@@ -517,12 +590,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
     tc_fence_after();
     const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16);
     const int c_begin = part * (BN / 64);
-    switch (p.mode) {
-      case TC_EPI_PLAIN: epilogue_plain<BN>(p, es, taddr, m, n0, c_begin); break;
-      case TC_EPI_GN:    epilogue_gn<BN>(p, es, taddr, m, n0, c_begin, row); break;
-      case TC_EPI_DDPM:  epilogue_ddpm<BN>(p, es, taddr, m, n0, c_begin); break;
-      default:           epilogue_ln<BN>(p, es, taddr, m, n0, c_begin, row, part); break;
-    }
+    if constexpr (MODE == TC_EPI_PLAIN) epilogue_plain<BN>(p, es, taddr, m, n0, c_begin);
+    else if constexpr (MODE == TC_EPI_GN) epilogue_gn<BN>(p, es, taddr, m, n0, c_begin, row);
+    else if constexpr (MODE == TC_EPI_DDPM)
+      epilogue_ddpm<BN>(p, es, taddr, reinterpret_cast<float*>(smem_raw + (smem_base - smem_u32(smem_raw))), tile_m, n0,
+                        c_begin, row, ew, lane);
+    else epilogue_ln<BN>(p, es, taddr, m, n0, c_begin, row, part);
   }
 
   tc_fence_before();
@@ -554,8 +627,8 @@ int tc_driver_check() {
   return LDP_OK;
 }
 
-int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
-                   const uint32_t* box) {
+int make_tmap_bf16_strided(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
+                           const uint64_t* strides_bytes, const uint32_t* box, const uint32_t* elem_strides) {
   PFN_encodeTiled fn = get_encode_fn();
   LDP_CHECK(fn != nullptr, LDP_ERR_NO_DEVICE, "cuTensorMapEncodeTiled driver entry point not available");
   LDP_CHECK(rank >= 2 && rank <= 4, LDP_ERR_INVALID_ARG, "tensor map rank must be 2..4");
@@ -565,7 +638,7 @@ int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t*
   for (int i = 0; i < rank; ++i) {
     gdim[i] = dims[i];
     bx[i] = box[i];
-    es[i] = 1;
+    es[i] = elem_strides ? elem_strides[i] : 1;
     if (i > 0) {
       gstr[i - 1] = strides_bytes[i - 1];
       LDP_CHECK((gstr[i - 1] & 15) == 0, LDP_ERR_INVALID_ARG, "tensor map strides must be multiples of 16 bytes");
@@ -583,21 +656,49 @@ int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t*
   return LDP_OK;
 }
 
+int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                   const uint32_t* box) {
+  return make_tmap_bf16_strided(out, base, rank, dims, strides_bytes, box, nullptr);
+}
+
+template <int BN, int MODE>
+static int set_smem_attr() {
+  LDP_CUDA_OK(cudaFuncSetAttribute(tc_gemm_kernel<BN, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcSmem<BN>::TOTAL));
+  return LDP_OK;
+}
+
+static bool g_use_pdl = true;
+
 int tc_gemm_init() {
   static bool done = false;
   if (done) return LDP_OK;
-  LDP_CUDA_OK(cudaFuncSetAttribute(tc_gemm_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcSmem<128>::TOTAL));
-  LDP_CUDA_OK(cudaFuncSetAttribute(tc_gemm_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcSmem<256>::TOTAL));
+  LDP_TRY((set_smem_attr<64, TC_EPI_PLAIN>()));
+  LDP_TRY((set_smem_attr<64, TC_EPI_GN>()));
+  LDP_TRY((set_smem_attr<128, TC_EPI_PLAIN>()));
+  LDP_TRY((set_smem_attr<128, TC_EPI_GN>()));
+  LDP_TRY((set_smem_attr<128, TC_EPI_DDPM>()));
+  LDP_TRY((set_smem_attr<256, TC_EPI_PLAIN>()));
+  LDP_TRY((set_smem_attr<256, TC_EPI_LN>()));
+  const char* env = getenv("LDP_NO_PDL");
+  g_use_pdl = !(env && env[0] == '1');
   done = true;
   return LDP_OK;
 }
 
-template <int BN>
-static int launch_tc_gemm_bn(const TcGemm& p, cudaStream_t s) {
+template <int BN, int MODE>
+static int launch_tc_gemm_inst(const TcGemm& p, cudaStream_t s) {
   LDP_TRY(tc_gemm_init());
-  dim3 grid(ceil_div(p.M, TC_BM), ceil_div(p.N, BN));
-  tc_gemm_kernel<BN><<<grid, TC_THREADS, TcSmem<BN>::TOTAL, s>>>(p);
-  cudaError_t e = cudaGetLastError();
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(ceil_div(p.M, TC_BM), ceil_div(p.N, BN), 1);
+  cfg.blockDim = dim3(TC_THREADS, 1, 1);
+  cfg.dynamicSmemBytes = TcSmem<BN>::TOTAL;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = g_use_pdl ? 1 : 0;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, tc_gemm_kernel<BN, MODE>, p);
   if (e != cudaSuccess) {
     set_last_error(std::string("tc_gemm launch failed: ") + cudaGetErrorString(e));
     return LDP_ERR_CUDA;
@@ -608,7 +709,8 @@ static int launch_tc_gemm_bn(const TcGemm& p, cudaStream_t s) {
 
 int launch_tc_gemm(const TcGemm& p, cudaStream_t s) {
   LDP_CHECK(p.kb && p.num_kb > 0 && p.M > 0 && p.N > 0, LDP_ERR_INVALID_ARG, "tc_gemm: bad arguments");
-  LDP_CHECK(p.block_n == 128 || p.block_n == 256, LDP_ERR_INVALID_ARG, "tc_gemm: block_n must be 128 or 256");
+  LDP_CHECK(p.block_n == 64 || p.block_n == 128 || p.block_n == 256, LDP_ERR_INVALID_ARG,
+            "tc_gemm: block_n must be 64, 128 or 256");
   if (p.mode == TC_EPI_GN) {
     LDP_CHECK(p.group_width % 32 == 0 && p.group_width <= p.block_n && p.N % p.group_width == 0, LDP_ERR_UNSUPPORTED,
               "tc_gemm GN epilogue: group width must be a multiple of 32 and fit the N tile");
@@ -617,7 +719,21 @@ int launch_tc_gemm(const TcGemm& p, cudaStream_t s) {
     LDP_CHECK(p.bias && p.gamma && p.beta, LDP_ERR_INVALID_ARG, "tc_gemm GN epilogue: bias/gamma/beta required");
   }
   if (p.mode == TC_EPI_LN) LDP_CHECK(p.N == p.block_n && p.out_f32 && p.bias, LDP_ERR_UNSUPPORTED, "tc_gemm LN epilogue: N must equal block_n");
-  return p.block_n == 128 ? launch_tc_gemm_bn<128>(p, s) : launch_tc_gemm_bn<256>(p, s);
+  if (p.mode == TC_EPI_DDPM) LDP_CHECK(p.x_io && p.coef, LDP_ERR_INVALID_ARG, "tc_gemm DDPM epilogue: x / coefficient table required");
+  const int key = p.block_n * 8 + p.mode;
+  switch (key) {
+    case 64 * 8 + TC_EPI_PLAIN:  return launch_tc_gemm_inst<64, TC_EPI_PLAIN>(p, s);
+    case 64 * 8 + TC_EPI_GN:     return launch_tc_gemm_inst<64, TC_EPI_GN>(p, s);
+    case 128 * 8 + TC_EPI_PLAIN: return launch_tc_gemm_inst<128, TC_EPI_PLAIN>(p, s);
+    case 128 * 8 + TC_EPI_GN:    return launch_tc_gemm_inst<128, TC_EPI_GN>(p, s);
+    case 128 * 8 + TC_EPI_DDPM:  return launch_tc_gemm_inst<128, TC_EPI_DDPM>(p, s);
+    case 256 * 8 + TC_EPI_PLAIN: return launch_tc_gemm_inst<256, TC_EPI_PLAIN>(p, s);
+    case 256 * 8 + TC_EPI_LN:    return launch_tc_gemm_inst<256, TC_EPI_LN>(p, s);
+    default: break;
+  }
+  set_last_error("tc_gemm: no kernel instantiated for block_n " + std::to_string(p.block_n) + " with epilogue " +
+                 std::to_string(p.mode));
+  return LDP_ERR_UNSUPPORTED;
 }
 
 }  // namespace ldp

@@ -181,6 +181,34 @@ class Planner:
         return out
 
 
+    def sample_host(self, x_T_host: torch.Tensor, cond_host: torch.Tensor, out_host: Optional[torch.Tensor] = None,
+                    **kw) -> torch.Tensor:
+        """Host-buffer form of `sample` (what an env-rollout caller holds, reference utils/rm_env_utils.py:168-188):
+        host -> device copies, the fused reverse loop, device -> host copy of x0, all on the current stream.
+        Pinned buffers make the copies asynchronous; the caller synchronises the stream before reading `out_host`."""
+        x = x_T_host.to("cuda", dtype=torch.float32, non_blocking=True)
+        c = cond_host.to("cuda", dtype=torch.float32, non_blocking=True)
+        out = self.sample(x, c, **kw)
+        if out_host is None:
+            out_host = torch.empty(out.shape, dtype=torch.float32, pin_memory=True)
+        out_host.copy_(out, non_blocking=True)
+        return out_host
+
+    def profile_step(self, B: int, T: int, reps: int = 20):
+        """Per-kernel timing of one bf16 denoising step (diagnostics): list of dicts with us, M, N, K, block_n, epilogue."""
+        us = np.zeros(128, np.float32)
+        meta = np.zeros(128 * 4, np.int32)
+        n = C.c_int(0)
+        N.check(self.lib.ldp_planner_profile_step(self._h, B, T, reps, us.ctypes.data, meta.ctypes.data, 128, C.byref(n),
+                                                  _stream()))
+        out = []
+        for i in range(n.value):
+            m, nn, kb, packed = (int(v) for v in meta[4 * i:4 * i + 4])
+            out.append(dict(us=float(us[i]), M=m, N=nn, K=kb * 64, block_n=packed & 0xffff,
+                            epilogue=("plain", "gn", "ddpm", "ln")[(packed >> 16) & 0xff], aux=(packed >> 24) & 1))
+        return out
+
+
 # ------------------------------------------------------------------------------------------------
 # inverse dynamics
 # ------------------------------------------------------------------------------------------------
