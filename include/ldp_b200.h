@@ -76,9 +76,15 @@ LDP_API int ldp_ddpm_step(int n_train_steps, int t, int sampler, const float* ep
 LDP_API int ldp_ddpm_add_noise(int n_train_steps, const float* x0_dev, const float* noise_dev, const int32_t* t_dev,
                                float* out_dev, int64_t rows, int64_t row_len, void* cuda_stream);
 
-/* Philox normals (the generator used when noise_dev == NULL), exposed for tests. */
+/* Philox normals (the generator ldp_ddpm_step uses when noise_dev == NULL: flat element index), exposed for tests. */
 LDP_API int ldp_philox_normal(uint64_t seed, uint32_t stream_id, uint32_t step, float* out_dev, int64_t n,
                               void* cuda_stream);
+/* The row-structured normals the fused sampling loops (ldp_planner_sample / ldp_idm_sample) draw at reverse step
+ * `step` when noise_dev == NULL: out (rows,row_len); element (r,c) is component c&3 of the Philox4x32-10 quad with
+ * counter (c>>2, row0+r, step, stream_id) and key seed, through a Box-Muller on MUFU approximations.  Keyed by the
+ * GLOBAL row, so a batch sharded over ranks (row_offset) draws exactly what the unsharded batch draws. */
+LDP_API int ldp_philox_normal_rows(uint64_t seed, uint32_t stream_id, uint32_t step, int64_t row0, int64_t rows,
+                                   int row_len, float* out_dev, void* cuda_stream);
 
 /* ---------------------------------------------------------------------------------------------------------
  * Planner score network  -  ConditionalUnet1D  (reference networks/diffusion_nets_v2.py:104-169)
@@ -115,7 +121,8 @@ LDP_API int ldp_unet_forward(LdpPlanner* h, int precision, const float* sample_d
 /* HOT LOOP 1  -  the fori_loop at agent/ldp_agent.py:465-476:
  *   for i in 0..n_steps-1: k = n_steps-1-i; eps = UNet(x,k,cond); x = step(eps,k,x,z_i)
  * x_T_dev (B,T,D) start noise; noise_dev (n_steps,B,T,D) injected z_i or NULL (Philox: seed, stream 0, step k,
- * element index offset by row_offset*T*D so that a batch sharded over ranks draws the same numbers as unsharded).
+ * keyed by global row (row_offset*T + local row) and column quad - see ldp_philox_normal_rows - so that a batch
+ * sharded over ranks draws the same numbers as unsharded).
  * The per-step eps-predict -> x0 -> clip -> posterior mean -> add-noise update runs in the epilogue of the UNet's
  * last GEMM (bf16 path); the 100 steps replay a captured CUDA graph.  x0_dev (B,T,D) may alias x_T_dev. */
 LDP_API int ldp_planner_sample(LdpPlanner* h, int precision, int sampler, const float* x_T_dev, const float* cond_dev,

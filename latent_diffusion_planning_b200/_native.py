@@ -19,7 +19,7 @@ SAMPLER_DDPM, SAMPLER_DDIM = 0, 1
 
 EXPORTS = [
     "ldp_last_error", "ldp_version", "ldp_device_check",
-    "ldp_ddpm_schedule", "ldp_ddpm_step", "ldp_ddpm_add_noise", "ldp_philox_normal",
+    "ldp_ddpm_schedule", "ldp_ddpm_step", "ldp_ddpm_add_noise", "ldp_philox_normal", "ldp_philox_normal_rows",
     "ldp_planner_create", "ldp_planner_destroy", "ldp_unet_param_count", "ldp_unet_forward", "ldp_planner_sample",
     "ldp_planner_profile_step",
     "ldp_idm_create", "ldp_idm_destroy", "ldp_idm_param_count", "ldp_idm_forward", "ldp_idm_sample",
@@ -74,6 +74,7 @@ def load() -> C.CDLL:
     lib.ldp_ddpm_step.argtypes = [i32, i32, i32, vp, vp, vp, u64, u32, vp, i64, vp]
     lib.ldp_ddpm_add_noise.argtypes = [i32, vp, vp, vp, vp, i64, i64, vp]
     lib.ldp_philox_normal.argtypes = [u64, u32, u32, vp, i64, vp]
+    lib.ldp_philox_normal_rows.argtypes = [u64, u32, u32, i64, i64, i32, vp, vp]
     lib.ldp_planner_create.argtypes = [C.POINTER(UnetConfig), vp, u64, C.POINTER(vp)]
     lib.ldp_planner_destroy.argtypes = [vp]
     lib.ldp_unet_param_count.argtypes = [C.POINTER(UnetConfig)]

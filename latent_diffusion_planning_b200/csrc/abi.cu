@@ -108,6 +108,12 @@ int ldp_philox_normal(uint64_t seed, uint32_t stream_id, uint32_t step, float* o
   return launch_philox_normal(seed, stream_id, step, out_dev, n, (cudaStream_t)cuda_stream);
 }
 
+int ldp_philox_normal_rows(uint64_t seed, uint32_t stream_id, uint32_t step, int64_t row0, int64_t rows, int row_len,
+                           float* out_dev, void* cuda_stream) {
+  LDP_CHECK(out_dev && rows > 0 && row_len > 0 && row0 >= 0, LDP_ERR_INVALID_ARG, "bad arguments");
+  return launch_philox_normal_rows(seed, stream_id, step, row0, rows, row_len, out_dev, (cudaStream_t)cuda_stream);
+}
+
 int ldp_tc_dense(const float* a_dev, const float* w_host, const float* bias_host, float* c_dev, int M, int K, int N,
                  void* cuda_stream) {
   LDP_CHECK(a_dev && w_host && c_dev && M > 0 && K > 0 && N > 0, LDP_ERR_INVALID_ARG, "bad arguments");
@@ -133,7 +139,7 @@ int ldp_tc_dense(const float* a_dev, const float* w_host, const float* bias_host
   std::vector<int32_t> kmap(kp);
   std::vector<TcKBlock> kb(kp / 64);
   for (int k = 0; k < kp; ++k) kmap[k] = k < K ? k : -1;
-  for (int i = 0; i < kp / 64; ++i) kb[i] = TcKBlock{0, i * 64, 0, 0};
+  for (int i = 0; i < kp / 64; ++i) kb[i] = make_stage(0, 0, 1, i * 64, 0, 0, i);
   LDP_CUDA_OK(cudaMemcpy(map_dev, kmap.data(), (size_t)kp * 4, cudaMemcpyHostToDevice));
   LDP_CUDA_OK(cudaMemcpy(kb_dev, kb.data(), kb.size() * sizeof(TcKBlock), cudaMemcpyHostToDevice));
   LDP_TRY(launch_pack_wt_bf16(w_dev, N, N, map_dev, kp, wt, kp, 0, n_pad, s));

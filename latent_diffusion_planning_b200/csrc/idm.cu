@@ -263,7 +263,7 @@ static int pack_dense(LdpIdm* h, const float* wgt, int K, int N, int block_n, Pa
   std::vector<int32_t> kmap(pw->kp);
   std::vector<TcKBlock> kb(pw->num_kb);
   for (int k = 0; k < pw->kp; ++k) kmap[k] = k < K ? k : -1;
-  for (int i = 0; i < pw->num_kb; ++i) kb[i] = TcKBlock{0, i * 64, 0, 0};
+  for (int i = 0; i < pw->num_kb; ++i) kb[i] = make_stage(0, 0, 1, i * 64, 0, 0, i);
   Arena tmp;
   int32_t* map_dev;
   LDP_TRY(tmp.alloc_t(&map_dev, pw->kp));
@@ -412,6 +412,8 @@ int ldp_idm_sample(LdpIdm* h, int precision, int sampler, const float* s_dev, co
   call.sampler = sampler;
   call.seed = seed;
   call.elem_offset = (long long)row_offset * A;
+  call.row_len = A;                                  // row-structured Philox: (transition row, column quad)
+  call.row_offset = (long long)row_offset;
   call.stream_id = 1;
   LDP_CUDA_OK(cudaMemcpyAsync(w->call_dev, &call, sizeof(call), cudaMemcpyHostToDevice, s));
   LDP_TRY(launch_set_i32(w->step_dev, n_steps - 1, s));

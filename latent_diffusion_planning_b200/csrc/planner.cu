@@ -69,6 +69,14 @@ struct CrbW {
   const float *c1w, *c1b, *g1s, *g1b, *fw, *fb, *c2w, *c2b, *g2s, *g2b, *rw, *rb;
 };
 
+// Packed weights + stage table of one convolution on the tcgen05 path (layouts described at get_packed).
+struct ConvPack : PackedW {
+  int n_acc = 1;
+  int shift[5] = {0, 0, 0, 0, 0};
+  int w_max = 1;
+  bool tapacc = false;
+};
+
 struct PlanWs {
   int B = 0, T = 0;
   Arena arena;
@@ -113,7 +121,7 @@ struct LdpPlanner {
   float* wc_all = nullptr;   // [Dc][sum_c2]       observation part of every FiLM Dense
   float* coef = nullptr;     // [n_train][8]
   std::map<std::pair<int, int>, std::unique_ptr<PlanWs>> ws;
-  std::map<std::pair<int, int>, PackedW> packed;   // (op id, T_in)
+  std::map<std::pair<int, int>, ConvPack> packed;   // (op id * 2 + layout, T_in)
   bool use_graph = true;
 };
 
@@ -433,75 +441,150 @@ static int forward_f32(LdpPlanner* h, PlanWs* w, const float* x, StepRef step, f
 }
 
 // ------------------------------- bf16 / tcgen05 program -------------------------------------------------------
-struct TcSrc { ActBf16 a; };
+// A convolution on the tcgen05 path.  Two K layouts:
+//  * tap-accumulator (k-tap conv, stride 1): K = (source, 64-channel block, tap).  One pipeline stage loads the
+//    un-shifted A tile of a channel block once plus the W tiles of all taps; tap j accumulates into its own TMEM
+//    accumulator and the epilogue recombines out[t] = sum_j acc_j[t + j - pad] with warp shuffles.  Against the
+//    per-tap layout this cuts the A traffic (the larger share of what an SM pulls from L2) by the tap count.
+//  * per-tap (strided / transposed convs, or when k accumulators do not fit the 512 TMEM columns): K = (tap, source,
+//    channel block); every tap re-fetches its shifted A tile through TMA (zero padding = out-of-bounds fill).
+// An optional aux part appends the K blocks of a 1x1 convolution on other sources (the residual projection of a
+// ConditionalResidualBlock1D) that accumulate into one more TMEM accumulator.
+struct ConvDesc {
+  int kind = CONV_K, taps_k = 1;
+  const ActBf16* srcs = nullptr; int nsrc = 0;
+  int t_in = 1;
+  const float* wgt = nullptr; int cout = 0;
+  const ActBf16* aux_srcs = nullptr; int aux_nsrc = 0; const float* aux_w = nullptr;   // 1x1 on the block input
+  int group_width = 1 << 30;      // GroupNorm group width the N tile must contain (1<<30: no constraint)
+};
 
-// Build (or fetch) the packed weights + K-block table of one convolution at input length t_in.
-static int get_packed(LdpPlanner* h, int op_id, int kind, int taps_k, const ActBf16* srcs, int nsrc, int t_in,
-                      const float* wgt, int cout, int block_n, PackedW** out) {
-  auto key = std::make_pair(op_id, t_in);   // n_pad is rounded to 128 below, so one packing serves both tile widths
+static bool env_off(const char* name) {
+  const char* e = getenv(name);
+  return e && e[0] == '0';
+}
+
+// N-tile width and K layout.  64-wide tiles double the CTA count of layers whose 128-wide grid would fill under half
+// of the 148 SMs; GroupNorm groups must fit inside one tile; (accumulators x BN) must fit the 512 TMEM columns.
+static void choose_tiling(int M, int N, const ConvDesc& d, int n_taps, int* bn_out, bool* tapacc_out) {
+  const int aux = d.aux_nsrc > 0 ? 1 : 0;
+  const int ctas128 = ceil_div(M, 128) * ceil_div(N, 128);
+  const bool ok64 = N % 64 == 0 && d.group_width <= 64 && !env_off("LDP_BN64");
+  const bool ok128 = d.group_width <= 128 || d.group_width == (1 << 30);
+  bool tapacc = d.kind == CONV_K && n_taps >= 2 && !env_off("LDP_TAPACC");
+  int bn = 128;
+  if (tapacc) {
+    const bool t128 = ok128 && (n_taps + aux) * 128 <= 512;
+    const bool t64 = ok64 && (n_taps + aux) * 64 <= 512;
+    if (t128 && (!t64 || ctas128 > 74)) bn = 128;
+    else if (t64) bn = 64;
+    else tapacc = false;
+  }
+  if (!tapacc) bn = (ok64 && ctas128 <= 74) ? 64 : 128;
+  *bn_out = bn;
+  *tapacc_out = tapacc;
+}
+
+// Build (or fetch) the packed weights + stage table of one convolution at input length t_in.
+static int get_packed(LdpPlanner* h, int op_id, const ConvDesc& d, bool tapacc, ConvPack** out) {
+  auto key = std::make_pair(op_id * 2 + (tapacc ? 1 : 0), d.t_in);
   auto it = h->packed.find(key);
   if (it != h->packed.end()) {
     *out = &it->second;
     return LDP_OK;
   }
-  (void)block_n;
   int ctot = 0;
-  for (int i = 0; i < nsrc; ++i) ctot += srcs[i].c;
-  std::vector<TcKBlock> kb;
+  for (int i = 0; i < d.nsrc; ++i) ctot += d.srcs[i].c;
+  ConvPack pw;
+  std::vector<TcStage> st;
   std::vector<int32_t> kmap, kmap2;     // kmap2: odd output phase of the transposed conv
-  auto push_sources = [&](int d1, int d2, int tap_row, int tap_row2) {
-    int coff = 0;
-    for (int sidx = 0; sidx < nsrc; ++sidx) {
-      for (int c0 = 0; c0 < srcs[sidx].c; c0 += 64) {
-        TcKBlock e;
-        e.src_acc = sidx;
-        e.c0 = c0; e.d1 = d1; e.d2 = d2;
-        kb.push_back(e);
-        for (int i = 0; i < 64; ++i) {
-          bool ok = c0 + i < srcs[sidx].c;
-          kmap.push_back(ok && tap_row >= 0 ? tap_row * ctot + coff + c0 + i : -1);
-          kmap2.push_back(ok && tap_row2 >= 0 ? tap_row2 * ctot + coff + c0 + i : -1);
-        }
-      }
-      coff += srcs[sidx].c;
+  auto push64 = [&](int src_c, int c0, int row_base, int row_base2) {
+    for (int i = 0; i < 64; ++i) {
+      const bool ok = c0 + i < src_c;
+      kmap.push_back(ok && row_base >= 0 ? row_base + c0 + i : -1);
+      kmap2.push_back(ok && row_base2 >= 0 ? row_base2 + c0 + i : -1);
     }
   };
-  if (kind == CONV_K) {
-    const int pad = taps_k / 2;
-    for (int j = 0; j < taps_k; ++j)
-      if (std::abs(j - pad) < t_in) push_sources(j - pad, 0, j, -1);     // taps that only ever see padding are dropped
-  } else if (kind == CONV_DOWN) {
-    // y[t] = sum_j W[j] x[2t+j] (pad_lo = 0 for even t_in); x viewed as (parity, t/2): tap j -> (j%2, t + j/2)
-    const int t_out = t_in / 2;
-    for (int j = 0; j < 3; ++j)
-      if (j < 2 || t_out >= 2) push_sources(j % 2, j / 2, j, -1);
+  if (d.kind == CONV_K && tapacc) {
+    const int pad = d.taps_k / 2;
+    std::vector<int> taps;
+    for (int j = 0; j < d.taps_k; ++j)
+      if (std::abs(j - pad) < d.t_in) taps.push_back(j);        // taps that only ever see padding are dropped
+    pw.n_acc = (int)taps.size();
+    pw.tapacc = true;
+    for (size_t a = 0; a < taps.size(); ++a) pw.shift[a] = taps[a] - pad;
+    pw.w_max = pw.n_acc;
+    int coff = 0;
+    for (int sidx = 0; sidx < d.nsrc; ++sidx) {
+      for (int c0 = 0; c0 < d.srcs[sidx].c; c0 += 64) {
+        st.push_back(make_stage(sidx, 0, pw.n_acc, c0, 0, 0, (int)kmap.size() / 64));
+        for (int j : taps) push64(d.srcs[sidx].c, c0, j * ctot + coff, -1);
+      }
+      coff += d.srcs[sidx].c;
+    }
   } else {
-    // y[2u] = W0 x[u-1] + W2 x[u];  y[2u+1] = W1 x[u] + W3 x[u+1]
-    if (t_in >= 2) push_sources(-1, 0, 0, -1);
-    push_sources(0, 0, 2, 1);
-    if (t_in >= 2) push_sources(1, 0, -1, 3);
+    auto push_sources = [&](int d1, int d2, int tap_row, int tap_row2) {
+      int coff = 0;
+      for (int sidx = 0; sidx < d.nsrc; ++sidx) {
+        for (int c0 = 0; c0 < d.srcs[sidx].c; c0 += 64) {
+          st.push_back(make_stage(sidx, 0, 1, c0, d1, d2, (int)kmap.size() / 64));
+          push64(d.srcs[sidx].c, c0, tap_row >= 0 ? tap_row * ctot + coff : -1, tap_row2 >= 0 ? tap_row2 * ctot + coff : -1);
+        }
+        coff += d.srcs[sidx].c;
+      }
+    };
+    if (d.kind == CONV_K) {
+      const int pad = d.taps_k / 2;
+      for (int j = 0; j < d.taps_k; ++j)
+        if (std::abs(j - pad) < d.t_in) push_sources(j - pad, 0, j, -1);
+    } else if (d.kind == CONV_DOWN) {
+      // y[t] = sum_j W[j] x[2t+j] (pad_lo = 0 for even t_in); x viewed as (parity, t/2): tap j -> (j%2, t + j/2)
+      const int t_out = d.t_in / 2;
+      for (int j = 0; j < 3; ++j)
+        if (j < 2 || t_out >= 2) push_sources(j % 2, j / 2, j, -1);
+    } else {
+      // y[2u] = W0 x[u-1] + W2 x[u];  y[2u+1] = W1 x[u] + W3 x[u+1]
+      if (d.t_in >= 2) push_sources(-1, 0, 0, -1);
+      push_sources(0, 0, 2, 1);
+      if (d.t_in >= 2) push_sources(1, 0, -1, 3);
+    }
   }
   const int kp_main = (int)kmap.size();
-  const int kp = kp_main;
-  const int n_out = kind == CONV_UP ? 2 * cout : cout;
-  PackedW pw;
-  pw.kp = kp;
+  std::vector<int32_t> kmap_aux;
+  {
+    int coff = 0;
+    for (int sidx = 0; sidx < d.aux_nsrc; ++sidx) {
+      for (int c0 = 0; c0 < d.aux_srcs[sidx].c; c0 += 64) {
+        st.push_back(make_stage(d.nsrc + sidx, pw.n_acc, 1, c0, 0, 0, (kp_main + (int)kmap_aux.size()) / 64));
+        for (int i = 0; i < 64; ++i) kmap_aux.push_back(c0 + i < d.aux_srcs[sidx].c ? coff + c0 + i : -1);
+      }
+      coff += d.aux_srcs[sidx].c;
+    }
+  }
+  LDP_CHECK(d.nsrc + d.aux_nsrc <= 4, LDP_ERR_UNSUPPORTED, "a convolution reads at most 4 activation tensors");
+  const int n_out = d.kind == CONV_UP ? 2 * d.cout : d.cout;
+  pw.kp = kp_main + (int)kmap_aux.size();
   pw.n_pad = round_up(n_out, 128);
-  pw.num_kb = (int)kb.size();
-  LDP_TRY(h->arena.alloc_t(&pw.wt, (size_t)pw.n_pad * kp));
-  LDP_TRY(h->arena.alloc_t(&pw.kb_dev, kb.size()));
-  LDP_CUDA_OK(cudaMemcpy(pw.kb_dev, kb.data(), kb.size() * sizeof(TcKBlock), cudaMemcpyHostToDevice));
-  int32_t* map_dev;
+  pw.num_kb = (int)st.size();
+  LDP_TRY(h->arena.alloc_t(&pw.wt, (size_t)pw.n_pad * pw.kp));
+  LDP_TRY(h->arena.alloc_t(&pw.kb_dev, st.size()));
+  LDP_CUDA_OK(cudaMemcpy(pw.kb_dev, st.data(), st.size() * sizeof(TcStage), cudaMemcpyHostToDevice));
   Arena tmp;
-  LDP_TRY(tmp.alloc_t(&map_dev, (size_t)kp * 2 + 16));
+  int32_t* map_dev;
+  LDP_TRY(tmp.alloc_t(&map_dev, (size_t)kp_main * 2 + kmap_aux.size() + 16));
   LDP_CUDA_OK(cudaMemcpy(map_dev, kmap.data(), (size_t)kp_main * 4, cudaMemcpyHostToDevice));
-  if (kind == CONV_UP) {
-    LDP_CUDA_OK(cudaMemcpy(map_dev + kp, kmap2.data(), (size_t)kp_main * 4, cudaMemcpyHostToDevice));
-    LDP_TRY(launch_pack_wt_bf16(wgt, cout, cout, map_dev, kp_main, pw.wt, kp, 0, cout, 0));
-    LDP_TRY(launch_pack_wt_bf16(wgt, cout, cout, map_dev + kp, kp_main, pw.wt + (size_t)cout * kp, kp, 0,
-                                pw.n_pad - cout, 0));
+  if (d.kind == CONV_UP) {
+    LDP_CUDA_OK(cudaMemcpy(map_dev + kp_main, kmap2.data(), (size_t)kp_main * 4, cudaMemcpyHostToDevice));
+    LDP_TRY(launch_pack_wt_bf16(d.wgt, d.cout, d.cout, map_dev, kp_main, pw.wt, pw.kp, 0, d.cout, 0));
+    LDP_TRY(launch_pack_wt_bf16(d.wgt, d.cout, d.cout, map_dev + kp_main, kp_main, pw.wt + (size_t)d.cout * pw.kp, pw.kp, 0,
+                                pw.n_pad - d.cout, 0));
   } else {
-    LDP_TRY(launch_pack_wt_bf16(wgt, cout, cout, map_dev, kp_main, pw.wt, kp, 0, pw.n_pad, 0));
+    LDP_TRY(launch_pack_wt_bf16(d.wgt, d.cout, d.cout, map_dev, kp_main, pw.wt, pw.kp, 0, pw.n_pad, 0));
+    if (!kmap_aux.empty()) {
+      LDP_CUDA_OK(cudaMemcpy(map_dev + 2 * kp_main, kmap_aux.data(), kmap_aux.size() * 4, cudaMemcpyHostToDevice));
+      LDP_TRY(launch_pack_wt_bf16(d.aux_w, d.cout, d.cout, map_dev + 2 * kp_main, (int)kmap_aux.size(), pw.wt, pw.kp, kp_main,
+                                  pw.n_pad, 0));
+    }
   }
   LDP_CUDA_OK(cudaDeviceSynchronize());
   h->packed[key] = pw;
@@ -524,39 +607,39 @@ static int act_map(CUtensorMap* m, const ActBf16& a, int kind, int t_in, int B) 
 }
 
 // Generic convolution op on the tcgen05 path; the caller fills in the epilogue afterwards.
-// N-tile width: 64-wide tiles double the CTA count of the layers whose 128-wide grid would fill under half of the
-// 148 SMs (up path, stride-2 convolutions); GroupNorm groups must still fit inside one tile.
-static int pick_block_n(int M, int N, int group_width) {
-  const char* env = getenv("LDP_BN64");
-  if (env && env[0] == '0') return 128;
-  const int ctas128 = ceil_div(M, 128) * ceil_div(N, 128);
-  if (ctas128 <= 74 && N % 64 == 0 && group_width <= 64) return 64;
-  return 128;
-}
-
-static int conv_tc(LdpPlanner* h, PlanWs* w, int op_id, int kind, int taps_k, const ActBf16* srcs, int nsrc, int t_in,
-                   const float* wgt, int cout, int group_width, TcGemm* op) {
-  const int rows = kind == CONV_DOWN ? t_in / 2 : t_in;
-  const int bn = pick_block_n(w->B * rows, kind == CONV_UP ? 2 * cout : cout, group_width);
+static int conv_tc(LdpPlanner* h, PlanWs* w, int op_id, const ConvDesc& d, TcGemm* op) {
+  const int rows = d.kind == CONV_DOWN ? d.t_in / 2 : d.t_in;
   LDP_CHECK(rows >= 1 && rows <= 32 && (rows & (rows - 1)) == 0, LDP_ERR_UNSUPPORTED,
             "bf16 path needs power-of-two level lengths <= 32 (use LDP_PREC_FP32 for other horizons)");
-  for (int i = 0; i < nsrc; ++i)
-    LDP_CHECK(srcs[i].ld % 8 == 0, LDP_ERR_INVALID_ARG, "activation pitch must be a multiple of 8 elements");
-  PackedW* pw;
-  LDP_TRY(get_packed(h, op_id, kind, taps_k, srcs, nsrc, t_in, wgt, cout, bn, &pw));
+  for (int i = 0; i < d.nsrc; ++i)
+    LDP_CHECK(d.srcs[i].ld % 8 == 0, LDP_ERR_INVALID_ARG, "activation pitch must be a multiple of 8 elements");
+  const int M = w->B * rows, N = d.kind == CONV_UP ? 2 * d.cout : d.cout;
+  int n_taps = 0;
+  if (d.kind == CONV_K)
+    for (int j = 0; j < d.taps_k; ++j) n_taps += std::abs(j - d.taps_k / 2) < d.t_in ? 1 : 0;
+  int bn;
+  bool tapacc;
+  choose_tiling(M, N, d, n_taps, &bn, &tapacc);
+  ConvPack* pw;
+  LDP_TRY(get_packed(h, op_id, d, tapacc, &pw));
   *op = TcGemm();
-  for (int i = 0; i < nsrc; ++i) LDP_TRY(act_map(&op->map_a[i], srcs[i], kind, t_in, w->B));
-  for (int i = nsrc; i < 4; ++i) op->map_a[i] = op->map_a[0];
+  for (int i = 0; i < d.nsrc; ++i) LDP_TRY(act_map(&op->map_a[i], d.srcs[i], d.kind, d.t_in, w->B));
+  for (int i = 0; i < d.aux_nsrc; ++i) LDP_TRY(act_map(&op->map_a[d.nsrc + i], d.aux_srcs[i], CONV_K, d.t_in, w->B));
+  for (int i = d.nsrc + d.aux_nsrc; i < 4; ++i) op->map_a[i] = op->map_a[0];
   uint64_t bd[2] = {(uint64_t)pw->kp, (uint64_t)pw->n_pad};
   uint64_t bs[1] = {(uint64_t)pw->kp * 2};
   uint32_t bb[2] = {64, (uint32_t)bn};
   LDP_TRY(make_tmap_bf16(&op->map_b, pw->wt, 2, bd, bs, bb));
   op->kb = pw->kb_dev;
   op->num_kb = pw->num_kb;
-  op->M = w->B * rows;
-  op->N = kind == CONV_UP ? 2 * cout : cout;
+  op->w_max = pw->w_max;
+  op->k_pad = pw->kp;
+  op->n_acc = pw->n_acc;
+  for (int j = 0; j < 5; ++j) op->shift[j] = pw->shift[j];
+  op->use_aux = d.aux_nsrc > 0 ? 1 : 0;
+  op->M = M;
+  op->N = N;
   op->block_n = bn;
-  op->use_aux = 0;
   op->tiles_per_item = 1;
   op->rows_step = 0;
   op->items_per_tile = 128 / rows;
@@ -577,77 +660,27 @@ static int crb_tc(LdpPlanner* h, PlanWs* w, int bi, const ActBf16* srcs, int nsr
   const CrbW& b = h->crb[bi];
   LDP_CHECK((b.cout / h->cfg.n_groups) % 32 == 0, LDP_ERR_UNSUPPORTED,
             "bf16 path needs GroupNorm group widths that are multiples of 32 channels");
-  TcGemm op;
   const int gw = b.cout / h->cfg.n_groups;
-  LDP_TRY(conv_tc(h, w, 4 * bi + 0, CONV_K, 5, srcs, nsrc, Tl, b.c1w, b.cout, gw, &op));
+  TcGemm op;
+  ConvDesc d;
+  d.kind = CONV_K; d.taps_k = 5; d.srcs = srcs; d.nsrc = nsrc; d.t_in = Tl; d.wgt = b.c1w; d.cout = b.cout; d.group_width = gw;
+  LDP_TRY(conv_tc(h, w, 4 * bi + 0, d, &op));
   set_gn(&op, b.c1b, b.g1s, b.g1b, b.cout, h->cfg.n_groups, h1buf);
   op.film = 1; op.ttab = h->ttab; op.ld_ttab = h->sum_c2; op.otab = w->otab; op.ld_otab = h->sum_c2;
   op.film_off = b.film_off; op.film_c = b.cout;
   w->ops.push_back(op);
   ActBf16 h1{h1buf, b.cout, b.cout};
+  d = ConvDesc();
+  d.kind = CONV_K; d.taps_k = 5; d.srcs = &h1; d.nsrc = 1; d.t_in = Tl; d.wgt = b.c2w; d.cout = b.cout; d.group_width = gw;
   if (b.proj) {
-    // conv2 on h1 (accumulator 0) + the 1x1 residual projection of the block input (accumulator 1) in ONE launch
-    ActBf16 both[3] = {h1, srcs[0], nsrc > 1 ? srcs[1] : srcs[0]};
-    // pack: main K blocks from h1, aux K blocks from the block input(s)
-    PackedW* pw;
-    auto key = std::make_pair(4 * bi + 1, Tl);
-    if (h->packed.find(key) == h->packed.end()) {
-      // main part
-      std::vector<TcKBlock> kb;
-      std::vector<int32_t> kmap, kmap_aux;
-      for (int j = 0; j < 5; ++j) {
-        if (std::abs(j - 2) >= Tl) continue;
-        for (int c0 = 0; c0 < b.cout; c0 += 64) {
-          kb.push_back(TcKBlock{0, c0, j - 2, 0});
-          for (int i = 0; i < 64; ++i) kmap.push_back(c0 + i < b.cout ? j * b.cout + c0 + i : -1);
-        }
-      }
-      int coff = 0;
-      for (int sidx = 0; sidx < nsrc; ++sidx) {
-        for (int c0 = 0; c0 < srcs[sidx].c; c0 += 64) {
-          kb.push_back(TcKBlock{(1 + sidx) | (1 << 8), c0, 0, 0});
-          for (int i = 0; i < 64; ++i) kmap_aux.push_back(c0 + i < srcs[sidx].c ? coff + c0 + i : -1);
-        }
-        coff += srcs[sidx].c;
-      }
-      PackedW p2;
-      const int kp_main = (int)kmap.size();
-      p2.kp = kp_main + (int)kmap_aux.size();
-      p2.n_pad = round_up(b.cout, 128);
-      p2.num_kb = (int)kb.size();
-      LDP_TRY(h->arena.alloc_t(&p2.wt, (size_t)p2.n_pad * p2.kp));
-      LDP_TRY(h->arena.alloc_t(&p2.kb_dev, kb.size()));
-      LDP_CUDA_OK(cudaMemcpy(p2.kb_dev, kb.data(), kb.size() * sizeof(TcKBlock), cudaMemcpyHostToDevice));
-      Arena tmp;
-      int32_t* map_dev;
-      LDP_TRY(tmp.alloc_t(&map_dev, (size_t)p2.kp + 16));
-      LDP_CUDA_OK(cudaMemcpy(map_dev, kmap.data(), kmap.size() * 4, cudaMemcpyHostToDevice));
-      LDP_CUDA_OK(cudaMemcpy(map_dev + kp_main, kmap_aux.data(), kmap_aux.size() * 4, cudaMemcpyHostToDevice));
-      LDP_TRY(launch_pack_wt_bf16(b.c2w, b.cout, b.cout, map_dev, kp_main, p2.wt, p2.kp, 0, p2.n_pad, 0));
-      LDP_TRY(launch_pack_wt_bf16(b.rw, b.cout, b.cout, map_dev + kp_main, (int)kmap_aux.size(), p2.wt, p2.kp, kp_main,
-                                  p2.n_pad, 0));
-      LDP_CUDA_OK(cudaDeviceSynchronize());
-      h->packed[key] = p2;
-    }
-    pw = &h->packed[key];
-    op = TcGemm();
-    LDP_TRY(act_map(&op.map_a[0], both[0], CONV_K, Tl, w->B));
-    LDP_TRY(act_map(&op.map_a[1], both[1], CONV_K, Tl, w->B));
-    LDP_TRY(act_map(&op.map_a[2], both[2], CONV_K, Tl, w->B));
-    op.map_a[3] = op.map_a[2];
-    uint64_t bd[2] = {(uint64_t)pw->kp, (uint64_t)pw->n_pad};
-    uint64_t bs[1] = {(uint64_t)pw->kp * 2};
-    const int bn = pick_block_n(w->B * Tl, b.cout, gw);
-    uint32_t bb[2] = {64, (uint32_t)bn};
-    LDP_TRY(make_tmap_bf16(&op.map_b, pw->wt, 2, bd, bs, bb));
-    op.kb = pw->kb_dev; op.num_kb = pw->num_kb;
-    op.M = w->B * Tl; op.N = b.cout; op.block_n = bn; op.use_aux = 1;
-    op.items_per_tile = 128 / Tl; op.rows_per_item = Tl;
-    set_gn(&op, b.c2b, b.g2s, b.g2b, b.cout, h->cfg.n_groups, outbuf);
+    // conv2 on h1 + the 1x1 residual projection of the block input (one more accumulator) in ONE launch
+    d.aux_srcs = srcs; d.aux_nsrc = nsrc; d.aux_w = b.rw;
+  }
+  LDP_TRY(conv_tc(h, w, 4 * bi + 1, d, &op));
+  set_gn(&op, b.c2b, b.g2s, b.g2b, b.cout, h->cfg.n_groups, outbuf);
+  if (b.proj) {
     op.bias_aux = b.rb;
   } else {
-    LDP_TRY(conv_tc(h, w, 4 * bi + 1, CONV_K, 5, &h1, 1, Tl, b.c2w, b.cout, gw, &op));
-    set_gn(&op, b.c2b, b.g2s, b.g2b, b.cout, h->cfg.n_groups, outbuf);
     op.res_bf16 = srcs[0].p; op.ld_res_bf16 = srcs[0].ld;
   }
   w->ops.push_back(op);
@@ -688,7 +721,10 @@ static int prepare_bf16(LdpPlanner* h, PlanWs* w) {
       ActBf16 o;
       LDP_TRY(new_act(Tl / 2, d, &o));
       TcGemm op;
-      LDP_TRY(conv_tc(h, w, 1000 + l, CONV_DOWN, 3, &cur, 1, Tl, h->down_w[l], d, 32, &op));
+      ConvDesc cd;
+      cd.kind = CONV_DOWN; cd.taps_k = 3; cd.srcs = &cur; cd.nsrc = 1; cd.t_in = Tl; cd.wgt = h->down_w[l]; cd.cout = d;
+      cd.group_width = 32;
+      LDP_TRY(conv_tc(h, w, 1000 + l, cd, &op));
       op.mode = TC_EPI_PLAIN; op.bias = h->down_b[l]; op.out_bf16 = o.p; op.ld_out_bf16 = d;
       w->ops.push_back(op);
       cur = o;
@@ -718,7 +754,10 @@ static int prepare_bf16(LdpPlanner* h, PlanWs* w) {
     const int d = c.down_dims[lvl - 1];
     LDP_TRY(new_act(2 * Tl, d, &o));
     TcGemm op;
-    LDP_TRY(conv_tc(h, w, 2000 + u, CONV_UP, 4, &cur, 1, Tl, h->up_w[u], d, 32, &op));
+    ConvDesc cd;
+    cd.kind = CONV_UP; cd.taps_k = 4; cd.srcs = &cur; cd.nsrc = 1; cd.t_in = Tl; cd.wgt = h->up_w[u]; cd.cout = d;
+    cd.group_width = 32;
+    LDP_TRY(conv_tc(h, w, 2000 + u, cd, &op));
     op.mode = TC_EPI_PLAIN; op.bias = h->up_bias2[u]; op.out_bf16 = o.p; op.ld_out_bf16 = 2 * d;
     w->ops.push_back(op);
     cur = o;
@@ -728,10 +767,14 @@ static int prepare_bf16(LdpPlanner* h, PlanWs* w) {
   ActBf16 f;
   LDP_TRY(new_act(T, d0, &f));
   TcGemm op;
-  LDP_TRY(conv_tc(h, w, 3000, CONV_K, 5, &cur, 1, T, h->fcw, d0, d0 / 8, &op));
+  ConvDesc cd;
+  cd.kind = CONV_K; cd.taps_k = 5; cd.srcs = &cur; cd.nsrc = 1; cd.t_in = T; cd.wgt = h->fcw; cd.cout = d0; cd.group_width = d0 / 8;
+  LDP_TRY(conv_tc(h, w, 3000, cd, &op));
   set_gn(&op, h->fcb, h->fgs, h->fgb, d0, 8, f.p);
   w->ops.push_back(op);
-  LDP_TRY(conv_tc(h, w, 3001, CONV_K, 1, &f, 1, T, h->ow, c.input_dim, 1 << 30, &op));
+  cd = ConvDesc();
+  cd.kind = CONV_K; cd.taps_k = 1; cd.srcs = &f; cd.nsrc = 1; cd.t_in = T; cd.wgt = h->ow; cd.cout = c.input_dim;
+  LDP_TRY(conv_tc(h, w, 3001, cd, &op));
   op.mode = TC_EPI_DDPM;
   op.bias = h->ob;
   op.coef = h->coef;
@@ -830,6 +873,8 @@ int ldp_planner_sample(LdpPlanner* h, int precision, int sampler, const float* x
   call.sampler = sampler;
   call.seed = seed;
   call.elem_offset = (long long)row_offset * T * D;
+  call.row_len = D;                                  // row-structured Philox: (plan row, column quad)
+  call.row_offset = (long long)row_offset * T;
   call.stream_id = 0;
   LDP_CUDA_OK(cudaMemcpyAsync(w->call_dev, &call, sizeof(call), cudaMemcpyHostToDevice, s));
   LDP_TRY(launch_set_i32(w->step_dev, n_steps - 1, s));
@@ -892,6 +937,7 @@ int ldp_planner_profile_step(LdpPlanner* h, int B, int T, int reps, float* us_ho
   DdpmCall call;
   call.n_steps = 1;
   call.seed = 1;
+  call.row_len = h->cfg.input_dim;
   LDP_CUDA_OK(cudaMemcpyAsync(w->call_dev, &call, sizeof(call), cudaMemcpyHostToDevice, s));
   LDP_TRY(launch_set_i32(w->step_dev, h->cfg.n_train_steps / 2, s));
   StepRef step;
@@ -912,8 +958,8 @@ int ldp_planner_profile_step(LdpPlanner* h, int B, int T, int reps, float* us_ho
     us_host[i] = ms * 1000.f / reps;
     meta_host[4 * i + 0] = op.M;
     meta_host[4 * i + 1] = op.N;
-    meta_host[4 * i + 2] = op.num_kb;
-    meta_host[4 * i + 3] = op.block_n | (op.mode << 16) | (op.use_aux << 24);
+    meta_host[4 * i + 2] = op.k_pad / 64;
+    meta_host[4 * i + 3] = op.block_n | (op.mode << 16) | (op.use_aux << 24) | (op.n_acc << 25);
   }
   cudaEventDestroy(e0);
   cudaEventDestroy(e1);

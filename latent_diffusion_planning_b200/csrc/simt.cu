@@ -253,8 +253,19 @@ __global__ void ddpm_step_kernel(const DdpmStep p) {
     } else {
       o = c0 * x0 + ct * x;
       if (t > 0) {
-        float z = noise ? noise[i] : philox_normal(call.seed, call.stream_id, (uint32_t)t, (unsigned long long)(call.elem_offset + i));
-        o += sigma * z;
+        float z;
+        if (noise) {
+          z = noise[i];
+        } else if (call.row_len > 0) {       // row-structured noise of the sampling loops (same draw as the fused epilogue)
+          const long long row = i / call.row_len;
+          const int col = (int)(i - row * call.row_len);
+          float z4[4];
+          philox_normal4_rows(call.seed, call.stream_id, (uint32_t)t, (uint32_t)(call.row_offset + row), (uint32_t)(col >> 2), z4);
+          z = (col & 3) == 0 ? z4[0] : ((col & 3) == 1 ? z4[1] : ((col & 3) == 2 ? z4[2] : z4[3]));
+        } else {
+          z = philox_normal(call.seed, call.stream_id, (uint32_t)t, (unsigned long long)(call.elem_offset + i));
+        }
+        o = fmaf(sigma, z, o);
       }
     }
     p.out[i] = o;
@@ -300,6 +311,29 @@ int launch_philox_normal(unsigned long long seed, uint32_t stream_id, uint32_t s
   int blocks = (int)((n + 255) / 256);
   if (blocks > 148 * 16) blocks = 148 * 16;
   philox_normal_kernel<<<blocks, 256, 0, s>>>(seed, stream_id, step, out, n);
+  LDP_LAUNCH_OK();
+  return LDP_OK;
+}
+
+__global__ void philox_normal_rows_kernel(unsigned long long seed, uint32_t stream_id, uint32_t step, long long row0,
+                                          long long rows, int row_len, float* out) {
+  const int nq = (row_len + 3) >> 2;
+  const long long total = rows * nq;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / nq;
+    const int g = (int)(i - r * nq);
+    float z[4];
+    philox_normal4_rows(seed, stream_id, step, (uint32_t)(row0 + r), (uint32_t)g, z);
+    for (int k = 0; k < 4; ++k)
+      if (4 * g + k < row_len) out[r * row_len + 4 * g + k] = z[k];
+  }
+}
+
+int launch_philox_normal_rows(unsigned long long seed, uint32_t stream_id, uint32_t step, long long row0, long long rows,
+                              int row_len, float* out, cudaStream_t s) {
+  const long long total = rows * ((row_len + 3) >> 2);
+  int blocks = (int)std::min<long long>((total + 255) / 256, 148 * 8);
+  philox_normal_rows_kernel<<<blocks, 256, 0, s>>>(seed, stream_id, step, row0, rows, row_len, out);
   LDP_LAUNCH_OK();
   return LDP_OK;
 }

@@ -40,13 +40,18 @@ constexpr int TC_THREADS = 64 + TC_EPI_THREADS; // warp 0: TMA, warp 1: MMA, war
 constexpr int TC_MAX_KB_SMEM = 256;
 constexpr int TC_MAX_STAGES = 8;
 
+constexpr int TC_SMEM_RING = 196 * 1024;        // shared-memory budget of the TMA ring (static smem takes <= 20 KB more)
+
 template <int BN>
 struct TcSmem {
-  static constexpr int STAGES = BN == 64 ? 8 : (BN == 128 ? 6 : 4);
   static constexpr int B_BYTES = BN * TC_BK * 2;
-  static constexpr int STAGE_BYTES = TC_A_BYTES + B_BYTES;
-  static constexpr int TOTAL = STAGES * STAGE_BYTES + 1024;   // + alignment slack
 };
+// ring geometry of a launch: a stage holds one A tile and w_max W tiles
+static inline int tc_stage_bytes(int bn, int w_max) { return TC_A_BYTES + w_max * bn * TC_BK * 2; }
+static inline int tc_num_stages(int bn, int w_max) {
+  int n = TC_SMEM_RING / tc_stage_bytes(bn, w_max);
+  return n > TC_MAX_STAGES ? TC_MAX_STAGES : n;
+}
 
 // Per-CTA staging of everything the epilogue needs per output column (filled while the main loop runs).
 template <int BN>
@@ -165,10 +170,48 @@ __device__ __forceinline__ void add_smem32(float (&v)[32], const float* s) {
   }
 }
 
+// v = sum_j acc_j[row + shift_j][32-column chunk c]  (the recombination of a k-tap convolution computed as k un-shifted
+// GEMMs).  Thread `lane` of the warp owns TMEM lane = output row; rows of one sample are adjacent lanes, so a shifted
+// row is a warp shuffle away, and rows that fall outside the sample contribute zero (the convolution's zero padding).
+template <int BN>
+__device__ __forceinline__ void load_acc_chunk(const TcGemm& p, uint32_t taddr, int c, int lane, float (&v)[32]) {
+  tmem_ld_32x32(taddr + c * 32, v);
+  if (p.n_acc == 1 && p.shift[0] == 0) return;       // uniform: dense GEMM / per-tap mode
+  const int T = p.rows_per_item, t = lane & (T - 1);
+  {
+    const int s = p.shift[0];
+    if (s != 0) {
+      const bool ok = (unsigned)(t + s) < (unsigned)T;
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        const float q = __shfl_sync(0xffffffffu, v[i], (lane + s) & 31);
+        v[i] = ok ? q : 0.f;
+      }
+    }
+  }
+#pragma unroll 1
+  for (int j = 1; j < p.n_acc; ++j) {
+    float r[32];
+    tmem_ld_32x32(taddr + j * BN + c * 32, r);
+    const int s = p.shift[j];
+    if (s != 0) {                                     // uniform
+      const bool ok = (unsigned)(t + s) < (unsigned)T;
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        const float q = __shfl_sync(0xffffffffu, r[i], (lane + s) & 31);
+        v[i] += ok ? q : 0.f;
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) v[i] += r[i];
+    }
+  }
+}
+
 // ---- epilogues: thread owns row `m`; this warp covers chunks [c_begin, c_begin + CPP) of the N tile ------------
 template <int BN>
 __device__ __forceinline__ void epilogue_plain(const TcGemm& p, EpiSmem<BN>& es, uint32_t taddr, int m, int n0,
-                                               int c_begin) {
+                                               int c_begin, int lane) {
   constexpr int CPP = BN / 64;
   const bool row_ok = m < p.M;
   const bool vf = (p.ld_out_f32 & 3) == 0, vb = (p.ld_out_bf16 & 7) == 0;
@@ -180,7 +223,7 @@ __device__ __forceinline__ void epilogue_plain(const TcGemm& p, EpiSmem<BN>& es,
     const int nvalid = min(32, p.N - nb);
     if (nvalid <= 0) continue;           // uniform across the warp
     float v[32];
-    tmem_ld_32x32(taddr + c * 32, v);
+    load_acc_chunk<BN>(p, taddr, c, lane, v);
     add_smem32(v, es.bias + c * 32);
     if (p.relu) {
 #pragma unroll
@@ -197,7 +240,7 @@ __device__ __forceinline__ void epilogue_plain(const TcGemm& p, EpiSmem<BN>& es,
 
 template <int BN>
 __device__ __forceinline__ void epilogue_gn(const TcGemm& p, EpiSmem<BN>& es, uint32_t taddr, int m, int n0, int c_begin,
-                                            int row) {
+                                            int row, int lane) {
   constexpr int NC = BN / 32, CPP = BN / 64;
   const int T = p.rows_per_item;
   const int cpg = p.group_width >> 5;                    // chunks per group: 1, 2 or 4
@@ -210,7 +253,7 @@ __device__ __forceinline__ void epilogue_gn(const TcGemm& p, EpiSmem<BN>& es, ui
     const int c = c_begin + cc;
     float s = 0.f, ss = 0.f;
     if (c < nchunks) {
-      tmem_ld_32x32(taddr + c * 32, v[cc]);
+      load_acc_chunk<BN>(p, taddr, c, lane, v[cc]);
       add_smem32(v[cc], es.bias + c * 32);
 #pragma unroll
       for (int i = 0; i < 32; ++i) {
@@ -296,7 +339,7 @@ __device__ __forceinline__ void epilogue_gn(const TcGemm& p, EpiSmem<BN>& es, ui
     }
     if (p.use_aux) {
       float r[32];
-      tmem_ld_32x32(taddr + BN + c * 32, r);
+      tmem_ld_32x32(taddr + p.n_acc * BN + c * 32, r);
       add_smem32(r, es.bias2 + c * 32);
 #pragma unroll
       for (int i = 0; i < 32; ++i) w[i] += r[i];
@@ -310,29 +353,13 @@ __device__ __forceinline__ void epilogue_gn(const TcGemm& p, EpiSmem<BN>& es, ui
   }
 }
 
-// Four standard normals of Philox quad q (elements 4q..4q+3): two Box-Muller pairs.
-__device__ __forceinline__ void philox_normal4(unsigned long long seed, uint32_t stream, uint32_t step,
-                                               unsigned long long q, float* z) {
-  uint4 r = philox4x32_10(make_uint4((uint32_t)q, (uint32_t)(q >> 32), step, stream),
-                          make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
-  const float k = 2.3283064365386963e-10f;
-  float u0 = ((float)r.x + 0.5f) * k, u1 = ((float)r.y + 0.5f) * k;
-  float u2 = ((float)r.z + 0.5f) * k, u3 = ((float)r.w + 0.5f) * k;
-  float ra = sqrtf(-2.f * logf(u0)), rb = sqrtf(-2.f * logf(u2));
-  float s, c;
-  sincospif(2.f * u1, &s, &c);
-  z[0] = ra * c; z[1] = ra * s;
-  sincospif(2.f * u3, &s, &c);
-  z[2] = rb * c; z[3] = rb * s;
-}
-
 // DDPM / DDIM update fused behind the score net's last GEMM.  Phase 1: every epilogue thread drops its row of
 // eps = acc + bias into a padded shared-memory tile (the pipeline buffers, idle by now).  Phase 2: the tile is
-// walked row-major, a lane per group of 4 consecutive columns, so x, the injected noise and the bf16 copy of x
-// are accessed coalesced and one or two Philox calls serve four elements.
+// walked row-major, one thread per group of 4 consecutive columns, so x, the injected noise and the bf16 copy of x
+// are accessed coalesced and one Philox call serves four elements (row-structured quads, see DdpmCall).
 template <int BN>
 __device__ __forceinline__ void epilogue_ddpm(const TcGemm& p, EpiSmem<BN>& es, uint32_t taddr, float* tile, int tile_m,
-                                              int n0, int c_begin, int row, int ewarp, int lane) {
+                                              int n0, int c_begin, int row, int et, int lane) {
   constexpr int CPP = BN / 64;
   constexpr int TS = BN + 1;
 #pragma unroll 1
@@ -340,7 +367,7 @@ __device__ __forceinline__ void epilogue_ddpm(const TcGemm& p, EpiSmem<BN>& es, 
     const int c = c_begin + cc;
     if (n0 + c * 32 >= p.N) continue;          // uniform
     float v[32];
-    tmem_ld_32x32(taddr + c * 32, v);
+    load_acc_chunk<BN>(p, taddr, c, lane, v);
     add_smem32(v, es.bias + c * 32);
     float* trow = tile + row * TS + c * 32;
 #pragma unroll
@@ -355,66 +382,58 @@ __device__ __forceinline__ void epilogue_ddpm(const TcGemm& p, EpiSmem<BN>& es, 
   const bool ddim = call.sampler == LDP_SAMPLER_DDIM;
   const bool add_noise = !ddim && t > 0;
   const int nv = min(BN, p.N - n0);
+  const int nq = (nv + 3) >> 2;                                  // column quads of this tile (n0 is a multiple of 4)
+  const int rows_here = min(TC_BM, p.M - tile_m * TC_BM);
+  const int total = rows_here * nq;
   const bool vb = p.out_bf16 != nullptr && (p.ld_out_bf16 & 3) == 0;
 #pragma unroll 1
-  for (int r = ewarp; r < TC_BM; r += TC_EPI_WARPS) {
+  for (int idx = et; idx < total; idx += TC_EPI_THREADS) {
+    const int r = idx / nq, g = idx - r * nq;
     const int m = tile_m * TC_BM + r;
-    if (m >= p.M) break;                        // uniform
-#pragma unroll 1
-    for (int g = lane; g * 4 < nv; g += 32) {
-      const int cb = g * 4;
-      const int cnt = min(4, nv - cb);
-      const long long e0 = (long long)m * p.N + n0 + cb;
-      float* xr = p.x_io + (long long)m * p.ld_x + n0 + cb;
-      float z[4] = {0.f, 0.f, 0.f, 0.f};
-      if (add_noise) {
-        if (noise) {
+    const int cb = g * 4;
+    const int cnt = min(4, nv - cb);
+    const long long e0 = (long long)m * p.N + n0 + cb;
+    float* xr = p.x_io + (long long)m * p.ld_x + n0 + cb;
+    float z[4] = {0.f, 0.f, 0.f, 0.f};
+    if (add_noise) {
+      if (noise) {
 #pragma unroll
-          for (int i = 0; i < 4; ++i)
-            if (i < cnt) z[i] = noise[e0 + i];
-        } else {
-          const unsigned long long ge = (unsigned long long)(call.elem_offset + e0);
-          const uint32_t off = (uint32_t)ge & 3u;
-          float zz[8];
-          philox_normal4(call.seed, call.stream_id, (uint32_t)t, ge >> 2, zz);
-          if (off != 0) philox_normal4(call.seed, call.stream_id, (uint32_t)t, (ge >> 2) + 1, zz + 4);
-          else { zz[4] = zz[5] = zz[6] = zz[7] = 0.f; }
-#pragma unroll
-          for (int i = 0; i < 4; ++i)
-            z[i] = off == 0 ? zz[i] : (off == 1 ? zz[i + 1] : (off == 2 ? zz[i + 2] : zz[i + 3]));
-        }
+        for (int i = 0; i < 4; ++i)
+          if (i < cnt) z[i] = noise[e0 + i];
+      } else {
+        philox_normal4_rows(call.seed, call.stream_id, (uint32_t)t, (uint32_t)(call.row_offset + m), (uint32_t)((n0 + cb) >> 2), z);
       }
-      float o[4];
+    }
+    float o[4];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        o[i] = 0.f;
-        if (i < cnt) {
-          const float e = tile[r * TS + cb + i];
-          const float x = xr[i];
-          const float x0 = fminf(fmaxf((x - s1a * e) * inv_sa, -1.f), 1.f);
-          float y;
-          if (ddim) {
-            y = sap * x0 + s1ap * e;
-          } else {
-            y = c0 * x0 + ct * x;
-            if (add_noise) y = fmaf(sigma, z[i], y);
-          }
-          xr[i] = y;
-          o[i] = y;
-        }
-      }
-      if (p.out_bf16) {
-        __nv_bfloat16* ob = p.out_bf16 + (long long)m * p.ld_out_bf16 + n0 + cb;
-        if (vb && cnt == 4) {
-          uint2 u;
-          u.x = pack_bf16x2(o[0], o[1]);
-          u.y = pack_bf16x2(o[2], o[3]);
-          *reinterpret_cast<uint2*>(ob) = u;
+    for (int i = 0; i < 4; ++i) {
+      o[i] = 0.f;
+      if (i < cnt) {
+        const float e = tile[r * TS + cb + i];
+        const float x = xr[i];
+        const float x0 = fminf(fmaxf((x - s1a * e) * inv_sa, -1.f), 1.f);
+        float y;
+        if (ddim) {
+          y = sap * x0 + s1ap * e;
         } else {
-#pragma unroll
-          for (int i = 0; i < 4; ++i)
-            if (i < cnt) ob[i] = __float2bfloat16(o[i]);
+          y = c0 * x0 + ct * x;
+          if (add_noise) y = fmaf(sigma, z[i], y);
         }
+        xr[i] = y;
+        o[i] = y;
+      }
+    }
+    if (p.out_bf16) {
+      __nv_bfloat16* ob = p.out_bf16 + (long long)m * p.ld_out_bf16 + n0 + cb;
+      if (vb && cnt == 4) {
+        uint2 u;
+        u.x = pack_bf16x2(o[0], o[1]);
+        u.y = pack_bf16x2(o[2], o[3]);
+        *reinterpret_cast<uint2*>(ob) = u;
+      } else {
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          if (i < cnt) ob[i] = __float2bfloat16(o[i]);
       }
     }
   }
@@ -422,7 +441,7 @@ __device__ __forceinline__ void epilogue_ddpm(const TcGemm& p, EpiSmem<BN>& es, 
 
 template <int BN>
 __device__ __forceinline__ void epilogue_ln(const TcGemm& p, EpiSmem<BN>& es, uint32_t taddr, int m, int n0, int c_begin,
-                                            int row, int part) {
+                                            int row, int part, int lane) {
   // requires N == BN: the whole feature row lives in this tile, split over the two warps of the lane quarter
   constexpr int CPP = BN / 64;
   const bool row_ok = m < p.M;
@@ -434,7 +453,7 @@ __device__ __forceinline__ void epilogue_ln(const TcGemm& p, EpiSmem<BN>& es, ui
     const int c = c_begin + cc;
     const int nb = n0 + c * 32;
     float v[32];
-    tmem_ld_32x32(taddr + c * 32, v);
+    load_acc_chunk<BN>(p, taddr, c, lane, v);
     add_smem32(v, es.bias + c * 32);
     if (p.res_f32 && row_ok) add_f32x32(v, p.res_f32 + (long long)m * p.ld_res_f32 + nb, vr, 32);
 #pragma unroll
@@ -473,12 +492,14 @@ __device__ __forceinline__ void epilogue_ln(const TcGemm& p, EpiSmem<BN>& es, ui
 template <int BN, int MODE>
 __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_constant__ TcGemm p) {
   extern __shared__ uint8_t smem_raw[];
-  constexpr int STAGES = TcSmem<BN>::STAGES;
+  constexpr int B_BYTES = TcSmem<BN>::B_BYTES;
+  const int STAGES = p.num_stages;
+  const uint32_t stage_bytes = TC_A_BYTES + (uint32_t)p.w_max * B_BYTES;
   __shared__ __align__(8) uint64_t bar_full[TC_MAX_STAGES];
   __shared__ __align__(8) uint64_t bar_empty[TC_MAX_STAGES];
   __shared__ __align__(8) uint64_t bar_accum;
   __shared__ uint32_t tmem_holder;
-  __shared__ __align__(16) TcKBlock kb_s[TC_MAX_KB_SMEM];     // K-block table staged once per CTA
+  __shared__ __align__(16) TcStage kb_s[TC_MAX_KB_SMEM];      // stage table staged once per CTA
   __shared__ __align__(16) EpiSmem<BN> es;
 
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -486,12 +507,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
   const int lane = threadIdx.x & 31;
   const int tile_m = blockIdx.x, tile_n = blockIdx.y;
   const int n0 = tile_n * BN;
-  constexpr uint32_t NCOLS_MAIN = BN;
-  const uint32_t ncols = p.use_aux ? 2 * BN : BN;     // 64 .. 512: powers of two >= 32
+  const uint32_t ncols = (uint32_t)p.tmem_cols;        // power of two in [32, 512] covering (n_acc + aux) * BN columns
 
   // ---- prologue: touches only constants, shared memory and TMEM -> may overlap the previous kernel (PDL) ----
   if (threadIdx.x == 0) {
-#pragma unroll
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(smem_u32(&bar_full[s]), 1);
       mbar_init(smem_u32(&bar_empty[s]), 1);
@@ -508,7 +527,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
   const bool kb_in_smem = p.num_kb <= TC_MAX_KB_SMEM;
   if (kb_in_smem)
     for (int i = threadIdx.x; i < p.num_kb; i += TC_THREADS) kb_s[i] = p.kb[i];
-  const TcKBlock* kbt = kb_in_smem ? kb_s : p.kb;
+  const TcStage* kbt = kb_in_smem ? kb_s : p.kb;
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -523,15 +542,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
       uint32_t stage = 0, phase = 0;
       griddep_wait();                                   // activations of the previous layer are complete from here on
       for (int kb = 0; kb < p.num_kb; ++kb) {
-        const TcKBlock e = kbt[kb];
+        const TcStage e = kbt[kb];
+        const int nw = (e.src_acc >> 16) & 0xff;
+        const int d1 = (int)(short)(e.d12 & 0xffff), d2 = e.d12 >> 16;
         mbar_wait(smem_u32(&bar_empty[stage]), phase ^ 1u);
         const uint32_t bar = smem_u32(&bar_full[stage]);
-        const uint32_t sa = smem_base + stage * TcSmem<BN>::STAGE_BYTES;
-        const uint32_t sb = sa + TC_A_BYTES;
-        mbar_arrive_expect_tx(bar, TcSmem<BN>::STAGE_BYTES);
-        tma_load_4d(sa, &p.map_a[e.src_acc & 0xff], bar, e.c0, e.d1, c2_base + e.d2, c3);
-        tma_load_2d(sb, &p.map_b, bar, kb * TC_BK, n0);
-        if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+        const uint32_t sa = smem_base + stage * stage_bytes;
+        mbar_arrive_expect_tx(bar, TC_A_BYTES + (uint32_t)nw * B_BYTES);
+        tma_load_4d(sa, &p.map_a[e.src_acc & 0xff], bar, e.c0, d1, c2_base + d2, c3);
+        for (int j = 0; j < nw; ++j) tma_load_2d(sa + TC_A_BYTES + j * B_BYTES, &p.map_b, bar, (e.wk + j) * TC_BK, n0);
+        if (++stage == (uint32_t)STAGES) { stage = 0; phase ^= 1u; }
       }
     }
   } else if (warp == 1) {
@@ -541,21 +561,25 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
       uint32_t stage = 0, phase = 0;
       uint32_t started = 0;    // bit a set once accumulator a has received its first MMA
       for (int kb = 0; kb < p.num_kb; ++kb) {
-        const uint32_t acc = ((uint32_t)kbt[kb].src_acc >> 8) & 0xffu;
+        const uint32_t sa_word = (uint32_t)kbt[kb].src_acc;
+        const uint32_t acc0 = (sa_word >> 8) & 0xffu, nw = (sa_word >> 16) & 0xffu;
         mbar_wait(smem_u32(&bar_full[stage]), phase);
         tc_fence_after();
-        const uint32_t sa = smem_base + stage * TcSmem<BN>::STAGE_BYTES;
+        const uint32_t sa = smem_base + stage * stage_bytes;
         const uint64_t da = umma_desc_sw128(sa);
-        const uint64_t db = umma_desc_sw128(sa + TC_A_BYTES);
-        const uint32_t d_tmem = tmem_base + acc * NCOLS_MAIN;
+        for (uint32_t j = 0; j < nw; ++j) {             // the A tile is shared by the nw taps' accumulators
+          const uint32_t acc = acc0 + j;
+          const uint64_t db = umma_desc_sw128(sa + TC_A_BYTES + j * B_BYTES);
+          const uint32_t d_tmem = tmem_base + acc * BN;
 #pragma unroll
-        for (int k = 0; k < TC_BK / 16; ++k) {
-          // advance 16 bf16 = 32 bytes along K inside the 128B swizzle row: +2 in the (addr >> 4) field
-          umma_bf16_ss(d_tmem, da + 2 * k, db + 2 * k, idesc, ((started >> acc) & 1u) | (k > 0 ? 1u : 0u));
+          for (int k = 0; k < TC_BK / 16; ++k) {
+            // advance 16 bf16 = 32 bytes along K inside the 128B swizzle row: +2 in the (addr >> 4) field
+            umma_bf16_ss(d_tmem, da + 2 * k, db + 2 * k, idesc, ((started >> acc) & 1u) | (k > 0 ? 1u : 0u));
+          }
+          started |= 1u << acc;
         }
-        started |= 1u << acc;
         umma_commit(smem_u32(&bar_empty[stage]));       // frees the smem stage when these MMAs retire
-        if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+        if (++stage == (uint32_t)STAGES) { stage = 0; phase ^= 1u; }
       }
       umma_commit(smem_u32(&bar_accum));                // accumulator(s) complete
     }
@@ -590,12 +614,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
     tc_fence_after();
     const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16);
     const int c_begin = part * (BN / 64);
-    if constexpr (MODE == TC_EPI_PLAIN) epilogue_plain<BN>(p, es, taddr, m, n0, c_begin);
-    else if constexpr (MODE == TC_EPI_GN) epilogue_gn<BN>(p, es, taddr, m, n0, c_begin, row);
+    if constexpr (MODE == TC_EPI_PLAIN) epilogue_plain<BN>(p, es, taddr, m, n0, c_begin, lane);
+    else if constexpr (MODE == TC_EPI_GN) epilogue_gn<BN>(p, es, taddr, m, n0, c_begin, row, lane);
     else if constexpr (MODE == TC_EPI_DDPM)
       epilogue_ddpm<BN>(p, es, taddr, reinterpret_cast<float*>(smem_raw + (smem_base - smem_u32(smem_raw))), tile_m, n0,
-                        c_begin, row, ew, lane);
-    else epilogue_ln<BN>(p, es, taddr, m, n0, c_begin, row, part);
+                        c_begin, row, (int)threadIdx.x - 64, lane);
+    else epilogue_ln<BN>(p, es, taddr, m, n0, c_begin, row, part, lane);
   }
 
   tc_fence_before();
@@ -663,7 +687,7 @@ int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t*
 
 template <int BN, int MODE>
 static int set_smem_attr() {
-  LDP_CUDA_OK(cudaFuncSetAttribute(tc_gemm_kernel<BN, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcSmem<BN>::TOTAL));
+  LDP_CUDA_OK(cudaFuncSetAttribute(tc_gemm_kernel<BN, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_RING + 1024));
   return LDP_OK;
 }
 
@@ -686,12 +710,28 @@ int tc_gemm_init() {
 }
 
 template <int BN, int MODE>
-static int launch_tc_gemm_inst(const TcGemm& p, cudaStream_t s) {
+static int launch_tc_gemm_inst(const TcGemm& p_in, cudaStream_t s) {
   LDP_TRY(tc_gemm_init());
+  TcGemm p = p_in;
+  const int n_acc_total = p.n_acc + (p.use_aux ? 1 : 0);
+  LDP_CHECK(p.n_acc >= 1 && p.n_acc <= 5 && n_acc_total * BN <= 512, LDP_ERR_UNSUPPORTED,
+            "tc_gemm: accumulators exceed the 512 TMEM columns");
+  LDP_CHECK(p.w_max >= 1 && p.w_max <= 5, LDP_ERR_INVALID_ARG, "tc_gemm: w_max must be 1..5");
+  int cols = 32;
+  while (cols < n_acc_total * BN) cols <<= 1;
+  p.tmem_cols = cols;
+  p.num_stages = tc_num_stages(BN, p.w_max);
+  LDP_CHECK(p.num_stages >= 2, LDP_ERR_UNSUPPORTED, "tc_gemm: stage does not fit the shared-memory ring twice");
+  if (MODE == TC_EPI_DDPM)
+    LDP_CHECK(p.num_stages * tc_stage_bytes(BN, p.w_max) >= TC_BM * (BN + 1) * 4, LDP_ERR_UNSUPPORTED,
+              "tc_gemm DDPM epilogue: transposition tile does not fit the ring");
+  if (p.n_acc > 1 || p.shift[0] != 0)
+    LDP_CHECK(p.rows_per_item >= 1 && p.rows_per_item <= 32 && (p.rows_per_item & (p.rows_per_item - 1)) == 0,
+              LDP_ERR_UNSUPPORTED, "tc_gemm: shifted accumulators need power-of-two rows per sample <= 32");
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(ceil_div(p.M, TC_BM), ceil_div(p.N, BN), 1);
   cfg.blockDim = dim3(TC_THREADS, 1, 1);
-  cfg.dynamicSmemBytes = TcSmem<BN>::TOTAL;
+  cfg.dynamicSmemBytes = p.num_stages * tc_stage_bytes(BN, p.w_max) + 1024;
   cfg.stream = s;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;

@@ -102,6 +102,14 @@ def philox_normal(seed: int, stream_id: int, step: int, n: int, device="cuda") -
     return out
 
 
+def philox_normal_rows(seed: int, stream_id: int, step: int, row0: int, rows: int, row_len: int, device="cuda") -> torch.Tensor:
+    """The noise the fused loops draw at reverse step `step` for global rows [row0, row0+rows)."""
+    lib = N.load()
+    out = torch.empty(rows, row_len, dtype=torch.float32, device=device)
+    N.check(lib.ldp_philox_normal_rows(seed, stream_id, step, row0, rows, row_len, out.data_ptr(), _stream()))
+    return out
+
+
 def tc_dense(a: torch.Tensor, w: np.ndarray, bias: Optional[np.ndarray]) -> torch.Tensor:
     """C = A W + b on the tcgen05 path (bf16 operands, fp32 accumulate) - test / roofline helper."""
     lib = N.load()
@@ -205,7 +213,8 @@ class Planner:
         for i in range(n.value):
             m, nn, kb, packed = (int(v) for v in meta[4 * i:4 * i + 4])
             out.append(dict(us=float(us[i]), M=m, N=nn, K=kb * 64, block_n=packed & 0xffff,
-                            epilogue=("plain", "gn", "ddpm", "ln")[(packed >> 16) & 0xff], aux=(packed >> 24) & 1))
+                            epilogue=("plain", "gn", "ddpm", "ln")[(packed >> 16) & 0xff], aux=(packed >> 24) & 1,
+                            n_acc=(packed >> 25) & 7))
         return out
 
 

@@ -40,7 +40,7 @@ print(f"[{tag}] B={B} loop {loop_ms:.2f} ms / 100 steps = {loop_ms * 10:.1f} us/
 for i, o in enumerate(ops):
     ctas = -(-o["M"] // 128) * -(-o["N"] // o["block_n"])
     fl = 2.0 * o["M"] * o["N"] * o["K"]
-    print(f"  {i:2d} {o['epilogue']:5s} M={o['M']:5d} N={o['N']:4d} K={o['K']:5d} bn={o['block_n']:3d} aux={o['aux']} ctas={ctas:3d} "
+    print(f"  {i:2d} {o['epilogue']:5s} M={o['M']:5d} N={o['N']:4d} K={o['K']:5d} bn={o['block_n']:3d} acc={o['n_acc']}+{o['aux']} ctas={ctas:3d} "
           f"{o['us']:7.2f} us  {fl / o['us'] / 1e6:7.1f} TF/s(padded)")
 out = ROOT / "gpurun_out"
 out.mkdir(exist_ok=True)

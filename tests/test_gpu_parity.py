@@ -70,6 +70,16 @@ def test_philox_normal_matches_oracle(H, cuda):
     assert np.abs(z - ref).max() < 2e-5
 
 
+def test_philox_rows_matches_oracle(H, cuda):
+    """The row-structured noise of the fused loops (MUFU Box-Muller) against the float64 restatement."""
+    z = H.philox_normal_rows(0x1234ABCD5678, 1, 37, 5, 33, 265).cpu().numpy()
+    ref = O.philox_normal_rows(0x1234ABCD5678, 1, 37, 5, 33, 265)
+    assert z.shape == ref.shape and np.abs(z - ref).max() < 1e-4
+    # keyed by global row: rows [5, 38) of a block starting at 0 are the same numbers
+    z0 = H.philox_normal_rows(0x1234ABCD5678, 1, 37, 0, 38, 265).cpu().numpy()
+    assert np.array_equal(z0[5:], z)
+
+
 @pytest.mark.parametrize("t", [99, 98, 50, 1, 0])
 @pytest.mark.parametrize("sampler", ["ddpm", "ddim"])
 def test_ddpm_step(H, cuda, t, sampler):
@@ -222,6 +232,33 @@ def test_planner_loop_ddim_and_philox_are_deterministic(unet_full):
     assert _maxerr(half, a[4:]) < 1e-5
     d = planner.sample(x.cuda(), c.cuda(), n_steps=6, sampler="ddim", precision="bf16")
     assert torch.isfinite(d).all() and float(d.abs().max()) <= 1.0 + 1e-5     # DDIM ends on the clipped x0
+
+
+@pytest.mark.parametrize("prec", ["bf16", "fp32"])
+def test_planner_loop_philox_equals_injected_noise(unet_full, H, prec):
+    """In-kernel Philox == the same loop fed ldp_philox_normal_rows through noise_dev (bit for bit), incl. row_offset."""
+    p, planner = unet_full
+    B, T, n, seed, off = 6, 8, 5, 77, 3
+    x, c = _inputs(B, T, D_RM, seed=61)
+    z = torch.stack([H.philox_normal_rows(seed, 0, n - 1 - i, off * T, B * T, D_RM).reshape(B, T, D_RM) for i in range(n)])
+    a = planner.sample(x.cuda(), c.cuda(), seed=seed, row_offset=off, n_steps=n, precision=prec)
+    b = planner.sample(x.cuda(), c.cuda(), noise=z, n_steps=n, precision=prec)
+    assert torch.equal(a, b)
+
+
+def test_unet_bf16_aloha_shape(H):
+    """BASELINE config #5 shape: T=16, D=270 (the deepest level runs 5 taps at 128-wide groups -> per-tap K layout)."""
+    D = 270
+    p = P.init_params(P.unet_spec(D, D), seed=3)
+    planner = H.Planner(p, D, D)
+    x, c = _inputs(5, 16, D, seed=71)
+    out = planner.forward(x.cuda(), 40, c.cuda(), precision="bf16")
+    ref = O.unet_forward(p, x, 40, c)
+    assert _maxerr(out, ref) < TOL_BF16 * max(1.0, float(ref.abs().max()))
+    out32 = planner.forward(x.cuda(), 40, c.cuda(), precision="fp32")
+    assert _maxerr(out32, ref) < TOL_FP32
+    d = planner.sample(x.cuda(), c.cuda(), n_steps=4, sampler="ddim", precision="bf16")
+    assert torch.isfinite(d).all()
 
 
 def test_planner_loop_bf16_statistics(unet_full):

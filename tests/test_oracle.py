@@ -136,3 +136,11 @@ def test_philox_normal_moments():
     assert abs(z.mean()) < 0.01 and abs(z.std() - 1) < 0.01
     z2 = O.philox_normal(1234, 0, 6, 1000)
     assert not np.allclose(z[:1000], z2)
+
+
+def test_philox_rows_layout():
+    """Row-structured noise: keyed by (global row, column quad); a shard is a slice of the unsharded draw."""
+    full = O.philox_normal_rows(9, 0, 12, 0, 10, 7)
+    part = O.philox_normal_rows(9, 0, 12, 4, 6, 7)
+    assert full.shape == (10, 7) and np.array_equal(full[4:], part)
+    assert abs(full.mean()) < 0.5 and 0.5 < full.std() < 1.5
