@@ -131,9 +131,11 @@ LDP_API int ldp_planner_sample(LdpPlanner* h, int precision, int sampler, const 
 
 /* Diagnostics (no reference counterpart): times every kernel of one bf16 denoising step in isolation - `reps`
  * back-to-back launches between two CUDA events per kernel.  us_host[i] = microseconds per launch of kernel i;
- * meta_host[4i..4i+3] = {M, N, K/64, block_n | epilogue << 16 | aux << 24}.  *n_ops = number of kernels. */
+ * meta_host[4i..4i+3] = {M, N, K/64, block_n | epilogue << 16 | aux << 24 | accumulators << 25}.  phases_host (may
+ * be NULL): [8i] = CTAs, [8i+1..8i+7] = mean SM-clock cycles from kernel entry to {prologue done, dependency
+ * resolved, first operands landed, last MMA issued, accumulators complete, epilogue done, exit}.  *n_ops = kernels. */
 LDP_API int ldp_planner_profile_step(LdpPlanner* h, int B, int T, int reps, float* us_host, int32_t* meta_host,
-                                     int max_ops, int* n_ops, void* cuda_stream);
+                                     float* phases_host, int max_ops, int* n_ops, void* cuda_stream);
 
 /* ---------------------------------------------------------------------------------------------------------
  * Inverse-dynamics score network  -  MLPDiffusion(FourierFeatures -> MLP -> MLPResNet)

@@ -81,7 +81,7 @@ def load() -> C.CDLL:
     lib.ldp_unet_param_count.restype = i64
     lib.ldp_unet_forward.argtypes = [vp, i32, vp, vp, i32, vp, i32, i32, vp, vp]
     lib.ldp_planner_sample.argtypes = [vp, i32, i32, vp, vp, vp, u64, i64, i32, i32, i32, vp, vp]
-    lib.ldp_planner_profile_step.argtypes = [vp, i32, i32, i32, vp, vp, i32, vp, vp]
+    lib.ldp_planner_profile_step.argtypes = [vp, i32, i32, i32, vp, vp, vp, i32, vp, vp]
     lib.ldp_idm_create.argtypes = [C.POINTER(IdmConfig), vp, u64, C.POINTER(vp)]
     lib.ldp_idm_destroy.argtypes = [vp]
     lib.ldp_idm_param_count.argtypes = [C.POINTER(IdmConfig)]

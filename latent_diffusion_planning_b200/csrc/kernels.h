@@ -97,6 +97,8 @@ int launch_philox_normal(unsigned long long seed, uint32_t stream_id, uint32_t s
 // out[r][c] for r < rows, c < row_len: the row-structured normals the sampling loops draw (see DdpmCall)
 int launch_philox_normal_rows(unsigned long long seed, uint32_t stream_id, uint32_t step, long long row0, long long rows,
                               int row_len, float* out, cudaStream_t s);
+// out[(c / 4) * rows + r] (float4) = in[r * ld + c .. c+3]   (cols a multiple of 4)
+int launch_transpose_quads(const float* in, int ld, float* out, int rows, int cols, cudaStream_t s);
 int launch_add_i32(int32_t* p, int delta, cudaStream_t s);     // *p += delta (advances the device step counter)
 int launch_set_i32(int32_t* p, int v, cudaStream_t s);
 
@@ -142,6 +144,8 @@ struct TcGemm {
   int n_acc = 1;
   int shift[5] = {0, 0, 0, 0, 0};
   int num_stages = 0, tmem_cols = 0; // filled by launch_tc_gemm
+  int epi_skip = 0;                 // diagnostics (LDP_EPI_SKIP): 1 stores, 2 FiLM loads, 4 residual, 8 activation, 16 tap shuffles
+  long long* dbg = nullptr;         // diagnostics: per-CTA phase timestamps [ctas][8] (clock64 deltas)
   int k_pad = 0;                    // host-side bookkeeping: padded K of the packed weights
   int M = 0, N = 0;                 // logical output size
   int block_n = 128;                // 64, 128 or 256
@@ -162,7 +166,8 @@ struct TcGemm {
   int rows_per_item = 1;            // T_l: rows of one sample inside a tile (power of two <= 32)
   int group_width = 32;             // C/G
   const float* gamma = nullptr; const float* beta = nullptr; float eps = 1e-6f;
-  int film = 0; const float* ttab = nullptr; int ld_ttab = 0; const float* otab = nullptr; int ld_otab = 0;
+  int film = 0; const float* ttab = nullptr; int ld_ttab = 0;
+  const float* otab_q = nullptr; int otab_B = 0;   // observation part, quad-transposed: [column / 4][sample] float4
   int film_off = 0; int film_c = 0;
   StepRef step;
   // LN: out_f32 <- h = acc + bias + res_f32;  out_bf16 <- LN(h) gamma + beta  (or relu(h) if relu)

@@ -81,6 +81,7 @@ struct PlanWs {
   int B = 0, T = 0;
   Arena arena;
   float* otab = nullptr;
+  float* otab_q = nullptr;       // quad-transposed copy for the tcgen05 epilogues
   float* x_state = nullptr;
   float* eps_buf = nullptr;
   int32_t* step_dev = nullptr;
@@ -293,6 +294,7 @@ static int get_ws(LdpPlanner* h, int B, int T, PlanWs** out) {
   std::unique_ptr<PlanWs> w(new PlanWs());
   w->B = B; w->T = T;
   LDP_TRY(w->arena.alloc_t(&w->otab, (size_t)B * h->sum_c2));
+  LDP_TRY(w->arena.alloc_t(&w->otab_q, (size_t)B * h->sum_c2));
   LDP_TRY(w->arena.alloc_t(&w->x_state, (size_t)B * T * c.input_dim));
   LDP_TRY(w->arena.alloc_t(&w->eps_buf, (size_t)B * T * c.input_dim));
   LDP_TRY(w->arena.alloc_t(&w->step_dev, 4));
@@ -306,7 +308,8 @@ static int compute_otab(LdpPlanner* h, PlanWs* w, const float* cond, cudaStream_
   GemmF32 g;
   g.x1 = cond; g.c1 = h->cfg.global_cond_dim; g.ld1 = h->cfg.global_cond_dim; g.a_act = 1;
   g.w = h->wc_all; g.ldw = h->sum_c2; g.out = w->otab; g.ldo = h->sum_c2; g.m = w->B; g.n = h->sum_c2;
-  return launch_gemm_f32(g, s);
+  LDP_TRY(launch_gemm_f32(g, s));
+  return launch_transpose_quads(w->otab, h->sum_c2, w->otab_q, w->B, h->sum_c2, s);
 }
 
 // ------------------------------- fp32 program -------------------------------------------------------
@@ -479,6 +482,8 @@ static void choose_tiling(int M, int N, const ConvDesc& d, int n_taps, int* bn_o
     if (t128 && (!t64 || ctas128 > 74)) bn = 128;
     else if (t64) bn = 64;
     else tapacc = false;
+    // a 64-wide tap-accumulator grid that spills into a second wave loses to the one-wave per-tap grid (measured)
+    if (tapacc && ceil_div(M, 128) * ceil_div(N, bn) > 148 && ctas128 <= 148 && ok128) tapacc = false;
   }
   if (!tapacc) bn = (ok64 && ctas128 <= 74) ? 64 : 128;
   *bn_out = bn;
@@ -666,7 +671,7 @@ static int crb_tc(LdpPlanner* h, PlanWs* w, int bi, const ActBf16* srcs, int nsr
   d.kind = CONV_K; d.taps_k = 5; d.srcs = srcs; d.nsrc = nsrc; d.t_in = Tl; d.wgt = b.c1w; d.cout = b.cout; d.group_width = gw;
   LDP_TRY(conv_tc(h, w, 4 * bi + 0, d, &op));
   set_gn(&op, b.c1b, b.g1s, b.g1b, b.cout, h->cfg.n_groups, h1buf);
-  op.film = 1; op.ttab = h->ttab; op.ld_ttab = h->sum_c2; op.otab = w->otab; op.ld_otab = h->sum_c2;
+  op.film = 1; op.ttab = h->ttab; op.ld_ttab = h->sum_c2; op.otab_q = w->otab_q; op.otab_B = w->B;
   op.film_off = b.film_off; op.film_c = b.cout;
   w->ops.push_back(op);
   ActBf16 h1{h1buf, b.cout, b.cout};
@@ -926,8 +931,8 @@ int ldp_planner_sample(LdpPlanner* h, int precision, int sampler, const float* x
 
 
 // Diagnostics: time every kernel of one bf16 denoising step in isolation (reps back-to-back launches, CUDA events).
-int ldp_planner_profile_step(LdpPlanner* h, int B, int T, int reps, float* us_host, int32_t* meta_host, int max_ops,
-                             int* n_ops, void* cuda_stream) {
+int ldp_planner_profile_step(LdpPlanner* h, int B, int T, int reps, float* us_host, int32_t* meta_host, float* phases_host,
+                             int max_ops, int* n_ops, void* cuda_stream) {
   LDP_CHECK(h && us_host && meta_host && n_ops && reps > 0, LDP_ERR_INVALID_ARG, "bad arguments");
   cudaStream_t s = (cudaStream_t)cuda_stream;
   PlanWs* w;
@@ -956,6 +961,23 @@ int ldp_planner_profile_step(LdpPlanner* h, int B, int T, int reps, float* us_ho
     float ms = 0.f;
     LDP_CUDA_OK(cudaEventElapsedTime(&ms, e0, e1));
     us_host[i] = ms * 1000.f / reps;
+    if (phases_host) {          // one more launch with the in-kernel phase clocks; mean over CTAs
+      const int ctas = ceil_div(op.M, 128) * ceil_div(op.N, op.block_n);
+      std::vector<long long> hb((size_t)ctas * 8);
+      long long* db;
+      Arena tmp;
+      LDP_TRY(tmp.alloc_t(&db, hb.size()));
+      op.dbg = db;
+      LDP_TRY(launch_tc_gemm(op, s));
+      LDP_CUDA_OK(cudaStreamSynchronize(s));
+      LDP_CUDA_OK(cudaMemcpy(hb.data(), db, hb.size() * 8, cudaMemcpyDeviceToHost));
+      for (int k = 1; k < 8; ++k) {
+        double acc = 0;
+        for (int c = 0; c < ctas; ++c) acc += (double)hb[(size_t)c * 8 + k];
+        phases_host[8 * i + k] = (float)(acc / ctas);
+      }
+      phases_host[8 * i + 0] = (float)ctas;
+    }
     meta_host[4 * i + 0] = op.M;
     meta_host[4 * i + 1] = op.N;
     meta_host[4 * i + 2] = op.k_pad / 64;

@@ -338,6 +338,29 @@ int launch_philox_normal_rows(unsigned long long seed, uint32_t stream_id, uint3
   return LDP_OK;
 }
 
+__global__ void transpose_quads_kernel(const float* __restrict__ in, int ld, float4* __restrict__ out, int rows, int nq) {
+  // tile of 32 rows x 32 quads through shared memory so that both sides are coalesced
+  __shared__ float4 t[32][33];
+  const int r0 = blockIdx.x * 32, q0 = blockIdx.y * 32;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int r = r0 + i, q = q0 + threadIdx.x;
+    if (r < rows && q < nq) t[i][threadIdx.x] = *reinterpret_cast<const float4*>(in + (long long)r * ld + 4 * q);
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int q = q0 + i, r = r0 + threadIdx.x;
+    if (r < rows && q < nq) out[(long long)q * rows + r] = t[threadIdx.x][i];
+  }
+}
+
+int launch_transpose_quads(const float* in, int ld, float* out, int rows, int cols, cudaStream_t s) {
+  const int nq = cols / 4;
+  dim3 grid((rows + 31) / 32, (nq + 31) / 32), block(32, 8);
+  transpose_quads_kernel<<<grid, block, 0, s>>>(in, ld, reinterpret_cast<float4*>(out), rows, nq);
+  LDP_LAUNCH_OK();
+  return LDP_OK;
+}
+
 __global__ void add_i32_kernel(int32_t* p, int delta) { *p += delta; }
 __global__ void set_i32_kernel(int32_t* p, int v) { *p = v; }
 int launch_add_i32(int32_t* p, int delta, cudaStream_t s) {

@@ -27,6 +27,8 @@
 //     LN     h = acc + bias + residual -> f32;  LayerNorm(h) (or ReLU(h)) -> bf16   (IDM MLPResNet block)
 // * Programmatic dependent launch: the prologue (barrier init, TMEM allocation, descriptor prefetch) runs before
 //   griddepcontrol.wait, i.e. it overlaps the tail of the previous layer's kernel inside the captured graph.
+#include <cuda_fp16.h>
+
 #include "kernels.h"
 
 namespace ldp {
@@ -34,9 +36,20 @@ namespace ldp {
 constexpr int TC_BM = 128;
 constexpr int TC_BK = 64;
 constexpr int TC_A_BYTES = TC_BM * TC_BK * 2;   // 16 KB
-constexpr int TC_EPI_WARPS = 8;                 // two warps per TMEM lane quarter, each takes half of the columns
-constexpr int TC_EPI_THREADS = TC_EPI_WARPS * 32;
-constexpr int TC_THREADS = 64 + TC_EPI_THREADS; // warp 0: TMA, warp 1: MMA, warps 2..9: epilogue
+// Thread geometry: warp 0 = TMA producer, warp 1 = MMA issuer, then the epilogue warps.  A warp may only read the TMEM
+// lane quarter (warp index mod 4), so the epilogue warps come in groups of four (one per quarter); group g owns column
+// slice g of the tile.  BN = 128 runs 16 epilogue warps with one 32-column chunk per thread: the epilogue is a long
+// dependent chain (TMEM load -> statistics -> barrier -> MUFU-heavy activation -> FiLM / residual loads -> store), and
+// four resident warps per scheduler are what hides its latencies (8 warps took 13-15k cycles per tile, as long as
+// the main loop itself; profiles/).
+template <int BN>
+struct TcGeo {
+  static constexpr int EPI_WARPS = BN == 64 ? 8 : 16;
+  static constexpr int EPI_THREADS = EPI_WARPS * 32;
+  static constexpr int THREADS = 64 + EPI_THREADS;
+  static constexpr int PARTS = EPI_WARPS / 4;              // column slices of the tile
+  static constexpr int CPP = BN / 32 / PARTS;              // 32-column chunks per thread: 1 (BN 64, 128), 2 (BN 256)
+};
 constexpr int TC_MAX_KB_SMEM = 256;
 constexpr int TC_MAX_STAGES = 8;
 
@@ -65,7 +78,8 @@ struct EpiSmem {
   float2 part[TC_BM][BN / 32];   // per-row, per-32-column-chunk (sum, sum of squares)
 };
 
-__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, %0;" ::"n"(TC_EPI_THREADS) : "memory"); }
+template <int BN>
+__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, %0;" ::"n"(TcGeo<BN>::EPI_THREADS) : "memory"); }
 __device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void griddep_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
@@ -176,7 +190,7 @@ __device__ __forceinline__ void add_smem32(float (&v)[32], const float* s) {
 template <int BN>
 __device__ __forceinline__ void load_acc_chunk(const TcGemm& p, uint32_t taddr, int c, int lane, float (&v)[32]) {
   tmem_ld_32x32(taddr + c * 32, v);
-  if (p.n_acc == 1 && p.shift[0] == 0) return;       // uniform: dense GEMM / per-tap mode
+  if ((p.n_acc == 1 && p.shift[0] == 0) || (p.epi_skip & 16)) return;       // uniform: dense GEMM / per-tap mode
   const int T = p.rows_per_item, t = lane & (T - 1);
   {
     const int s = p.shift[0];
@@ -212,7 +226,7 @@ __device__ __forceinline__ void load_acc_chunk(const TcGemm& p, uint32_t taddr, 
 template <int BN>
 __device__ __forceinline__ void epilogue_plain(const TcGemm& p, EpiSmem<BN>& es, uint32_t taddr, int m, int n0,
                                                int c_begin, int lane) {
-  constexpr int CPP = BN / 64;
+  constexpr int CPP = TcGeo<BN>::CPP;
   const bool row_ok = m < p.M;
   const bool vf = (p.ld_out_f32 & 3) == 0, vb = (p.ld_out_bf16 & 7) == 0;
   const bool vrf = (p.ld_res_f32 & 3) == 0, vrb = (p.ld_res_bf16 & 7) == 0;
@@ -238,10 +252,79 @@ __device__ __forceinline__ void epilogue_plain(const TcGemm& p, EpiSmem<BN>& es,
   }
 }
 
+// Operands of the GN epilogue that do not depend on the accumulator - the FiLM scale/shift of this thread's sample and
+// the residual row - are fetched into registers BEFORE the epilogue warps block on the accumulator barrier: the
+// row-per-thread access pattern is uncoalesced (6k cycles per tile when issued after the main loop), but the epilogue
+// warps are idle for the whole main loop, so issuing the loads up front hides them completely.  FiLM pairs are kept as
+// half2 (scale, shift): O(1) values, 2^-11 relative rounding, far below the bf16 rounding of the activations.
+template <int BN>
+struct GnPrefetch {
+  uint32_t film[TcGeo<BN>::CPP][32];   // half2(scale, shift) per column
+  uint4 res[TcGeo<BN>::CPP][4];        // 32 bf16 of the residual row per chunk
+};
+
+template <int BN>
+__device__ __forceinline__ void gn_prefetch(const TcGemm& p, const EpiSmem<BN>& es, int m, int n0, int c_begin,
+                                            GnPrefetch<BN>& pf) {
+  constexpr int NC = BN / 32, CPP = TcGeo<BN>::CPP;
+  const int nchunks = min(NC, (p.N - n0) >> 5);
+  const bool row_ok = m < p.M;
+  const int mm = row_ok ? m : 0;
+  const int b = mm / p.rows_per_item;
+  // observation part of the FiLM embedding, quad-transposed [column quad][sample] float4: the lanes of a warp are
+  // consecutive rows = consecutive (or equal) samples, so one load instruction touches one or two 128-byte lines
+  // instead of one line per lane (which made this the most expensive piece of the epilogue)
+  const float4* oq = reinterpret_cast<const float4*>(p.otab_q);
+  const float* trow = (p.film && p.step.rows) ? p.ttab + (long long)step_of(p.step, mm) * p.ld_ttab + p.film_off : nullptr;
+  const bool film = p.film && !(p.epi_skip & 2);
+  const bool res = p.res_bf16 && !p.use_aux && row_ok && !(p.epi_skip & 4);
+#pragma unroll
+  for (int cc = 0; cc < CPP; ++cc) {
+    const int c = c_begin + cc;
+    const int nb = n0 + c * 32;
+    if (film && c < nchunks) {
+      const float4* fs4 = reinterpret_cast<const float4*>(es.fscale + c * 32);
+      const float4* fb4 = reinterpret_cast<const float4*>(es.fshift + c * 32);
+      const float4* os4 = oq + (long long)((p.film_off + nb) >> 2) * p.otab_B + b;
+      const float4* ob4 = oq + (long long)((p.film_off + p.film_c + nb) >> 2) * p.otab_B + b;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float4 sc = fs4[j], sh = fb4[j];
+        const float4 o1 = __ldg(os4 + (long long)j * p.otab_B), o2 = __ldg(ob4 + (long long)j * p.otab_B);
+        sc.x += o1.x; sc.y += o1.y; sc.z += o1.z; sc.w += o1.w;
+        sh.x += o2.x; sh.y += o2.y; sh.z += o2.z; sh.w += o2.w;
+        if (trow) {
+          const float4 t1 = __ldg(reinterpret_cast<const float4*>(trow + nb) + j);
+          const float4 t2 = __ldg(reinterpret_cast<const float4*>(trow + p.film_c + nb) + j);
+          sc.x += t1.x; sc.y += t1.y; sc.z += t1.z; sc.w += t1.w;
+          sh.x += t2.x; sh.y += t2.y; sh.z += t2.z; sh.w += t2.w;
+        }
+        __half2 h0 = __floats2half2_rn(sc.x, sh.x), h1 = __floats2half2_rn(sc.y, sh.y);
+        __half2 h2 = __floats2half2_rn(sc.z, sh.z), h3 = __floats2half2_rn(sc.w, sh.w);
+        pf.film[cc][4 * j + 0] = *reinterpret_cast<uint32_t*>(&h0);
+        pf.film[cc][4 * j + 1] = *reinterpret_cast<uint32_t*>(&h1);
+        pf.film[cc][4 * j + 2] = *reinterpret_cast<uint32_t*>(&h2);
+        pf.film[cc][4 * j + 3] = *reinterpret_cast<uint32_t*>(&h3);
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) pf.film[cc][i] = 0x00003c00u;     // half2(1, 0): identity
+    }
+    if (res && c < nchunks) {
+      const uint4* rp = reinterpret_cast<const uint4*>(p.res_bf16 + (long long)m * p.ld_res_bf16 + nb);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) pf.res[cc][j] = rp[j];
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) pf.res[cc][j] = make_uint4(0u, 0u, 0u, 0u);
+    }
+  }
+}
+
 template <int BN>
 __device__ __forceinline__ void epilogue_gn(const TcGemm& p, EpiSmem<BN>& es, uint32_t taddr, int m, int n0, int c_begin,
-                                            int row, int lane) {
-  constexpr int NC = BN / 32, CPP = BN / 64;
+                                            int row, int lane, const GnPrefetch<BN>& pf) {
+  constexpr int NC = BN / 32, CPP = TcGeo<BN>::CPP;
   const int T = p.rows_per_item;
   const int cpg = p.group_width >> 5;                    // chunks per group: 1, 2 or 4
   const int nchunks = min(NC, (p.N - n0) >> 5);          // N and the group widths are multiples of 32 here
@@ -263,7 +346,7 @@ __device__ __forceinline__ void epilogue_gn(const TcGemm& p, EpiSmem<BN>& es, ui
     }
     es.part[row][c] = make_float2(s, ss);
   }
-  epi_bar();
+  epi_bar<BN>();
   // group statistics: chunks of the group (from smem) x the T rows of the sample (adjacent lanes)
   float mean[CPP], rstd[CPP];
   const float inv_cnt = 1.f / (float)(T * p.group_width);
@@ -286,10 +369,6 @@ __device__ __forceinline__ void epilogue_gn(const TcGemm& p, EpiSmem<BN>& es, ui
     rstd[cc] = rsqrtf(fmaxf(ss * inv_cnt - mu * mu, 0.f) + p.eps);
   }
   // normalise -> activation -> FiLM -> residual -> store
-  const int b = (row_ok ? m : 0) / T;
-  const float* orow = p.film ? p.otab + (long long)b * p.ld_otab + p.film_off : nullptr;
-  const float* trow = (p.film && p.step.rows) ? p.ttab + (long long)step_of(p.step, row_ok ? m : 0) * p.ld_ttab + p.film_off
-                                              : nullptr;        // per-row timesteps (training-style call)
 #pragma unroll
   for (int cc = 0; cc < CPP; ++cc) {
     const int c = c_begin + cc;
@@ -297,44 +376,29 @@ __device__ __forceinline__ void epilogue_gn(const TcGemm& p, EpiSmem<BN>& es, ui
     const int nb = n0 + c * 32;
     const float4* g4 = reinterpret_cast<const float4*>(es.gamma + c * 32);
     const float4* be4 = reinterpret_cast<const float4*>(es.beta + c * 32);
-    const float mu = mean[cc], rs = rstd[cc];
+    const float rs = rstd[cc], nmr = -mean[cc] * rstd[cc];
     float(&w)[32] = v[cc];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const float4 gg = g4[j], be = be4[j];
-      w[4 * j + 0] = fmaf(w[4 * j + 0] - mu, rs * gg.x, be.x);
-      w[4 * j + 1] = fmaf(w[4 * j + 1] - mu, rs * gg.y, be.y);
-      w[4 * j + 2] = fmaf(w[4 * j + 2] - mu, rs * gg.z, be.z);
-      w[4 * j + 3] = fmaf(w[4 * j + 3] - mu, rs * gg.w, be.w);
+      w[4 * j + 0] = fmaf(fmaf(w[4 * j + 0], rs, nmr), gg.x, be.x);
+      w[4 * j + 1] = fmaf(fmaf(w[4 * j + 1], rs, nmr), gg.y, be.y);
+      w[4 * j + 2] = fmaf(fmaf(w[4 * j + 2], rs, nmr), gg.z, be.z);
+      w[4 * j + 3] = fmaf(fmaf(w[4 * j + 3], rs, nmr), gg.w, be.w);
     }
-    if (p.gn_act == 1) {
+    if (p.epi_skip & 8) {
+    } else if (p.gn_act == 1) {
 #pragma unroll
       for (int i = 0; i < 32; ++i) w[i] = swish_fast(w[i]);
-    } else {
+    } else if (p.gn_act == 0) {
 #pragma unroll
       for (int i = 0; i < 32; ++i) w[i] = mish_fast(w[i]);
     }
     if (p.film) {
-      const float4* fs4 = reinterpret_cast<const float4*>(es.fscale + c * 32);
-      const float4* fb4 = reinterpret_cast<const float4*>(es.fshift + c * 32);
-      const float4* os4 = reinterpret_cast<const float4*>(orow + nb);
-      const float4* ob4 = reinterpret_cast<const float4*>(orow + p.film_c + nb);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        float4 sc = fs4[j], sh = fb4[j];
-        const float4 o1 = __ldg(os4 + j), o2 = __ldg(ob4 + j);
-        sc.x += o1.x; sc.y += o1.y; sc.z += o1.z; sc.w += o1.w;
-        sh.x += o2.x; sh.y += o2.y; sh.z += o2.z; sh.w += o2.w;
-        if (trow) {
-          const float4 t1 = __ldg(reinterpret_cast<const float4*>(trow + nb) + j);
-          const float4 t2 = __ldg(reinterpret_cast<const float4*>(trow + p.film_c + nb) + j);
-          sc.x += t1.x; sc.y += t1.y; sc.z += t1.z; sc.w += t1.w;
-          sh.x += t2.x; sh.y += t2.y; sh.z += t2.z; sh.w += t2.w;
-        }
-        w[4 * j + 0] = fmaf(sc.x, w[4 * j + 0], sh.x);
-        w[4 * j + 1] = fmaf(sc.y, w[4 * j + 1], sh.y);
-        w[4 * j + 2] = fmaf(sc.z, w[4 * j + 2], sh.z);
-        w[4 * j + 3] = fmaf(sc.w, w[4 * j + 3], sh.w);
+      for (int i = 0; i < 32; ++i) {
+        const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&pf.film[cc][i]));
+        w[i] = fmaf(f.x, w[i], f.y);
       }
     }
     if (p.use_aux) {
@@ -343,10 +407,20 @@ __device__ __forceinline__ void epilogue_gn(const TcGemm& p, EpiSmem<BN>& es, ui
       add_smem32(r, es.bias2 + c * 32);
 #pragma unroll
       for (int i = 0; i < 32; ++i) w[i] += r[i];
-    } else if (p.res_bf16 && row_ok) {
-      add_bf16x32(w, p.res_bf16 + (long long)m * p.ld_res_bf16 + nb, true, 32);
+    } else if (p.res_bf16) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const uint4 u = pf.res[cc][j];
+        const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float2 f = __bfloat1622float2(h[q]);
+          w[8 * j + 2 * q] += f.x;
+          w[8 * j + 2 * q + 1] += f.y;
+        }
+      }
     }
-    if (row_ok) {
+    if (row_ok && !((p.epi_skip & 1) && w[0] != 12345.678f)) {
       if (p.out_bf16) store_bf16x32(p.out_bf16 + (long long)m * p.ld_out_bf16 + nb, w, true, 32);
       if (p.out_f32) store_f32x32(p.out_f32 + (long long)m * p.ld_out_f32 + nb, w, true, 32);
     }
@@ -360,7 +434,7 @@ __device__ __forceinline__ void epilogue_gn(const TcGemm& p, EpiSmem<BN>& es, ui
 template <int BN>
 __device__ __forceinline__ void epilogue_ddpm(const TcGemm& p, EpiSmem<BN>& es, uint32_t taddr, float* tile, int tile_m,
                                               int n0, int c_begin, int row, int et, int lane) {
-  constexpr int CPP = BN / 64;
+  constexpr int CPP = TcGeo<BN>::CPP;
   constexpr int TS = BN + 1;
 #pragma unroll 1
   for (int cc = 0; cc < CPP; ++cc) {
@@ -373,7 +447,7 @@ __device__ __forceinline__ void epilogue_ddpm(const TcGemm& p, EpiSmem<BN>& es, 
 #pragma unroll
     for (int i = 0; i < 32; ++i) trow[i] = v[i];
   }
-  epi_bar();
+  epi_bar<BN>();
   const int t = step_of(p.step, 0);
   const float* cf = p.coef + t * 8;
   const float inv_sa = cf[0], s1a = cf[1], c0 = cf[2], ct = cf[3], sigma = cf[4], sap = cf[5], s1ap = cf[6];
@@ -387,7 +461,7 @@ __device__ __forceinline__ void epilogue_ddpm(const TcGemm& p, EpiSmem<BN>& es, 
   const int total = rows_here * nq;
   const bool vb = p.out_bf16 != nullptr && (p.ld_out_bf16 & 3) == 0;
 #pragma unroll 1
-  for (int idx = et; idx < total; idx += TC_EPI_THREADS) {
+  for (int idx = et; idx < total; idx += TcGeo<BN>::EPI_THREADS) {
     const int r = idx / nq, g = idx - r * nq;
     const int m = tile_m * TC_BM + r;
     const int cb = g * 4;
@@ -443,7 +517,7 @@ template <int BN>
 __device__ __forceinline__ void epilogue_ln(const TcGemm& p, EpiSmem<BN>& es, uint32_t taddr, int m, int n0, int c_begin,
                                             int row, int part, int lane) {
   // requires N == BN: the whole feature row lives in this tile, split over the two warps of the lane quarter
-  constexpr int CPP = BN / 64;
+  constexpr int CPP = TcGeo<BN>::CPP;
   const bool row_ok = m < p.M;
   float s = 0.f, ss = 0.f;
   float* hrow = p.out_f32 + (long long)(row_ok ? m : 0) * p.ld_out_f32;
@@ -464,10 +538,16 @@ __device__ __forceinline__ void epilogue_ln(const TcGemm& p, EpiSmem<BN>& es, ui
     if (row_ok) store_f32x32(hrow + nb, v, vf, 32);
   }
   es.part[row][part] = make_float2(s, ss);
-  epi_bar();
-  const float2 q0 = es.part[row][0], q1 = es.part[row][1];
-  const float mu = (q0.x + q1.x) / (float)BN;
-  const float rs = rsqrtf(fmaxf((q0.y + q1.y) / (float)BN - mu * mu, 0.f) + p.eps);
+  epi_bar<BN>();
+  float ts = 0.f, tss = 0.f;
+#pragma unroll
+  for (int q = 0; q < TcGeo<BN>::PARTS; ++q) {
+    const float2 pq = es.part[row][q];
+    ts += pq.x;
+    tss += pq.y;
+  }
+  const float mu = ts / (float)BN;
+  const float rs = rsqrtf(fmaxf(tss / (float)BN - mu * mu, 0.f) + p.eps);
   if (!row_ok || !p.out_bf16) return;
 #pragma unroll 1
   for (int cc = 0; cc < CPP; ++cc) {
@@ -490,7 +570,7 @@ __device__ __forceinline__ void epilogue_ln(const TcGemm& p, EpiSmem<BN>& es, ui
 
 // ---- the kernel --------------------------------------------------------------------------------
 template <int BN, int MODE>
-__global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_constant__ TcGemm p) {
+__global__ void __launch_bounds__(TcGeo<BN>::THREADS, 1) tc_gemm_kernel(const __grid_constant__ TcGemm p) {
   extern __shared__ uint8_t smem_raw[];
   constexpr int B_BYTES = TcSmem<BN>::B_BYTES;
   const int STAGES = p.num_stages;
@@ -501,6 +581,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
   __shared__ uint32_t tmem_holder;
   __shared__ __align__(16) TcStage kb_s[TC_MAX_KB_SMEM];      // stage table staged once per CTA
   __shared__ __align__(16) EpiSmem<BN> es;
+  __shared__ long long ts[8];                                 // phase timestamps (diagnostics, only when p.dbg != nullptr)
+  if (p.dbg && threadIdx.x == 0) ts[0] = clock64();
 
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const int warp = threadIdx.x >> 5;
@@ -526,13 +608,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
   }
   const bool kb_in_smem = p.num_kb <= TC_MAX_KB_SMEM;
   if (kb_in_smem)
-    for (int i = threadIdx.x; i < p.num_kb; i += TC_THREADS) kb_s[i] = p.kb[i];
+    for (int i = threadIdx.x; i < p.num_kb; i += TcGeo<BN>::THREADS) kb_s[i] = p.kb[i];
   const TcStage* kbt = kb_in_smem ? kb_s : p.kb;
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_holder;
   griddep_launch();
+  if (p.dbg && threadIdx.x == 0) ts[1] = clock64();           // prologue done
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -541,6 +624,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
       const int c2_base = r * p.rows_step, c3 = q * p.items_per_tile;
       uint32_t stage = 0, phase = 0;
       griddep_wait();                                   // activations of the previous layer are complete from here on
+      if (p.dbg) ts[2] = clock64();                     // dependency resolved
       for (int kb = 0; kb < p.num_kb; ++kb) {
         const TcStage e = kbt[kb];
         const int nw = (e.src_acc >> 16) & 0xff;
@@ -565,6 +649,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
         const uint32_t acc0 = (sa_word >> 8) & 0xffu, nw = (sa_word >> 16) & 0xffu;
         mbar_wait(smem_u32(&bar_full[stage]), phase);
         tc_fence_after();
+        if (p.dbg && kb == 0) ts[3] = clock64();        // first operands landed
         const uint32_t sa = smem_base + stage * stage_bytes;
         const uint64_t da = umma_desc_sw128(sa);
         for (uint32_t j = 0; j < nw; ++j) {             // the A tile is shared by the nw taps' accumulators
@@ -582,12 +667,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
         if (++stage == (uint32_t)STAGES) { stage = 0; phase ^= 1u; }
       }
       umma_commit(smem_u32(&bar_accum));                // accumulator(s) complete
+      if (p.dbg) ts[4] = clock64();                     // all MMAs issued
     }
   } else {
     // ===================== epilogue warps (2..9) =====================
     const int ew = warp - 2;
     const int quarter = warp & 3;                        // TMEM lane quarter this warp may access
-    const int part = ew >> 2;                            // which half of the tile's columns
+    const int part = ew >> 2;                            // which column slice of the tile
     const int row = quarter * 32 + lane;
     const int m = tile_m * TC_BM + row;
     griddep_wait();                                      // the step counter / residuals / x belong to earlier kernels
@@ -596,7 +682,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
       const int et = threadIdx.x - 64;
       const bool uniform_step = p.film && p.step.rows == nullptr;
       const float* trow = uniform_step ? p.ttab + (long long)step_of(p.step, 0) * p.ld_ttab + p.film_off : nullptr;
-      for (int i = et; i < BN; i += TC_EPI_THREADS) {
+      for (int i = et; i < BN; i += TcGeo<BN>::EPI_THREADS) {
         const int n = n0 + i;
         const bool ok = n < p.N;
         es.bias[i] = (ok && p.bias) ? __ldg(p.bias + n) : 0.f;
@@ -608,23 +694,34 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
           es.fshift[i] = (ok && trow) ? __ldg(trow + p.film_c + n) : 0.f;
         }
       }
-      epi_bar();
+      epi_bar<BN>();
     }
+    const int c_begin = part * TcGeo<BN>::CPP;
+    GnPrefetch<MODE == TC_EPI_GN ? BN : 64> pf;
+    if constexpr (MODE == TC_EPI_GN) gn_prefetch<BN>(p, es, m, n0, c_begin, pf);
     mbar_wait(smem_u32(&bar_accum), 0);
     tc_fence_after();
+    if (p.dbg && threadIdx.x == 64) ts[5] = clock64();   // accumulators complete
     const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16);
-    const int c_begin = part * (BN / 64);
     if constexpr (MODE == TC_EPI_PLAIN) epilogue_plain<BN>(p, es, taddr, m, n0, c_begin, lane);
-    else if constexpr (MODE == TC_EPI_GN) epilogue_gn<BN>(p, es, taddr, m, n0, c_begin, row, lane);
+    else if constexpr (MODE == TC_EPI_GN) epilogue_gn<BN>(p, es, taddr, m, n0, c_begin, row, lane, pf);
     else if constexpr (MODE == TC_EPI_DDPM)
       epilogue_ddpm<BN>(p, es, taddr, reinterpret_cast<float*>(smem_raw + (smem_base - smem_u32(smem_raw))), tile_m, n0,
                         c_begin, row, (int)threadIdx.x - 64, lane);
     else epilogue_ln<BN>(p, es, taddr, m, n0, c_begin, row, part, lane);
   }
 
+  if (p.dbg && threadIdx.x == 64) ts[6] = clock64();     // this warp's epilogue done
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc(tmem_base, ncols);
+  if (p.dbg && threadIdx.x == 0) {
+    long long* d = p.dbg + (long long)(blockIdx.y * gridDim.x + blockIdx.x) * 8;
+    const long long t0 = ts[0];
+    for (int i = 1; i < 7; ++i) d[i] = ts[i] - t0;
+    d[7] = clock64() - t0;
+    d[0] = (long long)(__cvta_generic_to_shared(&ts[0]) & 0) + (long long)blockIdx.x;   // tile id
+  }
 }
 
 // ---- host side -----------------------------------------------------------------------------------
@@ -720,6 +817,11 @@ static int launch_tc_gemm_inst(const TcGemm& p_in, cudaStream_t s) {
   int cols = 32;
   while (cols < n_acc_total * BN) cols <<= 1;
   p.tmem_cols = cols;
+  {
+    static int skip = -1;                      // diagnostics: LDP_EPI_SKIP bit mask disables parts of the GN epilogue
+    if (skip < 0) { const char* e = getenv("LDP_EPI_SKIP"); skip = e ? atoi(e) : 0; }
+    p.epi_skip = skip;
+  }
   p.num_stages = tc_num_stages(BN, p.w_max);
   LDP_CHECK(p.num_stages >= 2, LDP_ERR_UNSUPPORTED, "tc_gemm: stage does not fit the shared-memory ring twice");
   if (MODE == TC_EPI_DDPM)
@@ -730,7 +832,7 @@ static int launch_tc_gemm_inst(const TcGemm& p_in, cudaStream_t s) {
               LDP_ERR_UNSUPPORTED, "tc_gemm: shifted accumulators need power-of-two rows per sample <= 32");
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(ceil_div(p.M, TC_BM), ceil_div(p.N, BN), 1);
-  cfg.blockDim = dim3(TC_THREADS, 1, 1);
+  cfg.blockDim = dim3(TcGeo<BN>::THREADS, 1, 1);
   cfg.dynamicSmemBytes = p.num_stages * tc_stage_bytes(BN, p.w_max) + 1024;
   cfg.stream = s;
   cudaLaunchAttribute attr[1];

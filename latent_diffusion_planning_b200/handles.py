@@ -206,15 +206,16 @@ class Planner:
         """Per-kernel timing of one bf16 denoising step (diagnostics): list of dicts with us, M, N, K, block_n, epilogue."""
         us = np.zeros(128, np.float32)
         meta = np.zeros(128 * 4, np.int32)
+        ph = np.zeros(128 * 8, np.float32)
         n = C.c_int(0)
-        N.check(self.lib.ldp_planner_profile_step(self._h, B, T, reps, us.ctypes.data, meta.ctypes.data, 128, C.byref(n),
-                                                  _stream()))
+        N.check(self.lib.ldp_planner_profile_step(self._h, B, T, reps, us.ctypes.data, meta.ctypes.data, ph.ctypes.data, 128,
+                                                  C.byref(n), _stream()))
         out = []
         for i in range(n.value):
             m, nn, kb, packed = (int(v) for v in meta[4 * i:4 * i + 4])
             out.append(dict(us=float(us[i]), M=m, N=nn, K=kb * 64, block_n=packed & 0xffff,
                             epilogue=("plain", "gn", "ddpm", "ln")[(packed >> 16) & 0xff], aux=(packed >> 24) & 1,
-                            n_acc=(packed >> 25) & 7))
+                            n_acc=(packed >> 25) & 7, phases=[float(v) for v in ph[8 * i:8 * i + 8]]))
         return out
 
 

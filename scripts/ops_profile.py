@@ -41,7 +41,7 @@ for i, o in enumerate(ops):
     ctas = -(-o["M"] // 128) * -(-o["N"] // o["block_n"])
     fl = 2.0 * o["M"] * o["N"] * o["K"]
     print(f"  {i:2d} {o['epilogue']:5s} M={o['M']:5d} N={o['N']:4d} K={o['K']:5d} bn={o['block_n']:3d} acc={o['n_acc']}+{o['aux']} ctas={ctas:3d} "
-          f"{o['us']:7.2f} us  {fl / o['us'] / 1e6:7.1f} TF/s(padded)")
+          f"{o['us']:7.2f} us  {fl / o['us'] / 1e6:7.1f} TF/s(padded)  cyc: " + " ".join(f"{v:6.0f}" for v in o["phases"][1:]))
 out = ROOT / "gpurun_out"
 out.mkdir(exist_ok=True)
 (out / f"ops_{tag}.json").write_text(json.dumps({"tag": tag, "B": B, "loop_ms": loop_ms, "sum_isolated_us": tot, "ops": ops}))
