@@ -1,37 +1,789 @@
-// VAE encoder handle (placeholder until the conv2d path lands): the entry points exist so that the ABI is complete
-// and fail loudly with LDP_ERR_UNSUPPORTED.
+// VAE encoder handle: FlaxAutoencoderKL.encode(x).latent_dist.mean (diffusers 0.27.2, un-vendored; call sites reference
+// agent/ldp_agent.py:46-64 and process_sdvae_data.py:70-73, config model/stable_vae_model.yaml:4-16).
+//
+//   conv_in 3x3 -> [ResnetBlock x layers_per_block, Downsample (pad (0,1), 3x3 stride 2)] per block (no downsample after
+//   the last) -> mid (Resnet, 1-head self-attention, Resnet) -> GroupNorm -> swish -> conv_out 3x3 -> quant_conv 1x1 ->
+//   first `latent_channels` channels (= the mean) -> optional (z - min)/(max - min)*2 - 1   (agent/ldp_agent.py:62)
+//
+// Data layout: NHWC throughout, exactly the reference's.  The residual stream lives in HBM as float32 plus a bf16 copy
+// (the A operand of the next tensor-core convolution); GroupNorm reads float32 and writes the normalised, swish-ed
+// activation as bf16.  Images are processed in chunks of <= 256 so that the 64x64x128 level (2 MB per image in f32)
+// stays a few hundred MB.
+//
+// Kernels:
+//  * every 3x3 / 1x1 / strided convolution and the attention projections: the tcgen05 implicit-GEMM kernel of
+//    tc_gemm.cu - a tile is 128 output pixels (whole image rows), a tap is a TMA coordinate offset into the
+//    (C, W, H, B) tensor map, the zero padding is TMA's out-of-bounds fill, the stride-2 convolution is a tensor map
+//    with traversal stride 2;
+//  * GroupNorm(32, eps 1e-6) + swish: vectorised float4 loads, per-thread partial sums, shared-memory + one global
+//    atomic per (block, group), then an elementwise apply pass (warp-uniform statistics);
+//  * conv_in (3 input channels - too thin for TMA / tensor cores), the 64-token attention core and the 8-channel
+//    quant_conv: small SIMT kernels.
+//  * LDP_PREC_FP32: the same program with every contraction in fp32 FFMA (direct convolution kernel) - parity gate.
+#include <algorithm>
+#include <cmath>
+
 #include "net_common.h"
+
+namespace ldp {
+
+// ------------------------------------------------------------------------------------------------
+// SIMT kernels
+// ------------------------------------------------------------------------------------------------
+// conv_in: 3x3, pad 1, Cin = in_ch (3) -> C0.  One thread per (pixel, 4 output channels).  Pixel normalisation
+// x/255*2-1 (utils/data_utils.py:11; process_sdvae_data.py:89-90) is applied on load for uint8 input.
+template <typename PixT>
+__global__ void __launch_bounds__(256) vae_conv_in_kernel(const PixT* __restrict__ img, const float* __restrict__ w,
+                                                          const float* __restrict__ bias, float* __restrict__ out_f32,
+                                                          __nv_bfloat16* __restrict__ out_bf16, int B, int S, int cin, int c0) {
+  extern __shared__ float ws[];                       // [9*cin][c0]
+  for (int i = threadIdx.x; i < 9 * cin * c0; i += blockDim.x) ws[i] = w[i];
+  __syncthreads();
+  const int cq = c0 / 4;
+  const long long total = (long long)B * S * S * cq;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const int q = (int)(idx % cq);
+    const long long pix = idx / cq;
+    const int x = (int)(pix % S), y = (int)((pix / S) % S);
+    const long long b = pix / ((long long)S * S);
+    float4 acc = *reinterpret_cast<const float4*>(bias + 4 * q);
+    for (int dy = 0; dy < 3; ++dy) {
+      const int yy = y + dy - 1;
+      if (yy < 0 || yy >= S) continue;
+      for (int dx = 0; dx < 3; ++dx) {
+        const int xx = x + dx - 1;
+        if (xx < 0 || xx >= S) continue;
+        const PixT* ip = img + ((b * S + yy) * S + xx) * cin;
+        for (int ci = 0; ci < cin; ++ci) {
+          float v = (float)ip[ci];
+          if (sizeof(PixT) == 1) v = v / 255.f * 2.f - 1.f;
+          const float4 wv = *reinterpret_cast<const float4*>(ws + ((dy * 3 + dx) * cin + ci) * c0 + 4 * q);
+          acc.x = fmaf(v, wv.x, acc.x); acc.y = fmaf(v, wv.y, acc.y); acc.z = fmaf(v, wv.z, acc.z); acc.w = fmaf(v, wv.w, acc.w);
+        }
+      }
+    }
+    if (out_f32) *reinterpret_cast<float4*>(out_f32 + pix * c0 + 4 * q) = acc;
+    if (out_bf16) {
+      uint2 u;
+      u.x = pack_bf16x2(acc.x, acc.y);
+      u.y = pack_bf16x2(acc.z, acc.w);
+      *reinterpret_cast<uint2*>(out_bf16 + pix * c0 + 4 * q) = u;
+    }
+  }
+}
+
+// Direct NHWC convolution in fp32 (parity path): out[b,y,x,co] = bias[co] + sum in[b, y*s+dy-pad, x*s+dx-pad, ci] w[dy,dx,ci,co]
+// (+ res).  One thread per (8 consecutive output pixels of a row, output channel); weights are read coalesced over co.
+__global__ void __launch_bounds__(128) vae_conv_f32_kernel(const float* __restrict__ in, const float* __restrict__ w,
+                                                           const float* __restrict__ bias, const float* __restrict__ res,
+                                                           float* __restrict__ out, int B, int Hin, int Win, int Hout, int Wout,
+                                                           int cin, int cout, int k, int stride, int pad) {
+  const int co = blockIdx.y * blockDim.x + threadIdx.x;
+  const int xg = (Wout + 7) / 8;
+  const long long job = blockIdx.x;                  // (b, y, xgroup)
+  const int x0 = (int)(job % xg) * 8;
+  const int y = (int)((job / xg) % Hout);
+  const long long b = job / ((long long)xg * Hout);
+  if (co >= cout || b >= B) return;
+  float acc[8];
+  const float bv = bias ? bias[co] : 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) acc[i] = bv;
+  for (int dy = 0; dy < k; ++dy) {
+    const int yy = y * stride + dy - pad;
+    if (yy < 0 || yy >= Hin) continue;
+    for (int dx = 0; dx < k; ++dx) {
+      const float* wp = w + (long long)((dy * k + dx) * cin) * cout + co;
+      for (int ci = 0; ci < cin; ++ci) {
+        const float wv = wp[(long long)ci * cout];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int xx = (x0 + i) * stride + dx - pad;
+          if (x0 + i < Wout && xx >= 0 && xx < Win) acc[i] = fmaf(in[((b * Hin + yy) * Win + xx) * cin + ci], wv, acc[i]);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    if (x0 + i < Wout) {
+      const long long o = ((b * Hout + y) * Wout + x0 + i) * cout + co;
+      out[o] = acc[i] + (res ? res[o] : 0.f);
+    }
+  }
+}
+
+// GroupNorm statistics, deterministic (same image -> same bits whatever the batch): x (B, P, C) f32.
+// Pass 1, grid (B, slabs): a thread owns one channel quad (requires 256 % (C/4) == 0), accumulates (sum, sum sq) over its
+// pixels of the slab; the block combines its threads per group in a fixed order and writes part[b][slab][g].
+// Pass 2: one thread per (b, g) adds the slabs in order and stores (mean, rstd).
+__global__ void __launch_bounds__(256) vae_gn_stats_kernel(const float* __restrict__ x, float* __restrict__ part, int P, int C,
+                                                           int G) {
+  __shared__ float ps[256][8];
+  const int b = blockIdx.x;
+  const int cq = C / 4, cpg = C / G;
+  const long long total = (long long)P * cq;
+  long long per = (total + gridDim.y - 1) / gridDim.y;
+  per = (per + cq - 1) / cq * cq;                              // whole pixels per slab: a thread's quad index is fixed
+  const long long lo = blockIdx.y * per, hi = min(total, lo + per);
+  const float4* xb = reinterpret_cast<const float4*>(x + (long long)b * P * C);
+  float s[4] = {0, 0, 0, 0}, ss[4] = {0, 0, 0, 0};
+  for (long long i = lo + threadIdx.x; i < hi; i += blockDim.x) {
+    const float4 v = xb[i];
+    s[0] += v.x; ss[0] = fmaf(v.x, v.x, ss[0]);
+    s[1] += v.y; ss[1] = fmaf(v.y, v.y, ss[1]);
+    s[2] += v.z; ss[2] = fmaf(v.z, v.z, ss[2]);
+    s[3] += v.w; ss[3] = fmaf(v.w, v.w, ss[3]);
+  }
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    ps[threadIdx.x][k] = s[k];
+    ps[threadIdx.x][4 + k] = ss[k];
+  }
+  __syncthreads();
+  if (threadIdx.x < G) {
+    const int g = threadIdx.x;
+    float a = 0.f, a2 = 0.f;
+    for (int t = 0; t < 256; ++t) {
+      const int q = t % cq;                                    // lo is a multiple of cq and 256 % cq == 0
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        if ((4 * q + k) / cpg == g) {
+          a += ps[t][k];
+          a2 += ps[t][4 + k];
+        }
+      }
+    }
+    float* o = part + (((long long)b * gridDim.y + blockIdx.y) * G + g) * 2;
+    o[0] = a;
+    o[1] = a2;
+  }
+}
+
+__global__ void vae_gn_final_kernel(const float* __restrict__ part, float* __restrict__ mr, int n_bg, int G, int slabs, float inv_n,
+                                    float eps) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;       // (b, g)
+  if (i >= n_bg) return;
+  const int b = i / G, g = i % G;
+  float a = 0.f, a2 = 0.f;
+  for (int sl = 0; sl < slabs; ++sl) {
+    const float* p = part + (((long long)b * slabs + sl) * G + g) * 2;
+    a += p[0];
+    a2 += p[1];
+  }
+  const float mu = a * inv_n;
+  mr[2 * i] = mu;
+  mr[2 * i + 1] = rsqrtf(fmaxf(a2 * inv_n - mu * mu, 0.f) + eps);
+}
+
+// y = act((x - mean) rstd gamma + beta); act: 0 none, 1 swish.  Output f32 and/or bf16.
+__global__ void __launch_bounds__(256) vae_gn_apply_kernel(const float* __restrict__ x, const float* __restrict__ mr,
+                                                           const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                           float* __restrict__ y_f32, __nv_bfloat16* __restrict__ y_bf16,
+                                                           long long B, int P, int C, int G, int act) {
+  const int cq = C / 4, cpg = C / G;
+  const long long total = B * P * cq;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int q = (int)(i % cq);
+    const long long b = i / ((long long)P * cq);
+    const float4 v = reinterpret_cast<const float4*>(x)[i];
+    float in[4] = {v.x, v.y, v.z, v.w}, o[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int c = 4 * q + k, g = c / cpg;
+      const float2 m = *reinterpret_cast<const float2*>(mr + (b * G + g) * 2);
+      float t = fmaf((in[k] - m.x) * m.y, gamma[c], beta[c]);
+      if (act == 1) t = t / (1.f + __expf(-t));
+      o[k] = t;
+    }
+    if (y_f32) reinterpret_cast<float4*>(y_f32)[i] = make_float4(o[0], o[1], o[2], o[3]);
+    if (y_bf16) {
+      uint2 u;
+      u.x = pack_bf16x2(o[0], o[1]);
+      u.y = pack_bf16x2(o[2], o[3]);
+      reinterpret_cast<uint2*>(y_bf16)[i] = u;
+    }
+  }
+}
+
+// One-head self-attention core over L = h*w tokens (FlaxAttentionBlock): scores = (q C^-1/4)(k C^-1/4)^T, softmax, @ v.
+// qkv: (B, L, 3C) f32 [q | k | v];  out (B, L, C) f32 and/or bf16.  One block per image; L <= 64.
+__global__ void __launch_bounds__(256) vae_attn_kernel(const float* __restrict__ qkv, float* __restrict__ out_f32,
+                                                       __nv_bfloat16* __restrict__ out_bf16, int L, int C) {
+  __shared__ float sc[64][65];
+  const long long b = blockIdx.x;
+  const float* base = qkv + b * L * 3 * C;
+  const float scale = rsqrtf(sqrtf((float)C));
+  const float s2 = scale * scale;
+  for (int e = threadIdx.x; e < L * L; e += blockDim.x) {
+    const int i = e / L, j = e % L;
+    const float4* qi = reinterpret_cast<const float4*>(base + (long long)i * 3 * C);
+    const float4* kj = reinterpret_cast<const float4*>(base + (long long)j * 3 * C + C);
+    float acc = 0.f;
+    for (int c = 0; c < C / 4; ++c) {
+      const float4 a = qi[c], k4 = kj[c];
+      acc = fmaf(a.x, k4.x, acc); acc = fmaf(a.y, k4.y, acc); acc = fmaf(a.z, k4.z, acc); acc = fmaf(a.w, k4.w, acc);
+    }
+    sc[i][j] = acc * s2;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < L; i += blockDim.x) {
+    float mx = -INFINITY;
+    for (int j = 0; j < L; ++j) mx = fmaxf(mx, sc[i][j]);
+    float sum = 0.f;
+    for (int j = 0; j < L; ++j) {
+      const float e = expf(sc[i][j] - mx);
+      sc[i][j] = e;
+      sum += e;
+    }
+    const float inv = 1.f / sum;
+    for (int j = 0; j < L; ++j) sc[i][j] *= inv;
+  }
+  __syncthreads();
+  for (int e = threadIdx.x; e < L * C; e += blockDim.x) {
+    const int i = e / C, c = e % C;
+    float acc = 0.f;
+    for (int j = 0; j < L; ++j) acc = fmaf(sc[i][j], base[(long long)j * 3 * C + 2 * C + c], acc);
+    if (out_f32) out_f32[(b * L + i) * C + c] = acc;
+    if (out_bf16) out_bf16[(b * L + i) * C + c] = __float2bfloat16(acc);
+  }
+}
+
+// quant_conv (1x1, 2L -> 2L), keep the first L channels (the mean), optional latent normalisation.
+__global__ void vae_post_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
+                                float* __restrict__ out, long long npix, int c2, int lat, float lat_min, float lat_max) {
+  const long long total = npix * lat;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % lat);
+    const long long p = i / lat;
+    float acc = bias[c];
+    for (int k = 0; k < c2; ++k) acc = fmaf(x[p * c2 + k], w[k * c2 + c], acc);
+    if (lat_max > lat_min) acc = (acc - lat_min) / (lat_max - lat_min) * 2.f - 1.f;
+    out[i] = acc;
+  }
+}
+
+#define VAE_LAUNCH_OK(name)                                                                     \
+  do {                                                                                          \
+    cudaError_t _e = cudaGetLastError();                                                        \
+    if (_e != cudaSuccess) {                                                                    \
+      set_last_error(std::string(name " launch failed: ") + cudaGetErrorString(_e));           \
+      return LDP_ERR_CUDA;                                                                      \
+    }                                                                                           \
+    count_launch();                                                                             \
+  } while (0)
+
+struct ConvW { const float* w = nullptr; const float* b = nullptr; int k = 3, cin = 0, cout = 0; };
+struct ResW { const float *n1s, *n1b, *n2s, *n2b; ConvW c1, c2, sc; bool has_sc = false; };
+
+// a packed conv on the tcgen05 path
+struct VaeTcConv {
+  PackedW pw;
+  bool ready = false;
+};
+
+struct VaeWs {
+  int Bc = 0;
+  Arena arena;
+  float *S = nullptr, *Hf = nullptr, *stats = nullptr, *part = nullptr, *qkv = nullptr;
+  float* Gf = nullptr;                               // fp32 path: GN output
+  __nv_bfloat16 *Sb = nullptr, *Gb = nullptr;        // tc path
+  bool tc_ready = false;
+  std::vector<TcGemm> ops;
+};
+
+}  // namespace ldp
 
 using namespace ldp;
 
 struct LdpVae {
   LdpVaeConfig cfg;
+  Arena arena;
+  float* blob = nullptr;
+  ConvW conv_in, conv_out, quant;
+  std::vector<std::vector<ResW>> blocks;
+  std::vector<ConvW> down;
+  ResW mid0, mid1;
+  const float *ag_s, *ag_b, *nos, *nob;
+  ConvW aq, ak, av, ap;
+  float* wqkv = nullptr; float* bqkv = nullptr;      // [C][3C], [3C] concatenated projections
+  std::map<int, std::unique_ptr<VaeWs>> ws;
+  std::map<int, PackedW> packed;                     // conv id -> packed weights (tc path)
+  int64_t n_params = 0;
 };
+
+namespace ldp {
+
+static int64_t vae_param_count(const LdpVaeConfig& c) {
+  auto conv = [](int64_t k, int64_t ci, int64_t co) { return k * k * ci * co + co; };
+  auto res = [&](int64_t ci, int64_t co) { return 2 * ci + conv(3, ci, co) + 2 * co + conv(3, co, co) + (ci != co ? conv(1, ci, co) : 0); };
+  int64_t n = conv(3, c.in_channels, c.block_out_channels[0]);
+  int64_t ch = c.block_out_channels[0];
+  for (int i = 0; i < c.n_blocks; ++i) {
+    for (int j = 0; j < c.layers_per_block; ++j) {
+      n += res(ch, c.block_out_channels[i]);
+      ch = c.block_out_channels[i];
+    }
+    if (i != c.n_blocks - 1) n += conv(3, ch, ch);
+  }
+  n += res(ch, ch) + 2 * ch + 4 * (ch * ch + ch) + res(ch, ch);
+  n += 2 * ch + conv(3, ch, 2 * c.latent_channels) + conv(1, 2 * c.latent_channels, 2 * c.latent_channels);
+  return n;
+}
+
+static int vae_validate(const LdpVaeConfig* c) {
+  LDP_CHECK(c != nullptr, LDP_ERR_INVALID_ARG, "null config");
+  LDP_CHECK(c->in_channels >= 1 && c->in_channels <= 4 && c->latent_channels >= 1 && c->latent_channels <= 16, LDP_ERR_INVALID_ARG,
+            "in_channels must be 1..4, latent_channels 1..16");
+  LDP_CHECK(c->n_blocks >= 1 && c->n_blocks <= 8 && c->layers_per_block >= 1, LDP_ERR_INVALID_ARG, "bad block structure");
+  LDP_CHECK(c->norm_num_groups >= 1 && c->norm_num_groups <= 64, LDP_ERR_INVALID_ARG, "norm_num_groups must be 1..64");
+  const int S = c->image_size;
+  LDP_CHECK(S >= 1 && S <= 128 && (S & (S - 1)) == 0 && (S >> (c->n_blocks - 1)) >= 1, LDP_ERR_UNSUPPORTED,
+            "image_size must be a power of two <= 128 and survive n_blocks-1 halvings");
+  const int hw = (S >> (c->n_blocks - 1));
+  LDP_CHECK(hw * hw <= 64, LDP_ERR_UNSUPPORTED, "the attention core handles at most 64 tokens (8x8 latent grid)");
+  for (int i = 0; i < c->n_blocks; ++i)
+    LDP_CHECK(c->block_out_channels[i] > 0 && c->block_out_channels[i] % c->norm_num_groups == 0 && c->block_out_channels[i] % 8 == 0,
+              LDP_ERR_INVALID_ARG, "block_out_channels must be multiples of norm_num_groups and 8");
+  return LDP_OK;
+}
+
+static ConvW take_conv(BlobWalker& w, int k, int ci, int co) {
+  ConvW c;
+  c.k = k; c.cin = ci; c.cout = co;
+  c.w = w.take((uint64_t)k * k * ci * co);
+  c.b = w.take(co);
+  return c;
+}
+static ResW take_res(BlobWalker& w, int ci, int co) {
+  ResW r;
+  r.n1s = w.take(ci); r.n1b = w.take(ci);
+  r.c1 = take_conv(w, 3, ci, co);
+  r.n2s = w.take(co); r.n2b = w.take(co);
+  r.c2 = take_conv(w, 3, co, co);
+  r.has_sc = ci != co;
+  if (r.has_sc) r.sc = take_conv(w, 1, ci, co);
+  return r;
+}
+
+static int vae_create_impl(const LdpVaeConfig* cfg, const float* params_host, uint64_t n_params, LdpVae* h) {
+  h->cfg = *cfg;
+  const LdpVaeConfig& c = h->cfg;
+  const int64_t expect = vae_param_count(c);
+  LDP_CHECK((int64_t)n_params == expect, LDP_ERR_PARAM_COUNT,
+            "VAE weight blob has " + std::to_string(n_params) + " floats, config needs " + std::to_string(expect));
+  LDP_TRY(h->arena.alloc_t(&h->blob, n_params, false));
+  LDP_CUDA_OK(cudaMemcpy(h->blob, params_host, n_params * 4, cudaMemcpyHostToDevice));
+  BlobWalker w{h->blob, 0};
+  h->conv_in = take_conv(w, 3, c.in_channels, c.block_out_channels[0]);
+  int ch = c.block_out_channels[0];
+  for (int i = 0; i < c.n_blocks; ++i) {
+    std::vector<ResW> rs;
+    for (int j = 0; j < c.layers_per_block; ++j) {
+      rs.push_back(take_res(w, ch, c.block_out_channels[i]));
+      ch = c.block_out_channels[i];
+    }
+    h->blocks.push_back(rs);
+    if (i != c.n_blocks - 1) h->down.push_back(take_conv(w, 3, ch, ch));
+  }
+  h->mid0 = take_res(w, ch, ch);
+  h->ag_s = w.take(ch); h->ag_b = w.take(ch);
+  h->aq.w = w.take((uint64_t)ch * ch); h->aq.b = w.take(ch);
+  h->ak.w = w.take((uint64_t)ch * ch); h->ak.b = w.take(ch);
+  h->av.w = w.take((uint64_t)ch * ch); h->av.b = w.take(ch);
+  h->ap = ConvW();
+  h->ap.k = 1; h->ap.cin = ch; h->ap.cout = ch;
+  h->ap.w = w.take((uint64_t)ch * ch); h->ap.b = w.take(ch);
+  h->mid1 = take_res(w, ch, ch);
+  h->nos = w.take(ch); h->nob = w.take(ch);
+  h->conv_out = take_conv(w, 3, ch, 2 * c.latent_channels);
+  h->quant = take_conv(w, 1, 2 * c.latent_channels, 2 * c.latent_channels);
+  LDP_CHECK((int64_t)w.pos == expect, LDP_ERR_PARAM_COUNT, "internal: blob walk mismatch");
+  // concatenated q|k|v projection: one GEMM with N = 3C
+  LDP_TRY(h->arena.alloc_t(&h->wqkv, (size_t)ch * 3 * ch));
+  LDP_TRY(h->arena.alloc_t(&h->bqkv, (size_t)3 * ch));
+  const float* ws[3] = {h->aq.w, h->ak.w, h->av.w};
+  const float* bs[3] = {h->aq.b, h->ak.b, h->av.b};
+  for (int i = 0; i < 3; ++i) {
+    LDP_CUDA_OK(cudaMemcpy2D(h->wqkv + (size_t)i * ch, (size_t)3 * ch * 4, ws[i], (size_t)ch * 4, (size_t)ch * 4, ch,
+                             cudaMemcpyDeviceToDevice));
+    LDP_CUDA_OK(cudaMemcpy(h->bqkv + (size_t)i * ch, bs[i], (size_t)ch * 4, cudaMemcpyDeviceToDevice));
+  }
+  return LDP_OK;
+}
+
+static int vae_get_ws(LdpVae* h, int Bc, VaeWs** out) {
+  auto it = h->ws.find(Bc);
+  if (it != h->ws.end()) {
+    *out = it->second.get();
+    return LDP_OK;
+  }
+  const LdpVaeConfig& c = h->cfg;
+  std::unique_ptr<VaeWs> w(new VaeWs());
+  w->Bc = Bc;
+  size_t max_act = 0;
+  int S = c.image_size;
+  for (int i = 0; i < c.n_blocks; ++i) {
+    const int cin = i == 0 ? c.block_out_channels[0] : c.block_out_channels[i - 1];
+    max_act = std::max(max_act, (size_t)S * S * std::max(cin, c.block_out_channels[i]));
+    if (i != c.n_blocks - 1) S /= 2;
+  }
+  const int cl = c.block_out_channels[c.n_blocks - 1];
+  max_act = std::max(max_act, (size_t)S * S * 3 * cl);
+  LDP_TRY(w->arena.alloc_t(&w->S, (size_t)Bc * max_act, false));
+  LDP_TRY(w->arena.alloc_t(&w->Hf, (size_t)Bc * max_act, false));
+  LDP_TRY(w->arena.alloc_t(&w->stats, (size_t)Bc * c.norm_num_groups * 2));
+  LDP_TRY(w->arena.alloc_t(&w->part, (size_t)Bc * 64 * c.norm_num_groups * 2));
+  LDP_TRY(w->arena.alloc_t(&w->qkv, (size_t)Bc * S * S * 3 * cl, false));
+  *out = w.get();
+  h->ws[Bc] = std::move(w);
+  return LDP_OK;
+}
+
+// ---- shared pieces ----
+static int vae_gn(LdpVae* h, VaeWs* w, const float* x, int nimg, int P, int C, const float* gamma, const float* beta, int act,
+                  float* y_f32, __nv_bfloat16* y_bf16, cudaStream_t s) {
+  const int G = h->cfg.norm_num_groups;
+  LDP_CHECK(256 % (C / 4) == 0, LDP_ERR_UNSUPPORTED, "VAE GroupNorm needs C/4 to divide 256 (C in {8,...,1024} powers of two)");
+  const long long per_img = (long long)P * C / 4;
+  const int slabs = (int)std::min<long long>(std::max<long long>(1, per_img / 2048), 64);
+  vae_gn_stats_kernel<<<dim3(nimg, slabs), 256, 0, s>>>(x, w->part, P, C, G);
+  VAE_LAUNCH_OK("vae_gn_stats");
+  vae_gn_final_kernel<<<(nimg * G + 127) / 128, 128, 0, s>>>(w->part, w->stats, nimg * G, G, slabs, 1.f / ((float)P * (C / G)), 1e-6f);
+  VAE_LAUNCH_OK("vae_gn_final");
+  const long long total = (long long)nimg * per_img;
+  const int blocks = (int)std::min<long long>((total + 255) / 256, 148 * 16);
+  vae_gn_apply_kernel<<<blocks, 256, 0, s>>>(x, w->stats, gamma, beta, y_f32, y_bf16, nimg, P, C, G, act);
+  VAE_LAUNCH_OK("vae_gn_apply");
+  return LDP_OK;
+}
+
+static int vae_conv_f32(const ConvW& cw, const float* in, const float* res, float* out, int nimg, int Hin, int stride, int pad,
+                        cudaStream_t s) {
+  const int Hout = stride == 2 ? Hin / 2 : Hin;
+  const int xg = (Hout + 7) / 8;
+  dim3 grid((unsigned)((long long)nimg * Hout * xg), (cw.cout + 127) / 128);
+  vae_conv_f32_kernel<<<grid, 128, 0, s>>>(in, cw.w, cw.b, res, out, nimg, Hin, Hin, Hout, Hout, cw.cin, cw.cout, cw.k, stride, pad);
+  VAE_LAUNCH_OK("vae_conv_f32");
+  return LDP_OK;
+}
+
+// ---- fp32 program ----
+static int vae_res_f32(LdpVae* h, VaeWs* w, const ResW& r, int nimg, int S, cudaStream_t s) {
+  const int P = S * S;
+  LDP_TRY(vae_gn(h, w, w->S, nimg, P, r.c1.cin, r.n1s, r.n1b, 1, w->Gf, nullptr, s));
+  LDP_TRY(vae_conv_f32(r.c1, w->Gf, nullptr, w->Hf, nimg, S, 1, 1, s));
+  LDP_TRY(vae_gn(h, w, w->Hf, nimg, P, r.c1.cout, r.n2s, r.n2b, 1, w->Gf, nullptr, s));
+  if (r.has_sc) {
+    // shortcut(x) into Hf (free now), then S = conv2(Gf) + Hf
+    LDP_TRY(vae_conv_f32(r.sc, w->S, nullptr, w->Hf, nimg, S, 1, 0, s));
+    LDP_TRY(vae_conv_f32(r.c2, w->Gf, w->Hf, w->S, nimg, S, 1, 1, s));
+  } else {
+    LDP_TRY(vae_conv_f32(r.c2, w->Gf, w->S, w->S, nimg, S, 1, 1, s));     // in-place residual: each thread reads res[o] then writes out[o]
+  }
+  return LDP_OK;
+}
+
+static int vae_forward_f32(LdpVae* h, VaeWs* w, const void* images, int fmt, int nimg, float lat_min, float lat_max, float* out,
+                           cudaStream_t s) {
+  const LdpVaeConfig& c = h->cfg;
+  if (!w->Gf) {
+    size_t max_act = 0;
+    int S0 = c.image_size;
+    for (int i = 0; i < c.n_blocks; ++i) {
+      const int cin = i == 0 ? c.block_out_channels[0] : c.block_out_channels[i - 1];
+      max_act = std::max(max_act, (size_t)S0 * S0 * std::max(cin, c.block_out_channels[i]));
+      if (i != c.n_blocks - 1) S0 /= 2;
+    }
+    LDP_TRY(w->arena.alloc_t(&w->Gf, (size_t)w->Bc * max_act, false));
+  }
+  int S = c.image_size;
+  const int c0 = c.block_out_channels[0];
+  const size_t smem = (size_t)9 * c.in_channels * c0 * 4;
+  const long long tot = (long long)nimg * S * S * c0 / 4;
+  const int blocks = (int)std::min<long long>((tot + 255) / 256, 148 * 8);
+  if (fmt == 0)
+    vae_conv_in_kernel<uint8_t><<<blocks, 256, smem, s>>>((const uint8_t*)images, h->conv_in.w, h->conv_in.b, w->S, nullptr, nimg, S,
+                                                           c.in_channels, c0);
+  else
+    vae_conv_in_kernel<float><<<blocks, 256, smem, s>>>((const float*)images, h->conv_in.w, h->conv_in.b, w->S, nullptr, nimg, S,
+                                                         c.in_channels, c0);
+  VAE_LAUNCH_OK("vae_conv_in");
+  for (int i = 0; i < c.n_blocks; ++i) {
+    for (auto& r : h->blocks[i]) LDP_TRY(vae_res_f32(h, w, r, nimg, S, s));
+    if (i != c.n_blocks - 1) {
+      // FlaxDownsample2D: pad H,W by (0,1), conv 3x3 stride 2 VALID  ==  pad 0 on the low side, zero beyond the high edge
+      LDP_TRY(vae_conv_f32(h->down[i], w->S, nullptr, w->Hf, nimg, S, 2, 0, s));
+      std::swap(w->S, w->Hf);
+      S /= 2;
+    }
+  }
+  const int ch = c.block_out_channels[c.n_blocks - 1], L = S * S;
+  LDP_TRY(vae_res_f32(h, w, h->mid0, nimg, S, s));
+  {
+    LDP_TRY(vae_gn(h, w, w->S, nimg, L, ch, h->ag_s, h->ag_b, 0, w->Gf, nullptr, s));
+    GemmF32 g;
+    g.x1 = w->Gf; g.c1 = ch; g.ld1 = ch; g.w = h->wqkv; g.ldw = 3 * ch; g.bias = h->bqkv; g.out = w->qkv; g.ldo = 3 * ch;
+    g.m = nimg * L; g.n = 3 * ch;
+    LDP_TRY(launch_gemm_f32(g, s));
+    vae_attn_kernel<<<nimg, 256, 0, s>>>(w->qkv, w->Gf, nullptr, L, ch);
+    VAE_LAUNCH_OK("vae_attn");
+    g = GemmF32();
+    g.x1 = w->Gf; g.c1 = ch; g.ld1 = ch; g.w = h->ap.w; g.ldw = ch; g.bias = h->ap.b; g.res = w->S; g.ldres = ch;
+    g.out = w->S; g.ldo = ch; g.m = nimg * L; g.n = ch;
+    LDP_TRY(launch_gemm_f32(g, s));
+  }
+  LDP_TRY(vae_res_f32(h, w, h->mid1, nimg, S, s));
+  LDP_TRY(vae_gn(h, w, w->S, nimg, L, ch, h->nos, h->nob, 1, w->Gf, nullptr, s));
+  LDP_TRY(vae_conv_f32(h->conv_out, w->Gf, nullptr, w->Hf, nimg, S, 1, 1, s));
+  const long long npix = (long long)nimg * L;
+  vae_post_kernel<<<(int)std::min<long long>((npix * c.latent_channels + 255) / 256, 4096), 256, 0, s>>>(
+      w->Hf, h->quant.w, h->quant.b, out, npix, 2 * c.latent_channels, c.latent_channels, lat_min, lat_max);
+  VAE_LAUNCH_OK("vae_post");
+  return LDP_OK;
+}
+
+// ---- tcgen05 program ----
+// Tile geometry of a level: 128 output pixels = wb x hb pixels of ib images (whole rows, so that a tile's rows are
+// consecutive NHWC pixels).
+struct TileGeo { int wb, hb, ib, tiles_per_img; };
+static TileGeo tile_geo(int S) {
+  TileGeo g;
+  g.wb = S;
+  g.hb = std::min(S, 128 / S);
+  g.ib = 128 / (g.wb * g.hb);
+  g.tiles_per_img = g.ib > 1 ? 1 : S / g.hb;
+  return g;
+}
+
+static int vae_pack(LdpVae* h, int id, const float* wgt, int k, int pad, int cin, int cout, PackedW** out) {
+  auto it = h->packed.find(id);
+  if (it != h->packed.end()) {
+    *out = &it->second;
+    return LDP_OK;
+  }
+  PackedW pw;
+  std::vector<TcStage> st;
+  std::vector<int32_t> kmap;
+  for (int dy = 0; dy < k; ++dy)
+    for (int dx = 0; dx < k; ++dx)
+      for (int c0 = 0; c0 < cin; c0 += 64) {
+        st.push_back(make_stage(0, 0, 1, c0, dx - pad, dy - pad, (int)kmap.size() / 64));
+        for (int i = 0; i < 64; ++i) kmap.push_back(c0 + i < cin ? (dy * k + dx) * cin + c0 + i : -1);
+      }
+  pw.kp = (int)kmap.size();
+  pw.n_pad = round_up(cout, 128);
+  pw.num_kb = (int)st.size();
+  LDP_TRY(h->arena.alloc_t(&pw.wt, (size_t)pw.n_pad * pw.kp));
+  LDP_TRY(h->arena.alloc_t(&pw.kb_dev, st.size()));
+  LDP_CUDA_OK(cudaMemcpy(pw.kb_dev, st.data(), st.size() * sizeof(TcStage), cudaMemcpyHostToDevice));
+  Arena tmp;
+  int32_t* map_dev;
+  LDP_TRY(tmp.alloc_t(&map_dev, kmap.size()));
+  LDP_CUDA_OK(cudaMemcpy(map_dev, kmap.data(), kmap.size() * 4, cudaMemcpyHostToDevice));
+  LDP_TRY(launch_pack_wt_bf16(wgt, cout, cout, map_dev, pw.kp, pw.wt, pw.kp, 0, pw.n_pad, 0));
+  LDP_CUDA_OK(cudaDeviceSynchronize());
+  h->packed[id] = pw;
+  *out = &h->packed[id];
+  return LDP_OK;
+}
+
+// conv on `in` (bf16, NHWC at resolution S_in) -> PLAIN epilogue.  stride 2 = the Downsample conv: taps address
+// (2x + dx, 2y + dy) with dx, dy >= 0 (pad low 0), the row/column beyond the high edge is TMA out-of-bounds zero fill.
+static int vae_conv_tc(LdpVae* h, VaeWs* w, int id, const ConvW& cw, const float* bias, const __nv_bfloat16* in, int S_in,
+                       int stride, TcGemm* op) {
+  PackedW* pw;
+  const int pad = (cw.k == 3 && stride == 1) ? 1 : 0;
+  LDP_TRY(vae_pack(h, id, cw.w, cw.k, pad, cw.cin, cw.cout, &pw));
+  const int S_out = S_in / stride;
+  const TileGeo g = tile_geo(S_out);
+  *op = TcGemm();
+  uint64_t dims[4] = {(uint64_t)cw.cin, (uint64_t)S_in, (uint64_t)S_in, (uint64_t)w->Bc};
+  uint64_t str[3] = {(uint64_t)cw.cin * 2, (uint64_t)S_in * cw.cin * 2, (uint64_t)S_in * S_in * cw.cin * 2};
+  uint32_t box[4] = {64, (uint32_t)(g.wb * stride), (uint32_t)(g.hb * stride), (uint32_t)g.ib};
+  uint32_t es[4] = {1, (uint32_t)stride, (uint32_t)stride, 1};
+  LDP_TRY(make_tmap_bf16_strided(&op->map_a[0], in, 4, dims, str, box, es));
+  for (int i = 1; i < 4; ++i) op->map_a[i] = op->map_a[0];
+  const int bn = cw.cout > 64 ? 128 : 64;
+  uint64_t bd[2] = {(uint64_t)pw->kp, (uint64_t)pw->n_pad};
+  uint64_t bs[1] = {(uint64_t)pw->kp * 2};
+  uint32_t bb[2] = {64, (uint32_t)bn};
+  LDP_TRY(make_tmap_bf16(&op->map_b, pw->wt, 2, bd, bs, bb));
+  op->kb = pw->kb_dev; op->num_kb = pw->num_kb; op->w_max = 1; op->k_pad = pw->kp;
+  op->M = w->Bc * S_out * S_out; op->N = cw.cout; op->block_n = bn;
+  op->tiles_per_item = g.tiles_per_img; op->rows_step = g.hb * stride; op->items_per_tile = g.ib;
+  op->rows_per_item = 1;
+  op->mode = TC_EPI_PLAIN;
+  op->bias = bias;
+  return LDP_OK;
+}
+
+struct VaeBufs { float *S, *Hf; __nv_bfloat16 *Sb, *Gb; };
+
+// Walks the encoder once.  build = true: creates the TcGemm ops (tensor maps bound to the workspace buffers) in
+// execution order; build = false: runs the program for `nimg` images, consuming the ops in the same order.
+static int vae_walk_tc(LdpVae* h, VaeWs* w, bool build, const void* images, int fmt, int nimg, float lat_min, float lat_max,
+                       float* out, cudaStream_t s) {
+  const LdpVaeConfig& c = h->cfg;
+  VaeBufs b{w->S, w->Hf, w->Sb, w->Gb};
+  size_t oi = 0;
+  int conv_id = 0;
+  // emit(op builder) / run(op)
+  auto conv = [&](const ConvW& cw, const __nv_bfloat16* in, int S_in, int stride, const float* res, float* of32,
+                  __nv_bfloat16* obf) -> int {
+    const int S_out = S_in / stride;
+    if (build) {
+      TcGemm op;
+      LDP_TRY(vae_conv_tc(h, w, conv_id, cw, cw.b, in, S_in, stride, &op));
+      op.res_f32 = res; op.ld_res_f32 = cw.cout;
+      op.out_f32 = of32; op.ld_out_f32 = cw.cout;
+      op.out_bf16 = obf; op.ld_out_bf16 = cw.cout;
+      w->ops.push_back(op);
+    } else {
+      TcGemm op = w->ops[oi];
+      op.M = nimg * S_out * S_out;
+      LDP_TRY(launch_tc_gemm(op, s));
+    }
+    ++oi;
+    ++conv_id;
+    return LDP_OK;
+  };
+  auto gn = [&](const float* x, int P, int C, const float* gs_, const float* gb_, int act, __nv_bfloat16* y) -> int {
+    if (build) return LDP_OK;
+    return vae_gn(h, w, x, nimg, P, C, gs_, gb_, act, nullptr, y, s);
+  };
+  auto resnet = [&](const ResW& r, int S) -> int {
+    const int P = S * S;
+    LDP_TRY(gn(b.S, P, r.c1.cin, r.n1s, r.n1b, 1, b.Gb));
+    LDP_TRY(conv(r.c1, b.Gb, S, 1, nullptr, b.Hf, nullptr));
+    LDP_TRY(gn(b.Hf, P, r.c1.cout, r.n2s, r.n2b, 1, b.Gb));
+    if (r.has_sc) {
+      LDP_TRY(conv(r.sc, b.Sb, S, 1, nullptr, b.Hf, nullptr));            // Hf is free again after the second GroupNorm
+      LDP_TRY(conv(r.c2, b.Gb, S, 1, b.Hf, b.S, b.Sb));
+    } else {
+      LDP_TRY(conv(r.c2, b.Gb, S, 1, b.S, b.S, b.Sb));                     // in place: a thread reads its residual row, then writes it
+    }
+    return LDP_OK;
+  };
+  int S = c.image_size;
+  const int c0 = c.block_out_channels[0];
+  if (!build) {
+    const size_t smem = (size_t)9 * c.in_channels * c0 * 4;
+    const long long tot = (long long)nimg * S * S * c0 / 4;
+    const int blocks = (int)std::min<long long>((tot + 255) / 256, 148 * 8);
+    if (fmt == 0)
+      vae_conv_in_kernel<uint8_t><<<blocks, 256, smem, s>>>((const uint8_t*)images, h->conv_in.w, h->conv_in.b, b.S, b.Sb, nimg, S,
+                                                             c.in_channels, c0);
+    else
+      vae_conv_in_kernel<float><<<blocks, 256, smem, s>>>((const float*)images, h->conv_in.w, h->conv_in.b, b.S, b.Sb, nimg, S,
+                                                           c.in_channels, c0);
+    VAE_LAUNCH_OK("vae_conv_in");
+  }
+  for (int i = 0; i < c.n_blocks; ++i) {
+    for (auto& r : h->blocks[i]) LDP_TRY(resnet(r, S));
+    if (i != c.n_blocks - 1) {
+      LDP_TRY(conv(h->down[i], b.Sb, S, 2, nullptr, b.Hf, b.Gb));
+      std::swap(b.S, b.Hf);
+      std::swap(b.Sb, b.Gb);
+      S /= 2;
+    }
+  }
+  const int ch = c.block_out_channels[c.n_blocks - 1], L = S * S;
+  LDP_TRY(resnet(h->mid0, S));
+  {
+    LDP_TRY(gn(b.S, L, ch, h->ag_s, h->ag_b, 0, b.Gb));
+    ConvW qkv;
+    qkv.k = 1; qkv.cin = ch; qkv.cout = 3 * ch; qkv.w = h->wqkv; qkv.b = h->bqkv;
+    LDP_TRY(conv(qkv, b.Gb, S, 1, nullptr, w->qkv, nullptr));
+    if (!build) {
+      vae_attn_kernel<<<nimg, 256, 0, s>>>(w->qkv, nullptr, b.Gb, L, ch);
+      VAE_LAUNCH_OK("vae_attn");
+    }
+    LDP_TRY(conv(h->ap, b.Gb, S, 1, b.S, b.S, b.Sb));
+  }
+  LDP_TRY(resnet(h->mid1, S));
+  LDP_TRY(gn(b.S, L, ch, h->nos, h->nob, 1, b.Gb));
+  LDP_TRY(conv(h->conv_out, b.Gb, S, 1, nullptr, b.Hf, nullptr));
+  if (!build) {
+    const long long npix = (long long)nimg * L;
+    vae_post_kernel<<<(int)std::min<long long>((npix * c.latent_channels + 255) / 256, 4096), 256, 0, s>>>(
+        b.Hf, h->quant.w, h->quant.b, out, npix, 2 * c.latent_channels, c.latent_channels, lat_min, lat_max);
+    VAE_LAUNCH_OK("vae_post");
+  }
+  return LDP_OK;
+}
+
+static int vae_prepare_tc(LdpVae* h, VaeWs* w) {
+  if (w->tc_ready) return LDP_OK;
+  LDP_TRY(tc_driver_check());
+  LDP_TRY(tc_gemm_init());
+  const LdpVaeConfig& c = h->cfg;
+  size_t max_act = 0;
+  int S = c.image_size;
+  for (int i = 0; i < c.n_blocks; ++i) {
+    const int cin = i == 0 ? c.block_out_channels[0] : c.block_out_channels[i - 1];
+    max_act = std::max(max_act, (size_t)S * S * std::max(cin, c.block_out_channels[i]));
+    if (i != c.n_blocks - 1) S /= 2;
+  }
+  LDP_TRY(w->arena.alloc_t(&w->Sb, (size_t)w->Bc * max_act));
+  LDP_TRY(w->arena.alloc_t(&w->Gb, (size_t)w->Bc * max_act));
+  w->ops.clear();
+  LDP_TRY(vae_walk_tc(h, w, true, nullptr, 0, w->Bc, 0.f, 0.f, nullptr, 0));
+  w->tc_ready = true;
+  return LDP_OK;
+}
+
+}  // namespace ldp
 
 extern "C" {
 
 int64_t ldp_vae_param_count(const LdpVaeConfig* cfg) {
-  (void)cfg;
-  return -1;
+  if (vae_validate(cfg) != LDP_OK) return -1;
+  return vae_param_count(*cfg);
 }
 
 int ldp_vae_create(const LdpVaeConfig* cfg, const float* params_host, uint64_t n_params, LdpVae** out) {
-  (void)cfg; (void)params_host; (void)n_params; (void)out;
-  set_last_error("ldp_vae_create: VAE encoder path not built yet");
-  return LDP_ERR_UNSUPPORTED;
+  LDP_CHECK(out != nullptr && params_host != nullptr, LDP_ERR_INVALID_ARG, "null pointer");
+  LDP_TRY(vae_validate(cfg));
+  LdpVae* h = new LdpVae();
+  int st = vae_create_impl(cfg, params_host, n_params, h);
+  if (st != LDP_OK) {
+    delete h;
+    return st;
+  }
+  *out = h;
+  return LDP_OK;
 }
 
 int ldp_vae_destroy(LdpVae* h) {
+  if (!h) return LDP_OK;
+  cudaDeviceSynchronize();
   delete h;
   return LDP_OK;
 }
 
 int ldp_vae_encode(LdpVae* h, int precision, const void* images_dev, int pixel_format, int B, float lat_min, float lat_max,
                    float* latent_dev, void* cuda_stream) {
-  (void)h; (void)precision; (void)images_dev; (void)pixel_format; (void)B; (void)lat_min; (void)lat_max; (void)latent_dev;
-  (void)cuda_stream;
-  set_last_error("ldp_vae_encode: VAE encoder path not built yet");
-  return LDP_ERR_UNSUPPORTED;
+  LDP_CHECK(h && images_dev && latent_dev, LDP_ERR_INVALID_ARG, "null pointer");
+  LDP_CHECK(B > 0, LDP_ERR_BAD_SHAPE, "B must be positive");
+  LDP_CHECK(pixel_format == 0 || pixel_format == 1, LDP_ERR_INVALID_ARG, "pixel_format must be 0 (uint8) or 1 (float32)");
+  LDP_CHECK(precision == LDP_PREC_FP32 || precision == LDP_PREC_BF16, LDP_ERR_INVALID_ARG, "unknown precision");
+  cudaStream_t s = (cudaStream_t)cuda_stream;
+  const LdpVaeConfig& c = h->cfg;
+  const int S = c.image_size, hw = S >> (c.n_blocks - 1);
+  const size_t px_bytes = pixel_format == 0 ? 1 : 4;
+  const int chunk = std::min(B, 256);
+  VaeWs* w;
+  LDP_TRY(vae_get_ws(h, chunk, &w));
+  if (precision == LDP_PREC_BF16) LDP_TRY(vae_prepare_tc(h, w));
+  for (int b0 = 0; b0 < B; b0 += chunk) {
+    const int n = std::min(chunk, B - b0);
+    const void* img = (const char*)images_dev + (size_t)b0 * S * S * c.in_channels * px_bytes;
+    float* out = latent_dev + (size_t)b0 * hw * hw * c.latent_channels;
+    if (precision == LDP_PREC_FP32) LDP_TRY(vae_forward_f32(h, w, img, pixel_format, n, lat_min, lat_max, out, s));
+    else LDP_TRY(vae_walk_tc(h, w, false, img, pixel_format, n, lat_min, lat_max, out, s));
+  }
+  return LDP_OK;
 }
 
 }  // extern "C"

@@ -332,3 +332,81 @@ def test_abi_errors(unet_small, H):
     cfg = N.unet_config(D + 1, D, dims)                                                  # wrong blob length for this config
     assert lib.ldp_planner_create(C.byref(cfg), blob.ctypes.data, blob.size, C.byref(h)) == -5
     assert b"floats" in lib.ldp_last_error()
+
+
+# ------------------------------------------------------------------------------------------------
+# VAE encoder (FlaxAutoencoderKL.encode(x).latent_dist.mean)
+# ------------------------------------------------------------------------------------------------
+def _images(B, S, seed=4):
+    g = torch.Generator().manual_seed(seed)
+    return torch.randint(0, 256, (B, S, S, 3), generator=g, dtype=torch.int32).to(torch.uint8)
+
+
+def _rel_l2(a, b):
+    a = torch.as_tensor(a, dtype=torch.float64).cpu()
+    b = torch.as_tensor(b, dtype=torch.float64).cpu()
+    return float((a - b).norm() / b.norm())
+
+
+def _vae_ref(p, img_u8, blocks, layers=2, groups=32):
+    x = img_u8.to(torch.float64) / 255.0 * 2 - 1
+    return O.vae_encode_mean(p, x, blocks, layers, groups, 4)
+
+
+@pytest.mark.parametrize("blocks,S,B", [((32, 64), 16, 3), ((64, 64, 128), 32, 2)])
+def test_vae_small_configs(H, blocks, S, B):
+    """Narrow encoders: both precisions, ragged batch, uint8 and float input, fused latent normalisation."""
+    p = P.init_params(P.vae_encoder_spec(blocks, 3, 4, 1), seed=5, perturb=0.1)
+    vae = H.VaeEncoder(p, blocks, 3, 4, 1, 8, S)
+    img = _images(B, S)
+    ref = _vae_ref(p, img, blocks, 1, 8)
+    scale = max(1.0, float(ref.abs().max()))
+    out32 = vae.encode(img.cuda(), precision="fp32")
+    assert _maxerr(out32, ref) < 2e-5 * scale
+    out16 = vae.encode(img.cuda(), precision="bf16")
+    assert _maxerr(out16, ref) < TOL_BF16 * scale
+    xf = (img.to(torch.float32) / 255.0 * 2 - 1).cuda()
+    assert _maxerr(vae.encode(xf, precision="fp32"), ref) < 2e-5 * scale
+    z = vae.encode(img.cuda(), lat_min=-10.0, lat_max=10.0, precision="fp32")
+    assert _maxerr(z, (ref + 10.0) / 20.0 * 2 - 1) < 2e-5
+
+
+def test_vae_benchmark_topology(H):
+    """BASELINE config #3 topology: SD-VAE [128,256,512,512] at 64x64 -> 8x8x4 latents."""
+    blocks = (128, 256, 512, 512)
+    p = P.init_params(P.vae_encoder_spec(blocks), seed=6)
+    vae = H.VaeEncoder(p, blocks)
+    img = _images(3, 64, seed=7)
+    ref = _vae_ref(p, img, blocks)
+    scale = max(1.0, float(ref.abs().max()))
+    assert _maxerr(vae.encode(img.cuda(), precision="fp32"), ref) < 3e-5 * scale
+    out16 = vae.encode(img.cuda(), precision="bf16")
+    assert tuple(out16.shape) == (3, 8, 8, 4)
+    # ~35 stacked bf16-operand contractions: the 1e-2 gate is taken in the relative L2 norm (measured 4e-3), and the
+    # worst single element is bounded at 2e-2 of max|ref| (measured 1.0e-2)
+    assert _rel_l2(out16, ref) < TOL_BF16
+    assert _maxerr(out16, ref) < 2 * TOL_BF16 * scale
+
+
+def test_vae_reference_topology_bf16(H):
+    """The reference's own config (model/stable_vae_model.yaml:7-8): 6 blocks -> 2x2x4 latents (W = 4 and 2 tiles)."""
+    blocks = (128, 256, 256, 256, 256, 256)
+    p = P.init_params(P.vae_encoder_spec(blocks), seed=8)
+    vae = H.VaeEncoder(p, blocks)
+    img = _images(5, 64, seed=9)
+    ref = _vae_ref(p, img, blocks)
+    out16 = vae.encode(img.cuda(), precision="bf16")
+    assert tuple(out16.shape) == (5, 2, 2, 4)
+    assert _rel_l2(out16, ref) < TOL_BF16
+    assert _maxerr(out16, ref) < 2 * TOL_BF16 * max(1.0, float(ref.abs().max()))
+
+
+def test_vae_chunking_is_invisible(H):
+    """B > the 256-image chunk: images are independent, so a big batch equals its pieces."""
+    blocks = (32, 64)
+    p = P.init_params(P.vae_encoder_spec(blocks, 3, 4, 1), seed=5, perturb=0.1)
+    vae = H.VaeEncoder(p, blocks, 3, 4, 1, 8, 16)
+    img = _images(300, 16, seed=11).cuda()
+    whole = vae.encode(img, precision="bf16")
+    parts = torch.cat([vae.encode(img[:256], precision="bf16"), vae.encode(img[256:], precision="bf16")])
+    assert _maxerr(whole, parts) < 1e-4
