@@ -297,6 +297,12 @@ def run_ours(args) -> None:
                                         key=lambda o: -o["us"])[:3]}
         except Exception as e:                                              # diagnostics only
             per_op = {"error": str(e)}
+        extras = None
+        if not args.no_extras:
+            try:
+                extras = side_metrics(torch, H, P, rank)
+            except Exception as e:                                          # side numbers never break the headline line
+                extras = {"error": str(e)}
         cpu = cpu_baseline_leg() if world == 1 and not args.no_cpu_baseline else None
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
@@ -323,12 +329,55 @@ def run_ours(args) -> None:
             "clocks": clocks,
             "host_cores": os.cpu_count(),
         }
+        if extras is not None:
+            line["extras"] = extras
         if cpu is not None:
             line["cpu_baseline"] = cpu
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def side_metrics(torch, H, P, rank):
+    """Per-GPU side numbers for the other BASELINE configs (not the headline): VAE-encode img/s at B=4096 (config #3),
+    IDM loop and full act() = encode + planner + IDM at B=1024 (rm_lift shapes).  Device-resident inputs, CUDA events."""
+    from latent_diffusion_planning_b200.agent import LDPAgent
+    out = {}
+
+    def timeit(fn, reps):
+        fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / reps
+
+    lowdim = ["robot0_eef_pos", "robot0_eef_quat", "robot0_gripper_qpos"]
+    shapes = {"robot0_eef_pos": [3], "robot0_eef_quat": [4], "robot0_gripper_qpos": [2], "latent_agentview_image": [LATENT]}
+    import numpy as np
+    norm = {"obs": {"agentview_image": {"min": 0, "max": 255},
+                    "latent_agentview_image": {"min": np.full(LATENT, -10.0, np.float32), "max": np.full(LATENT, 10.0, np.float32)},
+                    **{k: {"min": -np.ones(shapes[k][0], np.float32), "max": np.ones(shapes[k][0], np.float32)} for k in lowdim}},
+            "actions": {"clip_min": -np.ones(7, np.float32), "clip_max": np.ones(7, np.float32)}}
+    agent = LDPAgent.create(0, None, {"ac_dim": 7, "all_shapes": shapes}, rgb_obs=["latent_agentview_image"], lowdim_obs=lowdim,
+                            obs_normalization=norm, vae_feature_dim=LATENT, obs_horizon=1, pred_horizon=T_PRED, action_horizon=4)
+    g = torch.Generator().manual_seed(4 + rank)
+    img = torch.randint(0, 256, (4096, 64, 64, 3), generator=g, dtype=torch.int32).to(torch.uint8).cuda()
+    ms = timeit(lambda: agent.vae.encode(img, lat_min=-10.0, lat_max=10.0, precision="bf16"), 2)
+    out["vae_encode_imgs_per_sec"] = 4096 / ms * 1e3
+    out["vae_encode_config"] = "stable_vae_model.encode 64x64x3 uint8, B=4096, SD-VAE [128,256,512,512] -> 8x8x4, bf16"
+    out["vae_tflops_useful"] = 4096 * 16.92 / ms
+    batch = {"obs": {"agentview_image": img[:B_PLANS].reshape(B_PLANS, 1, 64, 64, 3),
+                     **{k: torch.rand(B_PLANS, 1, shapes[k][0], generator=g).cuda() * 2 - 1 for k in lowdim}}}
+    ms = timeit(lambda: agent.act(batch, 1), 2)
+    out["act_plans_per_sec"] = B_PLANS / ms * 1e3
+    out["act_config"] = "LDPAgent.act: VAE encode + 100 planner DDPM steps + 100 IDM DDPM steps, B=1024, rm_lift shapes, bf16"
+    out["act_ms"] = ms
+    return out
 
 
 def main():
@@ -338,6 +387,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the CPU oracle leg (profiling runs)")
+    ap.add_argument("--no-extras", action="store_true", help="skip the side metrics (VAE encode, act())")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

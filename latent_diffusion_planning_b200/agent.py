@@ -1,0 +1,271 @@
+"""LDPAgent - host-side mirror of the reference agent's sampling surface (reference agent/ldp_agent.py:28-672).
+
+Same method names and argument meaning as the reference (`create`, `sample`, `sample_viz`, `sample_action`,
+`sample_action_from_plan`, `vae_encode`, `get_obs_cond`, `get_params`, `config[...]`) plus `act` (= `sample`, the
+name BASELINE.json uses).  Batches are dicts of tensors exactly like the reference's:
+`{'obs': {key: (B, H, ...)}, ['actions': (B, H, A)]}` with raw pixels 0..255.  Everything numerical runs in
+libldp_b200 (VAE encoder, planner loop, IDM loop); this file only does the reference's glue: normalisation constants,
+concatenations, reshapes.  Training (`update`, `update_mixed`) is the next scope row and raises.
+
+`rng` replaces the JAX PRNG key: an int seed (or anything `int()` accepts).  Noise is counter-based Philox keyed by
+(seed, stream, step, GLOBAL row), so a batch sharded over ranks (`row_offset`) reproduces the unsharded result.
+"""
+from __future__ import annotations
+
+from typing import Any, Dict, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from . import handles as H
+from . import params as P
+
+# Philox stream ids (disjoint streams for the independent draws of one act())
+STREAM_PLANNER_LOOP, STREAM_IDM_LOOP, STREAM_PLANNER_INIT, STREAM_IDM_INIT = 0, 1, 2, 3
+
+
+# ------------------------------------------------------------------------------------------------
+# normalisation (reference utils/data_utils.py:9-80)
+# ------------------------------------------------------------------------------------------------
+def _as_t(v, like: torch.Tensor) -> torch.Tensor:
+    return torch.as_tensor(np.asarray(v, dtype=np.float32), device=like.device)
+
+
+def normalize_unnormalize(val: torch.Tensor, spec: Dict[str, Any], normalize: bool) -> torch.Tensor:
+    """One entry of `normalize_unnormalize_obs` (utils/data_utils.py:24-68)."""
+    if "mean" in spec:
+        raise NotImplementedError("mean/std normalisation is NotImplemented in the reference too (utils/data_utils.py:30)")
+    if "min" in spec:
+        lo, hi = _as_t(spec["min"], val), _as_t(spec["max"], val)
+        if normalize:
+            return (val - lo) / (hi - lo) * 2 - 1
+        out = (val + 1) / 2 * (hi - lo) + lo
+        return torch.minimum(torch.maximum(out, lo), hi)
+    if "clip_min" in spec:
+        return torch.minimum(torch.maximum(val, _as_t(spec["clip_min"], val)), _as_t(spec["clip_max"], val))
+    raise NotImplementedError(f"unknown normalisation spec {sorted(spec)}")
+
+
+def shard_rows(n: int, rank: int, world: int) -> Tuple[int, int]:
+    """Contiguous row range of `rank` when n independent units are split over `world` ranks (sizes differ by <= 1).
+    The reference requires `batch % n_devices == 0` (train_bc.py:73); eval batches are ragged, so we do not."""
+    base, rem = divmod(n, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+class LDPAgent:
+    """Sampling-side LDP agent on the B200-native kernels."""
+
+    def __init__(self, planner: H.Planner, idm: H.Idm, vae: Optional[H.VaeEncoder], obs_normalization: Dict[str, Any],
+                 config: Dict[str, Any], planner_params, idm_params, precision: str = "bf16", sampler: str = "ddpm"):
+        self.planner, self.idm, self.vae = planner, idm, vae
+        self.obs_normalization = obs_normalization
+        self.config = config
+        self._planner_params, self._idm_params = planner_params, idm_params
+        self.precision, self.sampler = precision, sampler
+        self.use_planner = self.use_idm = True
+
+    # ---------------------------------------------------------------- construction
+    @classmethod
+    def create(cls, rng, batch=None, shape_meta=None, *, name: str = "ldp", planner: Optional[dict] = None,
+               idm_net: Optional[dict] = None, preprocess_time: Optional[dict] = None, cond_encoder: Optional[dict] = None,
+               vae_pretrain_path: Optional[str] = None, vae_feature_dim: int = 256, use_planner: bool = True, use_idm: bool = True,
+               lowdim_obs: Sequence[str] = (), rgb_obs: Sequence[str] = (), obs_normalization: Optional[dict] = None,
+               data_name: str = "", obs_horizon: int = 1, pred_horizon: int = 8, action_horizon: int = 4,
+               planner_n_diffusion_steps: int = 100, idm_n_diffusion_steps: int = 100, alpha_planner: float = 1.0,
+               alpha_idm: float = 1.0, lr: float = 1e-4, end_lr: float = 1e-6, idm_lr: float = 1e-4, idm_end_lr: float = 1e-6,
+               warmup_steps: int = 1000, decay_steps: int = 500000, update_planner_every: int = 1, update_idm_every: int = 1,
+               update_idm_after: int = 0, update_planner_until: int = 10 ** 12, update_planner_after: int = 0, grad_clip=None,
+               # additions (not in the reference): weights, VAE topology, compute mode
+               planner_params: Optional[dict] = None, idm_params: Optional[dict] = None, vae_params: Optional[dict] = None,
+               vae_block_out_channels: Sequence[int] = (128, 256, 512, 512), precision: str = "bf16", sampler: str = "ddpm"):
+        """Keyword surface of the reference's `LDPAgent.create` (agent/ldp_agent.py:516-532).  `shape_meta` is the data
+        config's `{'ac_dim': A, 'all_shapes': {key: [...]}}`.  Weights: pass Flax-layout trees (flat 'a/b/kernel' dicts or
+        nested), otherwise they are drawn with the reference's initialisers from `rng` (no checkpoints without network)."""
+        seed = int(rng)
+        shape_meta = shape_meta or {}
+        all_shapes = shape_meta.get("all_shapes", {})
+        action_dim = int(shape_meta["ac_dim"])
+        lowdim_dim = int(sum(int(np.prod(all_shapes[k])) for k in lowdim_obs))
+        obs_dim = lowdim_dim + int(vae_feature_dim) * len(rgb_obs)                    # agent/ldp_agent.py:534-539
+        planner = dict(planner or {})
+        down_dims = tuple(planner.get("down_dims", (256, 512, 1024)))
+        dsed = int(planner.get("diffusion_step_embed_dim", 256))
+        ksize = int(planner.get("kernel_size", 5))
+        n_groups = int(planner.get("n_groups", 8))
+        cond_dim = obs_dim * obs_horizon
+        uspec = P.unet_spec(obs_dim, cond_dim, down_dims, ksize, dsed)
+        if planner_params is None:
+            planner_params = P.init_params(uspec, seed=seed)
+        else:
+            planner_params = P.canonicalize_flax_names(P.unnest(planner_params) if _is_nested(planner_params) else planner_params)
+        idm_net = dict(idm_net or {})
+        hidden = int(idm_net.get("hidden_dim", 256))
+        n_blocks = int(idm_net.get("num_blocks", 3))
+        time_dim = int((preprocess_time or {}).get("output_size", 256))
+        cond_hidden = tuple((cond_encoder or {}).get("hidden_dims", (256, 256)))
+        ispec = P.idm_spec(obs_dim, action_dim, hidden, n_blocks, time_dim, cond_hidden)
+        if idm_params is None:
+            idm_params = P.init_params(ispec, seed=seed + 1)
+        else:
+            idm_params = P.canonicalize_flax_names(P.unnest(idm_params) if _is_nested(idm_params) else idm_params)
+        pl = H.Planner(planner_params, obs_dim, cond_dim, down_dims, dsed, ksize, n_groups, planner_n_diffusion_steps)
+        idm = H.Idm(idm_params, obs_dim, action_dim, hidden, n_blocks, time_dim, cond_hidden, idm_n_diffusion_steps)
+        vae = None
+        if len(rgb_obs) > 0:
+            vspec = P.vae_encoder_spec(vae_block_out_channels)
+            if vae_params is None:
+                vae_params = P.init_params(vspec, seed=seed + 2)
+            else:
+                vae_params = P.unnest(vae_params) if _is_nested(vae_params) else vae_params
+            vae = H.VaeEncoder(vae_params, vae_block_out_channels)
+            lat = vae.latent_hw * vae.latent_hw * vae.latent_channels
+            if lat != int(vae_feature_dim):
+                raise ValueError(f"vae_feature_dim={vae_feature_dim} but the encoder produces {lat} features per frame")
+        config = dict(name=name, obs_horizon=obs_horizon, action_dim=action_dim, pred_horizon=pred_horizon,
+                      action_horizon=action_horizon, obs_dim=obs_dim, rgb_obs=list(rgb_obs), lowdim_obs=list(lowdim_obs),
+                      vae_feature_dim=int(vae_feature_dim), planner_n_diffusion_steps=planner_n_diffusion_steps,
+                      idm_n_diffusion_steps=idm_n_diffusion_steps, data_name=data_name)   # agent/ldp_agent.py:653-665
+        return cls(pl, idm, vae, obs_normalization or {}, config, planner_params, idm_params, precision, sampler)
+
+    # ---------------------------------------------------------------- reference-named pieces
+    def get_params(self):
+        """`{planner_params, idm_params}` as nested Flax-style trees (agent/ldp_agent.py:508-514)."""
+        return dict(planner_params=P.nest(self._planner_params), idm_params=P.nest(self._idm_params))
+
+    def _postprocess_obs(self, obs: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
+        """`postprocess_batch_obs` for the low-dim keys; image keys stay raw (their x/255*2-1 is fused into the encoder)."""
+        norm = self.obs_normalization.get("obs", {})
+        out = {}
+        for k, v in obs.items():
+            v = v.cuda() if not v.is_cuda else v
+            if f"latent_{k}" in self.config["rgb_obs"]:
+                out[k] = v
+            else:
+                if k not in norm:
+                    raise AssertionError(f"obs_normalization keys {sorted(norm)} do not match batch key {k}")
+                out[k] = normalize_unnormalize(v.to(torch.float32), norm[k], True)
+        return out
+
+    def vae_encode(self, obs: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
+        """agent/ldp_agent.py:46-64: every image key whose `latent_<key>` is an rgb_obs is replaced by its normalised
+        latent features (B, H, h*w*c)."""
+        norm = self.obs_normalization.get("obs", {})
+        out = {}
+        for k, v in obs.items():
+            lk = f"latent_{k}"
+            if lk not in self.config["rgb_obs"]:
+                out[k] = v
+                continue
+            B, Hh = v.shape[:2]
+            img = v.reshape(-1, *v.shape[-3:])
+            if img.dtype != torch.uint8:                 # float pixels 0..255 -> [-1, 1] with the key's own constants
+                spec = norm.get(k, {"min": 0, "max": 255})
+                img = normalize_unnormalize(img.to(torch.float32), spec, True)
+            lspec = norm.get(lk)
+            lo, hi = (float(np.min(lspec["min"])), float(np.max(lspec["max"]))) if lspec and "min" in lspec else (0.0, 0.0)
+            z = self.vae.encode(img.contiguous(), lat_min=lo, lat_max=hi, precision=self.precision)
+            out[lk] = z.reshape(B, Hh, -1)
+        return out
+
+    def get_obs_cond(self, obs: Dict[str, torch.Tensor]) -> torch.Tensor:
+        """agent/ldp_agent.py:88-97 - including its quirk of concatenating several cameras along the horizon axis."""
+        low = torch.cat([obs[k] for k in self.config["lowdim_obs"]], dim=-1).to(torch.float32)
+        B, Hh = low.shape[:2]
+        feats = torch.cat([obs[k] for k in self.config["rgb_obs"]], dim=1).reshape(B, Hh, -1) if self.config["rgb_obs"] else \
+            low.new_zeros(B, Hh, 0)
+        return torch.cat([feats, low.reshape(B, Hh, -1)], dim=-1)
+
+    def _unnormalize_actions(self, a: torch.Tensor) -> torch.Tensor:
+        spec = self.obs_normalization.get("actions")
+        return normalize_unnormalize(a, spec, False) if spec else a
+
+    # ---------------------------------------------------------------- sampling
+    def _idm_loop(self, ssp: torch.Tensor, seed: int, row_offset: int) -> torch.Tensor:
+        n, A = ssp.shape[0], self.config["action_dim"]
+        a_T = H.philox_normal_rows(seed, STREAM_IDM_INIT, 0, row_offset, n, A)
+        return self.idm.sample(ssp, a_T, seed=seed, row_offset=row_offset, n_steps=self.config["idm_n_diffusion_steps"],
+                               sampler=self.sampler, precision=self.precision)
+
+    def sample_viz(self, batch: Dict[str, Any], eval_rng, row_offset: int = 0):
+        """agent/ldp_agent.py:435-506: encode -> planner loop -> plan -> IDM loop -> actions.
+        Returns `(action (B, Ha, A), {'plan': (B, Ha+1, D), 'plan_viz': None[, 'plan_mse']})`; `plan_viz` needs the VAE
+        decoder (next scope row N2)."""
+        seed = int(eval_rng)
+        cfg = self.config
+        obs = self.vae_encode(self._postprocess_obs(batch["obs"]))
+        obs_emb = self.get_obs_cond(obs)
+        B, oh, T, D = obs_emb.shape[0], cfg["obs_horizon"], cfg["pred_horizon"], cfg["obs_dim"]
+        obs_cond = obs_emb[:, :oh].reshape(B, -1).contiguous()
+        x_T = H.philox_normal_rows(seed, STREAM_PLANNER_INIT, 0, row_offset * T, B * T, D).reshape(B, T, D)
+        x0 = self.planner.sample(x_T, obs_cond, seed=seed, row_offset=row_offset, n_steps=cfg["planner_n_diffusion_steps"],
+                                 sampler=self.sampler, precision=self.precision)
+        Ha = cfg["action_horizon"]
+        plan = torch.cat([obs_emb[:, oh - 1:oh], x0[:, :Ha]], dim=1)
+        ssp = torch.cat([plan[:, :-1], plan[:, 1:]], dim=-1).reshape(B * Ha, 2 * D).contiguous()
+        action = self._idm_loop(ssp, seed, row_offset * Ha).reshape(B, Ha, cfg["action_dim"])
+        action = self._unnormalize_actions(action)
+        metrics = dict(plan_viz=None, plan=plan)
+        if obs_emb.shape[1] > oh:                                   # training batch: ground-truth future is present
+            metrics["plan_mse"] = ((x0 - obs_emb[:, oh:]) ** 2).mean()
+        return action, metrics
+
+    def sample(self, batch, eval_rng, **kw):
+        return self.sample_viz(batch, eval_rng, **kw)
+
+    act = sample
+
+    def sample_action(self, batch, eval_rng, row_offset: int = 0) -> torch.Tensor:
+        """agent/ldp_agent.py:391-430: IDM only, on consecutive ground-truth observation pairs."""
+        obs = self.vae_encode(self._postprocess_obs(batch["obs"]))
+        plan = self.get_obs_cond(obs)
+        B, Hh, D = plan.shape
+        ssp = torch.cat([plan[:, :-1], plan[:, 1:]], dim=-1).reshape(B * (Hh - 1), 2 * D).contiguous()
+        a = self._idm_loop(ssp, int(eval_rng), row_offset * (Hh - 1)).reshape(B, Hh - 1, self.config["action_dim"])
+        return self._unnormalize_actions(a)
+
+    def sample_action_from_plan(self, batch, next_plan: torch.Tensor, eval_rng, row_offset: int = 0) -> torch.Tensor:
+        """agent/ldp_agent.py:350-389."""
+        obs = self.vae_encode(self._postprocess_obs(batch["obs"]))
+        start = self.get_obs_cond(obs)
+        B, Hh, D = start.shape
+        ssp = torch.cat([start, next_plan.to(start)], dim=-1).reshape(B * Hh, 2 * D).contiguous()
+        a = self._idm_loop(ssp, int(eval_rng), row_offset * Hh).reshape(B, Hh, self.config["action_dim"])
+        return self._unnormalize_actions(a)
+
+    def sample_sharded(self, batch, eval_rng, gather: bool = True):
+        """Data-parallel `sample`: this rank computes its contiguous slice of the plans (no collective on the data path);
+        with `gather` the (B, Ha, A) actions are all-gathered over NCCL so every rank returns the full batch."""
+        import torch.distributed as dist
+        world, rank = (dist.get_world_size(), dist.get_rank()) if dist.is_initialized() else (1, 0)
+        B = next(iter(batch["obs"].values())).shape[0]
+        lo, hi = shard_rows(B, rank, world)
+        part = {"obs": {k: v[lo:hi] for k, v in batch["obs"].items()}}
+        action, metrics = self.sample_viz(part, eval_rng, row_offset=lo)
+        if not gather or world == 1:
+            return action, metrics
+        return gather_rows(action, B, world), metrics
+
+    # ---------------------------------------------------------------- training (next scope row)
+    def update(self, batch, rng, step):
+        raise NotImplementedError("LDPAgent.update (backward + Adam + gradient all-reduce) is scope row N1 (SURVEY.md 8f); "
+                                  "this build covers the sampling path")
+
+    update_mixed = update
+
+
+def gather_rows(local: torch.Tensor, n_total: int, world: int) -> torch.Tensor:
+    """All-gather row shards of unequal size (`shard_rows` partition) into the full (n_total, ...) tensor."""
+    import torch.distributed as dist
+    sizes = [shard_rows(n_total, r, world)[1] - shard_rows(n_total, r, world)[0] for r in range(world)]
+    mx = max(sizes)
+    pad = local.new_zeros((mx,) + tuple(local.shape[1:]))
+    pad[:local.shape[0]] = local
+    outs = [torch.empty_like(pad) for _ in range(world)]
+    dist.all_gather(outs, pad)
+    return torch.cat([o[:s] for o, s in zip(outs, sizes)], dim=0)
+
+
+def _is_nested(tree: dict) -> bool:
+    return any(isinstance(v, dict) for v in tree.values())
