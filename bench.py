@@ -157,7 +157,8 @@ def _oracle_reverse_steps(n_rev: int, reps: int, warm: int, threads: int):
 
 def cpu_baseline_leg() -> dict:
     threads = os.cpu_count() or 1
-    n_rev = 8
+    t1 = _oracle_reverse_steps(1, reps=1, warm=0, threads=threads)[0]          # size the sample: ~15 s of CPU work
+    n_rev = max(4, min(N_DIFF, int(15.0 / max(t1, 1e-3))))
     t = _oracle_reverse_steps(n_rev, reps=1, warm=0, threads=threads)[0]
     plans_per_s = B_PLANS / (t / n_rev * N_DIFF)
     return {"value": plans_per_s, "unit": UNIT, "cores": threads, "kind": "port",
@@ -246,13 +247,16 @@ def run_ours(args) -> None:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()                     # nvidia-smi needs ~1 s to produce its first sample: start it before the warm-up
+    t_w = time.perf_counter()
     for i in range(max(args.warmup, 3)):
         one_step(1000 + i)
     torch.cuda.synchronize()
-
-    sampler = ClockSampler(local) if rank == 0 else None
-    if sampler:
-        sampler.start()
+    while sampler and time.perf_counter() - t_w < 1.5:      # keep the GPU under the same load until samples flow
+        one_step(2000)
+        torch.cuda.synchronize()
     lib.ldp_launch_count_reset()
     ms_total = timed(lambda i: one_step(i), args.steps)
     launches = int(lib.ldp_launch_count())
