@@ -142,15 +142,19 @@ __global__ void __launch_bounds__(256) vae_gn_stats_kernel(const float* __restri
   }
   __syncthreads();
   if (threadIdx.x < G) {
+    // thread t holds quad t % cq (lo is a multiple of cq and 256 % cq == 0): visit only the threads / components of
+    // group g, in a fixed order
     const int g = threadIdx.x;
+    const int q_lo = (g * cpg) >> 2, q_hi = ((g + 1) * cpg + 3) >> 2;
     float a = 0.f, a2 = 0.f;
-    for (int t = 0; t < 256; ++t) {
-      const int q = t % cq;                                    // lo is a multiple of cq and 256 % cq == 0
+    for (int q = q_lo; q < q_hi; ++q) {
+      for (int t = q; t < 256; t += cq) {
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        if ((4 * q + k) / cpg == g) {
-          a += ps[t][k];
-          a2 += ps[t][4 + k];
+        for (int k = 0; k < 4; ++k) {
+          if ((4 * q + k) / cpg == g) {
+            a += ps[t][k];
+            a2 += ps[t][4 + k];
+          }
         }
       }
     }
@@ -208,24 +212,47 @@ __global__ void __launch_bounds__(256) vae_gn_apply_kernel(const float* __restri
 
 // One-head self-attention core over L = h*w tokens (FlaxAttentionBlock): scores = (q C^-1/4)(k C^-1/4)^T, softmax, @ v.
 // qkv: (B, L, 3C) f32 [q | k | v];  out (B, L, C) f32 and/or bf16.  One block per image; L <= 64.
+// Scores: the block walks C in chunks of 32 channels staged in shared memory (coalesced loads), every thread owns
+// a 4x4 patch of the L x L score matrix.  P V: thread = channel, loop over tokens (coalesced over channels).
 __global__ void __launch_bounds__(256) vae_attn_kernel(const float* __restrict__ qkv, float* __restrict__ out_f32,
                                                        __nv_bfloat16* __restrict__ out_bf16, int L, int C) {
   __shared__ float sc[64][65];
+  __shared__ float qs[64][33], ks[64][33];           // 32-channel chunks (static shared memory stays under 48 KB)
   const long long b = blockIdx.x;
   const float* base = qkv + b * L * 3 * C;
   const float scale = rsqrtf(sqrtf((float)C));
   const float s2 = scale * scale;
-  for (int e = threadIdx.x; e < L * L; e += blockDim.x) {
-    const int i = e / L, j = e % L;
-    const float4* qi = reinterpret_cast<const float4*>(base + (long long)i * 3 * C);
-    const float4* kj = reinterpret_cast<const float4*>(base + (long long)j * 3 * C + C);
-    float acc = 0.f;
-    for (int c = 0; c < C / 4; ++c) {
-      const float4 a = qi[c], k4 = kj[c];
-      acc = fmaf(a.x, k4.x, acc); acc = fmaf(a.y, k4.y, acc); acc = fmaf(a.z, k4.z, acc); acc = fmaf(a.w, k4.w, acc);
+  const int ti = (threadIdx.x >> 4) * 4, tj = (threadIdx.x & 15) * 4;     // 16 x 16 threads x (4 x 4) = 64 x 64
+  float acc[4][4] = {};
+  for (int c0 = 0; c0 < C; c0 += 32) {
+    for (int e = threadIdx.x; e < L * 32; e += blockDim.x) {
+      const int i = e >> 5, c = e & 31;
+      const bool ok = c0 + c < C;
+      qs[i][c] = ok ? base[(long long)i * 3 * C + c0 + c] : 0.f;
+      ks[i][c] = ok ? base[(long long)i * 3 * C + C + c0 + c] : 0.f;
     }
-    sc[i][j] = acc * s2;
+    __syncthreads();
+    if (ti < L && tj < L) {
+      for (int c = 0; c < 32; ++c) {
+        float qa[4], kb[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          qa[u] = ti + u < L ? qs[ti + u][c] : 0.f;
+          kb[u] = tj + u < L ? ks[tj + u][c] : 0.f;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+#pragma unroll
+          for (int v = 0; v < 4; ++v) acc[u][v] = fmaf(qa[u], kb[v], acc[u][v]);
+      }
+    }
+    __syncthreads();
   }
+#pragma unroll
+  for (int u = 0; u < 4; ++u)
+#pragma unroll
+    for (int v = 0; v < 4; ++v)
+      if (ti + u < L && tj + v < L) sc[ti + u][tj + v] = acc[u][v] * s2;
   __syncthreads();
   for (int i = threadIdx.x; i < L; i += blockDim.x) {
     float mx = -INFINITY;
@@ -240,12 +267,22 @@ __global__ void __launch_bounds__(256) vae_attn_kernel(const float* __restrict__
     for (int j = 0; j < L; ++j) sc[i][j] *= inv;
   }
   __syncthreads();
-  for (int e = threadIdx.x; e < L * C; e += blockDim.x) {
-    const int i = e / C, c = e % C;
-    float acc = 0.f;
-    for (int j = 0; j < L; ++j) acc = fmaf(sc[i][j], base[(long long)j * 3 * C + 2 * C + c], acc);
-    if (out_f32) out_f32[(b * L + i) * C + c] = acc;
-    if (out_bf16) out_bf16[(b * L + i) * C + c] = __float2bfloat16(acc);
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    for (int i0 = 0; i0 < L; i0 += 8) {
+      float o[8] = {};
+      for (int j = 0; j < L; ++j) {
+        const float vv = base[(long long)j * 3 * C + 2 * C + c];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) o[u] = fmaf(sc[min(i0 + u, L - 1)][j], vv, o[u]);
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        if (i0 + u < L) {
+          if (out_f32) out_f32[(b * L + i0 + u) * C + c] = o[u];
+          if (out_bf16) out_bf16[(b * L + i0 + u) * C + c] = __float2bfloat16(o[u]);
+        }
+      }
+    }
   }
 }
 
@@ -446,7 +483,7 @@ static int vae_gn(LdpVae* h, VaeWs* w, const float* x, int nimg, int P, int C, c
   const int G = h->cfg.norm_num_groups;
   LDP_CHECK(256 % (C / 4) == 0, LDP_ERR_UNSUPPORTED, "VAE GroupNorm needs C/4 to divide 256 (C in {8,...,1024} powers of two)");
   const long long per_img = (long long)P * C / 4;
-  const int slabs = (int)std::min<long long>(std::max<long long>(1, per_img / 2048), 64);
+  const int slabs = (int)std::min<long long>(std::max<long long>(1, per_img / 8192), 64);
   vae_gn_stats_kernel<<<dim3(nimg, slabs), 256, 0, s>>>(x, w->part, P, C, G);
   VAE_LAUNCH_OK("vae_gn_stats");
   vae_gn_final_kernel<<<(nimg * G + 127) / 128, 128, 0, s>>>(w->part, w->stats, nimg * G, G, slabs, 1.f / ((float)P * (C / G)), 1e-6f);
