@@ -133,7 +133,8 @@ enum { TC_EPI_PLAIN = 0, TC_EPI_GN = 1, TC_EPI_DDPM = 2, TC_EPI_LN = 3 };
 
 struct TcGemm {
   CUtensorMap map_a[4];
-  CUtensorMap map_b;
+  CUtensorMap map_b;                // W^T tiles: box {64, BN}; in pair mode {64, BN/2} (see `pair`)
+  int pair = 0;                     // 1: map_b was built with the half-width box -> eligible for the cta_group::2 kernel
   const TcStage* kb = nullptr;      // device table of pipeline stages
   int num_kb = 0;                   // number of stages
   int w_max = 1;                    // largest nw of any stage (sizes the shared-memory ring)
@@ -145,6 +146,7 @@ struct TcGemm {
   int shift[5] = {0, 0, 0, 0, 0};
   int num_stages = 0, tmem_cols = 0; // filled by launch_tc_gemm
   int epi_skip = 0;                 // diagnostics (LDP_EPI_SKIP): 1 stores, 2 FiLM loads, 4 residual, 8 activation, 16 tap shuffles
+  long long* dbg_stage = nullptr;   // diagnostics: CTA (0,0)'s first 24 stage-arrival times
   long long* dbg = nullptr;         // diagnostics: per-CTA phase timestamps [ctas][8] (clock64 deltas)
   int k_pad = 0;                    // host-side bookkeeping: padded K of the packed weights
   int M = 0, N = 0;                 // logical output size

@@ -460,6 +460,7 @@ struct ConvDesc {
   const float* wgt = nullptr; int cout = 0;
   const ActBf16* aux_srcs = nullptr; int aux_nsrc = 0; const float* aux_w = nullptr;   // 1x1 on the block input
   int group_width = 1 << 30;      // GroupNorm group width the N tile must contain (1<<30: no constraint)
+  bool no_pair = false;
 };
 
 static bool env_off(const char* name) {
@@ -633,8 +634,14 @@ static int conv_tc(LdpPlanner* h, PlanWs* w, int op_id, const ConvDesc& d, TcGem
   for (int i = d.nsrc + d.aux_nsrc; i < 4; ++i) op->map_a[i] = op->map_a[0];
   uint64_t bd[2] = {(uint64_t)pw->kp, (uint64_t)pw->n_pad};
   uint64_t bs[1] = {(uint64_t)pw->kp * 2};
-  uint32_t bb[2] = {64, (uint32_t)bn};
+  // CTA pairs (cta_group::2): each CTA of a pair fetches half of every W tile.  Measured: the tap-accumulator layout
+  // (W is the larger share of a stage) gains ~4k cycles of main loop per layer; the per-tap layout gains nothing and
+  // pays ~0.9 us of cluster launch + cluster barriers, so it stays single-CTA (LDP_PAIR=2 forces pairs everywhere).
+  const char* pe = getenv("LDP_PAIR");
+  const bool pair = !d.no_pair && !(pe && pe[0] == '0') && (tapacc || (pe && pe[0] == '2'));
+  uint32_t bb[2] = {64, (uint32_t)(pair ? bn / 2 : bn)};
   LDP_TRY(make_tmap_bf16(&op->map_b, pw->wt, 2, bd, bs, bb));
+  op->pair = pair ? 1 : 0;
   op->kb = pw->kb_dev;
   op->num_kb = pw->num_kb;
   op->w_max = pw->w_max;
@@ -779,6 +786,7 @@ static int prepare_bf16(LdpPlanner* h, PlanWs* w) {
   w->ops.push_back(op);
   cd = ConvDesc();
   cd.kind = CONV_K; cd.taps_k = 1; cd.srcs = &f; cd.nsrc = 1; cd.t_in = T; cd.wgt = h->ow; cd.cout = c.input_dim;
+  cd.no_pair = true;                                   // the DDPM epilogue kernel is single-CTA
   LDP_TRY(conv_tc(h, w, 3001, cd, &op));
   op.mode = TC_EPI_DDPM;
   op.bias = h->ob;
@@ -962,12 +970,13 @@ int ldp_planner_profile_step(LdpPlanner* h, int B, int T, int reps, float* us_ho
     LDP_CUDA_OK(cudaEventElapsedTime(&ms, e0, e1));
     us_host[i] = ms * 1000.f / reps;
     if (phases_host) {          // one more launch with the in-kernel phase clocks; mean over CTAs
-      const int ctas = ceil_div(op.M, 128) * ceil_div(op.N, op.block_n);
-      std::vector<long long> hb((size_t)ctas * 8);
+      const int ctas = (op.pair ? round_up(ceil_div(op.M, 128), 2) : ceil_div(op.M, 128)) * ceil_div(op.N, op.block_n);
+      std::vector<long long> hb((size_t)ctas * 8 + 64);
       long long* db;
       Arena tmp;
-      LDP_TRY(tmp.alloc_t(&db, hb.size()));
+      LDP_TRY(tmp.alloc_t(&db, hb.size() + 64));
       op.dbg = db;
+      op.dbg_stage = db + (size_t)ctas * 8;
       LDP_TRY(launch_tc_gemm(op, s));
       LDP_CUDA_OK(cudaStreamSynchronize(s));
       LDP_CUDA_OK(cudaMemcpy(hb.data(), db, hb.size() * 8, cudaMemcpyDeviceToHost));
@@ -977,6 +986,13 @@ int ldp_planner_profile_step(LdpPlanner* h, int B, int T, int reps, float* us_ho
         phases_host[8 * i + k] = (float)(acc / ctas);
       }
       phases_host[8 * i + 0] = (float)ctas;
+      if (getenv("LDP_DBG_STAGES")) {
+        fprintf(stderr, "op %zu stage arrivals (CTA 0):", i);
+        for (int k = 0; k < 23; ++k) fprintf(stderr, " %lld", hb[(size_t)ctas * 8 + k]);
+        fprintf(stderr, " | epilogue deltas:");
+        for (int k = 24; k < 29; ++k) fprintf(stderr, " %lld", hb[(size_t)ctas * 8 + k] - hb[(size_t)ctas * 8 + 23]);
+        fprintf(stderr, "\n");
+      }
     }
     meta_host[4 * i + 0] = op.M;
     meta_host[4 * i + 1] = op.N;

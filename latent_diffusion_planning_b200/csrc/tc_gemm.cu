@@ -93,12 +93,12 @@ __device__ __forceinline__ float rcp_approx(float x) {
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
-// Mish(y) = y tanh(softplus(y)) = y n/(n+2), n = e^y (e^y + 2); the exponent is clamped so that n stays finite
-// (the ratio is 1 to fp32 there).  Two MUFU ops per element.
+// Mish(y) = y tanh(softplus(y)) = y n/(n+2) = y - 2y/(n+2), n = e^y (e^y + 2).  Written as y - 2 y r with
+// r = 1/(e (e+2) + 2): when e^y overflows, r = 0 and the result is y (no clamp needed); 7 instructions, 2 of them MUFU.
 __device__ __forceinline__ float mish_fast(float y) {
-  const float e = ex2_approx(fminf(y, 20.f) * 1.4426950408889634f);
-  const float n = e * (e + 2.f);
-  return y * (n * rcp_approx(n + 2.f));
+  const float e = ex2_approx(y * 1.4426950408889634f);
+  const float r = rcp_approx(fmaf(e, e + 2.f, 2.f));
+  return fmaf(-2.f * r, y, y);
 }
 // swish(y) = y / (1 + e^-y)
 __device__ __forceinline__ float swish_fast(float y) {
@@ -346,7 +346,10 @@ __device__ __forceinline__ void epilogue_gn(const TcGemm& p, EpiSmem<BN>& es, ui
     }
     es.part[row][c] = make_float2(s, ss);
   }
+  const bool dbg_t = p.dbg_stage && threadIdx.x == 64 && blockIdx.x == 0 && blockIdx.y == 0;
+  if (dbg_t) p.dbg_stage[24] = clock64();          // accumulators read, partial statistics written
   epi_bar<BN>();
+  if (dbg_t) p.dbg_stage[25] = clock64();          // statistics barrier passed
   // group statistics: chunks of the group (from smem) x the T rows of the sample (adjacent lanes)
   float mean[CPP], rstd[CPP];
   const float inv_cnt = 1.f / (float)(T * p.group_width);
@@ -394,6 +397,7 @@ __device__ __forceinline__ void epilogue_gn(const TcGemm& p, EpiSmem<BN>& es, ui
 #pragma unroll
       for (int i = 0; i < 32; ++i) w[i] = mish_fast(w[i]);
     }
+    if (dbg_t) p.dbg_stage[26] = clock64();        // normalised + activation
     if (p.film) {
 #pragma unroll
       for (int i = 0; i < 32; ++i) {
@@ -420,10 +424,12 @@ __device__ __forceinline__ void epilogue_gn(const TcGemm& p, EpiSmem<BN>& es, ui
         }
       }
     }
+    if (dbg_t) p.dbg_stage[27] = clock64();        // FiLM + residual applied
     if (row_ok && !((p.epi_skip & 1) && w[0] != 12345.678f)) {
       if (p.out_bf16) store_bf16x32(p.out_bf16 + (long long)m * p.ld_out_bf16 + nb, w, true, 32);
       if (p.out_f32) store_f32x32(p.out_f32 + (long long)m * p.ld_out_f32 + nb, w, true, 32);
     }
+    if (dbg_t) p.dbg_stage[28] = clock64();        // stores issued
   }
 }
 
@@ -569,10 +575,15 @@ __device__ __forceinline__ void epilogue_ln(const TcGemm& p, EpiSmem<BN>& es, ui
 }
 
 // ---- the kernel --------------------------------------------------------------------------------
-template <int BN, int MODE>
+template <int BN, int MODE, bool PAIR>
 __global__ void __launch_bounds__(TcGeo<BN>::THREADS, 1) tc_gemm_kernel(const __grid_constant__ TcGemm p) {
   extern __shared__ uint8_t smem_raw[];
-  constexpr int B_BYTES = TcSmem<BN>::B_BYTES;
+  // PAIR: two CTAs of a cluster (adjacent M tiles, same N tile) run one cta_group::2 MMA (M = 256): each CTA loads its
+  // own A tile but only its half of every W tile - the peer's half is read over the SM-to-SM path, not through this
+  // SM's L2 ingest port, which is what bounds the single-CTA kernel.
+  constexpr int B_BYTES = PAIR ? TcSmem<BN>::B_BYTES / 2 : TcSmem<BN>::B_BYTES;
+  const uint32_t cta_rank = PAIR ? cluster_ctarank() : 0u;
+  const bool leader = cta_rank == 0;
   const int STAGES = p.num_stages;
   const uint32_t stage_bytes = TC_A_BYTES + (uint32_t)p.w_max * B_BYTES;
   __shared__ __align__(8) uint64_t bar_full[TC_MAX_STAGES];
@@ -582,7 +593,12 @@ __global__ void __launch_bounds__(TcGeo<BN>::THREADS, 1) tc_gemm_kernel(const __
   __shared__ __align__(16) TcStage kb_s[TC_MAX_KB_SMEM];      // stage table staged once per CTA
   __shared__ __align__(16) EpiSmem<BN> es;
   __shared__ long long ts[8];                                 // phase timestamps (diagnostics, only when p.dbg != nullptr)
-  if (p.dbg && threadIdx.x == 0) ts[0] = clock64();
+  __shared__ long long tk[24];                                // arrival time of the first 24 stages at the MMA issuer
+  if (p.dbg && threadIdx.x == 0) {
+    for (int i = 0; i < 8; ++i) ts[i] = 0;
+    for (int i = 0; i < 24; ++i) tk[i] = 0;
+    ts[0] = clock64();
+  }
 
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const int warp = threadIdx.x >> 5;
@@ -594,7 +610,7 @@ __global__ void __launch_bounds__(TcGeo<BN>::THREADS, 1) tc_gemm_kernel(const __
   // ---- prologue: touches only constants, shared memory and TMEM -> may overlap the previous kernel (PDL) ----
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) {
-      mbar_init(smem_u32(&bar_full[s]), 1);
+      mbar_init(smem_u32(&bar_full[s]), 1);                 // PAIR: the leader's arrive.expect_tx covers the bytes of both CTAs
       mbar_init(smem_u32(&bar_empty[s]), 1);
     }
     mbar_init(smem_u32(&bar_accum), 1);
@@ -603,15 +619,25 @@ __global__ void __launch_bounds__(TcGeo<BN>::THREADS, 1) tc_gemm_kernel(const __
     tma_prefetch_desc(&p.map_a[0]);
   }
   if (warp == 1) {
-    tmem_alloc(smem_u32(&tmem_holder), ncols);
-    tmem_relinquish();
+    if (PAIR) {
+      tmem_alloc_2sm(smem_u32(&tmem_holder), ncols);
+      tmem_relinquish_2sm();
+    } else {
+      tmem_alloc(smem_u32(&tmem_holder), ncols);
+      tmem_relinquish();
+    }
   }
   const bool kb_in_smem = p.num_kb <= TC_MAX_KB_SMEM;
   if (kb_in_smem)
     for (int i = threadIdx.x; i < p.num_kb; i += TcGeo<BN>::THREADS) kb_s[i] = p.kb[i];
   const TcStage* kbt = kb_in_smem ? kb_s : p.kb;
   tc_fence_before();
-  __syncthreads();
+  if (PAIR) {
+    __syncwarp();
+    cluster_sync_all();
+  } else {
+    __syncthreads();
+  }
   tc_fence_after();
   const uint32_t tmem_base = tmem_holder;
   griddep_launch();
@@ -632,16 +658,24 @@ __global__ void __launch_bounds__(TcGeo<BN>::THREADS, 1) tc_gemm_kernel(const __
         mbar_wait(smem_u32(&bar_empty[stage]), phase ^ 1u);
         const uint32_t bar = smem_u32(&bar_full[stage]);
         const uint32_t sa = smem_base + stage * stage_bytes;
-        mbar_arrive_expect_tx(bar, TC_A_BYTES + (uint32_t)nw * B_BYTES);
-        tma_load_4d(sa, &p.map_a[e.src_acc & 0xff], bar, e.c0, d1, c2_base + d2, c3);
-        for (int j = 0; j < nw; ++j) tma_load_2d(sa + TC_A_BYTES + j * B_BYTES, &p.map_b, bar, (e.wk + j) * TC_BK, n0);
+        if (PAIR) {
+          const uint32_t bar_leader = mapa_shared(bar, 0);
+          if (leader) mbar_arrive_expect_tx(bar, 2u * (TC_A_BYTES + (uint32_t)nw * B_BYTES));
+          tma_load_4d_2sm(sa, &p.map_a[e.src_acc & 0xff], bar_leader, e.c0, d1, c2_base + d2, c3);
+          for (int j = 0; j < nw; ++j)
+            tma_load_2d_2sm(sa + TC_A_BYTES + j * B_BYTES, &p.map_b, bar_leader, (e.wk + j) * TC_BK, n0 + (int)cta_rank * (BN / 2));
+        } else {
+          mbar_arrive_expect_tx(bar, TC_A_BYTES + (uint32_t)nw * B_BYTES);
+          tma_load_4d(sa, &p.map_a[e.src_acc & 0xff], bar, e.c0, d1, c2_base + d2, c3);
+          for (int j = 0; j < nw; ++j) tma_load_2d(sa + TC_A_BYTES + j * B_BYTES, &p.map_b, bar, (e.wk + j) * TC_BK, n0);
+        }
         if (++stage == (uint32_t)STAGES) { stage = 0; phase ^= 1u; }
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    if (elect_one()) {
-      constexpr uint32_t idesc = umma_idesc_bf16(TC_BM, BN);
+    // ===================== MMA issuer (PAIR: the leader CTA issues for both) =====================
+    if (leader && elect_one()) {
+      constexpr uint32_t idesc = umma_idesc_bf16(PAIR ? 2 * TC_BM : TC_BM, BN);
       uint32_t stage = 0, phase = 0;
       uint32_t started = 0;    // bit a set once accumulator a has received its first MMA
       for (int kb = 0; kb < p.num_kb; ++kb) {
@@ -650,6 +684,7 @@ __global__ void __launch_bounds__(TcGeo<BN>::THREADS, 1) tc_gemm_kernel(const __
         mbar_wait(smem_u32(&bar_full[stage]), phase);
         tc_fence_after();
         if (p.dbg && kb == 0) ts[3] = clock64();        // first operands landed
+        if (p.dbg && kb < 24) tk[kb] = clock64();
         const uint32_t sa = smem_base + stage * stage_bytes;
         const uint64_t da = umma_desc_sw128(sa);
         for (uint32_t j = 0; j < nw; ++j) {             // the A tile is shared by the nw taps' accumulators
@@ -659,14 +694,17 @@ __global__ void __launch_bounds__(TcGeo<BN>::THREADS, 1) tc_gemm_kernel(const __
 #pragma unroll
           for (int k = 0; k < TC_BK / 16; ++k) {
             // advance 16 bf16 = 32 bytes along K inside the 128B swizzle row: +2 in the (addr >> 4) field
-            umma_bf16_ss(d_tmem, da + 2 * k, db + 2 * k, idesc, ((started >> acc) & 1u) | (k > 0 ? 1u : 0u));
+            if (PAIR) umma_bf16_ss_2sm(d_tmem, da + 2 * k, db + 2 * k, idesc, ((started >> acc) & 1u) | (k > 0 ? 1u : 0u));
+            else umma_bf16_ss(d_tmem, da + 2 * k, db + 2 * k, idesc, ((started >> acc) & 1u) | (k > 0 ? 1u : 0u));
           }
           started |= 1u << acc;
         }
-        umma_commit(smem_u32(&bar_empty[stage]));       // frees the smem stage when these MMAs retire
+        if (PAIR) umma_commit_2sm(smem_u32(&bar_empty[stage]), 3);   // frees the stage in both CTAs
+        else umma_commit(smem_u32(&bar_empty[stage]));               // frees the smem stage when these MMAs retire
         if (++stage == (uint32_t)STAGES) { stage = 0; phase ^= 1u; }
       }
-      umma_commit(smem_u32(&bar_accum));                // accumulator(s) complete
+      if (PAIR) umma_commit_2sm(smem_u32(&bar_accum), 3);
+      else umma_commit(smem_u32(&bar_accum));           // accumulator(s) complete
       if (p.dbg) ts[4] = clock64();                     // all MMAs issued
     }
   } else {
@@ -702,6 +740,7 @@ __global__ void __launch_bounds__(TcGeo<BN>::THREADS, 1) tc_gemm_kernel(const __
     mbar_wait(smem_u32(&bar_accum), 0);
     tc_fence_after();
     if (p.dbg && threadIdx.x == 64) ts[5] = clock64();   // accumulators complete
+    if (p.dbg_stage && threadIdx.x == 64 && blockIdx.x == 0 && blockIdx.y == 0) p.dbg_stage[23] = clock64();
     const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16);
     if constexpr (MODE == TC_EPI_PLAIN) epilogue_plain<BN>(p, es, taddr, m, n0, c_begin, lane);
     else if constexpr (MODE == TC_EPI_GN) epilogue_gn<BN>(p, es, taddr, m, n0, c_begin, row, lane, pf);
@@ -713,13 +752,21 @@ __global__ void __launch_bounds__(TcGeo<BN>::THREADS, 1) tc_gemm_kernel(const __
 
   if (p.dbg && threadIdx.x == 64) ts[6] = clock64();     // this warp's epilogue done
   tc_fence_before();
-  __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem_base, ncols);
+  if (PAIR) {
+    __syncwarp();
+    cluster_sync_all();       // the peer's MMAs read this CTA's shared memory and arrive on its barriers until here
+    if (warp == 1) tmem_dealloc_2sm(tmem_base, ncols);
+  } else {
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, ncols);
+  }
   if (p.dbg && threadIdx.x == 0) {
     long long* d = p.dbg + (long long)(blockIdx.y * gridDim.x + blockIdx.x) * 8;
     const long long t0 = ts[0];
-    for (int i = 1; i < 7; ++i) d[i] = ts[i] - t0;
+    for (int i = 1; i < 7; ++i) d[i] = ts[i] ? ts[i] - t0 : 0;
     d[7] = clock64() - t0;
+    if (p.dbg_stage && blockIdx.x == 0 && blockIdx.y == 0)
+      for (int i = 0; i < 24; ++i) p.dbg_stage[i] = tk[i] ? tk[i] - t0 : 0;
     d[0] = (long long)(__cvta_generic_to_shared(&ts[0]) & 0) + (long long)blockIdx.x;   // tile id
   }
 }
@@ -784,7 +831,11 @@ int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t*
 
 template <int BN, int MODE>
 static int set_smem_attr() {
-  LDP_CUDA_OK(cudaFuncSetAttribute(tc_gemm_kernel<BN, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_RING + 1024));
+  LDP_CUDA_OK(cudaFuncSetAttribute(tc_gemm_kernel<BN, MODE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_RING + 1024));
+  constexpr bool kPairable = (MODE == TC_EPI_PLAIN || MODE == TC_EPI_GN) && BN <= 128;
+  if (kPairable)
+    LDP_CUDA_OK(cudaFuncSetAttribute(tc_gemm_kernel<BN, MODE, kPairable>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     TC_SMEM_RING + 1024));
   return LDP_OK;
 }
 
@@ -806,7 +857,7 @@ int tc_gemm_init() {
   return LDP_OK;
 }
 
-template <int BN, int MODE>
+template <int BN, int MODE, bool PAIR>
 static int launch_tc_gemm_inst(const TcGemm& p_in, cudaStream_t s) {
   LDP_TRY(tc_gemm_init());
   TcGemm p = p_in;
@@ -822,25 +873,37 @@ static int launch_tc_gemm_inst(const TcGemm& p_in, cudaStream_t s) {
     if (skip < 0) { const char* e = getenv("LDP_EPI_SKIP"); skip = e ? atoi(e) : 0; }
     p.epi_skip = skip;
   }
-  p.num_stages = tc_num_stages(BN, p.w_max);
+  const int stage_bytes = PAIR ? TC_A_BYTES + p.w_max * (BN / 2) * TC_BK * 2 : tc_stage_bytes(BN, p.w_max);
+  p.num_stages = std::min(TC_MAX_STAGES, TC_SMEM_RING / stage_bytes);
   LDP_CHECK(p.num_stages >= 2, LDP_ERR_UNSUPPORTED, "tc_gemm: stage does not fit the shared-memory ring twice");
   if (MODE == TC_EPI_DDPM)
-    LDP_CHECK(p.num_stages * tc_stage_bytes(BN, p.w_max) >= TC_BM * (BN + 1) * 4, LDP_ERR_UNSUPPORTED,
+    LDP_CHECK(p.num_stages * stage_bytes >= TC_BM * (BN + 1) * 4, LDP_ERR_UNSUPPORTED,
               "tc_gemm DDPM epilogue: transposition tile does not fit the ring");
   if (p.n_acc > 1 || p.shift[0] != 0)
     LDP_CHECK(p.rows_per_item >= 1 && p.rows_per_item <= 32 && (p.rows_per_item & (p.rows_per_item - 1)) == 0,
               LDP_ERR_UNSUPPORTED, "tc_gemm: shifted accumulators need power-of-two rows per sample <= 32");
   cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(ceil_div(p.M, TC_BM), ceil_div(p.N, BN), 1);
+  cfg.gridDim = dim3(PAIR ? round_up(ceil_div(p.M, TC_BM), 2) : ceil_div(p.M, TC_BM), ceil_div(p.N, BN), 1);
   cfg.blockDim = dim3(TcGeo<BN>::THREADS, 1, 1);
-  cfg.dynamicSmemBytes = p.num_stages * tc_stage_bytes(BN, p.w_max) + 1024;
+  cfg.dynamicSmemBytes = p.num_stages * stage_bytes + 1024;
   cfg.stream = s;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cudaLaunchAttribute attr[2];
+  int na = 0;
+  if (g_use_pdl) {
+    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
+  if (PAIR) {
+    attr[na].id = cudaLaunchAttributeClusterDimension;
+    attr[na].val.clusterDim.x = 2;
+    attr[na].val.clusterDim.y = 1;
+    attr[na].val.clusterDim.z = 1;
+    ++na;
+  }
   cfg.attrs = attr;
-  cfg.numAttrs = g_use_pdl ? 1 : 0;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, tc_gemm_kernel<BN, MODE>, p);
+  cfg.numAttrs = na;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, tc_gemm_kernel<BN, MODE, PAIR>, p);
   if (e != cudaSuccess) {
     set_last_error(std::string("tc_gemm launch failed: ") + cudaGetErrorString(e));
     return LDP_ERR_CUDA;
@@ -862,15 +925,27 @@ int launch_tc_gemm(const TcGemm& p, cudaStream_t s) {
   }
   if (p.mode == TC_EPI_LN) LDP_CHECK(p.N == p.block_n && p.out_f32 && p.bias, LDP_ERR_UNSUPPORTED, "tc_gemm LN epilogue: N must equal block_n");
   if (p.mode == TC_EPI_DDPM) LDP_CHECK(p.x_io && p.coef, LDP_ERR_INVALID_ARG, "tc_gemm DDPM epilogue: x / coefficient table required");
+  const bool pair = p.pair != 0;
+  if (pair) LDP_CHECK((p.mode == TC_EPI_PLAIN || p.mode == TC_EPI_GN) && p.block_n <= 128, LDP_ERR_UNSUPPORTED,
+                      "tc_gemm: pair mode exists for the PLAIN / GN epilogues at BN <= 128");
   const int key = p.block_n * 8 + p.mode;
+  if (pair) {
+    switch (key) {
+      case 64 * 8 + TC_EPI_PLAIN:  return launch_tc_gemm_inst<64, TC_EPI_PLAIN, true>(p, s);
+      case 64 * 8 + TC_EPI_GN:     return launch_tc_gemm_inst<64, TC_EPI_GN, true>(p, s);
+      case 128 * 8 + TC_EPI_PLAIN: return launch_tc_gemm_inst<128, TC_EPI_PLAIN, true>(p, s);
+      case 128 * 8 + TC_EPI_GN:    return launch_tc_gemm_inst<128, TC_EPI_GN, true>(p, s);
+      default: break;
+    }
+  }
   switch (key) {
-    case 64 * 8 + TC_EPI_PLAIN:  return launch_tc_gemm_inst<64, TC_EPI_PLAIN>(p, s);
-    case 64 * 8 + TC_EPI_GN:     return launch_tc_gemm_inst<64, TC_EPI_GN>(p, s);
-    case 128 * 8 + TC_EPI_PLAIN: return launch_tc_gemm_inst<128, TC_EPI_PLAIN>(p, s);
-    case 128 * 8 + TC_EPI_GN:    return launch_tc_gemm_inst<128, TC_EPI_GN>(p, s);
-    case 128 * 8 + TC_EPI_DDPM:  return launch_tc_gemm_inst<128, TC_EPI_DDPM>(p, s);
-    case 256 * 8 + TC_EPI_PLAIN: return launch_tc_gemm_inst<256, TC_EPI_PLAIN>(p, s);
-    case 256 * 8 + TC_EPI_LN:    return launch_tc_gemm_inst<256, TC_EPI_LN>(p, s);
+    case 64 * 8 + TC_EPI_PLAIN:  return launch_tc_gemm_inst<64, TC_EPI_PLAIN, false>(p, s);
+    case 64 * 8 + TC_EPI_GN:     return launch_tc_gemm_inst<64, TC_EPI_GN, false>(p, s);
+    case 128 * 8 + TC_EPI_PLAIN: return launch_tc_gemm_inst<128, TC_EPI_PLAIN, false>(p, s);
+    case 128 * 8 + TC_EPI_GN:    return launch_tc_gemm_inst<128, TC_EPI_GN, false>(p, s);
+    case 128 * 8 + TC_EPI_DDPM:  return launch_tc_gemm_inst<128, TC_EPI_DDPM, false>(p, s);
+    case 256 * 8 + TC_EPI_PLAIN: return launch_tc_gemm_inst<256, TC_EPI_PLAIN, false>(p, s);
+    case 256 * 8 + TC_EPI_LN:    return launch_tc_gemm_inst<256, TC_EPI_LN, false>(p, s);
     default: break;
   }
   set_last_error("tc_gemm: no kernel instantiated for block_n " + std::to_string(p.block_n) + " with epilogue " +
