@@ -144,7 +144,8 @@ struct TcGemm {
   // (use_aux) sits behind them at index n_acc.
   int n_acc = 1;
   int shift[5] = {0, 0, 0, 0, 0};
-  int num_stages = 0, tmem_cols = 0; // filled by launch_tc_gemm
+  int num_stages = 0, tmem_cols = 0; // filled by launch_tc_gemm (tc_gemm_geometry)
+  int tiles_m = 0, tiles_n = 0, grid_ctas = 0, acc_bufs = 1, acc_stride = 0, persistent = 0;
   int epi_skip = 0;                 // diagnostics (LDP_EPI_SKIP): 1 stores, 2 FiLM loads, 4 residual, 8 activation, 16 tap shuffles
   long long* dbg_stage = nullptr;   // diagnostics: CTA (0,0)'s first 24 stage-arrival times
   long long* dbg = nullptr;         // diagnostics: per-CTA phase timestamps [ctas][8] (clock64 deltas)
@@ -179,6 +180,7 @@ struct TcGemm {
   float* x_io = nullptr; int ld_x = 0;
 };
 int launch_tc_gemm(const TcGemm& p, cudaStream_t s);
+int tc_gemm_geometry(TcGemm* p);   // fills tiles_m/n, grid_ctas, acc_bufs, acc_stride, tmem_cols
 
 // cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time libcuda dependency).
 // bf16 tensor, up to 4-D, dims/strides innermost-first (strides in BYTES for dims 1..rank-1), SWIZZLE_128B.

@@ -970,7 +970,8 @@ int ldp_planner_profile_step(LdpPlanner* h, int B, int T, int reps, float* us_ho
     LDP_CUDA_OK(cudaEventElapsedTime(&ms, e0, e1));
     us_host[i] = ms * 1000.f / reps;
     if (phases_host) {          // one more launch with the in-kernel phase clocks; mean over CTAs
-      const int ctas = (op.pair ? round_up(ceil_div(op.M, 128), 2) : ceil_div(op.M, 128)) * ceil_div(op.N, op.block_n);
+      LDP_TRY(tc_gemm_geometry(&op));
+      const int ctas = op.grid_ctas;
       std::vector<long long> hb((size_t)ctas * 8 + 64);
       long long* db;
       Arena tmp;

@@ -575,7 +575,7 @@ __device__ __forceinline__ void epilogue_ln(const TcGemm& p, EpiSmem<BN>& es, ui
 }
 
 // ---- the kernel --------------------------------------------------------------------------------
-template <int BN, int MODE, bool PAIR>
+template <int BN, int MODE, bool PAIR, bool PERSIST>
 __global__ void __launch_bounds__(TcGeo<BN>::THREADS, 1) tc_gemm_kernel(const __grid_constant__ TcGemm p) {
   extern __shared__ uint8_t smem_raw[];
   // PAIR: two CTAs of a cluster (adjacent M tiles, same N tile) run one cta_group::2 MMA (M = 256): each CTA loads its
@@ -588,7 +588,8 @@ __global__ void __launch_bounds__(TcGeo<BN>::THREADS, 1) tc_gemm_kernel(const __
   const uint32_t stage_bytes = TC_A_BYTES + (uint32_t)p.w_max * B_BYTES;
   __shared__ __align__(8) uint64_t bar_full[TC_MAX_STAGES];
   __shared__ __align__(8) uint64_t bar_empty[TC_MAX_STAGES];
-  __shared__ __align__(8) uint64_t bar_accum;
+  __shared__ __align__(8) uint64_t bar_tfull[2];              // accumulator buffer b complete (MMA -> epilogue)
+  __shared__ __align__(8) uint64_t bar_tempty[2];             // accumulator buffer b drained (epilogue -> MMA)
   __shared__ uint32_t tmem_holder;
   __shared__ __align__(16) TcStage kb_s[TC_MAX_KB_SMEM];      // stage table staged once per CTA
   __shared__ __align__(16) EpiSmem<BN> es;
@@ -603,9 +604,12 @@ __global__ void __launch_bounds__(TcGeo<BN>::THREADS, 1) tc_gemm_kernel(const __
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int tile_m = blockIdx.x, tile_n = blockIdx.y;
-  const int n0 = tile_n * BN;
-  const uint32_t ncols = (uint32_t)p.tmem_cols;        // power of two in [32, 512] covering (n_acc + aux) * BN columns
+  // Tiles.  !PERSIST: one tile per CTA, (tile_m, tile_n) = (blockIdx.x, blockIdx.y) - the planner's layers.
+  // PERSIST (launches with more tiles than SMs, i.e. the VAE convolutions): 1-D grid of one CTA per SM, CTA c walks
+  // tiles c, c + gridDim.x, ... (tile t -> (t % tiles_m, t / tiles_m)); with two accumulator buffers in TMEM the
+  // epilogue of one tile overlaps the main loop of the next, and the smem ring simply keeps running across tiles.
+  const int num_tiles = p.tiles_m * p.tiles_n;
+  const uint32_t ncols = (uint32_t)p.tmem_cols;        // power of two in [32, 512] covering acc_bufs * (n_acc + aux) * BN columns
 
   // ---- prologue: touches only constants, shared memory and TMEM -> may overlap the previous kernel (PDL) ----
   if (threadIdx.x == 0) {
@@ -613,7 +617,10 @@ __global__ void __launch_bounds__(TcGeo<BN>::THREADS, 1) tc_gemm_kernel(const __
       mbar_init(smem_u32(&bar_full[s]), 1);                 // PAIR: the leader's arrive.expect_tx covers the bytes of both CTAs
       mbar_init(smem_u32(&bar_empty[s]), 1);
     }
-    mbar_init(smem_u32(&bar_accum), 1);
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(smem_u32(&bar_tfull[b]), 1);
+      mbar_init(smem_u32(&bar_tempty[b]), TcGeo<BN>::EPI_THREADS);
+    }
     fence_mbar_init();
     tma_prefetch_desc(&p.map_b);
     tma_prefetch_desc(&p.map_a[0]);
@@ -646,11 +653,14 @@ __global__ void __launch_bounds__(TcGeo<BN>::THREADS, 1) tc_gemm_kernel(const __
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (elect_one()) {
-      const int q = tile_m / p.tiles_per_item, r = tile_m - q * p.tiles_per_item;
-      const int c2_base = r * p.rows_step, c3 = q * p.items_per_tile;
       uint32_t stage = 0, phase = 0;
       griddep_wait();                                   // activations of the previous layer are complete from here on
       if (p.dbg) ts[2] = clock64();                     // dependency resolved
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int tile_m = PERSIST ? tile % p.tiles_m : (int)blockIdx.x;
+      const int n0 = (PERSIST ? tile / p.tiles_m : (int)blockIdx.y) * BN;
+      const int q = tile_m / p.tiles_per_item, r = tile_m - q * p.tiles_per_item;
+      const int c2_base = r * p.rows_step, c3 = q * p.items_per_tile;
       for (int kb = 0; kb < p.num_kb; ++kb) {
         const TcStage e = kbt[kb];
         const int nw = (e.src_acc >> 16) & 0xff;
@@ -671,12 +681,23 @@ __global__ void __launch_bounds__(TcGeo<BN>::THREADS, 1) tc_gemm_kernel(const __
         }
         if (++stage == (uint32_t)STAGES) { stage = 0; phase ^= 1u; }
       }
+      if (!PERSIST) break;
+      }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer (PAIR: the leader CTA issues for both) =====================
     if (leader && elect_one()) {
       constexpr uint32_t idesc = umma_idesc_bf16(PAIR ? 2 * TC_BM : TC_BM, BN);
       uint32_t stage = 0, phase = 0;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      const int buf = PERSIST ? it % p.acc_bufs : 0;
+      const uint32_t use = PERSIST ? (uint32_t)(it / p.acc_bufs) : 0u;
+      if (PERSIST) {
+        mbar_wait(smem_u32(&bar_tempty[buf]), (use & 1u) ^ 1u);     // epilogue drained this buffer (first use: passes)
+        tc_fence_after();
+      }
+      const uint32_t acc_base = tmem_base + (uint32_t)buf * (uint32_t)p.acc_stride;
       uint32_t started = 0;    // bit a set once accumulator a has received its first MMA
       for (int kb = 0; kb < p.num_kb; ++kb) {
         const uint32_t sa_word = (uint32_t)kbt[kb].src_acc;
@@ -690,7 +711,7 @@ __global__ void __launch_bounds__(TcGeo<BN>::THREADS, 1) tc_gemm_kernel(const __
         for (uint32_t j = 0; j < nw; ++j) {             // the A tile is shared by the nw taps' accumulators
           const uint32_t acc = acc0 + j;
           const uint64_t db = umma_desc_sw128(sa + TC_A_BYTES + j * B_BYTES);
-          const uint32_t d_tmem = tmem_base + acc * BN;
+          const uint32_t d_tmem = acc_base + acc * BN;
 #pragma unroll
           for (int k = 0; k < TC_BK / 16; ++k) {
             // advance 16 bf16 = 32 bytes along K inside the 128B swizzle row: +2 in the (addr >> 4) field
@@ -703,9 +724,11 @@ __global__ void __launch_bounds__(TcGeo<BN>::THREADS, 1) tc_gemm_kernel(const __
         else umma_commit(smem_u32(&bar_empty[stage]));               // frees the smem stage when these MMAs retire
         if (++stage == (uint32_t)STAGES) { stage = 0; phase ^= 1u; }
       }
-      if (PAIR) umma_commit_2sm(smem_u32(&bar_accum), 3);
-      else umma_commit(smem_u32(&bar_accum));           // accumulator(s) complete
-      if (p.dbg) ts[4] = clock64();                     // all MMAs issued
+      if (PAIR) umma_commit_2sm(smem_u32(&bar_tfull[buf]), 3);
+      else umma_commit(smem_u32(&bar_tfull[buf]));      // accumulator(s) of this tile complete
+      if (p.dbg && it == 0) ts[4] = clock64();          // all MMAs of the first tile issued
+      if (!PERSIST) break;
+      }
     }
   } else {
     // ===================== epilogue warps (2..9) =====================
@@ -713,8 +736,14 @@ __global__ void __launch_bounds__(TcGeo<BN>::THREADS, 1) tc_gemm_kernel(const __
     const int quarter = warp & 3;                        // TMEM lane quarter this warp may access
     const int part = ew >> 2;                            // which column slice of the tile
     const int row = quarter * 32 + lane;
-    const int m = tile_m * TC_BM + row;
     griddep_wait();                                      // the step counter / residuals / x belong to earlier kernels
+    int it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+    const int tile_m = PERSIST ? tile % p.tiles_m : (int)blockIdx.x;
+    const int n0 = (PERSIST ? tile / p.tiles_m : (int)blockIdx.y) * BN;
+    const int buf = PERSIST ? it % p.acc_bufs : 0;
+    const uint32_t use = PERSIST ? (uint32_t)(it / p.acc_bufs) : 0u;
+    const int m = tile_m * TC_BM + row;
     // stage the per-column vectors while the main loop runs
     {
       const int et = threadIdx.x - 64;
@@ -737,17 +766,21 @@ __global__ void __launch_bounds__(TcGeo<BN>::THREADS, 1) tc_gemm_kernel(const __
     const int c_begin = part * TcGeo<BN>::CPP;
     GnPrefetch<MODE == TC_EPI_GN ? BN : 64> pf;
     if constexpr (MODE == TC_EPI_GN) gn_prefetch<BN>(p, es, m, n0, c_begin, pf);
-    mbar_wait(smem_u32(&bar_accum), 0);
+    mbar_wait(smem_u32(&bar_tfull[buf]), use & 1u);
     tc_fence_after();
-    if (p.dbg && threadIdx.x == 64) ts[5] = clock64();   // accumulators complete
-    if (p.dbg_stage && threadIdx.x == 64 && blockIdx.x == 0 && blockIdx.y == 0) p.dbg_stage[23] = clock64();
-    const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16);
+    if (p.dbg && threadIdx.x == 64 && it == 0) ts[5] = clock64();   // accumulators complete
+    const uint32_t taddr = tmem_base + (uint32_t)buf * (uint32_t)p.acc_stride + ((uint32_t)(quarter * 32) << 16);
     if constexpr (MODE == TC_EPI_PLAIN) epilogue_plain<BN>(p, es, taddr, m, n0, c_begin, lane);
     else if constexpr (MODE == TC_EPI_GN) epilogue_gn<BN>(p, es, taddr, m, n0, c_begin, row, lane, pf);
     else if constexpr (MODE == TC_EPI_DDPM)
       epilogue_ddpm<BN>(p, es, taddr, reinterpret_cast<float*>(smem_raw + (smem_base - smem_u32(smem_raw))), tile_m, n0,
                         c_begin, row, (int)threadIdx.x - 64, lane);
     else epilogue_ln<BN>(p, es, taddr, m, n0, c_begin, row, part, lane);
+    if (!PERSIST) break;
+    tc_fence_before();                                   // hand the accumulator buffer back, protect `es`
+    mbar_arrive(smem_u32(&bar_tempty[buf]));
+    epi_bar<BN>();
+    }
   }
 
   if (p.dbg && threadIdx.x == 64) ts[6] = clock64();     // this warp's epilogue done
@@ -766,7 +799,7 @@ __global__ void __launch_bounds__(TcGeo<BN>::THREADS, 1) tc_gemm_kernel(const __
     for (int i = 1; i < 7; ++i) d[i] = ts[i] ? ts[i] - t0 : 0;
     d[7] = clock64() - t0;
     if (p.dbg_stage && blockIdx.x == 0 && blockIdx.y == 0)
-      for (int i = 0; i < 24; ++i) p.dbg_stage[i] = tk[i] ? tk[i] - t0 : 0;
+      for (int i = 0; i < 23; ++i) p.dbg_stage[i] = tk[i] ? tk[i] - t0 : 0;
     d[0] = (long long)(__cvta_generic_to_shared(&ts[0]) & 0) + (long long)blockIdx.x;   // tile id
   }
 }
@@ -831,10 +864,15 @@ int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t*
 
 template <int BN, int MODE>
 static int set_smem_attr() {
-  LDP_CUDA_OK(cudaFuncSetAttribute(tc_gemm_kernel<BN, MODE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_RING + 1024));
+  LDP_CUDA_OK(cudaFuncSetAttribute(tc_gemm_kernel<BN, MODE, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   TC_SMEM_RING + 1024));
   constexpr bool kPairable = (MODE == TC_EPI_PLAIN || MODE == TC_EPI_GN) && BN <= 128;
   if (kPairable)
-    LDP_CUDA_OK(cudaFuncSetAttribute(tc_gemm_kernel<BN, MODE, kPairable>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    LDP_CUDA_OK(cudaFuncSetAttribute(tc_gemm_kernel<BN, MODE, kPairable, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     TC_SMEM_RING + 1024));
+  constexpr bool kPersistable = MODE == TC_EPI_PLAIN && BN <= 128;
+  if (kPersistable)
+    LDP_CUDA_OK(cudaFuncSetAttribute(tc_gemm_kernel<BN, MODE, false, kPersistable>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      TC_SMEM_RING + 1024));
   return LDP_OK;
 }
@@ -857,7 +895,29 @@ int tc_gemm_init() {
   return LDP_OK;
 }
 
-template <int BN, int MODE, bool PAIR>
+// Tile / grid / TMEM geometry of a launch (also used by the profiling entry point to size its per-CTA buffers).
+int tc_gemm_geometry(TcGemm* p) {
+  const int bn = p->block_n;
+  const int n_acc_total = p->n_acc + (p->use_aux ? 1 : 0);
+  LDP_CHECK(n_acc_total * bn <= 512, LDP_ERR_UNSUPPORTED, "tc_gemm: accumulators exceed the 512 TMEM columns");
+  const int tm = ceil_div(p->M, TC_BM);
+  p->tiles_m = p->pair ? round_up(tm, 2) : tm;
+  p->tiles_n = ceil_div(p->N, bn);
+  const int tiles = p->tiles_m * p->tiles_n;
+  static int persist = -1;
+  if (persist < 0) { const char* e = getenv("LDP_PERSIST"); persist = (e && e[0] == '0') ? 0 : 1; }
+  const bool persistent = persist && tiles > 148 && !p->pair && p->mode == TC_EPI_PLAIN && bn <= 128;
+  p->grid_ctas = persistent ? 148 : tiles;
+  p->persistent = persistent ? 1 : 0;
+  p->acc_stride = n_acc_total * bn;
+  p->acc_bufs = (persistent && 2 * p->acc_stride <= 512) ? 2 : 1;
+  int cols = 32;
+  while (cols < p->acc_bufs * p->acc_stride) cols <<= 1;
+  p->tmem_cols = cols;
+  return LDP_OK;
+}
+
+template <int BN, int MODE, bool PAIR, bool PERSIST>
 static int launch_tc_gemm_inst(const TcGemm& p_in, cudaStream_t s) {
   LDP_TRY(tc_gemm_init());
   TcGemm p = p_in;
@@ -865,9 +925,9 @@ static int launch_tc_gemm_inst(const TcGemm& p_in, cudaStream_t s) {
   LDP_CHECK(p.n_acc >= 1 && p.n_acc <= 5 && n_acc_total * BN <= 512, LDP_ERR_UNSUPPORTED,
             "tc_gemm: accumulators exceed the 512 TMEM columns");
   LDP_CHECK(p.w_max >= 1 && p.w_max <= 5, LDP_ERR_INVALID_ARG, "tc_gemm: w_max must be 1..5");
-  int cols = 32;
-  while (cols < n_acc_total * BN) cols <<= 1;
-  p.tmem_cols = cols;
+  LDP_TRY(tc_gemm_geometry(&p));
+  LDP_CHECK((p.pair != 0) == PAIR && (p.persistent != 0) == PERSIST, LDP_ERR_INVALID_ARG,
+            "tc_gemm: pair / persistent flags do not match the kernel");
   {
     static int skip = -1;                      // diagnostics: LDP_EPI_SKIP bit mask disables parts of the GN epilogue
     if (skip < 0) { const char* e = getenv("LDP_EPI_SKIP"); skip = e ? atoi(e) : 0; }
@@ -883,7 +943,7 @@ static int launch_tc_gemm_inst(const TcGemm& p_in, cudaStream_t s) {
     LDP_CHECK(p.rows_per_item >= 1 && p.rows_per_item <= 32 && (p.rows_per_item & (p.rows_per_item - 1)) == 0,
               LDP_ERR_UNSUPPORTED, "tc_gemm: shifted accumulators need power-of-two rows per sample <= 32");
   cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(PAIR ? round_up(ceil_div(p.M, TC_BM), 2) : ceil_div(p.M, TC_BM), ceil_div(p.N, BN), 1);
+  cfg.gridDim = PERSIST ? dim3(p.grid_ctas, 1, 1) : dim3(p.tiles_m, p.tiles_n, 1);
   cfg.blockDim = dim3(TcGeo<BN>::THREADS, 1, 1);
   cfg.dynamicSmemBytes = p.num_stages * stage_bytes + 1024;
   cfg.stream = s;
@@ -903,7 +963,7 @@ static int launch_tc_gemm_inst(const TcGemm& p_in, cudaStream_t s) {
   }
   cfg.attrs = attr;
   cfg.numAttrs = na;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, tc_gemm_kernel<BN, MODE, PAIR>, p);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, tc_gemm_kernel<BN, MODE, PAIR, PERSIST>, p);
   if (e != cudaSuccess) {
     set_last_error(std::string("tc_gemm launch failed: ") + cudaGetErrorString(e));
     return LDP_ERR_CUDA;
@@ -928,24 +988,33 @@ int launch_tc_gemm(const TcGemm& p, cudaStream_t s) {
   const bool pair = p.pair != 0;
   if (pair) LDP_CHECK((p.mode == TC_EPI_PLAIN || p.mode == TC_EPI_GN) && p.block_n <= 128, LDP_ERR_UNSUPPORTED,
                       "tc_gemm: pair mode exists for the PLAIN / GN epilogues at BN <= 128");
+  TcGemm g = p;
+  LDP_TRY(tc_gemm_geometry(&g));
   const int key = p.block_n * 8 + p.mode;
   if (pair) {
     switch (key) {
-      case 64 * 8 + TC_EPI_PLAIN:  return launch_tc_gemm_inst<64, TC_EPI_PLAIN, true>(p, s);
-      case 64 * 8 + TC_EPI_GN:     return launch_tc_gemm_inst<64, TC_EPI_GN, true>(p, s);
-      case 128 * 8 + TC_EPI_PLAIN: return launch_tc_gemm_inst<128, TC_EPI_PLAIN, true>(p, s);
-      case 128 * 8 + TC_EPI_GN:    return launch_tc_gemm_inst<128, TC_EPI_GN, true>(p, s);
+      case 64 * 8 + TC_EPI_PLAIN:  return launch_tc_gemm_inst<64, TC_EPI_PLAIN, true, false>(p, s);
+      case 64 * 8 + TC_EPI_GN:     return launch_tc_gemm_inst<64, TC_EPI_GN, true, false>(p, s);
+      case 128 * 8 + TC_EPI_PLAIN: return launch_tc_gemm_inst<128, TC_EPI_PLAIN, true, false>(p, s);
+      case 128 * 8 + TC_EPI_GN:    return launch_tc_gemm_inst<128, TC_EPI_GN, true, false>(p, s);
+      default: break;
+    }
+  }
+  if (g.persistent) {
+    switch (key) {
+      case 64 * 8 + TC_EPI_PLAIN:  return launch_tc_gemm_inst<64, TC_EPI_PLAIN, false, true>(p, s);
+      case 128 * 8 + TC_EPI_PLAIN: return launch_tc_gemm_inst<128, TC_EPI_PLAIN, false, true>(p, s);
       default: break;
     }
   }
   switch (key) {
-    case 64 * 8 + TC_EPI_PLAIN:  return launch_tc_gemm_inst<64, TC_EPI_PLAIN, false>(p, s);
-    case 64 * 8 + TC_EPI_GN:     return launch_tc_gemm_inst<64, TC_EPI_GN, false>(p, s);
-    case 128 * 8 + TC_EPI_PLAIN: return launch_tc_gemm_inst<128, TC_EPI_PLAIN, false>(p, s);
-    case 128 * 8 + TC_EPI_GN:    return launch_tc_gemm_inst<128, TC_EPI_GN, false>(p, s);
-    case 128 * 8 + TC_EPI_DDPM:  return launch_tc_gemm_inst<128, TC_EPI_DDPM, false>(p, s);
-    case 256 * 8 + TC_EPI_PLAIN: return launch_tc_gemm_inst<256, TC_EPI_PLAIN, false>(p, s);
-    case 256 * 8 + TC_EPI_LN:    return launch_tc_gemm_inst<256, TC_EPI_LN, false>(p, s);
+    case 64 * 8 + TC_EPI_PLAIN:  return launch_tc_gemm_inst<64, TC_EPI_PLAIN, false, false>(p, s);
+    case 64 * 8 + TC_EPI_GN:     return launch_tc_gemm_inst<64, TC_EPI_GN, false, false>(p, s);
+    case 128 * 8 + TC_EPI_PLAIN: return launch_tc_gemm_inst<128, TC_EPI_PLAIN, false, false>(p, s);
+    case 128 * 8 + TC_EPI_GN:    return launch_tc_gemm_inst<128, TC_EPI_GN, false, false>(p, s);
+    case 128 * 8 + TC_EPI_DDPM:  return launch_tc_gemm_inst<128, TC_EPI_DDPM, false, false>(p, s);
+    case 256 * 8 + TC_EPI_PLAIN: return launch_tc_gemm_inst<256, TC_EPI_PLAIN, false, false>(p, s);
+    case 256 * 8 + TC_EPI_LN:    return launch_tc_gemm_inst<256, TC_EPI_LN, false, false>(p, s);
     default: break;
   }
   set_last_error("tc_gemm: no kernel instantiated for block_n " + std::to_string(p.block_n) + " with epilogue " +
