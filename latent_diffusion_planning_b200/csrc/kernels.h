@@ -138,6 +138,11 @@ struct TcGemm {
   const TcStage* kb = nullptr;      // device table of pipeline stages
   int num_kb = 0;                   // number of stages
   int w_max = 1;                    // largest nw of any stage (sizes the shared-memory ring)
+  // Stage table shape (lets the MMA issuer run without reading the table): stages [0, kb_main) all carry nw_main W
+  // tiles for accumulators 0..nw_main-1; stages [kb_main, num_kb) are the aux part (one W tile, accumulator n_acc).
+  // kb_main = 0 means "uniform table": kb_main = num_kb, nw_main = w_max.
+  int kb_main = 0, nw_main = 0;
+  int tiles_m_group = 0;            // persistent loop kernel: M tiles owned by one group of CTAs (planner_loop.cu)
   // Accumulators: n_acc main accumulators at TMEM columns [j*BN, (j+1)*BN); the output row r is
   // sum_j acc_j[r + shift[j]] (rows outside the sample contribute zero) - a k-tap 1-D convolution computed as k
   // un-shifted GEMMs that share every A tile, recombined in the epilogue with warp shuffles.  The aux accumulator
@@ -150,6 +155,7 @@ struct TcGemm {
   long long* dbg_stage = nullptr;   // diagnostics: CTA (0,0)'s first 24 stage-arrival times
   long long* dbg = nullptr;         // diagnostics: per-CTA phase timestamps [ctas][8] (clock64 deltas)
   int k_pad = 0;                    // host-side bookkeeping: padded K of the packed weights
+  const void* wt_host_ref = nullptr; int n_pad = 0;   // host-side bookkeeping: packed weights [n_pad][k_pad] (to rebuild map_b)
   int M = 0, N = 0;                 // logical output size
   int block_n = 128;                // 64, 128 or 256
   int use_aux = 0;                  // second accumulator present (columns [BN, 2BN) of TMEM)
@@ -180,6 +186,20 @@ struct TcGemm {
   float* x_io = nullptr; int ld_x = 0;
 };
 int launch_tc_gemm(const TcGemm& p, cudaStream_t s);
+
+// The whole reverse-diffusion loop of the planner as one persistent kernel (planner_loop.cu).
+struct PlannerLoop {
+  const TcGemm* layers = nullptr;   // device array: the ops of one denoising step (non-pair), geometry filled in
+  int n_layers = 0;
+  int n_steps = 0;                  // reverse steps to run; iteration i uses timestep t_first - i
+  int t_first = 0;
+  int* group_counter = nullptr;     // [n_groups] arrival counters, zero at launch
+  int group_ctas = 8;               // CTAs that serve one group of samples
+  long long* dbg = nullptr;         // diagnostics: [n_layers][8] clock64 stamps of CTA 0 during iteration dbg_step
+  int dbg_step = 0;
+  int flags = 0;                    // diagnostics: 1 = no weight prefetch before the group barrier, 2 = every epilogue thread fences
+};
+int launch_planner_loop(const PlannerLoop& lp, int n_groups, cudaStream_t s);
 int tc_gemm_geometry(TcGemm* p);   // fills tiles_m/n, grid_ctas, acc_bufs, acc_stride, tmem_cols
 
 // cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time libcuda dependency).

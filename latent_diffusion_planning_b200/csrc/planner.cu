@@ -74,6 +74,7 @@ struct ConvPack : PackedW {
   int n_acc = 1;
   int shift[5] = {0, 0, 0, 0, 0};
   int w_max = 1;
+  int num_kb_main = 0;             // stages before the aux (residual projection) part
   bool tapacc = false;
 };
 
@@ -98,6 +99,12 @@ struct PlanWs {
   std::vector<TcGemm> ops;         // one denoising step; last op = final 1x1 with the DDPM epilogue
   cudaGraphExec_t graph = nullptr;
   cudaGraph_t graph_src = nullptr;
+  // persistent loop kernel (planner_loop.cu)
+  int loop_state = 0;              // 0 not prepared, 1 ready, -1 unsupported for this shape
+  TcGemm* layers_dev = nullptr;
+  int* group_counter = nullptr;
+  int n_groups = 0;
+  long long* loop_dbg = nullptr;
   ~PlanWs() {
     if (graph) cudaGraphExecDestroy(graph);
     if (graph_src) cudaGraphDestroy(graph_src);
@@ -556,6 +563,7 @@ static int get_packed(LdpPlanner* h, int op_id, const ConvDesc& d, bool tapacc, 
     }
   }
   const int kp_main = (int)kmap.size();
+  pw.num_kb_main = (int)st.size();
   std::vector<int32_t> kmap_aux;
   {
     int coff = 0;
@@ -645,7 +653,11 @@ static int conv_tc(LdpPlanner* h, PlanWs* w, int op_id, const ConvDesc& d, TcGem
   op->kb = pw->kb_dev;
   op->num_kb = pw->num_kb;
   op->w_max = pw->w_max;
+  op->kb_main = pw->num_kb_main;
+  op->nw_main = pw->w_max;
   op->k_pad = pw->kp;
+  op->wt_host_ref = pw->wt;
+  op->n_pad = pw->n_pad;
   op->n_acc = pw->n_acc;
   for (int j = 0; j < 5; ++j) op->shift[j] = pw->shift[j];
   op->use_aux = d.aux_nsrc > 0 ? 1 : 0;
@@ -815,6 +827,54 @@ static int run_ops_bf16(PlanWs* w, StepRef step, bool final_plain, float* eps_ou
   return LDP_OK;
 }
 
+
+// Persistent loop kernel: the ops of prepare_bf16 (CTA pairs undone: the loop kernel is single-CTA), with the group
+// geometry filled in, as a device array.  Unsupported shapes leave loop_state = -1 and the caller uses the graph path.
+static int prepare_loop(LdpPlanner* h, PlanWs* w) {
+  if (w->loop_state != 0) return LDP_OK;
+  w->loop_state = -1;
+  const char* env = getenv("LDP_LOOP");
+  if (!(env && env[0] == '1')) return LDP_OK;          // opt-in until it beats the per-layer graph path
+  const LdpUnetConfig& c = h->cfg;
+  const int t_deep = level_len(w->T, c.n_levels - 1);
+  if (t_deep < 1 || t_deep > 128 || (128 % t_deep) != 0) return LDP_OK;
+  const int spc = 128 / t_deep;                       // samples per group: 128 rows at the deepest level
+  const int n_groups = ceil_div(w->B, spc);
+  const int G = 8;
+  int dev = 0, sms = 0;
+  LDP_CUDA_OK(cudaGetDevice(&dev));
+  LDP_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  if (n_groups * G > sms) return LDP_OK;              // every CTA of a group must be resident: one CTA per SM
+  std::vector<TcGemm> ops = w->ops;
+  for (TcGemm& op : ops) {
+    if (op.mode != TC_EPI_PLAIN && op.mode != TC_EPI_GN && op.mode != TC_EPI_DDPM) return LDP_OK;
+    if (op.block_n != 64 && op.block_n != 128) return LDP_OK;
+    if (op.mode == TC_EPI_DDPM && op.block_n != 128) return LDP_OK;
+    if (op.num_kb > 256 || op.tiles_per_item != 1) return LDP_OK;
+    if ((spc * op.rows_per_item) % 128 != 0) return LDP_OK;
+    if (op.pair) {
+      uint64_t bd[2] = {(uint64_t)op.k_pad, (uint64_t)op.n_pad};
+      uint64_t bs[1] = {(uint64_t)op.k_pad * 2};
+      uint32_t bb[2] = {64, (uint32_t)op.block_n};
+      LDP_TRY(make_tmap_bf16(&op.map_b, op.wt_host_ref, 2, bd, bs, bb));
+      op.pair = 0;
+    }
+    LDP_TRY(tc_gemm_geometry(&op));
+    op.num_stages = std::min(8, (196 * 1024) / (16384 + op.w_max * op.block_n * 128));
+    if (op.num_stages < 2) return LDP_OK;
+    op.tiles_m_group = spc * op.rows_per_item / 128;
+    op.persistent = 0; op.acc_bufs = 1;
+    op.epi_skip = 0; op.dbg = nullptr; op.dbg_stage = nullptr;
+  }
+  LDP_TRY(w->arena.alloc_t(&w->layers_dev, ops.size()));
+  LDP_CUDA_OK(cudaMemcpy(w->layers_dev, ops.data(), ops.size() * sizeof(TcGemm), cudaMemcpyHostToDevice));
+  LDP_TRY(w->arena.alloc_t(&w->group_counter, (size_t)n_groups));
+  LDP_TRY(w->arena.alloc_t(&w->loop_dbg, ops.size() * 8 + 8));
+  w->n_groups = n_groups;
+  w->loop_state = 1;
+  return LDP_OK;
+}
+
 }  // namespace ldp
 
 // ------------------------------- C ABI -------------------------------------------------------
@@ -905,6 +965,27 @@ int ldp_planner_sample(LdpPlanner* h, int precision, int sampler, const float* x
   } else {
     LDP_TRY(prepare_bf16(h, w));
     LDP_TRY(launch_cast_bf16(w->x_state, D, w->x_bf16, w->ld_xb, (long long)B * T, D, 0, s));
+    LDP_TRY(prepare_loop(h, w));
+    if (w->loop_state == 1) {
+      // the whole loop in one persistent kernel; timestep of iteration i = n_steps - 1 - i
+      LDP_CUDA_OK(cudaMemsetAsync(w->group_counter, 0, (size_t)w->n_groups * sizeof(int), s));
+      PlannerLoop lp;
+      lp.layers = w->layers_dev; lp.n_layers = (int)w->ops.size();
+      lp.n_steps = n_steps; lp.t_first = n_steps - 1;
+      lp.group_counter = w->group_counter; lp.group_ctas = 8;
+      if (getenv("LDP_LOOP_FLAGS")) lp.flags = atoi(getenv("LDP_LOOP_FLAGS"));
+      if (getenv("LDP_LOOP_DBG")) { lp.dbg = w->loop_dbg; lp.dbg_step = std::min(n_steps - 1, atoi(getenv("LDP_LOOP_DBG"))); }
+      LDP_TRY(launch_planner_loop(lp, w->n_groups, s));
+      if (lp.dbg) {
+        std::vector<long long> hb(w->ops.size() * 8);
+        LDP_CUDA_OK(cudaStreamSynchronize(s));
+        LDP_CUDA_OK(cudaMemcpy(hb.data(), w->loop_dbg, hb.size() * 8, cudaMemcpyDeviceToHost));
+        const long long t0 = hb[0];
+        for (size_t i = 0; i < w->ops.size(); ++i)
+          fprintf(stderr, "loop layer %2zu: enter %8lld polled %8lld first-operands %8lld mma-issued %8lld epilogue-done %8lld\n", i,
+                  hb[i * 8 + 0] - t0, hb[i * 8 + 1] ? hb[i * 8 + 1] - t0 : 0, hb[i * 8 + 2] - t0, hb[i * 8 + 3] - t0, hb[i * 8 + 5] - t0);
+      }
+    } else
     if (h->use_graph && !w->graph) {
       // capture one denoising step (all GEMMs + the step-counter decrement) once per (B,T)
       cudaStream_t cs;
@@ -923,7 +1004,7 @@ int ldp_planner_sample(LdpPlanner* h, int precision, int sampler, const float* x
       LDP_CUDA_OK(cudaGraphInstantiate(&w->graph, w->graph_src, 0));
       LDP_CUDA_OK(cudaStreamDestroy(cs));
     }
-    for (int i = 0; i < n_steps; ++i) {
+    for (int i = 0; i < n_steps && w->loop_state != 1; ++i) {
       if (w->graph) {
         LDP_CUDA_OK(cudaGraphLaunch(w->graph, s));
         count_launch((int)w->ops.size() + 1);

@@ -1,0 +1,554 @@
+// Device-side pieces shared by the tcgen05 kernels (tc_gemm.cu: one launch per layer; planner_loop.cu: the persistent
+// reverse-diffusion kernel): tile geometry, per-CTA epilogue staging, and the fused epilogues.  See tc_gemm.cu for the
+// description of the layouts.
+#pragma once
+#include <cuda_fp16.h>
+
+#include "kernels.h"
+
+namespace ldp {
+
+constexpr int TC_BM = 128;
+constexpr int TC_BK = 64;
+constexpr int TC_A_BYTES = TC_BM * TC_BK * 2;   // 16 KB
+// Thread geometry: warp 0 = TMA producer, warp 1 = MMA issuer, then the epilogue warps.  A warp may only read the TMEM
+// lane quarter (warp index mod 4), so the epilogue warps come in groups of four (one per quarter); group g owns column
+// slice g of the tile.  BN = 128 runs 16 epilogue warps with one 32-column chunk per thread: the epilogue is a long
+// dependent chain (TMEM load -> statistics -> barrier -> MUFU-heavy activation -> FiLM / residual loads -> store), and
+// four resident warps per scheduler are what hides its latencies (8 warps took 13-15k cycles per tile, as long as
+// the main loop itself; profiles/).
+template <int BN>
+struct TcGeo {
+  static constexpr int EPI_WARPS = BN == 64 ? 8 : 16;
+  static constexpr int EPI_THREADS = EPI_WARPS * 32;
+  static constexpr int THREADS = 64 + EPI_THREADS;
+  static constexpr int PARTS = EPI_WARPS / 4;              // column slices of the tile
+  static constexpr int CPP = BN / 32 / PARTS;              // 32-column chunks per thread: 1 (BN 64, 128), 2 (BN 256)
+};
+constexpr int TC_MAX_KB_SMEM = 256;
+constexpr int TC_MAX_STAGES = 8;
+
+constexpr int TC_SMEM_RING = 196 * 1024;        // shared-memory budget of the TMA ring (static smem takes <= 20 KB more)
+
+template <int BN>
+struct TcSmem {
+  static constexpr int B_BYTES = BN * TC_BK * 2;
+};
+// ring geometry of a launch: a stage holds one A tile and w_max W tiles
+static inline int tc_stage_bytes(int bn, int w_max) { return TC_A_BYTES + w_max * bn * TC_BK * 2; }
+static inline int tc_num_stages(int bn, int w_max) {
+  int n = TC_SMEM_RING / tc_stage_bytes(bn, w_max);
+  return n > TC_MAX_STAGES ? TC_MAX_STAGES : n;
+}
+
+// Per-CTA staging of everything the epilogue needs per output column (filled while the main loop runs).
+template <int BN>
+struct EpiSmem {
+  float bias[BN];
+  float bias2[BN];      // bias of the aux accumulator (residual 1x1 projection)
+  float gamma[BN];
+  float beta[BN];
+  float fscale[BN];     // FiLM scale / shift, time part (valid when the whole launch shares one timestep)
+  float fshift[BN];
+  float2 part[TC_BM][BN / 32];   // per-row, per-32-column-chunk (sum, sum of squares)
+};
+
+template <int BN>
+__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, %0;" ::"n"(TcGeo<BN>::EPI_THREADS) : "memory"); }
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void griddep_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float rcp_approx(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// Mish(y) = y tanh(softplus(y)) = y n/(n+2) = y - 2y/(n+2), n = e^y (e^y + 2).  Written as y - 2 y r with
+// r = 1/(e (e+2) + 2): when e^y overflows, r = 0 and the result is y (no clamp needed); 7 instructions, 2 of them MUFU.
+__device__ __forceinline__ float mish_fast(float y) {
+  const float e = ex2_approx(y * 1.4426950408889634f);
+  const float r = rcp_approx(fmaf(e, e + 2.f, 2.f));
+  return fmaf(-2.f * r, y, y);
+}
+// swish(y) = y / (1 + e^-y)
+__device__ __forceinline__ float swish_fast(float y) {
+  const float e = ex2_approx(fminf(-y, 80.f) * 1.4426950408889634f);
+  return y * rcp_approx(1.f + e);
+}
+
+// ---- vector load/store helpers (32 consecutive columns of one row) -------------------------------------
+// Activations written earlier by other SMs (residual rows, x) are read with ld.global.cg: inside the persistent
+// reverse-diffusion kernel there is no kernel boundary to invalidate L1 between a layer's writes and a later layer's reads.
+__device__ __forceinline__ void store_bf16x32(__nv_bfloat16* dst, const float (&v)[32], bool vec_ok, int nvalid) {
+  if (vec_ok && nvalid == 32) {
+    uint4* d4 = reinterpret_cast<uint4*>(dst);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      uint4 u;
+      u.x = pack_bf16x2(v[8 * j + 0], v[8 * j + 1]);
+      u.y = pack_bf16x2(v[8 * j + 2], v[8 * j + 3]);
+      u.z = pack_bf16x2(v[8 * j + 4], v[8 * j + 5]);
+      u.w = pack_bf16x2(v[8 * j + 6], v[8 * j + 7]);
+      d4[j] = u;
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < 32; ++i)
+      if (i < nvalid) dst[i] = __float2bfloat16(v[i]);
+  }
+}
+
+__device__ __forceinline__ void store_f32x32(float* dst, const float (&v)[32], bool vec_ok, int nvalid) {
+  if (vec_ok && nvalid == 32) {
+    float4* d4 = reinterpret_cast<float4*>(dst);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) d4[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+  } else {
+#pragma unroll
+    for (int i = 0; i < 32; ++i)
+      if (i < nvalid) dst[i] = v[i];
+  }
+}
+
+__device__ __forceinline__ void add_f32x32(float (&v)[32], const float* src, bool vec_ok, int nvalid) {
+  if (vec_ok && nvalid == 32) {
+    const float4* s4 = reinterpret_cast<const float4*>(src);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float4 f = __ldcg(s4 + j);
+      v[4 * j] += f.x; v[4 * j + 1] += f.y; v[4 * j + 2] += f.z; v[4 * j + 3] += f.w;
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < 32; ++i)
+      if (i < nvalid) v[i] += __ldcg(src + i);
+  }
+}
+
+__device__ __forceinline__ void add_bf16x32(float (&v)[32], const __nv_bfloat16* src, bool vec_ok, int nvalid) {
+  if (vec_ok && nvalid == 32) {
+    const uint4* rp = reinterpret_cast<const uint4*>(src);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      uint4 u = __ldcg(rp + j);
+      const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        float2 f = __bfloat1622float2(h[q]);
+        v[8 * j + 2 * q] += f.x;
+        v[8 * j + 2 * q + 1] += f.y;
+      }
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < 32; ++i)
+      if (i < nvalid) v[i] += __bfloat162float(__ldcg(src + i));
+  }
+}
+
+// v[i] += s[i] for 32 consecutive floats of a shared-memory vector (LDS.128, broadcast across the warp)
+__device__ __forceinline__ void add_smem32(float (&v)[32], const float* s) {
+  const float4* s4 = reinterpret_cast<const float4*>(s);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    float4 f = s4[j];
+    v[4 * j] += f.x; v[4 * j + 1] += f.y; v[4 * j + 2] += f.z; v[4 * j + 3] += f.w;
+  }
+}
+
+// v = sum_j acc_j[row + shift_j][32-column chunk c]  (the recombination of a k-tap convolution computed as k un-shifted
+// GEMMs).  Thread `lane` of the warp owns TMEM lane = output row; rows of one sample are adjacent lanes, so a shifted
+// row is a warp shuffle away, and rows that fall outside the sample contribute zero (the convolution's zero padding).
+template <int BN>
+__device__ __forceinline__ void load_acc_chunk(const TcGemm& p, uint32_t taddr, int c, int lane, float (&v)[32]) {
+  tmem_ld_32x32(taddr + c * 32, v);
+  if ((p.n_acc == 1 && p.shift[0] == 0) || (p.epi_skip & 16)) return;       // uniform: dense GEMM / per-tap mode
+  const int T = p.rows_per_item, t = lane & (T - 1);
+  {
+    const int s = p.shift[0];
+    if (s != 0) {
+      const bool ok = (unsigned)(t + s) < (unsigned)T;
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        const float q = __shfl_sync(0xffffffffu, v[i], (lane + s) & 31);
+        v[i] = ok ? q : 0.f;
+      }
+    }
+  }
+#pragma unroll 1
+  for (int j = 1; j < p.n_acc; ++j) {
+    float r[32];
+    tmem_ld_32x32(taddr + j * BN + c * 32, r);
+    const int s = p.shift[j];
+    if (s != 0) {                                     // uniform
+      const bool ok = (unsigned)(t + s) < (unsigned)T;
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        const float q = __shfl_sync(0xffffffffu, r[i], (lane + s) & 31);
+        v[i] += ok ? q : 0.f;
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) v[i] += r[i];
+    }
+  }
+}
+
+// ---- epilogues: thread owns row `m`; this warp covers chunks [c_begin, c_begin + CPP) of the N tile ------------
+template <int BN>
+__device__ __forceinline__ void epilogue_plain(const TcGemm& p, EpiSmem<BN>& es, uint32_t taddr, int m, int n0,
+                                               int c_begin, int lane) {
+  constexpr int CPP = TcGeo<BN>::CPP;
+  const bool row_ok = m < p.M;
+  const bool vf = (p.ld_out_f32 & 3) == 0, vb = (p.ld_out_bf16 & 7) == 0;
+  const bool vrf = (p.ld_res_f32 & 3) == 0, vrb = (p.ld_res_bf16 & 7) == 0;
+#pragma unroll 1
+  for (int cc = 0; cc < CPP; ++cc) {
+    const int c = c_begin + cc;
+    const int nb = n0 + c * 32;
+    const int nvalid = min(32, p.N - nb);
+    if (nvalid <= 0) continue;           // uniform across the warp
+    float v[32];
+    load_acc_chunk<BN>(p, taddr, c, lane, v);
+    add_smem32(v, es.bias + c * 32);
+    if (p.relu) {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
+    }
+    if (row_ok) {
+      if (p.res_f32) add_f32x32(v, p.res_f32 + (long long)m * p.ld_res_f32 + nb, vrf, nvalid);
+      if (p.res_bf16) add_bf16x32(v, p.res_bf16 + (long long)m * p.ld_res_bf16 + nb, vrb, nvalid);
+      if (p.out_f32) store_f32x32(p.out_f32 + (long long)m * p.ld_out_f32 + nb, v, vf, nvalid);
+      if (p.out_bf16) store_bf16x32(p.out_bf16 + (long long)m * p.ld_out_bf16 + nb, v, vb, nvalid);
+    }
+  }
+}
+
+// Operands of the GN epilogue that do not depend on the accumulator - the FiLM scale/shift of this thread's sample and
+// the residual row - are fetched into registers BEFORE the epilogue warps block on the accumulator barrier: the
+// row-per-thread access pattern is uncoalesced (6k cycles per tile when issued after the main loop), but the epilogue
+// warps are idle for the whole main loop, so issuing the loads up front hides them completely.  FiLM pairs are kept as
+// half2 (scale, shift): O(1) values, 2^-11 relative rounding, far below the bf16 rounding of the activations.
+template <int BN>
+struct GnPrefetch {
+  uint32_t film[TcGeo<BN>::CPP][32];   // half2(scale, shift) per column
+  uint4 res[TcGeo<BN>::CPP][4];        // 32 bf16 of the residual row per chunk
+};
+
+template <int BN>
+__device__ __forceinline__ void gn_prefetch(const TcGemm& p, const EpiSmem<BN>& es, int m, int n0, int c_begin,
+                                            GnPrefetch<BN>& pf) {
+  constexpr int NC = BN / 32, CPP = TcGeo<BN>::CPP;
+  const int nchunks = min(NC, (p.N - n0) >> 5);
+  const bool row_ok = m < p.M;
+  const int mm = row_ok ? m : 0;
+  const int b = mm / p.rows_per_item;
+  // observation part of the FiLM embedding, quad-transposed [column quad][sample] float4: the lanes of a warp are
+  // consecutive rows = consecutive (or equal) samples, so one load instruction touches one or two 128-byte lines
+  // instead of one line per lane (which made this the most expensive piece of the epilogue)
+  const float4* oq = reinterpret_cast<const float4*>(p.otab_q);
+  const float* trow = (p.film && p.step.rows) ? p.ttab + (long long)step_of(p.step, mm) * p.ld_ttab + p.film_off : nullptr;
+  const bool film = p.film && !(p.epi_skip & 2);
+  const bool res = p.res_bf16 && !p.use_aux && row_ok && !(p.epi_skip & 4);
+#pragma unroll
+  for (int cc = 0; cc < CPP; ++cc) {
+    const int c = c_begin + cc;
+    const int nb = n0 + c * 32;
+    if (film && c < nchunks) {
+      const float4* fs4 = reinterpret_cast<const float4*>(es.fscale + c * 32);
+      const float4* fb4 = reinterpret_cast<const float4*>(es.fshift + c * 32);
+      const float4* os4 = oq + (long long)((p.film_off + nb) >> 2) * p.otab_B + b;
+      const float4* ob4 = oq + (long long)((p.film_off + p.film_c + nb) >> 2) * p.otab_B + b;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float4 sc = fs4[j], sh = fb4[j];
+        const float4 o1 = __ldg(os4 + (long long)j * p.otab_B), o2 = __ldg(ob4 + (long long)j * p.otab_B);
+        sc.x += o1.x; sc.y += o1.y; sc.z += o1.z; sc.w += o1.w;
+        sh.x += o2.x; sh.y += o2.y; sh.z += o2.z; sh.w += o2.w;
+        if (trow) {
+          const float4 t1 = __ldg(reinterpret_cast<const float4*>(trow + nb) + j);
+          const float4 t2 = __ldg(reinterpret_cast<const float4*>(trow + p.film_c + nb) + j);
+          sc.x += t1.x; sc.y += t1.y; sc.z += t1.z; sc.w += t1.w;
+          sh.x += t2.x; sh.y += t2.y; sh.z += t2.z; sh.w += t2.w;
+        }
+        __half2 h0 = __floats2half2_rn(sc.x, sh.x), h1 = __floats2half2_rn(sc.y, sh.y);
+        __half2 h2 = __floats2half2_rn(sc.z, sh.z), h3 = __floats2half2_rn(sc.w, sh.w);
+        pf.film[cc][4 * j + 0] = *reinterpret_cast<uint32_t*>(&h0);
+        pf.film[cc][4 * j + 1] = *reinterpret_cast<uint32_t*>(&h1);
+        pf.film[cc][4 * j + 2] = *reinterpret_cast<uint32_t*>(&h2);
+        pf.film[cc][4 * j + 3] = *reinterpret_cast<uint32_t*>(&h3);
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) pf.film[cc][i] = 0x00003c00u;     // half2(1, 0): identity
+    }
+    if (res && c < nchunks) {
+      const uint4* rp = reinterpret_cast<const uint4*>(p.res_bf16 + (long long)m * p.ld_res_bf16 + nb);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) pf.res[cc][j] = __ldcg(rp + j);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) pf.res[cc][j] = make_uint4(0u, 0u, 0u, 0u);
+    }
+  }
+}
+
+template <int BN>
+__device__ __forceinline__ void epilogue_gn(const TcGemm& p, EpiSmem<BN>& es, uint32_t taddr, int m, int n0, int c_begin,
+                                            int row, int lane, const GnPrefetch<BN>& pf) {
+  constexpr int NC = BN / 32, CPP = TcGeo<BN>::CPP;
+  const int T = p.rows_per_item;
+  const int cpg = p.group_width >> 5;                    // chunks per group: 1, 2 or 4
+  const int nchunks = min(NC, (p.N - n0) >> 5);          // N and the group widths are multiples of 32 here
+  const bool row_ok = m < p.M;
+  // one TMEM pass: acc + bias stays in registers; (sum, sum sq) per 32-column chunk goes to shared memory
+  float v[CPP][32];
+#pragma unroll
+  for (int cc = 0; cc < CPP; ++cc) {
+    const int c = c_begin + cc;
+    float s = 0.f, ss = 0.f;
+    if (c < nchunks) {
+      load_acc_chunk<BN>(p, taddr, c, lane, v[cc]);
+      add_smem32(v[cc], es.bias + c * 32);
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        s += v[cc][i];
+        ss = fmaf(v[cc][i], v[cc][i], ss);
+      }
+    }
+    es.part[row][c] = make_float2(s, ss);
+  }
+  const bool dbg_t = p.dbg_stage && threadIdx.x == 64 && blockIdx.x == 0 && blockIdx.y == 0;
+  if (dbg_t) p.dbg_stage[24] = clock64();          // accumulators read, partial statistics written
+  epi_bar<BN>();
+  if (dbg_t) p.dbg_stage[25] = clock64();          // statistics barrier passed
+  // group statistics: chunks of the group (from smem) x the T rows of the sample (adjacent lanes)
+  float mean[CPP], rstd[CPP];
+  const float inv_cnt = 1.f / (float)(T * p.group_width);
+#pragma unroll
+  for (int cc = 0; cc < CPP; ++cc) {
+    const int c = c_begin + cc;
+    const int g0 = (c / cpg) * cpg;
+    float s = 0.f, ss = 0.f;
+    for (int c2 = g0; c2 < g0 + cpg; ++c2) {
+      float2 q = es.part[row][c2];
+      s += q.x;
+      ss += q.y;
+    }
+    for (int off = 1; off < T; off <<= 1) {
+      s += __shfl_xor_sync(0xffffffffu, s, off);
+      ss += __shfl_xor_sync(0xffffffffu, ss, off);
+    }
+    const float mu = s * inv_cnt;
+    mean[cc] = mu;
+    rstd[cc] = rsqrtf(fmaxf(ss * inv_cnt - mu * mu, 0.f) + p.eps);
+  }
+  // normalise -> activation -> FiLM -> residual -> store
+#pragma unroll
+  for (int cc = 0; cc < CPP; ++cc) {
+    const int c = c_begin + cc;
+    if (c >= nchunks) continue;
+    const int nb = n0 + c * 32;
+    const float4* g4 = reinterpret_cast<const float4*>(es.gamma + c * 32);
+    const float4* be4 = reinterpret_cast<const float4*>(es.beta + c * 32);
+    const float rs = rstd[cc], nmr = -mean[cc] * rstd[cc];
+    float(&w)[32] = v[cc];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float4 gg = g4[j], be = be4[j];
+      w[4 * j + 0] = fmaf(fmaf(w[4 * j + 0], rs, nmr), gg.x, be.x);
+      w[4 * j + 1] = fmaf(fmaf(w[4 * j + 1], rs, nmr), gg.y, be.y);
+      w[4 * j + 2] = fmaf(fmaf(w[4 * j + 2], rs, nmr), gg.z, be.z);
+      w[4 * j + 3] = fmaf(fmaf(w[4 * j + 3], rs, nmr), gg.w, be.w);
+    }
+    if (p.epi_skip & 8) {
+    } else if (p.gn_act == 1) {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) w[i] = swish_fast(w[i]);
+    } else if (p.gn_act == 0) {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) w[i] = mish_fast(w[i]);
+    }
+    if (dbg_t) p.dbg_stage[26] = clock64();        // normalised + activation
+    if (p.film) {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&pf.film[cc][i]));
+        w[i] = fmaf(f.x, w[i], f.y);
+      }
+    }
+    if (p.use_aux) {
+      float r[32];
+      tmem_ld_32x32(taddr + p.n_acc * BN + c * 32, r);
+      add_smem32(r, es.bias2 + c * 32);
+#pragma unroll
+      for (int i = 0; i < 32; ++i) w[i] += r[i];
+    } else if (p.res_bf16) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const uint4 u = pf.res[cc][j];
+        const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float2 f = __bfloat1622float2(h[q]);
+          w[8 * j + 2 * q] += f.x;
+          w[8 * j + 2 * q + 1] += f.y;
+        }
+      }
+    }
+    if (dbg_t) p.dbg_stage[27] = clock64();        // FiLM + residual applied
+    if (row_ok && !((p.epi_skip & 1) && w[0] != 12345.678f)) {
+      if (p.out_bf16) store_bf16x32(p.out_bf16 + (long long)m * p.ld_out_bf16 + nb, w, true, 32);
+      if (p.out_f32) store_f32x32(p.out_f32 + (long long)m * p.ld_out_f32 + nb, w, true, 32);
+    }
+    if (dbg_t) p.dbg_stage[28] = clock64();        // stores issued
+  }
+}
+
+// DDPM / DDIM update fused behind the score net's last GEMM.  Phase 1: every epilogue thread drops its row of
+// eps = acc + bias into a padded shared-memory tile (the pipeline buffers, idle by now).  Phase 2: the tile is
+// walked row-major, one thread per group of 4 consecutive columns, so x, the injected noise and the bf16 copy of x
+// are accessed coalesced and one Philox call serves four elements (row-structured quads, see DdpmCall).
+template <int BN>
+__device__ __forceinline__ void epilogue_ddpm(const TcGemm& p, EpiSmem<BN>& es, uint32_t taddr, float* tile, int tile_m,
+                                              int n0, int c_begin, int row, int et, int lane) {
+  constexpr int CPP = TcGeo<BN>::CPP;
+  constexpr int TS = BN + 1;
+#pragma unroll 1
+  for (int cc = 0; cc < CPP; ++cc) {
+    const int c = c_begin + cc;
+    if (n0 + c * 32 >= p.N) continue;          // uniform
+    float v[32];
+    load_acc_chunk<BN>(p, taddr, c, lane, v);
+    add_smem32(v, es.bias + c * 32);
+    float* trow = tile + row * TS + c * 32;
+#pragma unroll
+    for (int i = 0; i < 32; ++i) trow[i] = v[i];
+  }
+  epi_bar<BN>();
+  const int t = step_of(p.step, 0);
+  const float* cf = p.coef + t * 8;
+  const float inv_sa = cf[0], s1a = cf[1], c0 = cf[2], ct = cf[3], sigma = cf[4], sap = cf[5], s1ap = cf[6];
+  const DdpmCall call = p.call_dev ? *p.call_dev : p.call;
+  const float* noise = call.noise ? call.noise + (long long)(call.n_steps - 1 - t) * call.noise_step_stride : nullptr;
+  const bool ddim = call.sampler == LDP_SAMPLER_DDIM;
+  const bool add_noise = !ddim && t > 0;
+  const int nv = min(BN, p.N - n0);
+  const int nq = (nv + 3) >> 2;                                  // column quads of this tile (n0 is a multiple of 4)
+  const int rows_here = min(TC_BM, p.M - tile_m * TC_BM);
+  const int total = rows_here * nq;
+  const bool vb = p.out_bf16 != nullptr && (p.ld_out_bf16 & 3) == 0;
+#pragma unroll 1
+  for (int idx = et; idx < total; idx += TcGeo<BN>::EPI_THREADS) {
+    const int r = idx / nq, g = idx - r * nq;
+    const int m = tile_m * TC_BM + r;
+    const int cb = g * 4;
+    const int cnt = min(4, nv - cb);
+    const long long e0 = (long long)m * p.N + n0 + cb;
+    float* xr = p.x_io + (long long)m * p.ld_x + n0 + cb;
+    float z[4] = {0.f, 0.f, 0.f, 0.f};
+    if (add_noise) {
+      if (noise) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          if (i < cnt) z[i] = noise[e0 + i];
+      } else {
+        philox_normal4_rows(call.seed, call.stream_id, (uint32_t)t, (uint32_t)(call.row_offset + m), (uint32_t)((n0 + cb) >> 2), z);
+      }
+    }
+    float o[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      o[i] = 0.f;
+      if (i < cnt) {
+        const float e = tile[r * TS + cb + i];
+        const float x = __ldcg(xr + i);
+        const float x0 = fminf(fmaxf((x - s1a * e) * inv_sa, -1.f), 1.f);
+        float y;
+        if (ddim) {
+          y = sap * x0 + s1ap * e;
+        } else {
+          y = c0 * x0 + ct * x;
+          if (add_noise) y = fmaf(sigma, z[i], y);
+        }
+        xr[i] = y;
+        o[i] = y;
+      }
+    }
+    if (p.out_bf16) {
+      __nv_bfloat16* ob = p.out_bf16 + (long long)m * p.ld_out_bf16 + n0 + cb;
+      if (vb && cnt == 4) {
+        uint2 u;
+        u.x = pack_bf16x2(o[0], o[1]);
+        u.y = pack_bf16x2(o[2], o[3]);
+        *reinterpret_cast<uint2*>(ob) = u;
+      } else {
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          if (i < cnt) ob[i] = __float2bfloat16(o[i]);
+      }
+    }
+  }
+}
+
+template <int BN>
+__device__ __forceinline__ void epilogue_ln(const TcGemm& p, EpiSmem<BN>& es, uint32_t taddr, int m, int n0, int c_begin,
+                                            int row, int part, int lane) {
+  // requires N == BN: the whole feature row lives in this tile, split over the two warps of the lane quarter
+  constexpr int CPP = TcGeo<BN>::CPP;
+  const bool row_ok = m < p.M;
+  float s = 0.f, ss = 0.f;
+  float* hrow = p.out_f32 + (long long)(row_ok ? m : 0) * p.ld_out_f32;
+  const bool vf = (p.ld_out_f32 & 3) == 0, vr = (p.ld_res_f32 & 3) == 0;
+#pragma unroll 1
+  for (int cc = 0; cc < CPP; ++cc) {
+    const int c = c_begin + cc;
+    const int nb = n0 + c * 32;
+    float v[32];
+    load_acc_chunk<BN>(p, taddr, c, lane, v);
+    add_smem32(v, es.bias + c * 32);
+    if (p.res_f32 && row_ok) add_f32x32(v, p.res_f32 + (long long)m * p.ld_res_f32 + nb, vr, 32);
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+      s += v[i];
+      ss = fmaf(v[i], v[i], ss);
+    }
+    if (row_ok) store_f32x32(hrow + nb, v, vf, 32);
+  }
+  es.part[row][part] = make_float2(s, ss);
+  epi_bar<BN>();
+  float ts = 0.f, tss = 0.f;
+#pragma unroll
+  for (int q = 0; q < TcGeo<BN>::PARTS; ++q) {
+    const float2 pq = es.part[row][q];
+    ts += pq.x;
+    tss += pq.y;
+  }
+  const float mu = ts / (float)BN;
+  const float rs = rsqrtf(fmaxf(tss / (float)BN - mu * mu, 0.f) + p.eps);
+  if (!row_ok || !p.out_bf16) return;
+#pragma unroll 1
+  for (int cc = 0; cc < CPP; ++cc) {
+    const int c = c_begin + cc;
+    const int nb = n0 + c * 32;
+    float v[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = 0.f;
+    add_f32x32(v, hrow + nb, vf, 32);                     // h written above by this same thread
+    if (p.relu) {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
+    } else {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) v[i] = fmaf((v[i] - mu) * rs, es.gamma[c * 32 + i], es.beta[c * 32 + i]);
+    }
+    store_bf16x32(p.out_bf16 + (long long)m * p.ld_out_bf16 + nb, v, (p.ld_out_bf16 & 7) == 0, 32);
+  }
+}
+
+}  // namespace ldp
