@@ -27,7 +27,7 @@ NVCC_FLAGS = [
     "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden",
     "--expt-relaxed-constexpr",
     "-Xptxas", "-v",
-]
+] + os.environ.get("LDP_EXTRA_NVCC", "").split()
 
 
 def _nvcc() -> str:

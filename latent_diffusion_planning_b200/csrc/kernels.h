@@ -189,7 +189,6 @@ int launch_tc_gemm(const TcGemm& p, cudaStream_t s);
 
 // The whole reverse-diffusion loop of the planner as one persistent kernel (planner_loop.cu).
 struct PlannerLoop {
-  const TcGemm* layers = nullptr;   // device array: the ops of one denoising step (non-pair), geometry filled in
   int n_layers = 0;
   int n_steps = 0;                  // reverse steps to run; iteration i uses timestep t_first - i
   int t_first = 0;
@@ -199,6 +198,8 @@ struct PlannerLoop {
   int dbg_step = 0;
   int flags = 0;                    // diagnostics: 1 = no weight prefetch before the group barrier, 2 = every epilogue thread fences
 };
+// the ops of one denoising step (non-pair, geometry filled in) go to the kernel's constant table before the launch
+int upload_planner_loop_layers(const TcGemm* layers_host, int n_layers, cudaStream_t s);
 int launch_planner_loop(const PlannerLoop& lp, int n_groups, cudaStream_t s);
 int tc_gemm_geometry(TcGemm* p);   // fills tiles_m/n, grid_ctas, acc_bufs, acc_stride, tmem_cols
 

@@ -101,7 +101,7 @@ struct PlanWs {
   cudaGraph_t graph_src = nullptr;
   // persistent loop kernel (planner_loop.cu)
   int loop_state = 0;              // 0 not prepared, 1 ready, -1 unsupported for this shape
-  TcGemm* layers_dev = nullptr;
+  std::vector<TcGemm> loop_ops;    // host copy of the loop kernel's layer table
   int* group_counter = nullptr;
   int n_groups = 0;
   long long* loop_dbg = nullptr;
@@ -864,10 +864,10 @@ static int prepare_loop(LdpPlanner* h, PlanWs* w) {
     if (op.num_stages < 2) return LDP_OK;
     op.tiles_m_group = spc * op.rows_per_item / 128;
     op.persistent = 0; op.acc_bufs = 1;
-    op.epi_skip = 0; op.dbg = nullptr; op.dbg_stage = nullptr;
+    op.epi_skip = getenv("LDP_LOOP_FLAGS") ? (atoi(getenv("LDP_LOOP_FLAGS")) >> 4 << 4) : 0; op.dbg = nullptr; op.dbg_stage = nullptr;
   }
-  LDP_TRY(w->arena.alloc_t(&w->layers_dev, ops.size()));
-  LDP_CUDA_OK(cudaMemcpy(w->layers_dev, ops.data(), ops.size() * sizeof(TcGemm), cudaMemcpyHostToDevice));
+  if (ops.size() > 40) return LDP_OK;
+  w->loop_ops = ops;
   LDP_TRY(w->arena.alloc_t(&w->group_counter, (size_t)n_groups));
   LDP_TRY(w->arena.alloc_t(&w->loop_dbg, ops.size() * 8 + 8));
   w->n_groups = n_groups;
@@ -970,20 +970,23 @@ int ldp_planner_sample(LdpPlanner* h, int precision, int sampler, const float* x
       // the whole loop in one persistent kernel; timestep of iteration i = n_steps - 1 - i
       LDP_CUDA_OK(cudaMemsetAsync(w->group_counter, 0, (size_t)w->n_groups * sizeof(int), s));
       PlannerLoop lp;
-      lp.layers = w->layers_dev; lp.n_layers = (int)w->ops.size();
+      // one loop launch uses the table at a time: uploads are stream-ordered behind the previous launch on this stream
+      LDP_TRY(upload_planner_loop_layers(w->loop_ops.data(), (int)w->loop_ops.size(), s));
+      lp.n_layers = (int)w->ops.size();
       lp.n_steps = n_steps; lp.t_first = n_steps - 1;
       lp.group_counter = w->group_counter; lp.group_ctas = 8;
       if (getenv("LDP_LOOP_FLAGS")) lp.flags = atoi(getenv("LDP_LOOP_FLAGS"));
       if (getenv("LDP_LOOP_DBG")) { lp.dbg = w->loop_dbg; lp.dbg_step = std::min(n_steps - 1, atoi(getenv("LDP_LOOP_DBG"))); }
       LDP_TRY(launch_planner_loop(lp, w->n_groups, s));
       if (lp.dbg) {
-        std::vector<long long> hb(w->ops.size() * 8);
+        std::vector<long long> hb(w->ops.size() * 8 + 8);
         LDP_CUDA_OK(cudaStreamSynchronize(s));
         LDP_CUDA_OK(cudaMemcpy(hb.data(), w->loop_dbg, hb.size() * 8, cudaMemcpyDeviceToHost));
         const long long t0 = hb[0];
+        { const long long* d = &hb[w->ops.size() * 8]; fprintf(stderr, "last-layer epilogue (thread 64): tfull %lld | phase1 %lld bar %lld phase2 %lld bar %lld phase3 %lld\n", d[5] - t0, d[0] - d[5], d[1] - d[0], d[2] - d[1], d[3] - d[2], d[4] - d[3]); }
         for (size_t i = 0; i < w->ops.size(); ++i)
-          fprintf(stderr, "loop layer %2zu: enter %8lld polled %8lld first-operands %8lld mma-issued %8lld epilogue-done %8lld\n", i,
-                  hb[i * 8 + 0] - t0, hb[i * 8 + 1] ? hb[i * 8 + 1] - t0 : 0, hb[i * 8 + 2] - t0, hb[i * 8 + 3] - t0, hb[i * 8 + 5] - t0);
+          fprintf(stderr, "loop layer %2zu: enter %8lld polled %8lld first-operands %8lld mma-issued %8lld epilogue-done %8lld tile0-done %8lld\n", i,
+                  hb[i * 8 + 0] - t0, hb[i * 8 + 1] ? hb[i * 8 + 1] - t0 : 0, hb[i * 8 + 2] - t0, hb[i * 8 + 3] - t0, hb[i * 8 + 5] - t0, hb[i * 8 + 4] - t0);
       }
     } else
     if (h->use_graph && !w->graph) {

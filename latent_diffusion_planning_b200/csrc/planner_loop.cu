@@ -24,9 +24,19 @@
 // Activations written by one CTA are read by the other CTAs of its group through TMA (async proxy) and ld.global.cg:
 // writer = st.global ... bar.sync (epilogue warps) ... fence.proxy.async + red.release.gpu; reader = ld.acquire.gpu +
 // fence.proxy.async before the TMA loads.
+#ifdef LDP_LOOP_BACKOFF
+#define LDP_MBAR_BACKOFF LDP_LOOP_BACKOFF
+#endif
 #include "tc_epilogue.cuh"
 
 namespace ldp {
+
+// The ops of one denoising step, uploaded before the launch.  Constant memory keeps every parameter access a uniform
+// constant-bank operand (as in the per-layer kernel, where the parameters are kernel arguments) and lets the TMA unit
+// fetch the tensor maps from it.
+constexpr int PL_MAX_LAYERS = 40;
+__constant__ __align__(64) uint8_t c_layers_raw[PL_MAX_LAYERS * sizeof(TcGemm)];     // TcGemm has default member initialisers
+#define c_layers (reinterpret_cast<const TcGemm*>(c_layers_raw))
 
 constexpr int PL_EPI_WARPS = 16;
 constexpr int PL_THREADS = 64 + PL_EPI_WARPS * 32;
@@ -53,14 +63,6 @@ __device__ __forceinline__ void umma_lohi(uint32_t d_tmem, uint32_t a_lo, uint32
       : "memory");
 }
 
-// copy one TcGemm from global to shared memory with n_threads threads (tid in [0, n_threads))
-__device__ __forceinline__ void copy_params(TcGemm* dst, const TcGemm* src, int tid, int n_threads) {
-  static_assert(sizeof(TcGemm) % 16 == 0, "TcGemm must be a multiple of 16 bytes");
-  const uint4* s = reinterpret_cast<const uint4*>(src);
-  uint4* d = reinterpret_cast<uint4*>(dst);
-  for (int i = tid; i < (int)(sizeof(TcGemm) / 16); i += n_threads) d[i] = __ldg(s + i);
-}
-
 struct TileIter {      // the tiles of one layer that belong to this CTA, in the order every role walks them
   int tm_g, ntiles, group, r, G, M;
   __device__ __forceinline__ TileIter(const TcGemm& p, int group_, int r_, int G_)
@@ -73,8 +75,9 @@ struct TileIter {      // the tiles of one layer that belong to this CTA, in the
 };
 
 template <int BN, int MODE>
-__device__ __noinline__ void epilogue_tile(const TcGemm& p, uint8_t* es_raw, uint32_t tmem_base, uint8_t* ring, int tile_m,
-                                              int n0, int warp, int lane, uint32_t bar_tfull, uint32_t tfull_parity, int flags) {
+__device__ __noinline__ void epilogue_tile(int layer, uint8_t* es_raw, uint32_t tmem_base, uint8_t* ring, int tile_m,
+                                              int n0, int warp, int lane, uint32_t bar_tfull, uint32_t tfull_parity, int flags, int timestep, long long* dbg) {
+  const TcGemm& p = c_layers[layer];              // formed here so that the accesses stay constant-bank loads
   EpiSmem<BN>& es = *reinterpret_cast<EpiSmem<BN>*>(es_raw);
   const int ew = warp - 2;
   const int quarter = warp & 3;
@@ -84,7 +87,7 @@ __device__ __noinline__ void epilogue_tile(const TcGemm& p, uint8_t* es_raw, uin
   {
     const int et = threadIdx.x - 64;
     const bool uniform_step = p.film && p.step.rows == nullptr;
-    const float* trow = uniform_step ? p.ttab + (long long)step_of(p.step, 0) * p.ld_ttab + p.film_off : nullptr;
+    const float* trow = uniform_step ? p.ttab + (long long)timestep * p.ld_ttab + p.film_off : nullptr;
     for (int i = et; i < BN; i += TcGeo<BN>::EPI_THREADS) {
       const int n = n0 + i;
       const bool ok = n < p.N;
@@ -104,10 +107,11 @@ __device__ __noinline__ void epilogue_tile(const TcGemm& p, uint8_t* es_raw, uin
   if constexpr (MODE == TC_EPI_GN) gn_prefetch<BN>(p, es, m, n0, c_begin, pf);
   mbar_wait(bar_tfull, tfull_parity);
   tc_fence_after();
+  if (dbg && threadIdx.x == 64) dbg[5] = clock64();
   const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16);
   if constexpr (MODE == TC_EPI_PLAIN) epilogue_plain<BN>(p, es, taddr, m, n0, c_begin, lane);
   else if constexpr (MODE == TC_EPI_GN) epilogue_gn<BN>(p, es, taddr, m, n0, c_begin, row, lane, pf);
-  else epilogue_ddpm<BN>(p, es, taddr, reinterpret_cast<float*>(ring), tile_m, n0, c_begin, row, (int)threadIdx.x - 64, lane);
+  else epilogue_ddpm<BN>(p, es, taddr, reinterpret_cast<float*>(ring), tile_m, n0, c_begin, row, (int)threadIdx.x - 64, lane, timestep, dbg);
   if (flags & 2) { __threadfence(); fence_proxy_async_all(); }
   tc_fence_before();
   epi_bar<BN>();      // all of this tile's accumulator reads and global stores are issued; `es` may be rewritten
@@ -122,10 +126,6 @@ __global__ void __launch_bounds__(PL_THREADS, 1) planner_loop_kernel(const __gri
   __shared__ uint32_t tmem_holder;
   __shared__ __align__(16) TcStage kb_s[TC_MAX_KB_SMEM];
   __shared__ __align__(16) uint8_t es_raw[sizeof(EpiSmem<128>)];
-  __shared__ __align__(64) uint8_t params_raw[3][sizeof(TcGemm)];     // per-role copies of the current layer's parameters
-  TcGemm& P_prod = *reinterpret_cast<TcGemm*>(params_raw[0]);
-  TcGemm& P_mma = *reinterpret_cast<TcGemm*>(params_raw[1]);
-  TcGemm& P_epi = *reinterpret_cast<TcGemm*>(params_raw[2]);
 
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* ring = smem_raw + (smem_base - smem_u32(smem_raw));
@@ -164,19 +164,17 @@ __global__ void __launch_bounds__(PL_THREADS, 1) planner_loop_kernel(const __gri
     int q = 0;                      // layers completed by the group before the current one (over all steps)
     for (int it = 0; it < lp.n_steps; ++it) {
       for (int l = 0; l < lp.n_layers; ++l, ++q) {
-        const TcGemm* gl = lp.layers + l;
-        __syncwarp();
-        copy_params(&P_prod, gl, lane, 32);
+        const TcGemm* gl = &c_layers[l];
         __syncwarp();
         {
-          const int nkb = P_prod.num_kb;
-          const uint4* src = reinterpret_cast<const uint4*>(P_prod.kb);
+          const int nkb = gl->num_kb;
+          const uint4* src = reinterpret_cast<const uint4*>(gl->kb);
           uint4* dst = reinterpret_cast<uint4*>(kb_s);
           for (int i = lane; i < nkb; i += 32) dst[i] = __ldg(src + i);
         }
         __syncwarp();
-        if (lane == 0) {
-          const TcGemm& p = P_prod;
+        if (elect_one()) {
+          const TcGemm& p = *gl;
           const int BN = p.block_n;
           const uint32_t b_bytes = (uint32_t)BN * TC_BK * 2;
           const uint32_t stage_bytes = TC_A_BYTES + (uint32_t)p.w_max * b_bytes;
@@ -223,6 +221,7 @@ __global__ void __launch_bounds__(PL_THREADS, 1) planner_loop_kernel(const __gri
               if (ld_acquire_gpu(counter) < target) {
                 const long long t0 = clock64();
                 while (ld_acquire_gpu(counter) < target) {
+                  if (lp.flags & 4) __nanosleep(200);
                   if (clock64() - t0 > 4000000000ll) {     // ~2 s: a lost arrival shows up as a CUDA error, not a hung GPU
                     printf("ldp_b200: planner loop group barrier timeout (block %d layer %d iteration %d)\n", blockIdx.x, l, it);
                     __trap();
@@ -270,10 +269,8 @@ __global__ void __launch_bounds__(PL_THREADS, 1) planner_loop_kernel(const __gri
     for (int it = 0; it < lp.n_steps; ++it) {
       for (int l = 0; l < lp.n_layers; ++l) {
         __syncwarp();
-        copy_params(&P_mma, lp.layers + l, lane, 32);
-        __syncwarp();
-        if (lane == 0) {
-          const TcGemm& p = P_mma;
+        if (elect_one()) {
+          const TcGemm& p = c_layers[l];
           const int BN = p.block_n;
           const uint32_t b_step = ((uint32_t)BN * TC_BK * 2) >> 4;                     // descriptor units (16 B)
           const uint32_t stage_step = (TC_A_BYTES + (uint32_t)p.w_max * BN * TC_BK * 2) >> 4;
@@ -299,7 +296,7 @@ __global__ void __launch_bounds__(PL_THREADS, 1) planner_loop_kernel(const __gri
               const uint32_t par = (use_bits >> stage) & 1u;
               mbar_wait(full0 + 8u * stage, par);
               tc_fence_after();
-              if (dbg_now && kb == 0) lp.dbg[l * 8 + 2] = clock64();
+              if (dbg_now && kb == 0 && t == r) lp.dbg[l * 8 + 2] = clock64();
               const uint32_t a_lo = a_lo0 + stage * stage_step;
               uint32_t b_lo = a_lo + (TC_A_BYTES >> 4);
               uint32_t d = tmem_base;
@@ -331,7 +328,7 @@ __global__ void __launch_bounds__(PL_THREADS, 1) planner_loop_kernel(const __gri
               if (++stage == S) stage = 0;
             }
             umma_commit(tfull);
-            if (dbg_now) lp.dbg[l * 8 + 3] = clock64();
+            if (dbg_now && t == r) lp.dbg[l * 8 + 3] = clock64();
             ++tile_seq;
           }
         }
@@ -344,17 +341,8 @@ __global__ void __launch_bounds__(PL_THREADS, 1) planner_loop_kernel(const __gri
     for (int it = 0; it < lp.n_steps; ++it) {
       const int timestep = lp.t_first - it;
       for (int l = 0; l < lp.n_layers; ++l) {
-        epi_all_bar();                                   // every epilogue warp is done with the previous layer
-        copy_params(&P_epi, lp.layers + l, (int)threadIdx.x - 64, PL_EPI_WARPS * 32);
-        epi_all_bar();
-        if (threadIdx.x == 64) {
-          P_epi.step.rows = nullptr;
-          P_epi.step.dev = nullptr;
-          P_epi.step.scalar = timestep;
-          P_epi.step.rows_per_t = 1;
-        }
-        epi_all_bar();
-        const TcGemm& p = P_epi;
+        epi_all_bar();                                   // every epilogue warp is done with the previous layer (`es` is free)
+        const TcGemm& p = c_layers[l];
         const int BN = p.block_n;
         const bool active = ew < (BN == 64 ? 8 : 16);
         const bool dbg_now = dbg_cta && it == lp.dbg_step && threadIdx.x == 64;
@@ -368,14 +356,17 @@ __global__ void __launch_bounds__(PL_THREADS, 1) planner_loop_kernel(const __gri
           if (active) {
             const int n0 = tile_n * BN;
             if (BN == 64) {
-              if (p.mode == TC_EPI_GN) epilogue_tile<64, TC_EPI_GN>(p, es_raw, tmem_base, ring, tile_m, n0, warp, lane, tfull, par, lp.flags);
-              else epilogue_tile<64, TC_EPI_PLAIN>(p, es_raw, tmem_base, ring, tile_m, n0, warp, lane, tfull, par, lp.flags);
+              if (p.mode == TC_EPI_GN) epilogue_tile<64, TC_EPI_GN>(l, es_raw, tmem_base, ring, tile_m, n0, warp, lane, tfull, par, lp.flags, timestep, (dbg_cta && it == lp.dbg_step && t == r) ? lp.dbg + lp.n_layers * 8 : nullptr);
+              else epilogue_tile<64, TC_EPI_PLAIN>(l, es_raw, tmem_base, ring, tile_m, n0, warp, lane, tfull, par, lp.flags, timestep, (dbg_cta && it == lp.dbg_step && t == r) ? lp.dbg + lp.n_layers * 8 : nullptr);
             } else {
-              if (p.mode == TC_EPI_GN) epilogue_tile<128, TC_EPI_GN>(p, es_raw, tmem_base, ring, tile_m, n0, warp, lane, tfull, par, lp.flags);
-              else if (p.mode == TC_EPI_DDPM) epilogue_tile<128, TC_EPI_DDPM>(p, es_raw, tmem_base, ring, tile_m, n0, warp, lane, tfull, par, lp.flags);
-              else epilogue_tile<128, TC_EPI_PLAIN>(p, es_raw, tmem_base, ring, tile_m, n0, warp, lane, tfull, par, lp.flags);
+              if (p.mode == TC_EPI_GN) epilogue_tile<128, TC_EPI_GN>(l, es_raw, tmem_base, ring, tile_m, n0, warp, lane, tfull, par, lp.flags, timestep, (dbg_cta && it == lp.dbg_step && t == r) ? lp.dbg + lp.n_layers * 8 : nullptr);
+              else if (p.mode == TC_EPI_DDPM) epilogue_tile<128, TC_EPI_DDPM>(l, es_raw, tmem_base, ring, tile_m, n0, warp, lane, tfull, par, lp.flags, timestep, (dbg_cta && it == lp.dbg_step && t == r) ? lp.dbg + lp.n_layers * 8 : nullptr);
+              else epilogue_tile<128, TC_EPI_PLAIN>(l, es_raw, tmem_base, ring, tile_m, n0, warp, lane, tfull, par, lp.flags, timestep, (dbg_cta && it == lp.dbg_step && t == r) ? lp.dbg + lp.n_layers * 8 : nullptr);
             }
-            if (threadIdx.x == 64) mbar_arrive(tempty);
+            if (threadIdx.x == 64) {
+              mbar_arrive(tempty);
+              if (dbg_now && t == r) lp.dbg[l * 8 + 4] = clock64();
+            }
           }
           ++tile_seq;
         }
@@ -407,13 +398,19 @@ __global__ void __launch_bounds__(PL_THREADS, 1) planner_loop_kernel(const __gri
   if (warp == 1) tmem_dealloc(tmem_base, 512);
 }
 
+int upload_planner_loop_layers(const TcGemm* layers_host, int n_layers, cudaStream_t s) {
+  LDP_CHECK(n_layers > 0 && n_layers <= PL_MAX_LAYERS, LDP_ERR_UNSUPPORTED, "planner loop: too many layers for the constant table");
+  LDP_CUDA_OK(cudaMemcpyToSymbolAsync(c_layers_raw, layers_host, (size_t)n_layers * sizeof(TcGemm), 0, cudaMemcpyHostToDevice, s));
+  return LDP_OK;
+}
+
 int launch_planner_loop(const PlannerLoop& lp, int n_groups, cudaStream_t s) {
   static bool attr_done = false;
   if (!attr_done) {
     LDP_CUDA_OK(cudaFuncSetAttribute(planner_loop_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_RING + 1024));
     attr_done = true;
   }
-  LDP_CHECK(lp.layers && lp.n_layers > 0 && lp.n_steps > 0 && lp.group_counter && lp.group_ctas > 0 && n_groups > 0,
+  LDP_CHECK(lp.n_layers > 0 && lp.n_layers <= PL_MAX_LAYERS && lp.n_steps > 0 && lp.group_counter && lp.group_ctas > 0 && n_groups > 0,
             LDP_ERR_INVALID_ARG, "planner loop: bad arguments");
   planner_loop_kernel<<<dim3(n_groups * lp.group_ctas), dim3(PL_THREADS), TC_SMEM_RING + 1024, s>>>(lp);
   {

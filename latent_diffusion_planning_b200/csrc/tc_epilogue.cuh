@@ -416,7 +416,7 @@ __device__ __forceinline__ void epilogue_gn(const TcGemm& p, EpiSmem<BN>& es, ui
 // are accessed coalesced and one Philox call serves four elements (row-structured quads, see DdpmCall).
 template <int BN>
 __device__ __forceinline__ void epilogue_ddpm(const TcGemm& p, EpiSmem<BN>& es, uint32_t taddr, float* tile, int tile_m,
-                                              int n0, int c_begin, int row, int et, int lane) {
+                                              int n0, int c_begin, int row, int et, int lane, int t_override = -1, long long* dbg = nullptr) {
   constexpr int CPP = TcGeo<BN>::CPP;
   constexpr int TS = BN + 1;
 #pragma unroll 1
@@ -431,7 +431,7 @@ __device__ __forceinline__ void epilogue_ddpm(const TcGemm& p, EpiSmem<BN>& es, 
     for (int i = 0; i < 32; ++i) trow[i] = v[i];
   }
   epi_bar<BN>();
-  const int t = step_of(p.step, 0);
+  const int t = t_override >= 0 ? t_override : step_of(p.step, 0);
   const float* cf = p.coef + t * 8;
   const float inv_sa = cf[0], s1a = cf[1], c0 = cf[2], ct = cf[3], sigma = cf[4], sap = cf[5], s1ap = cf[6];
   const DdpmCall call = p.call_dev ? *p.call_dev : p.call;
@@ -461,13 +461,18 @@ __device__ __forceinline__ void epilogue_ddpm(const TcGemm& p, EpiSmem<BN>& es, 
         philox_normal4_rows(call.seed, call.stream_id, (uint32_t)t, (uint32_t)(call.row_offset + m), (uint32_t)((n0 + cb) >> 2), z);
       }
     }
+    // all four x loads first: ld.global.cg is a strong access that the compiler keeps in program order with the stores
+    // below, so loading inside the per-element loop serialises four L2 round trips per iteration
+    float xv[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) xv[i] = i < cnt ? __ldcg(xr + i) : 0.f;
     float o[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       o[i] = 0.f;
       if (i < cnt) {
         const float e = tile[r * TS + cb + i];
-        const float x = __ldcg(xr + i);
+        const float x = xv[i];
         const float x0 = fminf(fmaxf((x - s1a * e) * inv_sa, -1.f), 1.f);
         float y;
         if (ddim) {
@@ -476,10 +481,12 @@ __device__ __forceinline__ void epilogue_ddpm(const TcGemm& p, EpiSmem<BN>& es, 
           y = c0 * x0 + ct * x;
           if (add_noise) y = fmaf(sigma, z[i], y);
         }
-        xr[i] = y;
         o[i] = y;
       }
     }
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      if (i < cnt) xr[i] = o[i];
     if (p.out_bf16) {
       __nv_bfloat16* ob = p.out_bf16 + (long long)m * p.ld_out_bf16 + n0 + cb;
       if (vb && cnt == 4) {

@@ -8,7 +8,8 @@ ROOT = Path(__file__).resolve().parents[1]
 sys.path.insert(0, str(ROOT))
 from latent_diffusion_planning_b200 import handles as H, params as P  # noqa: E402
 
-B, T, D = 1024, 8, 265
+import os
+B, T, D = int(os.environ.get("LDP_B", "1024")), 8, 265
 p = P.init_params(P.unet_spec(D, D), seed=0)
 pl = H.Planner(p, D, D)
 g = torch.Generator().manual_seed(0)
