@@ -259,7 +259,6 @@ static int pack_dense(LdpIdm* h, const float* wgt, int K, int N, int block_n, Pa
   pw->n_pad = round_up(N, block_n);
   pw->num_kb = pw->kp / 64;
   LDP_TRY(h->arena.alloc_t(&pw->wt, (size_t)pw->n_pad * pw->kp));
-  LDP_TRY(h->arena.alloc_t(&pw->kb_dev, pw->num_kb));
   std::vector<int32_t> kmap(pw->kp);
   std::vector<TcKBlock> kb(pw->num_kb);
   for (int k = 0; k < pw->kp; ++k) kmap[k] = k < K ? k : -1;
@@ -268,7 +267,7 @@ static int pack_dense(LdpIdm* h, const float* wgt, int K, int N, int block_n, Pa
   int32_t* map_dev;
   LDP_TRY(tmp.alloc_t(&map_dev, pw->kp));
   LDP_CUDA_OK(cudaMemcpy(map_dev, kmap.data(), (size_t)pw->kp * 4, cudaMemcpyHostToDevice));
-  LDP_CUDA_OK(cudaMemcpy(pw->kb_dev, kb.data(), kb.size() * sizeof(TcKBlock), cudaMemcpyHostToDevice));
+  LDP_TRY(upload_stage_table(h->arena, kb, pw));
   LDP_TRY(launch_pack_wt_bf16(wgt, N, N, map_dev, pw->kp, pw->wt, pw->kp, 0, pw->n_pad, 0));
   LDP_CUDA_OK(cudaDeviceSynchronize());
   return LDP_OK;
@@ -285,7 +284,7 @@ static int dense_op(const PackedW& pw, const __nv_bfloat16* a, int K, int lda, i
   uint64_t bs[1] = {(uint64_t)pw.kp * 2};
   uint32_t bb[2] = {64, (uint32_t)block_n};
   LDP_TRY(make_tmap_bf16(&op->map_b, pw.wt, 2, bd, bs, bb));
-  op->kb = pw.kb_dev; op->num_kb = pw.num_kb; op->M = M; op->N = N; op->block_n = block_n;
+  op->kb = pw.kb_dev; op->num_kb = pw.num_kb; op->runs = pw.runs_dev; op->num_runs = pw.num_runs; op->M = M; op->N = N; op->block_n = block_n;
   op->items_per_tile = 128; op->rows_per_item = 1;
   return LDP_OK;
 }

@@ -129,6 +129,18 @@ static inline TcStage make_stage(int map, int acc0, int nw, int c0, int d1, int 
 }
 typedef TcStage TcKBlock;
 
+// Run-length form of the stage table, which is what the TMA producer walks: `count` consecutive stages that read the
+// same tensor map at the same (d1, d2) offsets with the channel start advancing by 64 and the W tile index by nw.
+// (A k-tap convolution over C channels is k * ceil(C / 64) stages but only k runs.)
+struct TcRun {
+  int32_t src_acc;     // as TcStage
+  int32_t c0;          // channel start of the first stage
+  int32_t d12;         // as TcStage
+  int32_t wk;          // W tile index of the first stage
+  int32_t count;
+  int32_t pad[3];
+};
+
 enum { TC_EPI_PLAIN = 0, TC_EPI_GN = 1, TC_EPI_DDPM = 2, TC_EPI_LN = 3 };
 
 struct TcGemm {
@@ -136,6 +148,8 @@ struct TcGemm {
   CUtensorMap map_b;                // W^T tiles: box {64, BN}; in pair mode {64, BN/2} (see `pair`)
   int pair = 0;                     // 1: map_b was built with the half-width box -> eligible for the cta_group::2 kernel
   const TcStage* kb = nullptr;      // device table of pipeline stages
+  const TcRun* runs = nullptr;      // the same table run-length encoded (what the producer of tc_gemm_kernel reads)
+  int num_runs = 0;
   int num_kb = 0;                   // number of stages
   int w_max = 1;                    // largest nw of any stage (sizes the shared-memory ring)
   // Stage table shape (lets the MMA issuer run without reading the table): stages [0, kb_main) all carry nw_main W

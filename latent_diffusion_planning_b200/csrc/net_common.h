@@ -75,7 +75,35 @@ struct PackedW {
   int kp = 0, n_pad = 0;
   TcKBlock* kb_dev = nullptr;
   int num_kb = 0;
+  TcRun* runs_dev = nullptr;
+  int num_runs = 0;
 };
+
+// Upload a stage table and its run-length form into `arena`.
+inline int upload_stage_table(Arena& arena, const std::vector<TcStage>& st, PackedW* pw) {
+  std::vector<TcRun> runs;
+  for (const TcStage& e : st) {
+    const int nw = (e.src_acc >> 16) & 0xff;
+    if (!runs.empty()) {
+      TcRun& r = runs.back();
+      if (r.src_acc == e.src_acc && r.d12 == e.d12 && e.c0 == r.c0 + 64 * r.count && e.wk == r.wk + nw * r.count) {
+        ++r.count;
+        continue;
+      }
+    }
+    TcRun r;
+    r.src_acc = e.src_acc; r.c0 = e.c0; r.d12 = e.d12; r.wk = e.wk; r.count = 1;
+    r.pad[0] = r.pad[1] = r.pad[2] = 0;
+    runs.push_back(r);
+  }
+  pw->num_kb = (int)st.size();
+  pw->num_runs = (int)runs.size();
+  LDP_TRY(arena.alloc_t(&pw->kb_dev, st.size()));
+  LDP_TRY(arena.alloc_t(&pw->runs_dev, runs.size()));
+  LDP_CUDA_OK(cudaMemcpy(pw->kb_dev, st.data(), st.size() * sizeof(TcStage), cudaMemcpyHostToDevice));
+  LDP_CUDA_OK(cudaMemcpy(pw->runs_dev, runs.data(), runs.size() * sizeof(TcRun), cudaMemcpyHostToDevice));
+  return LDP_OK;
+}
 
 // DDPM coefficient table [n][8] (see kernels.h DdpmStep), fp32 arithmetic in the reference's op order
 // (diffusers FlaxDDPMScheduler.step / _get_variance).

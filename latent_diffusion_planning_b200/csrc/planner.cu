@@ -579,10 +579,8 @@ static int get_packed(LdpPlanner* h, int op_id, const ConvDesc& d, bool tapacc, 
   const int n_out = d.kind == CONV_UP ? 2 * d.cout : d.cout;
   pw.kp = kp_main + (int)kmap_aux.size();
   pw.n_pad = round_up(n_out, 128);
-  pw.num_kb = (int)st.size();
   LDP_TRY(h->arena.alloc_t(&pw.wt, (size_t)pw.n_pad * pw.kp));
-  LDP_TRY(h->arena.alloc_t(&pw.kb_dev, st.size()));
-  LDP_CUDA_OK(cudaMemcpy(pw.kb_dev, st.data(), st.size() * sizeof(TcStage), cudaMemcpyHostToDevice));
+  LDP_TRY(upload_stage_table(h->arena, st, &pw));
   Arena tmp;
   int32_t* map_dev;
   LDP_TRY(tmp.alloc_t(&map_dev, (size_t)kp_main * 2 + kmap_aux.size() + 16));
@@ -652,6 +650,8 @@ static int conv_tc(LdpPlanner* h, PlanWs* w, int op_id, const ConvDesc& d, TcGem
   op->pair = pair ? 1 : 0;
   op->kb = pw->kb_dev;
   op->num_kb = pw->num_kb;
+  op->runs = pw->runs_dev;
+  op->num_runs = pw->num_runs;
   op->w_max = pw->w_max;
   op->kb_main = pw->num_kb_main;
   op->nw_main = pw->w_max;

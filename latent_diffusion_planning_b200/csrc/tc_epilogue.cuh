@@ -26,6 +26,7 @@ struct TcGeo {
   static constexpr int CPP = BN / 32 / PARTS;              // 32-column chunks per thread: 1 (BN 64, 128), 2 (BN 256)
 };
 constexpr int TC_MAX_KB_SMEM = 256;
+constexpr int TC_MAX_RUNS = 64;            // (taps x sources) + aux sources of any layer
 constexpr int TC_MAX_STAGES = 8;
 
 constexpr int TC_SMEM_RING = 196 * 1024;        // shared-memory budget of the TMA ring (static smem takes <= 20 KB more)

@@ -31,6 +31,27 @@
 
 namespace ldp {
 
+// MMA with the 64-bit shared-memory descriptors given as (lo, hi) words: hi is a constant, lo advances by adds.
+template <bool PAIR>
+__device__ __forceinline__ void umma_lohi(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t hi, uint32_t idesc,
+                                          uint32_t accumulate) {
+  if (PAIR) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\tsetp.ne.b32 p, %5, 0;\n\t"
+        "mov.b64 da, {%1, %3};\n\tmov.b64 db, {%2, %3};\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %4, p;\n\t}"
+        ::"r"(d_tmem), "r"(a_lo), "r"(b_lo), "r"(hi), "r"(idesc), "r"(accumulate)
+        : "memory");
+  } else {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\tsetp.ne.b32 p, %5, 0;\n\t"
+        "mov.b64 da, {%1, %3};\n\tmov.b64 db, {%2, %3};\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, p;\n\t}"
+        ::"r"(d_tmem), "r"(a_lo), "r"(b_lo), "r"(hi), "r"(idesc), "r"(accumulate)
+        : "memory");
+  }
+}
+
 // ---- the kernel --------------------------------------------------------------------------------
 template <int BN, int MODE, bool PAIR, bool PERSIST>
 __global__ void __launch_bounds__(TcGeo<BN>::THREADS, 1) tc_gemm_kernel(const __grid_constant__ TcGemm p) {
@@ -48,7 +69,7 @@ __global__ void __launch_bounds__(TcGeo<BN>::THREADS, 1) tc_gemm_kernel(const __
   __shared__ __align__(8) uint64_t bar_tfull[2];              // accumulator buffer b complete (MMA -> epilogue)
   __shared__ __align__(8) uint64_t bar_tempty[2];             // accumulator buffer b drained (epilogue -> MMA)
   __shared__ uint32_t tmem_holder;
-  __shared__ __align__(16) TcStage kb_s[TC_MAX_KB_SMEM];      // stage table staged once per CTA
+  __shared__ __align__(16) TcRun runs_s[TC_MAX_RUNS];         // run-length stage table staged once per CTA
   __shared__ __align__(16) EpiSmem<BN> es;
   __shared__ long long ts[8];                                 // phase timestamps (diagnostics, only when p.dbg != nullptr)
   __shared__ long long tk[24];                                // arrival time of the first 24 stages at the MMA issuer
@@ -91,10 +112,8 @@ __global__ void __launch_bounds__(TcGeo<BN>::THREADS, 1) tc_gemm_kernel(const __
       tmem_relinquish();
     }
   }
-  const bool kb_in_smem = p.num_kb <= TC_MAX_KB_SMEM;
-  if (kb_in_smem)
-    for (int i = threadIdx.x; i < p.num_kb; i += TcGeo<BN>::THREADS) kb_s[i] = p.kb[i];
-  const TcStage* kbt = kb_in_smem ? kb_s : p.kb;
+  if (threadIdx.x < p.num_runs * 2)                  // num_runs <= TC_MAX_RUNS (host check); 2 x 16 bytes per run
+    reinterpret_cast<uint4*>(runs_s)[threadIdx.x] = reinterpret_cast<const uint4*>(p.runs)[threadIdx.x];
   tc_fence_before();
   if (PAIR) {
     __syncwarp();
@@ -111,6 +130,8 @@ __global__ void __launch_bounds__(TcGeo<BN>::THREADS, 1) tc_gemm_kernel(const __
     // ===================== TMA producer =====================
     if (elect_one()) {
       uint32_t stage = 0, phase = 0;
+      uint32_t full0 = smem_u32(&bar_full[0]), empty0 = smem_u32(&bar_empty[0]);
+      asm volatile("" : "+r"(full0), "+r"(empty0));
       griddep_wait();                                   // activations of the previous layer are complete from here on
       if (p.dbg) ts[2] = clock64();                     // dependency resolved
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -118,33 +139,61 @@ __global__ void __launch_bounds__(TcGeo<BN>::THREADS, 1) tc_gemm_kernel(const __
       const int n0 = (PERSIST ? tile / p.tiles_m : (int)blockIdx.y) * BN;
       const int q = tile_m / p.tiles_per_item, r = tile_m - q * p.tiles_per_item;
       const int c2_base = r * p.rows_step, c3 = q * p.items_per_tile;
-      for (int kb = 0; kb < p.num_kb; ++kb) {
-        const TcStage e = kbt[kb];
-        const int nw = (e.src_acc >> 16) & 0xff;
-        const int d1 = (int)(short)(e.d12 & 0xffff), d2 = e.d12 >> 16;
-        mbar_wait(smem_u32(&bar_empty[stage]), phase ^ 1u);
-        const uint32_t bar = smem_u32(&bar_full[stage]);
-        const uint32_t sa = smem_base + stage * stage_bytes;
-        if (PAIR) {
-          const uint32_t bar_leader = mapa_shared(bar, 0);
-          if (leader) mbar_arrive_expect_tx(bar, 2u * (TC_A_BYTES + (uint32_t)nw * B_BYTES));
-          tma_load_4d_2sm(sa, &p.map_a[e.src_acc & 0xff], bar_leader, e.c0, d1, c2_base + d2, c3);
-          for (int j = 0; j < nw; ++j)
-            tma_load_2d_2sm(sa + TC_A_BYTES + j * B_BYTES, &p.map_b, bar_leader, (e.wk + j) * TC_BK, n0 + (int)cta_rank * (BN / 2));
-        } else {
-          mbar_arrive_expect_tx(bar, TC_A_BYTES + (uint32_t)nw * B_BYTES);
-          tma_load_4d(sa, &p.map_a[e.src_acc & 0xff], bar, e.c0, d1, c2_base + d2, c3);
-          for (int j = 0; j < nw; ++j) tma_load_2d(sa + TC_A_BYTES + j * B_BYTES, &p.map_b, bar, (e.wk + j) * TC_BK, n0);
+      // Runs of stages that differ only by their channel block: the per-stage work is a barrier wait, the byte-count
+      // arrive and the TMA instructions with two coordinates advanced by adds (this thread is a scalar in-order
+      // stream; decoding a table entry per stage cost more cycles than the stage's MMAs take).
+      for (int ri = 0; ri < p.num_runs; ++ri) {
+        const TcRun e = runs_s[ri];
+        const uint32_t nw = (uint32_t)(e.src_acc >> 16) & 0xffu;
+        const int d1 = (int)(short)(e.d12 & 0xffff), c2 = c2_base + (e.d12 >> 16);
+        const CUtensorMap* map_a = &p.map_a[e.src_acc & 0xff];
+        const uint32_t tx = (PAIR ? 2u : 1u) * (TC_A_BYTES + nw * (uint32_t)B_BYTES);
+        int c0 = e.c0, wkc = e.wk * TC_BK;
+        for (int i = 0; i < e.count; ++i) {
+          mbar_wait(empty0 + 8u * stage, phase ^ 1u);
+          const uint32_t bar = full0 + 8u * stage;
+          const uint32_t sa = smem_base + stage * stage_bytes;
+          if (PAIR) {
+            const uint32_t bar_leader = mapa_shared(bar, 0);
+            if (leader) mbar_arrive_expect_tx(bar, tx);
+            tma_load_4d_2sm(sa, map_a, bar_leader, c0, d1, c2, c3);
+            for (uint32_t j = 0; j < nw; ++j)
+              tma_load_2d_2sm(sa + TC_A_BYTES + j * B_BYTES, &p.map_b, bar_leader, wkc + (int)j * TC_BK, n0 + (int)cta_rank * (BN / 2));
+          } else {
+            mbar_arrive_expect_tx(bar, tx);
+            tma_load_4d(sa, map_a, bar, c0, d1, c2, c3);
+            if (nw == 1) {
+              tma_load_2d(sa + TC_A_BYTES, &p.map_b, bar, wkc, n0);
+            } else {
+              for (uint32_t j = 0; j < nw; ++j) tma_load_2d(sa + TC_A_BYTES + j * B_BYTES, &p.map_b, bar, wkc + (int)j * TC_BK, n0);
+            }
+          }
+          c0 += TC_BK;
+          wkc += (int)nw * TC_BK;
+          if (++stage == (uint32_t)STAGES) { stage = 0; phase ^= 1u; }
         }
-        if (++stage == (uint32_t)STAGES) { stage = 0; phase ^= 1u; }
       }
       if (!PERSIST) break;
       }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer (PAIR: the leader CTA issues for both) =====================
+    // The issuing thread is a scalar in-order stream (~5-10 cycles per instruction) and the tensor pipe queues only a
+    // few MMAs ahead of it, so every instruction between two MMAs of consecutive stages shows up as idle tensor time
+    // (scripts/mma_ubench.cu).  The loop therefore never reads the stage table (the table's shape is two uniform
+    // segments: kb_main stages of nw_main W tiles, then the aux stages), keeps barrier addresses and the descriptor
+    // words in registers and advances them by adds.
     if (leader && elect_one()) {
       constexpr uint32_t idesc = umma_idesc_bf16(PAIR ? 2 * TC_BM : TC_BM, BN);
+      constexpr uint32_t DESC_HI = (uint32_t)(1024 >> 4) | (1u << 14) | (2u << 29);   // SBO 1024 B, version 1, SWIZZLE_128B
+      constexpr uint32_t B_STEP = (uint32_t)B_BYTES >> 4;
+      const uint32_t stage_step = stage_bytes >> 4;
+      const uint32_t a_lo0 = ((smem_base & 0x3FFFFu) >> 4) | (1u << 16);
+      uint32_t full0 = smem_u32(&bar_full[0]), empty0 = smem_u32(&bar_empty[0]);
+      asm volatile("" : "+r"(full0), "+r"(empty0));     // keep them in registers: recomputing costs an S2UR per stage
+      const int kb_main = p.kb_main > 0 ? p.kb_main : p.num_kb;
+      const uint32_t nw_main = p.kb_main > 0 ? (uint32_t)p.nw_main : (uint32_t)p.w_max;
+      const int kb_aux = p.num_kb - kb_main;
       uint32_t stage = 0, phase = 0;
       int it = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
@@ -155,30 +204,69 @@ __global__ void __launch_bounds__(TcGeo<BN>::THREADS, 1) tc_gemm_kernel(const __
         tc_fence_after();
       }
       const uint32_t acc_base = tmem_base + (uint32_t)buf * (uint32_t)p.acc_stride;
-      uint32_t started = 0;    // bit a set once accumulator a has received its first MMA
-      for (int kb = 0; kb < p.num_kb; ++kb) {
-        const uint32_t sa_word = (uint32_t)kbt[kb].src_acc;
-        const uint32_t acc0 = (sa_word >> 8) & 0xffu, nw = (sa_word >> 16) & 0xffu;
-        mbar_wait(smem_u32(&bar_full[stage]), phase);
+      uint32_t accf = 0;
+      if (nw_main == 1) {
+        // one W tile per stage (per-tap convolutions, dense layers): 4 MMAs per stage, so the loop body is kept to the
+        // barrier wait, four MMAs on running 64-bit descriptors, the commit and a handful of adds
+        uint64_t da = ((uint64_t)DESC_HI << 32) | (uint64_t)(a_lo0 + stage * stage_step);
+        uint32_t fb = full0 + 8u * stage, eb = empty0 + 8u * stage;
+        const uint64_t da_wrap = (uint64_t)((uint32_t)STAGES * stage_step);
+        const bool dbg_on = p.dbg != nullptr;
+        for (int kb = 0; kb < kb_main; ++kb) {
+          mbar_wait(fb, phase);
+          tc_fence_after();
+          if (dbg_on && kb == 0) ts[3] = clock64();
+          const uint64_t db = da + (TC_A_BYTES >> 4);
+          if (PAIR) {
+            umma_bf16_ss_2sm(acc_base, da, db, idesc, accf);
+            umma_bf16_ss_2sm(acc_base, da + 2, db + 2, idesc, 1u);
+            umma_bf16_ss_2sm(acc_base, da + 4, db + 4, idesc, 1u);
+            umma_bf16_ss_2sm(acc_base, da + 6, db + 6, idesc, 1u);
+            umma_commit_2sm(eb, 3);
+          } else {
+            umma_bf16_ss(acc_base, da, db, idesc, accf);
+            umma_bf16_ss(acc_base, da + 2, db + 2, idesc, 1u);
+            umma_bf16_ss(acc_base, da + 4, db + 4, idesc, 1u);
+            umma_bf16_ss(acc_base, da + 6, db + 6, idesc, 1u);
+            umma_commit(eb);
+          }
+          accf = 1u;
+          da += stage_step; fb += 8u; eb += 8u;
+          if (++stage == (uint32_t)STAGES) { stage = 0; phase ^= 1u; da -= da_wrap; fb = full0; eb = empty0; }
+        }
+      } else
+      for (int kb = 0; kb < kb_main; ++kb) {
+        mbar_wait(full0 + 8u * stage, phase);
         tc_fence_after();
         if (p.dbg && kb == 0) ts[3] = clock64();        // first operands landed
-        if (p.dbg && kb < 24) tk[kb] = clock64();
-        const uint32_t sa = smem_base + stage * stage_bytes;
-        const uint64_t da = umma_desc_sw128(sa);
-        for (uint32_t j = 0; j < nw; ++j) {             // the A tile is shared by the nw taps' accumulators
-          const uint32_t acc = acc0 + j;
-          const uint64_t db = umma_desc_sw128(sa + TC_A_BYTES + j * B_BYTES);
-          const uint32_t d_tmem = acc_base + acc * BN;
-#pragma unroll
-          for (int k = 0; k < TC_BK / 16; ++k) {
-            // advance 16 bf16 = 32 bytes along K inside the 128B swizzle row: +2 in the (addr >> 4) field
-            if (PAIR) umma_bf16_ss_2sm(d_tmem, da + 2 * k, db + 2 * k, idesc, ((started >> acc) & 1u) | (k > 0 ? 1u : 0u));
-            else umma_bf16_ss(d_tmem, da + 2 * k, db + 2 * k, idesc, ((started >> acc) & 1u) | (k > 0 ? 1u : 0u));
-          }
-          started |= 1u << acc;
+        const uint32_t a_lo = a_lo0 + stage * stage_step;
+        uint32_t b_lo = a_lo + (TC_A_BYTES >> 4);
+        uint32_t d = acc_base;
+        for (uint32_t j = 0; j < nw_main; ++j, b_lo += B_STEP, d += BN) {     // the A tile is shared by the taps' accumulators
+          umma_lohi<PAIR>(d, a_lo, b_lo, DESC_HI, idesc, accf);
+          umma_lohi<PAIR>(d, a_lo + 2, b_lo + 2, DESC_HI, idesc, 1u);          // +16 bf16 = 32 bytes along K inside the swizzle row
+          umma_lohi<PAIR>(d, a_lo + 4, b_lo + 4, DESC_HI, idesc, 1u);
+          umma_lohi<PAIR>(d, a_lo + 6, b_lo + 6, DESC_HI, idesc, 1u);
         }
-        if (PAIR) umma_commit_2sm(smem_u32(&bar_empty[stage]), 3);   // frees the stage in both CTAs
-        else umma_commit(smem_u32(&bar_empty[stage]));               // frees the smem stage when these MMAs retire
+        if (PAIR) umma_commit_2sm(empty0 + 8u * stage, 3);           // frees the stage in both CTAs
+        else umma_commit(empty0 + 8u * stage);                       // frees the smem stage when these MMAs retire
+        accf = 1u;
+        if (++stage == (uint32_t)STAGES) { stage = 0; phase ^= 1u; }
+      }
+      accf = 0;
+      const uint32_t d_aux = acc_base + (uint32_t)p.n_acc * BN;
+      for (int kb = 0; kb < kb_aux; ++kb) {
+        mbar_wait(full0 + 8u * stage, phase);
+        tc_fence_after();
+        const uint32_t a_lo = a_lo0 + stage * stage_step;
+        const uint32_t b_lo = a_lo + (TC_A_BYTES >> 4);
+        umma_lohi<PAIR>(d_aux, a_lo, b_lo, DESC_HI, idesc, accf);
+        umma_lohi<PAIR>(d_aux, a_lo + 2, b_lo + 2, DESC_HI, idesc, 1u);
+        umma_lohi<PAIR>(d_aux, a_lo + 4, b_lo + 4, DESC_HI, idesc, 1u);
+        umma_lohi<PAIR>(d_aux, a_lo + 6, b_lo + 6, DESC_HI, idesc, 1u);
+        if (PAIR) umma_commit_2sm(empty0 + 8u * stage, 3);
+        else umma_commit(empty0 + 8u * stage);
+        accf = 1u;
         if (++stage == (uint32_t)STAGES) { stage = 0; phase ^= 1u; }
       }
       if (PAIR) umma_commit_2sm(smem_u32(&bar_tfull[buf]), 3);
@@ -431,6 +519,7 @@ static int launch_tc_gemm_inst(const TcGemm& p_in, cudaStream_t s) {
 
 int launch_tc_gemm(const TcGemm& p, cudaStream_t s) {
   LDP_CHECK(p.kb && p.num_kb > 0 && p.M > 0 && p.N > 0, LDP_ERR_INVALID_ARG, "tc_gemm: bad arguments");
+  LDP_CHECK(p.runs && p.num_runs > 0 && p.num_runs <= TC_MAX_RUNS, LDP_ERR_UNSUPPORTED, "tc_gemm: run table missing or larger than TC_MAX_RUNS");
   LDP_CHECK(p.block_n == 64 || p.block_n == 128 || p.block_n == 256, LDP_ERR_INVALID_ARG,
             "tc_gemm: block_n must be 64, 128 or 256");
   if (p.mode == TC_EPI_GN) {
