@@ -156,11 +156,10 @@ int ldp_tc_dense(const float* a_dev, const float* w_host, const float* bias_host
   LDP_TRY(make_tmap_bf16(&op.map_b, wt, 2, bd, bs, bb));
   TcRun run;
   run.src_acc = kb[0].src_acc; run.c0 = 0; run.d12 = 0; run.wk = 0; run.count = kp / 64;
-  run.pad[0] = run.pad[1] = run.pad[2] = 0;
   TcRun* run_dev;
   LDP_TRY(tmp.alloc_t(&run_dev, 1));
   LDP_CUDA_OK(cudaMemcpy(run_dev, &run, sizeof(run), cudaMemcpyHostToDevice));
-  op.kb = kb_dev; op.num_kb = kp / 64; op.runs = run_dev; op.num_runs = 1; op.M = M; op.N = N; op.block_n = 128;
+  op.kb = kb_dev; op.num_kb = kp / 64; op.runs = run_dev; op.num_runs = 1; tc_set_inline_runs(&op, &run, 1); op.M = M; op.N = N; op.block_n = 128;
   op.items_per_tile = 128; op.rows_per_item = 1;
   op.mode = TC_EPI_PLAIN; op.bias = bias_dev; op.out_f32 = c_dev; op.ld_out_f32 = N;
   LDP_TRY(launch_tc_gemm(op, s));

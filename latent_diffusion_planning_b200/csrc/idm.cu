@@ -284,7 +284,7 @@ static int dense_op(const PackedW& pw, const __nv_bfloat16* a, int K, int lda, i
   uint64_t bs[1] = {(uint64_t)pw.kp * 2};
   uint32_t bb[2] = {64, (uint32_t)block_n};
   LDP_TRY(make_tmap_bf16(&op->map_b, pw.wt, 2, bd, bs, bb));
-  op->kb = pw.kb_dev; op->num_kb = pw.num_kb; op->runs = pw.runs_dev; op->num_runs = pw.num_runs; op->M = M; op->N = N; op->block_n = block_n;
+  op->kb = pw.kb_dev; op->num_kb = pw.num_kb; op->runs = pw.runs_dev; op->num_runs = pw.num_runs; tc_set_inline_runs(op, pw.runs_host.data(), pw.num_runs); op->M = M; op->N = N; op->block_n = block_n;
   op->items_per_tile = 128; op->rows_per_item = 1;
   return LDP_OK;
 }

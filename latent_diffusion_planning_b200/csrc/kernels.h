@@ -132,13 +132,14 @@ typedef TcStage TcKBlock;
 // Run-length form of the stage table, which is what the TMA producer walks: `count` consecutive stages that read the
 // same tensor map at the same (d1, d2) offsets with the channel start advancing by 64 and the W tile index by nw.
 // (A k-tap convolution over C channels is k * ceil(C / 64) stages but only k runs.)
+constexpr int TC_RUNS_INLINE = 12;
 struct TcRun {
-  int32_t src_acc;     // as TcStage
-  int32_t c0;          // channel start of the first stage
-  int32_t d12;         // as TcStage
-  int32_t wk;          // W tile index of the first stage
-  int32_t count;
-  int32_t pad[3];
+  int32_t src_acc = 0; // as TcStage
+  int32_t c0 = 0;      // channel start of the first stage
+  int32_t d12 = 0;     // as TcStage
+  int32_t wk = 0;      // W tile index of the first stage
+  int32_t count = 0;
+  int32_t pad[3] = {0, 0, 0};
 };
 
 enum { TC_EPI_PLAIN = 0, TC_EPI_GN = 1, TC_EPI_DDPM = 2, TC_EPI_LN = 3 };
@@ -150,6 +151,10 @@ struct TcGemm {
   const TcStage* kb = nullptr;      // device table of pipeline stages
   const TcRun* runs = nullptr;      // the same table run-length encoded (what the producer of tc_gemm_kernel reads)
   int num_runs = 0;
+  // Up to TC_RUNS_INLINE runs travel inside the kernel parameters: constant-bank operands are uniform registers, so the
+  // producer's per-stage loop needs no register-to-uniform moves (num_runs_c = 0: read the table from memory instead).
+  TcRun runs_c[TC_RUNS_INLINE];
+  int num_runs_c = 0;
   int num_kb = 0;                   // number of stages
   int w_max = 1;                    // largest nw of any stage (sizes the shared-memory ring)
   // Stage table shape (lets the MMA issuer run without reading the table): stages [0, kb_main) all carry nw_main W
@@ -199,6 +204,8 @@ struct TcGemm {
   DdpmCall call; const DdpmCall* call_dev = nullptr;
   float* x_io = nullptr; int ld_x = 0;
 };
+// copy a host run table into op->runs_c when it fits
+void tc_set_inline_runs(TcGemm* op, const TcRun* runs_host, int n);
 int launch_tc_gemm(const TcGemm& p, cudaStream_t s);
 
 // The whole reverse-diffusion loop of the planner as one persistent kernel (planner_loop.cu).

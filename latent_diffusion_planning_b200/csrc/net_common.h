@@ -77,6 +77,7 @@ struct PackedW {
   int num_kb = 0;
   TcRun* runs_dev = nullptr;
   int num_runs = 0;
+  std::vector<TcRun> runs_host;
 };
 
 // Upload a stage table and its run-length form into `arena`.
@@ -93,11 +94,11 @@ inline int upload_stage_table(Arena& arena, const std::vector<TcStage>& st, Pack
     }
     TcRun r;
     r.src_acc = e.src_acc; r.c0 = e.c0; r.d12 = e.d12; r.wk = e.wk; r.count = 1;
-    r.pad[0] = r.pad[1] = r.pad[2] = 0;
     runs.push_back(r);
   }
   pw->num_kb = (int)st.size();
   pw->num_runs = (int)runs.size();
+  pw->runs_host = runs;
   LDP_TRY(arena.alloc_t(&pw->kb_dev, st.size()));
   LDP_TRY(arena.alloc_t(&pw->runs_dev, runs.size()));
   LDP_CUDA_OK(cudaMemcpy(pw->kb_dev, st.data(), st.size() * sizeof(TcStage), cudaMemcpyHostToDevice));

@@ -652,6 +652,7 @@ static int conv_tc(LdpPlanner* h, PlanWs* w, int op_id, const ConvDesc& d, TcGem
   op->num_kb = pw->num_kb;
   op->runs = pw->runs_dev;
   op->num_runs = pw->num_runs;
+  tc_set_inline_runs(op, pw->runs_host.data(), pw->num_runs);
   op->w_max = pw->w_max;
   op->kb_main = pw->num_kb_main;
   op->nw_main = pw->w_max;
@@ -866,7 +867,7 @@ static int prepare_loop(LdpPlanner* h, PlanWs* w) {
     op.persistent = 0; op.acc_bufs = 1;
     op.epi_skip = getenv("LDP_LOOP_FLAGS") ? (atoi(getenv("LDP_LOOP_FLAGS")) >> 4 << 4) : 0; op.dbg = nullptr; op.dbg_stage = nullptr;
   }
-  if (ops.size() > 40) return LDP_OK;
+  if (ops.size() > 36) return LDP_OK;
   w->loop_ops = ops;
   LDP_TRY(w->arena.alloc_t(&w->group_counter, (size_t)n_groups));
   LDP_TRY(w->arena.alloc_t(&w->loop_dbg, ops.size() * 8 + 8));

@@ -34,7 +34,7 @@ namespace ldp {
 // The ops of one denoising step, uploaded before the launch.  Constant memory keeps every parameter access a uniform
 // constant-bank operand (as in the per-layer kernel, where the parameters are kernel arguments) and lets the TMA unit
 // fetch the tensor maps from it.
-constexpr int PL_MAX_LAYERS = 40;
+constexpr int PL_MAX_LAYERS = 36;
 __constant__ __align__(64) uint8_t c_layers_raw[PL_MAX_LAYERS * sizeof(TcGemm)];     // TcGemm has default member initialisers
 #define c_layers (reinterpret_cast<const TcGemm*>(c_layers_raw))
 

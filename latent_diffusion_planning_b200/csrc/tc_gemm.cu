@@ -142,14 +142,15 @@ __global__ void __launch_bounds__(TcGeo<BN>::THREADS, 1) tc_gemm_kernel(const __
       // Runs of stages that differ only by their channel block: the per-stage work is a barrier wait, the byte-count
       // arrive and the TMA instructions with two coordinates advanced by adds (this thread is a scalar in-order
       // stream; decoding a table entry per stage cost more cycles than the stage's MMAs take).
-      for (int ri = 0; ri < p.num_runs; ++ri) {
-        const TcRun e = runs_s[ri];
-        const uint32_t nw = (uint32_t)(e.src_acc >> 16) & 0xffu;
-        const int d1 = (int)(short)(e.d12 & 0xffff), c2 = c2_base + (e.d12 >> 16);
-        const CUtensorMap* map_a = &p.map_a[e.src_acc & 0xff];
+      // run fields come from the kernel parameters (constant bank -> uniform registers, no register-to-uniform moves
+      // in the per-stage loop) when the table fits there, else from shared memory; the loop body is instantiated twice
+      auto produce_run = [&](int r_src_acc, int r_c0, int r_d12, int r_wk, int r_count) {
+        const uint32_t nw = (uint32_t)(r_src_acc >> 16) & 0xffu;
+        const int d1 = (int)(short)(r_d12 & 0xffff), c2 = c2_base + (r_d12 >> 16);
+        const CUtensorMap* map_a = &p.map_a[r_src_acc & 0xff];
         const uint32_t tx = (PAIR ? 2u : 1u) * (TC_A_BYTES + nw * (uint32_t)B_BYTES);
-        int c0 = e.c0, wkc = e.wk * TC_BK;
-        for (int i = 0; i < e.count; ++i) {
+        int c0 = r_c0, wkc = r_wk * TC_BK;
+        for (int i = 0; i < r_count; ++i) {
           mbar_wait(empty0 + 8u * stage, phase ^ 1u);
           const uint32_t bar = full0 + 8u * stage;
           const uint32_t sa = smem_base + stage * stage_bytes;
@@ -171,6 +172,15 @@ __global__ void __launch_bounds__(TcGeo<BN>::THREADS, 1) tc_gemm_kernel(const __
           c0 += TC_BK;
           wkc += (int)nw * TC_BK;
           if (++stage == (uint32_t)STAGES) { stage = 0; phase ^= 1u; }
+        }
+      };
+      if (p.num_runs_c > 0) {
+        for (int ri = 0; ri < p.num_runs_c; ++ri)
+          produce_run(p.runs_c[ri].src_acc, p.runs_c[ri].c0, p.runs_c[ri].d12, p.runs_c[ri].wk, p.runs_c[ri].count);
+      } else {
+        for (int ri = 0; ri < p.num_runs; ++ri) {
+          const TcRun e = runs_s[ri];
+          produce_run(e.src_acc, e.c0, e.d12, e.wk, e.count);
         }
       }
       if (!PERSIST) break;
@@ -515,6 +525,13 @@ static int launch_tc_gemm_inst(const TcGemm& p_in, cudaStream_t s) {
   }
   count_launch();
   return LDP_OK;
+}
+
+void tc_set_inline_runs(TcGemm* op, const TcRun* runs_host, int n) {
+  op->num_runs_c = 0;
+  if (n <= 0 || n > TC_RUNS_INLINE) return;
+  for (int i = 0; i < n; ++i) op->runs_c[i] = runs_host[i];
+  op->num_runs_c = n;
 }
 
 int launch_tc_gemm(const TcGemm& p, cudaStream_t s) {

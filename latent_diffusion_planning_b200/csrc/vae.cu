@@ -644,7 +644,7 @@ static int vae_conv_tc(LdpVae* h, VaeWs* w, int id, const ConvW& cw, const float
   uint64_t bs[1] = {(uint64_t)pw->kp * 2};
   uint32_t bb[2] = {64, (uint32_t)bn};
   LDP_TRY(make_tmap_bf16(&op->map_b, pw->wt, 2, bd, bs, bb));
-  op->kb = pw->kb_dev; op->num_kb = pw->num_kb; op->runs = pw->runs_dev; op->num_runs = pw->num_runs; op->w_max = 1; op->k_pad = pw->kp;
+  op->kb = pw->kb_dev; op->num_kb = pw->num_kb; op->runs = pw->runs_dev; op->num_runs = pw->num_runs; tc_set_inline_runs(op, pw->runs_host.data(), pw->num_runs); op->w_max = 1; op->k_pad = pw->kp;
   op->M = w->Bc * S_out * S_out; op->N = cw.cout; op->block_n = bn;
   op->tiles_per_item = g.tiles_per_img; op->rows_step = g.hb * stride; op->items_per_tile = g.ib;
   op->rows_per_item = 1;
