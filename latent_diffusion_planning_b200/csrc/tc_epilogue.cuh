@@ -85,8 +85,33 @@ __device__ __forceinline__ float swish_fast(float y) {
 // ---- vector load/store helpers (32 consecutive columns of one row) -------------------------------------
 // Activations written earlier by other SMs (residual rows, x) are read with ld.global.cg: inside the persistent
 // reverse-diffusion kernel there is no kernel boundary to invalidate L1 between a layer's writes and a later layer's reads.
+// 256-bit global accesses (sm_100: LDG/STG.E.ENL2.256).  The epilogues own one row per thread, so every warp-level
+// access touches 32 different lines whatever its width; the LSU cost is per line touched, i.e. per instruction, and a
+// 32-byte access halves the instruction count of a 16-byte one (ncu on the VAE's residual convolution: `lg throttle`
+// was the top stall of the epilogue warps, 16 data bytes per sector).
+struct U32x8 { uint32_t r[8]; };
+__device__ __forceinline__ void st_global_256(void* p, const U32x8& u) {
+  asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(u.r[0]), "r"(u.r[1]), "r"(u.r[2]), "r"(u.r[3]),
+               "r"(u.r[4]), "r"(u.r[5]), "r"(u.r[6]), "r"(u.r[7]) : "memory");
+}
+__device__ __forceinline__ U32x8 ld_global_cg_256(const void* p) {
+  U32x8 u;
+  asm volatile("ld.global.cg.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];" : "=r"(u.r[0]), "=r"(u.r[1]), "=r"(u.r[2]), "=r"(u.r[3]),
+               "=r"(u.r[4]), "=r"(u.r[5]), "=r"(u.r[6]), "=r"(u.r[7]) : "l"(p) : "memory");
+  return u;
+}
+__device__ __forceinline__ bool aligned32(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 31) == 0; }
+
 __device__ __forceinline__ void store_bf16x32(__nv_bfloat16* dst, const float (&v)[32], bool vec_ok, int nvalid) {
-  if (vec_ok && nvalid == 32) {
+  if (vec_ok && nvalid == 32 && aligned32(dst)) {
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      U32x8 u;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) u.r[q] = pack_bf16x2(v[16 * j + 2 * q], v[16 * j + 2 * q + 1]);
+      st_global_256(dst + 16 * j, u);
+    }
+  } else if (vec_ok && nvalid == 32) {
     uint4* d4 = reinterpret_cast<uint4*>(dst);
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
@@ -105,7 +130,15 @@ __device__ __forceinline__ void store_bf16x32(__nv_bfloat16* dst, const float (&
 }
 
 __device__ __forceinline__ void store_f32x32(float* dst, const float (&v)[32], bool vec_ok, int nvalid) {
-  if (vec_ok && nvalid == 32) {
+  if (vec_ok && nvalid == 32 && aligned32(dst)) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      U32x8 u;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) u.r[q] = __float_as_uint(v[8 * j + q]);
+      st_global_256(dst + 8 * j, u);
+    }
+  } else if (vec_ok && nvalid == 32) {
     float4* d4 = reinterpret_cast<float4*>(dst);
 #pragma unroll
     for (int j = 0; j < 8; ++j) d4[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
@@ -117,7 +150,15 @@ __device__ __forceinline__ void store_f32x32(float* dst, const float (&v)[32], b
 }
 
 __device__ __forceinline__ void add_f32x32(float (&v)[32], const float* src, bool vec_ok, int nvalid) {
-  if (vec_ok && nvalid == 32) {
+  if (vec_ok && nvalid == 32 && aligned32(src)) {
+    U32x8 u[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) u[j] = ld_global_cg_256(src + 8 * j);
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+      for (int q = 0; q < 8; ++q) v[8 * j + q] += __uint_as_float(u[j].r[q]);
+  } else if (vec_ok && nvalid == 32) {
     const float4* s4 = reinterpret_cast<const float4*>(src);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
@@ -132,7 +173,19 @@ __device__ __forceinline__ void add_f32x32(float (&v)[32], const float* src, boo
 }
 
 __device__ __forceinline__ void add_bf16x32(float (&v)[32], const __nv_bfloat16* src, bool vec_ok, int nvalid) {
-  if (vec_ok && nvalid == 32) {
+  if (vec_ok && nvalid == 32 && aligned32(src)) {
+    U32x8 u[2];
+#pragma unroll
+    for (int j = 0; j < 2; ++j) u[j] = ld_global_cg_256(src + 16 * j);
+#pragma unroll
+    for (int j = 0; j < 2; ++j)
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u[j].r[q]));
+        v[16 * j + 2 * q] += f.x;
+        v[16 * j + 2 * q + 1] += f.y;
+      }
+  } else if (vec_ok && nvalid == 32) {
     const uint4* rp = reinterpret_cast<const uint4*>(src);
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
@@ -289,9 +342,19 @@ __device__ __forceinline__ void gn_prefetch(const TcGemm& p, const EpiSmem<BN>& 
       for (int i = 0; i < 32; ++i) pf.film[cc][i] = 0x00003c00u;     // half2(1, 0): identity
     }
     if (res && c < nchunks) {
-      const uint4* rp = reinterpret_cast<const uint4*>(p.res_bf16 + (long long)m * p.ld_res_bf16 + nb);
+      const __nv_bfloat16* rsrc = p.res_bf16 + (long long)m * p.ld_res_bf16 + nb;
+      if (aligned32(rsrc)) {
 #pragma unroll
-      for (int j = 0; j < 4; ++j) pf.res[cc][j] = __ldcg(rp + j);
+        for (int j = 0; j < 2; ++j) {
+          const U32x8 u = ld_global_cg_256(rsrc + 16 * j);
+          pf.res[cc][2 * j] = make_uint4(u.r[0], u.r[1], u.r[2], u.r[3]);
+          pf.res[cc][2 * j + 1] = make_uint4(u.r[4], u.r[5], u.r[6], u.r[7]);
+        }
+      } else {
+        const uint4* rp = reinterpret_cast<const uint4*>(rsrc);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) pf.res[cc][j] = __ldcg(rp + j);
+      }
     } else {
 #pragma unroll
       for (int j = 0; j < 4; ++j) pf.res[cc][j] = make_uint4(0u, 0u, 0u, 0u);
