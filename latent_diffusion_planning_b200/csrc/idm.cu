@@ -21,6 +21,7 @@ struct IdmWs {
   Arena arena;
   float *spre = nullptr, *h = nullptr, *hn = nullptr, *u = nullptr, *a_state = nullptr, *eps_buf = nullptr;
   int32_t* step_dev = nullptr;
+  unsigned int* done_counter = nullptr;
   DdpmCall* call_dev = nullptr;
   bool bf16_ready = false;
   __nv_bfloat16 *hn_b = nullptr, *u_b = nullptr;
@@ -204,6 +205,7 @@ static int idm_get_ws(LdpIdm* h, int N, IdmWs** out) {
   LDP_TRY(w->arena.alloc_t(&w->a_state, (size_t)N * A));
   LDP_TRY(w->arena.alloc_t(&w->eps_buf, (size_t)N * A));
   LDP_TRY(w->arena.alloc_t(&w->step_dev, 4));
+  LDP_TRY(w->arena.alloc_t(&w->done_counter, 4));
   LDP_TRY(w->arena.alloc_t(&w->call_dev, 1));
   *out = w.get();
   h->ws[N] = std::move(w);
@@ -324,6 +326,7 @@ static int idm_prepare_bf16(LdpIdm* h, IdmWs* w) {
   LDP_TRY(dense_op(h->pwout, w->hn_b, H, H, w->N, A, 128, &op));
   op.mode = TC_EPI_DDPM; op.bias = h->bout; op.coef = h->coef; op.call_dev = w->call_dev;
   op.x_io = w->a_state; op.ld_x = A;
+  op.step_dec = w->step_dev; op.done_counter = w->done_counter;      // the step counter advances inside this kernel
   w->ops.push_back(op);
   w->bf16_ready = true;
   return LDP_OK;
@@ -338,6 +341,7 @@ static int idm_run_bf16(LdpIdm* h, IdmWs* w, const float* a, StepRef step, bool 
       op.mode = TC_EPI_PLAIN;
       op.out_f32 = eps_out; op.ld_out_f32 = h->cfg.action_dim;
       op.x_io = nullptr;
+      op.step_dec = nullptr;
     }
     LDP_TRY(launch_tc_gemm(op, s));
   }
@@ -436,8 +440,7 @@ int ldp_idm_sample(LdpIdm* h, int precision, int sampler, const float* s_dev, co
       cudaError_t e = cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal);
       int st = LDP_OK;
       if (e == cudaSuccess) {
-        st = idm_run_bf16(h, w, w->a_state, step, false, nullptr, cs);
-        if (st == LDP_OK) st = launch_add_i32(w->step_dev, -1, cs);
+        st = idm_run_bf16(h, w, w->a_state, step, false, nullptr, cs);     // the DDPM kernel decrements the step counter
         e = cudaStreamEndCapture(cs, &w->graph_src);
       }
       count_launch((int)(before - launch_count_get()));
@@ -449,10 +452,9 @@ int ldp_idm_sample(LdpIdm* h, int precision, int sampler, const float* s_dev, co
     for (int i = 0; i < n_steps; ++i) {
       if (w->graph) {
         LDP_CUDA_OK(cudaGraphLaunch(w->graph, s));
-        count_launch((int)w->ops.size() + 2);
+        count_launch((int)w->ops.size() + 1);
       } else {
         LDP_TRY(idm_run_bf16(h, w, w->a_state, step, false, nullptr, s));
-        LDP_TRY(launch_add_i32(w->step_dev, -1, s));
       }
     }
   }

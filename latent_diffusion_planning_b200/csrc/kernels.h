@@ -203,6 +203,10 @@ struct TcGemm {
   const float* coef = nullptr;
   DdpmCall call; const DdpmCall* call_dev = nullptr;
   float* x_io = nullptr; int ld_x = 0;
+  // DDPM: the last CTA to finish decrements the device step counter (saves the one-thread kernel that did it between
+  // denoising steps); done_counter counts finished CTAs and is reset by that CTA
+  int32_t* step_dec = nullptr;
+  unsigned int* done_counter = nullptr;
 };
 // copy a host run table into op->runs_c when it fits
 void tc_set_inline_runs(TcGemm* op, const TcRun* runs_host, int n);

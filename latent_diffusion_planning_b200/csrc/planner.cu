@@ -86,6 +86,7 @@ struct PlanWs {
   float* x_state = nullptr;
   float* eps_buf = nullptr;
   int32_t* step_dev = nullptr;
+  unsigned int* done_counter = nullptr;
   DdpmCall* call_dev = nullptr;
   // fp32 path
   bool f32_ready = false;
@@ -305,6 +306,7 @@ static int get_ws(LdpPlanner* h, int B, int T, PlanWs** out) {
   LDP_TRY(w->arena.alloc_t(&w->x_state, (size_t)B * T * c.input_dim));
   LDP_TRY(w->arena.alloc_t(&w->eps_buf, (size_t)B * T * c.input_dim));
   LDP_TRY(w->arena.alloc_t(&w->step_dev, 4));
+  LDP_TRY(w->arena.alloc_t(&w->done_counter, 4));
   LDP_TRY(w->arena.alloc_t(&w->call_dev, 1));
   *out = w.get();
   h->ws[key] = std::move(w);
@@ -807,6 +809,7 @@ static int prepare_bf16(LdpPlanner* h, PlanWs* w) {
   op.call_dev = w->call_dev;
   op.x_io = w->x_state; op.ld_x = c.input_dim;
   op.out_bf16 = w->x_bf16; op.ld_out_bf16 = w->ld_xb;
+  op.step_dec = w->step_dev; op.done_counter = w->done_counter;      // the step counter advances inside this kernel
   w->ops.push_back(op);
   w->bf16_ready = true;
   return LDP_OK;
@@ -822,6 +825,7 @@ static int run_ops_bf16(PlanWs* w, StepRef step, bool final_plain, float* eps_ou
       op.out_f32 = eps_out; op.ld_out_f32 = D;
       op.out_bf16 = nullptr;
       op.x_io = nullptr;
+      op.step_dec = nullptr;
     }
     LDP_TRY(launch_tc_gemm(op, s));
   }
@@ -865,6 +869,7 @@ static int prepare_loop(LdpPlanner* h, PlanWs* w) {
     if (op.num_stages < 2) return LDP_OK;
     op.tiles_m_group = spc * op.rows_per_item / 128;
     op.persistent = 0; op.acc_bufs = 1;
+    op.step_dec = nullptr;
     op.epi_skip = getenv("LDP_LOOP_FLAGS") ? (atoi(getenv("LDP_LOOP_FLAGS")) >> 4 << 4) : 0; op.dbg = nullptr; op.dbg_stage = nullptr;
   }
   if (ops.size() > 36) return LDP_OK;
@@ -998,8 +1003,7 @@ int ldp_planner_sample(LdpPlanner* h, int precision, int sampler, const float* x
       cudaError_t e = cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal);
       int st = LDP_OK;
       if (e == cudaSuccess) {
-        st = run_ops_bf16(w, step, false, nullptr, D, cs);
-        if (st == LDP_OK) st = launch_add_i32(w->step_dev, -1, cs);
+        st = run_ops_bf16(w, step, false, nullptr, D, cs);     // the DDPM kernel decrements the step counter itself
         e = cudaStreamEndCapture(cs, &w->graph_src);
       }
       count_launch((int)(before - launch_count_get()));  // captured launches did not execute
@@ -1011,10 +1015,9 @@ int ldp_planner_sample(LdpPlanner* h, int precision, int sampler, const float* x
     for (int i = 0; i < n_steps && w->loop_state != 1; ++i) {
       if (w->graph) {
         LDP_CUDA_OK(cudaGraphLaunch(w->graph, s));
-        count_launch((int)w->ops.size() + 1);
+        count_launch((int)w->ops.size());
       } else {
         LDP_TRY(run_ops_bf16(w, step, false, nullptr, D, s));
-        LDP_TRY(launch_add_i32(w->step_dev, -1, s));
       }
     }
   }
@@ -1046,6 +1049,7 @@ int ldp_planner_profile_step(LdpPlanner* h, int B, int T, int reps, float* us_ho
   for (size_t i = 0; i < w->ops.size(); ++i) {
     TcGemm op = w->ops[i];
     op.step = step;
+    op.step_dec = nullptr;                      // isolated launches must not advance the timestep
     for (int r = 0; r < 3; ++r) LDP_TRY(launch_tc_gemm(op, s));
     LDP_CUDA_OK(cudaEventRecord(e0, s));
     for (int r = 0; r < reps; ++r) LDP_TRY(launch_tc_gemm(op, s));

@@ -339,6 +339,19 @@ __global__ void __launch_bounds__(TcGeo<BN>::THREADS, 1) tc_gemm_kernel(const __
   }
 
   if (p.dbg && threadIdx.x == 64) ts[6] = clock64();     // this warp's epilogue done
+  if (MODE == TC_EPI_DDPM && p.step_dec != nullptr) {
+    // every CTA has read the step counter by now; the last one to get here moves it to the next timestep
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      __threadfence();
+      const unsigned total = gridDim.x * gridDim.y;
+      if (atomicAdd(p.done_counter, 1u) == total - 1u) {
+        *reinterpret_cast<volatile int32_t*>(p.step_dec) = *reinterpret_cast<volatile int32_t*>(p.step_dec) - 1;
+        *reinterpret_cast<volatile unsigned int*>(p.done_counter) = 0u;
+        __threadfence();
+      }
+    }
+  }
   tc_fence_before();
   if (PAIR) {
     __syncwarp();
