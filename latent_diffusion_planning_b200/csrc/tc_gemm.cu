@@ -438,7 +438,7 @@ static int set_smem_attr() {
   if (kPairable)
     LDP_CUDA_OK(cudaFuncSetAttribute(tc_gemm_kernel<BN, MODE, kPairable, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      TC_SMEM_RING + 1024));
-  constexpr bool kPersistable = MODE == TC_EPI_PLAIN && BN <= 128;
+  constexpr bool kPersistable = MODE == TC_EPI_PLAIN;
   if (kPersistable)
     LDP_CUDA_OK(cudaFuncSetAttribute(tc_gemm_kernel<BN, MODE, false, kPersistable>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      TC_SMEM_RING + 1024));
@@ -474,7 +474,7 @@ int tc_gemm_geometry(TcGemm* p) {
   const int tiles = p->tiles_m * p->tiles_n;
   static int persist = -1;
   if (persist < 0) { const char* e = getenv("LDP_PERSIST"); persist = (e && e[0] == '0') ? 0 : 1; }
-  const bool persistent = persist && tiles > 148 && !p->pair && p->mode == TC_EPI_PLAIN && bn <= 128;
+  const bool persistent = persist && tiles > 148 && !p->pair && p->mode == TC_EPI_PLAIN;
   p->grid_ctas = persistent ? 148 : tiles;
   p->persistent = persistent ? 1 : 0;
   p->acc_stride = n_acc_total * bn;
@@ -580,6 +580,7 @@ int launch_tc_gemm(const TcGemm& p, cudaStream_t s) {
     switch (key) {
       case 64 * 8 + TC_EPI_PLAIN:  return launch_tc_gemm_inst<64, TC_EPI_PLAIN, false, true>(p, s);
       case 128 * 8 + TC_EPI_PLAIN: return launch_tc_gemm_inst<128, TC_EPI_PLAIN, false, true>(p, s);
+      case 256 * 8 + TC_EPI_PLAIN: return launch_tc_gemm_inst<256, TC_EPI_PLAIN, false, true>(p, s);
       default: break;
     }
   }

@@ -672,7 +672,10 @@ static int vae_conv_tc(LdpVae* h, VaeWs* w, int id, const ConvW& cw, const float
   uint32_t es[4] = {1, (uint32_t)stride, (uint32_t)stride, 1};
   LDP_TRY(make_tmap_bf16_strided(&op->map_a[0], in, 4, dims, str, box, es));
   for (int i = 1; i < 4; ++i) op->map_a[i] = op->map_a[0];
-  const int bn = cw.cout > 64 ? 128 : 64;
+  // 256-wide tiles where the channel count allows: one A tile feeds twice the MMA work (per-tap stages of 48 KB with
+  // 512 cycles of MMAs instead of 32 KB with 256), which is what the latency-bound per-tap ring needs
+  static const bool bn256 = !(getenv("LDP_VAE_BN256") && getenv("LDP_VAE_BN256")[0] == '0');
+  const int bn = (bn256 && cw.cout % 256 == 0) ? 256 : (cw.cout > 64 ? 128 : 64);
   uint64_t bd[2] = {(uint64_t)pw->kp, (uint64_t)pw->n_pad};
   uint64_t bs[1] = {(uint64_t)pw->kp * 2};
   uint32_t bb[2] = {64, (uint32_t)bn};
