@@ -301,7 +301,7 @@ static int idm_prepare_bf16(LdpIdm* h, IdmWs* w) {
     h->pw1.resize(nb);
     h->pw2.resize(nb);
     for (int b = 0; b < nb; ++b) {
-      LDP_TRY(pack_dense(h, h->blk[b].w1, H, 4 * H, 128, &h->pw1[b]));
+      LDP_TRY(pack_dense(h, h->blk[b].w1, H, 4 * H, 256, &h->pw1[b]));
       LDP_TRY(pack_dense(h, h->blk[b].w2, 4 * H, H, 256, &h->pw2[b]));
     }
     LDP_TRY(pack_dense(h, h->wout, H, A, 128, &h->pwout));
@@ -312,7 +312,7 @@ static int idm_prepare_bf16(LdpIdm* h, IdmWs* w) {
   w->ops.clear();
   for (int b = 0; b < nb; ++b) {
     TcGemm op;
-    LDP_TRY(dense_op(h->pw1[b], w->hn_b, H, H, w->N, 4 * H, 128, &op));
+    LDP_TRY(dense_op(h->pw1[b], w->hn_b, H, H, w->N, 4 * H, 256, &op));
     op.mode = TC_EPI_PLAIN; op.bias = h->blk[b].b1; op.relu = 1; op.out_bf16 = w->u_b; op.ld_out_bf16 = 4 * H;
     w->ops.push_back(op);
     LDP_TRY(dense_op(h->pw2[b], w->u_b, 4 * H, 4 * H, w->N, H, 256, &op));
