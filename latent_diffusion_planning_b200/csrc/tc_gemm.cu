@@ -355,7 +355,7 @@ __global__ void __launch_bounds__(TcGeo<BN>::THREADS, 1) tc_gemm_kernel(const __
   tc_fence_before();
   if (PAIR) {
     __syncwarp();
-    cluster_sync_all();       // the peer's MMAs read this CTA's shared memory and arrive on its barriers until here
+    cluster_sync_relaxed();   // the peer's MMAs read this CTA's shared memory and arrive on its barriers until here
     if (warp == 1) tmem_dealloc_2sm(tmem_base, ncols);
   } else {
     __syncthreads();
