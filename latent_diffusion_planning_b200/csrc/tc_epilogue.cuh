@@ -291,7 +291,6 @@ __device__ __forceinline__ void epilogue_plain(const TcGemm& p, EpiSmem<BN>& es,
 template <int BN>
 struct GnPrefetch {
   uint32_t film[TcGeo<BN>::CPP][32];   // half2(scale, shift) per column
-  uint4 res[TcGeo<BN>::CPP][4];        // 32 bf16 of the residual row per chunk
 };
 
 template <int BN>
@@ -308,7 +307,6 @@ __device__ __forceinline__ void gn_prefetch(const TcGemm& p, const EpiSmem<BN>& 
   const float4* oq = reinterpret_cast<const float4*>(p.otab_q);
   const float* trow = (p.film && p.step.rows) ? p.ttab + (long long)step_of(p.step, mm) * p.ld_ttab + p.film_off : nullptr;
   const bool film = p.film && !(p.epi_skip & 2);
-  const bool res = p.res_bf16 && !p.use_aux && row_ok && !(p.epi_skip & 4);
 #pragma unroll
   for (int cc = 0; cc < CPP; ++cc) {
     const int c = c_begin + cc;
@@ -340,24 +338,6 @@ __device__ __forceinline__ void gn_prefetch(const TcGemm& p, const EpiSmem<BN>& 
     } else {
 #pragma unroll
       for (int i = 0; i < 32; ++i) pf.film[cc][i] = 0x00003c00u;     // half2(1, 0): identity
-    }
-    if (res && c < nchunks) {
-      const __nv_bfloat16* rsrc = p.res_bf16 + (long long)m * p.ld_res_bf16 + nb;
-      if (aligned32(rsrc)) {
-#pragma unroll
-        for (int j = 0; j < 2; ++j) {
-          const U32x8 u = ld_global_cg_256(rsrc + 16 * j);
-          pf.res[cc][2 * j] = make_uint4(u.r[0], u.r[1], u.r[2], u.r[3]);
-          pf.res[cc][2 * j + 1] = make_uint4(u.r[4], u.r[5], u.r[6], u.r[7]);
-        }
-      } else {
-        const uint4* rp = reinterpret_cast<const uint4*>(rsrc);
-#pragma unroll
-        for (int j = 0; j < 4; ++j) pf.res[cc][j] = __ldcg(rp + j);
-      }
-    } else {
-#pragma unroll
-      for (int j = 0; j < 4; ++j) pf.res[cc][j] = make_uint4(0u, 0u, 0u, 0u);
     }
   }
 }
@@ -391,6 +371,35 @@ __device__ __forceinline__ void epilogue_gn(const TcGemm& p, EpiSmem<BN>& es, ui
   if (dbg_t) p.dbg_stage[24] = clock64();          // accumulators read, partial statistics written
   epi_bar<BN>();
   if (dbg_t) p.dbg_stage[25] = clock64();          // statistics barrier passed
+  // The residual row is fetched here rather than with the FiLM prefetch: its ~1k cycles of L2 latency hide behind the
+  // normalise + Mish phase below, and its 16 registers are not live while the tap accumulators are being recombined
+  // (v + the second accumulator + FiLM already fill the 96-register budget there).
+  uint4 res[CPP][4];
+  {
+    const bool have_res = p.res_bf16 && !p.use_aux && row_ok && !(p.epi_skip & 4);
+#pragma unroll
+    for (int cc = 0; cc < CPP; ++cc) {
+      const int c = c_begin + cc;
+      if (have_res && c < nchunks) {
+        const __nv_bfloat16* rsrc = p.res_bf16 + (long long)m * p.ld_res_bf16 + n0 + c * 32;
+        if (aligned32(rsrc)) {
+#pragma unroll
+          for (int j = 0; j < 2; ++j) {
+            const U32x8 u = ld_global_cg_256(rsrc + 16 * j);
+            res[cc][2 * j] = make_uint4(u.r[0], u.r[1], u.r[2], u.r[3]);
+            res[cc][2 * j + 1] = make_uint4(u.r[4], u.r[5], u.r[6], u.r[7]);
+          }
+        } else {
+          const uint4* rp = reinterpret_cast<const uint4*>(rsrc);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) res[cc][j] = __ldcg(rp + j);
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) res[cc][j] = make_uint4(0u, 0u, 0u, 0u);
+      }
+    }
+  }
   // group statistics: chunks of the group (from smem) x the T rows of the sample (adjacent lanes)
   float mean[CPP], rstd[CPP];
   const float inv_cnt = 1.f / (float)(T * p.group_width);
@@ -455,7 +464,7 @@ __device__ __forceinline__ void epilogue_gn(const TcGemm& p, EpiSmem<BN>& es, ui
     } else if (p.res_bf16) {
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        const uint4 u = pf.res[cc][j];
+        const uint4 u = res[cc][j];
         const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
