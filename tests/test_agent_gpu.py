@@ -101,3 +101,26 @@ def test_sample_action_and_from_plan(agent):
     assert tuple(a2.shape) == (B, Hh, 7) and torch.isfinite(a2).all()
     with pytest.raises(NotImplementedError):
         agent.update({}, 0, 0)
+
+
+def test_process_sdvae_data_matches_direct_encode(tmp_path):
+    """process_sdvae_data mirror (reference process_sdvae_data.py:52-118): the latent file holds exactly what
+    VaeEncoder.encode returns for the assembled episode frames, in shards, with the reference's min/max attributes."""
+    import numpy as np
+    from latent_diffusion_planning_b200 import handles as H, params as P, process_sdvae_data as PS
+    blocks = (32, 64)
+    vp = P.init_params(P.vae_encoder_spec(blocks, 3, 4, 1), seed=2, perturb=0.1)
+    vae = H.VaeEncoder(vp, blocks, 3, 4, 1, 8, 16)
+    g = np.random.default_rng(0)
+    eps = {f"demo_{i}": {"obs": {"agentview_image": g.integers(0, 256, (n, 16, 16, 3), dtype=np.uint8)},
+                         "next_obs": {"agentview_image": g.integers(0, 256, (n, 16, 16, 3), dtype=np.uint8)}}
+           for i, n in enumerate([5, 2])}
+    path = PS.process_sdvae_data(eps, ["agentview_image"], vae, tmp_path, data_name="rm_lift", shard=4)
+    with np.load(path) as z:
+        got = z["data/demo_0/latent/agentview_image"]
+        frames = PS.episode_frames(eps["demo_0"], "agentview_image", "rm_lift")
+        ref = vae.encode(torch.from_numpy(frames).cuda(), precision="bf16").cpu().numpy()
+        assert got.shape == (6, 8, 8, 4) and np.array_equal(got, ref)           # images are independent: shards == one batch
+        lo, hi = float(z["data.attrs/min_z"]), float(z["data.attrs/max_z"])
+        allz = np.concatenate([z[k].ravel() for k in z.files if k.startswith("data/")])
+        assert lo == min(0.0, float(allz.min())) and hi == max(0.0, float(allz.max())) and int(z["data.attrs/total"]) == 2
