@@ -203,6 +203,10 @@ struct TcGemm {
   const float* coef = nullptr;
   DdpmCall call; const DdpmCall* call_dev = nullptr;
   float* x_io = nullptr; int ld_x = 0;
+  // PLAIN: GroupNorm statistics of the OUTPUT fused into the epilogue (VAE: the convolution that produces a GroupNorm's
+  // input also produces its per-tile partial sums, deterministically): part[((image * gn_slabs + tile in image) * gn_G +
+  // group) * 2] = (sum, sum of squares) over this tile's rows of the image; a tile holds 128 / rows-per-image >= 1 images
+  float* gn_part = nullptr; int gn_cpg = 0, gn_G = 0, gn_slabs = 0, gn_imgs_per_tile = 1;
   // DDPM: the last CTA to finish decrements the device step counter (saves the one-thread kernel that did it between
   // denoising steps); done_counter counts finished CTAs and is reset by that CTA
   int32_t* step_dec = nullptr;

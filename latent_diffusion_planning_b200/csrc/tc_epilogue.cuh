@@ -254,13 +254,44 @@ __device__ __forceinline__ void load_acc_chunk(const TcGemm& p, uint32_t taddr, 
 }
 
 // ---- epilogues: thread owns row `m`; this warp covers chunks [c_begin, c_begin + CPP) of the N tile ------------
+// Per-group (sum, sum of squares) of one 32-column chunk over the 32 rows of this warp, NGR groups per chunk
+// (32 / NGR channels each).  Fixed xor-shuffle tree: deterministic.  Lane 0 returns the totals through `out`.
+template <int NGR>
+__device__ __forceinline__ void chunk_group_sums(const float (&v)[32], bool row_ok, float2* out, int lane) {
+  constexpr int W = 32 / NGR;
+  float s[NGR], ss[NGR];
+#pragma unroll
+  for (int g = 0; g < NGR; ++g) {
+    s[g] = 0.f; ss[g] = 0.f;
+#pragma unroll
+    for (int i = 0; i < W; ++i) {
+      const float x = row_ok ? v[g * W + i] : 0.f;
+      s[g] += x;
+      ss[g] = fmaf(x, x, ss[g]);
+    }
+  }
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) {
+#pragma unroll
+    for (int g = 0; g < NGR; ++g) {
+      s[g] += __shfl_xor_sync(0xffffffffu, s[g], off);
+      ss[g] += __shfl_xor_sync(0xffffffffu, ss[g], off);
+    }
+  }
+  if (lane == 0) {
+#pragma unroll
+    for (int g = 0; g < NGR; ++g) out[g] = make_float2(s[g], ss[g]);
+  }
+}
+
 template <int BN>
 __device__ __forceinline__ void epilogue_plain(const TcGemm& p, EpiSmem<BN>& es, uint32_t taddr, int m, int n0,
-                                               int c_begin, int lane) {
-  constexpr int CPP = TcGeo<BN>::CPP;
+                                               int c_begin, int lane, int tile_m = 0, int quarter = 0) {
+  constexpr int CPP = TcGeo<BN>::CPP, NC = BN / 32;
   const bool row_ok = m < p.M;
   const bool vf = (p.ld_out_f32 & 3) == 0, vb = (p.ld_out_bf16 & 7) == 0;
   const bool vrf = (p.ld_res_f32 & 3) == 0, vrb = (p.ld_res_bf16 & 7) == 0;
+  float2* gscr = &es.part[0][0];              // scratch [quarter][chunk][8]: `part` is unused by this epilogue otherwise
 #pragma unroll 1
   for (int cc = 0; cc < CPP; ++cc) {
     const int c = c_begin + cc;
@@ -279,6 +310,34 @@ __device__ __forceinline__ void epilogue_plain(const TcGemm& p, EpiSmem<BN>& es,
       if (p.res_bf16) add_bf16x32(v, p.res_bf16 + (long long)m * p.ld_res_bf16 + nb, vrb, nvalid);
       if (p.out_f32) store_f32x32(p.out_f32 + (long long)m * p.ld_out_f32 + nb, v, vf, nvalid);
       if (p.out_bf16) store_bf16x32(p.out_bf16 + (long long)m * p.ld_out_bf16 + nb, v, vb, nvalid);
+    }
+    if (p.gn_part) {                      // uniform
+      float2* o = gscr + (quarter * NC + c) * 8;
+      if (p.gn_cpg == 4) chunk_group_sums<8>(v, row_ok, o, lane);
+      else if (p.gn_cpg == 8) chunk_group_sums<4>(v, row_ok, o, lane);
+      else if (p.gn_cpg == 16) chunk_group_sums<2>(v, row_ok, o, lane);
+      else chunk_group_sums<1>(v, row_ok, o, lane);
+    }
+  }
+  if (p.gn_part) {
+    // combine the lane quarters of each image in a fixed order and publish this tile's partial sums
+    epi_bar<BN>();
+    const int ngr = 32 / p.gn_cpg, ipt = p.gn_imgs_per_tile, qpi = 4 / ipt;      // groups per chunk, images per tile, quarters per image
+    const int nchunks = min(NC, (p.N - n0 + 31) >> 5);
+    const int q = tile_m / p.tiles_per_item, r = tile_m - q * p.tiles_per_item;
+    for (int t = (int)threadIdx.x - 64; t < nchunks * ngr * ipt; t += TcGeo<BN>::EPI_THREADS) {
+      const int img = t / (nchunks * ngr), cg = t - img * (nchunks * ngr);
+      const int c = cg / ngr, g = cg - c * ngr;
+      float a = 0.f, a2 = 0.f;
+      for (int qq = img * qpi; qq < (img + 1) * qpi; ++qq) {
+        const float2 f = gscr[(qq * NC + c) * 8 + g];
+        a += f.x;
+        a2 += f.y;
+      }
+      const long long b = (long long)q * ipt + img;
+      float* dst = p.gn_part + ((b * p.gn_slabs + r) * p.gn_G + (n0 + c * 32) / p.gn_cpg + g) * 2;
+      dst[0] = a;
+      dst[1] = a2;
     }
   }
 }

@@ -325,7 +325,7 @@ __global__ void __launch_bounds__(TcGeo<BN>::THREADS, 1) tc_gemm_kernel(const __
     tc_fence_after();
     if (p.dbg && threadIdx.x == 64 && it == 0) ts[5] = clock64();   // accumulators complete
     const uint32_t taddr = tmem_base + (uint32_t)buf * (uint32_t)p.acc_stride + ((uint32_t)(quarter * 32) << 16);
-    if constexpr (MODE == TC_EPI_PLAIN) epilogue_plain<BN>(p, es, taddr, m, n0, c_begin, lane);
+    if constexpr (MODE == TC_EPI_PLAIN) epilogue_plain<BN>(p, es, taddr, m, n0, c_begin, lane, tile_m, quarter);
     else if constexpr (MODE == TC_EPI_GN) epilogue_gn<BN>(p, es, taddr, m, n0, c_begin, row, lane, pf);
     else if constexpr (MODE == TC_EPI_DDPM)
       epilogue_ddpm<BN>(p, es, taddr, reinterpret_cast<float*>(smem_raw + (smem_base - smem_u32(smem_raw))), tile_m, n0,

@@ -512,13 +512,16 @@ static int vae_get_ws(LdpVae* h, int Bc, VaeWs** out) {
 
 // ---- shared pieces ----
 static int vae_gn(LdpVae* h, VaeWs* w, const float* x, int nimg, int P, int C, const float* gamma, const float* beta, int act,
-                  float* y_f32, __nv_bfloat16* y_bf16, cudaStream_t s) {
+                  float* y_f32, __nv_bfloat16* y_bf16, cudaStream_t s, int fused_slabs = 0) {
   const int G = h->cfg.norm_num_groups;
   LDP_CHECK(256 % (C / 4) == 0, LDP_ERR_UNSUPPORTED, "VAE GroupNorm needs C/4 to divide 256 (C in {8,...,1024} powers of two)");
   const long long per_img = (long long)P * C / 4;
-  const int slabs = (int)std::min<long long>(std::max<long long>(1, per_img / 8192), 64);
-  vae_gn_stats_kernel<<<dim3(nimg, slabs), 256, 0, s>>>(x, w->part, P, C, G);
-  VAE_LAUNCH_OK("vae_gn_stats");
+  // fused_slabs > 0: the convolution that produced x already wrote part[image][tile][group] (tc_epilogue.cuh)
+  const int slabs = fused_slabs > 0 ? fused_slabs : (int)std::min<long long>(std::max<long long>(1, per_img / 8192), 64);
+  if (fused_slabs == 0) {
+    vae_gn_stats_kernel<<<dim3(nimg, slabs), 256, 0, s>>>(x, w->part, P, C, G);
+    VAE_LAUNCH_OK("vae_gn_stats");
+  }
   vae_gn_final_kernel<<<(nimg * G + 127) / 128, 128, 0, s>>>(w->part, w->stats, nimg * G, G, slabs, 1.f / ((float)P * (C / G)), 1e-6f);
   VAE_LAUNCH_OK("vae_gn_final");
   const long long total = (long long)nimg * per_img;
@@ -700,15 +703,26 @@ static int vae_walk_tc(LdpVae* h, VaeWs* w, bool build, const void* images, int 
   size_t oi = 0;
   int conv_id = 0;
   // emit(op builder) / run(op)
+  // gn_next: the f32 output is the input of a GroupNorm -> its statistics are accumulated in this epilogue
+  static const bool fuse_gn = !(getenv("LDP_VAE_FUSE_GN") && getenv("LDP_VAE_FUSE_GN")[0] == '0');
+  int fused_slabs = 0;            // > 0 after a conv that wrote the partial sums of its output
   auto conv = [&](const ConvW& cw, const __nv_bfloat16* in, int S_in, int stride, const float* res, float* of32,
-                  __nv_bfloat16* obf) -> int {
+                  __nv_bfloat16* obf, bool gn_next = false) -> int {
     const int S_out = S_in / stride;
+    const TileGeo tg = tile_geo(S_out);
+    const int G = c.norm_num_groups, cpg = cw.cout / G;
+    const bool fuse = fuse_gn && gn_next && of32 != nullptr && cw.cout % G == 0 && (cpg == 4 || cpg == 8 || cpg == 16 || cpg == 32) &&
+                      S_out * S_out >= 64 && tg.ib <= 2 && tg.tiles_per_img <= 64;
+    fused_slabs = fuse ? tg.tiles_per_img : 0;
     if (build) {
       TcGemm op;
       LDP_TRY(vae_conv_tc(h, w, conv_id, cw, cw.b, in, S_in, stride, &op));
       op.res_f32 = res; op.ld_res_f32 = cw.cout;
       op.out_f32 = of32; op.ld_out_f32 = cw.cout;
       op.out_bf16 = obf; op.ld_out_bf16 = cw.cout;
+      if (fuse) {
+        op.gn_part = w->part; op.gn_cpg = cpg; op.gn_G = G; op.gn_slabs = tg.tiles_per_img; op.gn_imgs_per_tile = tg.ib;
+      }
       w->ops.push_back(op);
     } else {
       TcGemm op = w->ops[oi];
@@ -720,19 +734,21 @@ static int vae_walk_tc(LdpVae* h, VaeWs* w, bool build, const void* images, int 
     return LDP_OK;
   };
   auto gn = [&](const float* x, int P, int C, const float* gs_, const float* gb_, int act, __nv_bfloat16* y) -> int {
+    const int slabs = fused_slabs;      // set by the conv that produced x (0: separate statistics kernel)
+    fused_slabs = 0;
     if (build) return LDP_OK;
-    return vae_gn(h, w, x, nimg, P, C, gs_, gb_, act, nullptr, y, s);
+    return vae_gn(h, w, x, nimg, P, C, gs_, gb_, act, nullptr, y, s, slabs);
   };
   auto resnet = [&](const ResW& r, int S) -> int {
     const int P = S * S;
     LDP_TRY(gn(b.S, P, r.c1.cin, r.n1s, r.n1b, 1, b.Gb));
-    LDP_TRY(conv(r.c1, b.Gb, S, 1, nullptr, b.Hf, nullptr));
+    LDP_TRY(conv(r.c1, b.Gb, S, 1, nullptr, b.Hf, nullptr, true));
     LDP_TRY(gn(b.Hf, P, r.c1.cout, r.n2s, r.n2b, 1, b.Gb));
     if (r.has_sc) {
       LDP_TRY(conv(r.sc, b.Sb, S, 1, nullptr, b.Hf, nullptr));            // Hf is free again after the second GroupNorm
-      LDP_TRY(conv(r.c2, b.Gb, S, 1, b.Hf, b.S, b.Sb));
+      LDP_TRY(conv(r.c2, b.Gb, S, 1, b.Hf, b.S, b.Sb, true));
     } else {
-      LDP_TRY(conv(r.c2, b.Gb, S, 1, b.S, b.S, b.Sb));                     // in place: a thread reads its residual row, then writes it
+      LDP_TRY(conv(r.c2, b.Gb, S, 1, b.S, b.S, b.Sb, true));               // in place: a thread reads its residual row, then writes it
     }
     return LDP_OK;
   };
@@ -753,7 +769,7 @@ static int vae_walk_tc(LdpVae* h, VaeWs* w, bool build, const void* images, int 
   for (int i = 0; i < c.n_blocks; ++i) {
     for (auto& r : h->blocks[i]) LDP_TRY(resnet(r, S));
     if (i != c.n_blocks - 1) {
-      LDP_TRY(conv(h->down[i], b.Sb, S, 2, nullptr, b.Hf, b.Gb));
+      LDP_TRY(conv(h->down[i], b.Sb, S, 2, nullptr, b.Hf, b.Gb, true));
       std::swap(b.S, b.Hf);
       std::swap(b.Sb, b.Gb);
       S /= 2;
@@ -770,7 +786,7 @@ static int vae_walk_tc(LdpVae* h, VaeWs* w, bool build, const void* images, int 
       vae_attn_kernel<<<nimg, 256, 0, s>>>(w->qkv, nullptr, b.Gb, L, ch);
       VAE_LAUNCH_OK("vae_attn");
     }
-    LDP_TRY(conv(h->ap, b.Gb, S, 1, b.S, b.S, b.Sb));
+    LDP_TRY(conv(h->ap, b.Gb, S, 1, b.S, b.S, b.Sb, true));
   }
   LDP_TRY(resnet(h->mid1, S));
   LDP_TRY(gn(b.S, L, ch, h->nos, h->nob, 1, b.Gb));
