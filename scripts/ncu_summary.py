@@ -50,7 +50,7 @@ if lc.exists():
         lines.append(f"| `{k}` | {a[0]} | {a[1] / 1e3:.1f} | {100 * a[1] / tot:.1f}% | {a[1] / a[0] / 1e3:.2f} | {a[2] / a[0] / 1e6:.2f} | {a[3] / a[0]:.1f} |")
     tc = [d for d in per.values() if "tc_gemm" in d["k"]]
     if tc:
-        n_step = 31
+        n_step = 30
         last = tc[-n_step:]
         lines += ["", f"## the last denoising step's {len(last)} tcgen05 launches", "",
                   "| # | kernel | grid | block | us | DRAM read MB | tensor % |", "|---|---|---|---|---|---|---|"]
