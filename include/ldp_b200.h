@@ -198,6 +198,15 @@ LDP_API int64_t ldp_vae_param_count(const LdpVaeConfig* cfg);
 LDP_API int ldp_vae_encode(LdpVae* h, int precision, const void* images_dev, int pixel_format, int B,
                            float lat_min, float lat_max, float* latent_dev, void* cuda_stream);
 
+/* Decoder: FlaxAutoencoderKL.decode(z).sample (reference agent/ldp_agent.py:66-85 `vae_decode`, the plan_viz of
+ * sample_viz :483).  Same config struct (in_channels = channels of the decoded image); weights in the order of
+ * params.py:vae_decoder_spec (post_quant_conv, decoder/conv_in, mid block, up blocks, conv_norm_out, conv_out).
+ * latent_dev: (B,h,w,latent_channels) float32, already un-normalised (the caller applies unnormalize_obs :82);
+ * images_dev: (B,S,S,in_channels) float32 NHWC (the reference views the same values as NCHW). */
+LDP_API int64_t ldp_vae_decoder_param_count(const LdpVaeConfig* cfg);
+LDP_API int ldp_vae_decoder_create(const LdpVaeConfig* cfg, const float* params_host, uint64_t n_params, LdpVae** out);
+LDP_API int ldp_vae_decode(LdpVae* h, int precision, const float* latent_dev, int B, float* images_dev, void* cuda_stream);
+
 /* ---------------------------------------------------------------------------------------------------------
  * Low-level operator exposed for tests and roofline measurement: C[M,N] = A[M,K] W[K,N] + bias on the
  * tcgen05 path (bf16 operands, fp32 accumulate).  a_dev (M,K) f32, w_host (K,N) f32 Flax Dense layout,

@@ -24,6 +24,7 @@ EXPORTS = [
     "ldp_planner_profile_step",
     "ldp_idm_create", "ldp_idm_destroy", "ldp_idm_param_count", "ldp_idm_forward", "ldp_idm_sample",
     "ldp_vae_create", "ldp_vae_destroy", "ldp_vae_param_count", "ldp_vae_encode",
+    "ldp_vae_decoder_create", "ldp_vae_decoder_param_count", "ldp_vae_decode",
     "ldp_tc_dense", "ldp_launch_count", "ldp_launch_count_reset",
 ]
 
@@ -93,6 +94,10 @@ def load() -> C.CDLL:
     lib.ldp_vae_param_count.argtypes = [C.POINTER(VaeConfig)]
     lib.ldp_vae_param_count.restype = i64
     lib.ldp_vae_encode.argtypes = [vp, i32, vp, i32, i32, f32, f32, vp, vp]
+    lib.ldp_vae_decoder_create.argtypes = [C.POINTER(VaeConfig), vp, u64, C.POINTER(vp)]
+    lib.ldp_vae_decoder_param_count.argtypes = [C.POINTER(VaeConfig)]
+    lib.ldp_vae_decoder_param_count.restype = i64
+    lib.ldp_vae_decode.argtypes = [vp, i32, vp, i32, vp, vp]
     lib.ldp_tc_dense.argtypes = [vp, vp, vp, vp, i32, i32, i32, vp]
     lib.ldp_launch_count.restype = i64
     lib.ldp_launch_count_reset.restype = None

@@ -58,8 +58,10 @@ class LDPAgent:
     """Sampling-side LDP agent on the B200-native kernels."""
 
     def __init__(self, planner: H.Planner, idm: H.Idm, vae: Optional[H.VaeEncoder], obs_normalization: Dict[str, Any],
-                 config: Dict[str, Any], planner_params, idm_params, precision: str = "bf16", sampler: str = "ddpm"):
+                 config: Dict[str, Any], planner_params, idm_params, precision: str = "bf16", sampler: str = "ddpm",
+                 vae_decoder: Optional["H.VaeDecoder"] = None, viz: bool = False):
         self.planner, self.idm, self.vae = planner, idm, vae
+        self.vae_decoder, self.viz = vae_decoder, viz
         self.obs_normalization = obs_normalization
         self.config = config
         self._planner_params, self._idm_params = planner_params, idm_params
@@ -79,7 +81,8 @@ class LDPAgent:
                update_idm_after: int = 0, update_planner_until: int = 10 ** 12, update_planner_after: int = 0, grad_clip=None,
                # additions (not in the reference): weights, VAE topology, compute mode
                planner_params: Optional[dict] = None, idm_params: Optional[dict] = None, vae_params: Optional[dict] = None,
-               vae_block_out_channels: Sequence[int] = (128, 256, 512, 512), precision: str = "bf16", sampler: str = "ddpm"):
+               vae_block_out_channels: Sequence[int] = (128, 256, 512, 512), precision: str = "bf16", sampler: str = "ddpm",
+               vae_decoder_params: Optional[dict] = None, viz: bool = False):
         """Keyword surface of the reference's `LDPAgent.create` (agent/ldp_agent.py:516-532).  `shape_meta` is the data
         config's `{'ac_dim': A, 'all_shapes': {key: [...]}}`.  Weights: pass Flax-layout trees (flat 'a/b/kernel' dicts or
         nested), otherwise they are drawn with the reference's initialisers from `rng` (no checkpoints without network)."""
@@ -123,11 +126,21 @@ class LDPAgent:
             lat = vae.latent_hw * vae.latent_hw * vae.latent_channels
             if lat != int(vae_feature_dim):
                 raise ValueError(f"vae_feature_dim={vae_feature_dim} but the encoder produces {lat} features per frame")
+        # `viz`: build the VAE decoder for plan_viz (reference vae_decode, agent/ldp_agent.py:66-85).  The reference always
+        # decodes inside sample_viz; here it is a flag because decoding Ha+1 frames per plan costs more than the plan.
+        vae_dec = None
+        if viz and len(rgb_obs) > 0:
+            dspec = P.vae_decoder_spec(vae_block_out_channels)
+            if vae_decoder_params is None:
+                vae_decoder_params = P.init_params(dspec, seed=seed + 3)
+            else:
+                vae_decoder_params = P.unnest(vae_decoder_params) if _is_nested(vae_decoder_params) else vae_decoder_params
+            vae_dec = H.VaeDecoder(vae_decoder_params, vae_block_out_channels)
         config = dict(name=name, obs_horizon=obs_horizon, action_dim=action_dim, pred_horizon=pred_horizon,
                       action_horizon=action_horizon, obs_dim=obs_dim, rgb_obs=list(rgb_obs), lowdim_obs=list(lowdim_obs),
                       vae_feature_dim=int(vae_feature_dim), planner_n_diffusion_steps=planner_n_diffusion_steps,
                       idm_n_diffusion_steps=idm_n_diffusion_steps, data_name=data_name)   # agent/ldp_agent.py:653-665
-        return cls(pl, idm, vae, obs_normalization or {}, config, planner_params, idm_params, precision, sampler)
+        return cls(pl, idm, vae, obs_normalization or {}, config, planner_params, idm_params, precision, sampler, vae_dec, viz)
 
     # ---------------------------------------------------------------- reference-named pieces
     def get_params(self):
@@ -188,10 +201,26 @@ class LDPAgent:
         return self.idm.sample(ssp, a_T, seed=seed, row_offset=row_offset, n_steps=self.config["idm_n_diffusion_steps"],
                                sampler=self.sampler, precision=self.precision)
 
+    def vae_decode(self, feats: torch.Tensor) -> torch.Tensor:
+        """agent/ldp_agent.py:66-85: the first `vae_feature_dim` features of every frame -> (h, w, 4) latents ->
+        unnormalize_obs with the first rgb key's min/max -> decode -> (B, H, 3, S, S)."""
+        if self.vae_decoder is None:
+            raise RuntimeError("the agent was created without viz=True: no VAE decoder")
+        B, Hh = feats.shape[:2]
+        d = self.vae_decoder
+        n = d.latent_hw * d.latent_hw * d.latent_channels
+        z = feats[:, :, :n].reshape(B * Hh, d.latent_hw, d.latent_hw, d.latent_channels).to(torch.float32)
+        key = self.config["rgb_obs"][0]
+        norm = self.obs_normalization.get("obs", {}).get(key)
+        if norm is not None:
+            z = normalize_unnormalize(z.reshape(B * Hh, -1), norm, False).reshape(z.shape)
+        img = d.decode(z.contiguous(), precision=self.precision)                      # (B*H, S, S, 3) NHWC
+        return img.permute(0, 3, 1, 2).reshape(B, Hh, d.out_channels, d.image_size, d.image_size)
+
     def sample_viz(self, batch: Dict[str, Any], eval_rng, row_offset: int = 0):
         """agent/ldp_agent.py:435-506: encode -> planner loop -> plan -> IDM loop -> actions.
-        Returns `(action (B, Ha, A), {'plan': (B, Ha+1, D), 'plan_viz': None[, 'plan_mse']})`; `plan_viz` needs the VAE
-        decoder (next scope row N2)."""
+        Returns `(action (B, Ha, A), {'plan': (B, Ha+1, D), 'plan_viz': (B, Ha+1, 3, S, S) | None[, 'plan_mse']})`;
+        `plan_viz` is decoded when the agent was created with `viz=True` (reference :483 always decodes)."""
         seed = int(eval_rng)
         cfg = self.config
         obs = self.vae_encode(self._postprocess_obs(batch["obs"]))
@@ -206,7 +235,7 @@ class LDPAgent:
         ssp = torch.cat([plan[:, :-1], plan[:, 1:]], dim=-1).reshape(B * Ha, 2 * D).contiguous()
         action = self._idm_loop(ssp, seed, row_offset * Ha).reshape(B, Ha, cfg["action_dim"])
         action = self._unnormalize_actions(action)
-        metrics = dict(plan_viz=None, plan=plan)
+        metrics = dict(plan_viz=self.vae_decode(plan) if (self.viz and self.vae_decoder is not None) else None, plan=plan)
         if obs_emb.shape[1] > oh:                                   # training batch: ground-truth future is present
             metrics["plan_mse"] = ((x0 - obs_emb[:, oh:]) ** 2).mean()
         return action, metrics

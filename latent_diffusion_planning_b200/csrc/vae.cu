@@ -380,6 +380,7 @@ struct LdpVae {
   std::map<int, std::unique_ptr<VaeWs>> ws;
   std::map<int, PackedW> packed;                     // conv id -> packed weights (tc path)
   int64_t n_params = 0;
+  bool is_decoder = false;                           // decoder handle: blocks = up blocks, down = upsampler convs, quant = post_quant_conv
 };
 
 namespace ldp {
@@ -482,6 +483,36 @@ static int vae_create_impl(const LdpVaeConfig* cfg, const float* params_host, ui
   return LDP_OK;
 }
 
+// largest (pixels x channels) any activation tensor reaches per image
+static size_t vae_max_act(const LdpVae* h) {
+  const LdpVaeConfig& c = h->cfg;
+  size_t max_act = 0;
+  if (!h->is_decoder) {
+    int S = c.image_size;
+    for (int i = 0; i < c.n_blocks; ++i) {
+      const int cin = i == 0 ? c.block_out_channels[0] : c.block_out_channels[i - 1];
+      max_act = std::max(max_act, (size_t)S * S * std::max(cin, c.block_out_channels[i]));
+      if (i != c.n_blocks - 1) S /= 2;
+    }
+    const int cl = c.block_out_channels[c.n_blocks - 1];
+    max_act = std::max(max_act, (size_t)S * S * 3 * cl);
+  } else {
+    int S = c.image_size >> (c.n_blocks - 1);
+    int ch = c.block_out_channels[c.n_blocks - 1];
+    max_act = (size_t)S * S * 3 * ch;
+    for (int i = 0; i < c.n_blocks; ++i) {
+      const int co = c.block_out_channels[c.n_blocks - 1 - i];
+      max_act = std::max(max_act, (size_t)S * S * std::max(ch, co));
+      ch = co;
+      if (i != c.n_blocks - 1) {
+        S *= 2;
+        max_act = std::max(max_act, (size_t)S * S * co);
+      }
+    }
+  }
+  return max_act;
+}
+
 static int vae_get_ws(LdpVae* h, int Bc, VaeWs** out) {
   auto it = h->ws.find(Bc);
   if (it != h->ws.end()) {
@@ -491,15 +522,9 @@ static int vae_get_ws(LdpVae* h, int Bc, VaeWs** out) {
   const LdpVaeConfig& c = h->cfg;
   std::unique_ptr<VaeWs> w(new VaeWs());
   w->Bc = Bc;
-  size_t max_act = 0;
-  int S = c.image_size;
-  for (int i = 0; i < c.n_blocks; ++i) {
-    const int cin = i == 0 ? c.block_out_channels[0] : c.block_out_channels[i - 1];
-    max_act = std::max(max_act, (size_t)S * S * std::max(cin, c.block_out_channels[i]));
-    if (i != c.n_blocks - 1) S /= 2;
-  }
+  const size_t max_act = vae_max_act(h);
+  const int S = c.image_size >> (c.n_blocks - 1);
   const int cl = c.block_out_channels[c.n_blocks - 1];
-  max_act = std::max(max_act, (size_t)S * S * 3 * cl);
   LDP_TRY(w->arena.alloc_t(&w->S, (size_t)Bc * max_act, false));
   LDP_TRY(w->arena.alloc_t(&w->Hf, (size_t)Bc * max_act, false));
   LDP_TRY(w->arena.alloc_t(&w->stats, (size_t)Bc * c.norm_num_groups * 2));
@@ -560,16 +585,7 @@ static int vae_res_f32(LdpVae* h, VaeWs* w, const ResW& r, int nimg, int S, cuda
 static int vae_forward_f32(LdpVae* h, VaeWs* w, const void* images, int fmt, int nimg, float lat_min, float lat_max, float* out,
                            cudaStream_t s) {
   const LdpVaeConfig& c = h->cfg;
-  if (!w->Gf) {
-    size_t max_act = 0;
-    int S0 = c.image_size;
-    for (int i = 0; i < c.n_blocks; ++i) {
-      const int cin = i == 0 ? c.block_out_channels[0] : c.block_out_channels[i - 1];
-      max_act = std::max(max_act, (size_t)S0 * S0 * std::max(cin, c.block_out_channels[i]));
-      if (i != c.n_blocks - 1) S0 /= 2;
-    }
-    LDP_TRY(w->arena.alloc_t(&w->Gf, (size_t)w->Bc * max_act, false));
-  }
+  if (!w->Gf) LDP_TRY(w->arena.alloc_t(&w->Gf, (size_t)w->Bc * vae_max_act(h), false));
   int S = c.image_size;
   const int c0 = c.block_out_channels[0];
   const size_t smem = (size_t)9 * c.in_channels * c0 * 4;
@@ -804,18 +820,251 @@ static int vae_prepare_tc(LdpVae* h, VaeWs* w) {
   if (w->tc_ready) return LDP_OK;
   LDP_TRY(tc_driver_check());
   LDP_TRY(tc_gemm_init());
-  const LdpVaeConfig& c = h->cfg;
-  size_t max_act = 0;
-  int S = c.image_size;
-  for (int i = 0; i < c.n_blocks; ++i) {
-    const int cin = i == 0 ? c.block_out_channels[0] : c.block_out_channels[i - 1];
-    max_act = std::max(max_act, (size_t)S * S * std::max(cin, c.block_out_channels[i]));
-    if (i != c.n_blocks - 1) S /= 2;
-  }
+  const size_t max_act = vae_max_act(h);
   LDP_TRY(w->arena.alloc_t(&w->Sb, (size_t)w->Bc * max_act));
   LDP_TRY(w->arena.alloc_t(&w->Gb, (size_t)w->Bc * max_act));
   w->ops.clear();
   LDP_TRY(vae_walk_tc(h, w, true, nullptr, 0, w->Bc, 0.f, 0.f, nullptr, 0));
+  w->tc_ready = true;
+  return LDP_OK;
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// Decoder: FlaxAutoencoderKL.decode(z).sample (reference agent/ldp_agent.py:66-85, the plan_viz of sample_viz :483).
+// post_quant_conv 1x1 -> conv_in -> mid (resnet, attention, resnet) -> up blocks over the reversed channel list
+// (layers_per_block + 1 resnets, nearest x2 + conv 3x3 on all but the last) -> GroupNorm -> swish -> conv_out.
+// Same handle type and building blocks as the encoder: `blocks` holds the up blocks, `down` the upsampler convs, `quant`
+// the post_quant_conv; the 4-channel conv_in and the 3-channel conv_out run on the SIMT convolution (K = 36 / N = 3 are
+// no tensor-core shapes), everything between on the tcgen05 path.
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) vae_upsample2x_kernel(const T* __restrict__ in, T* __restrict__ out, long long nimg, int S,
+                                                             int C) {
+  // out (n, 2S, 2S, C) = in (n, S, S, C) nearest: out[y][x] = in[y / 2][x / 2]; 16-byte vectors along C
+  constexpr int V = 16 / sizeof(T);
+  const int cv = C / V, S2 = 2 * S;
+  const long long total = nimg * S2 * S2 * cv;
+  const uint4* i4 = reinterpret_cast<const uint4*>(in);
+  uint4* o4 = reinterpret_cast<uint4*>(out);
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int q = (int)(i % cv);
+    const long long pix = i / cv;
+    const int x = (int)(pix % S2), y = (int)((pix / S2) % S2);
+    const long long b = pix / ((long long)S2 * S2);
+    o4[i] = i4[((b * S + (y >> 1)) * S + (x >> 1)) * cv + q];
+  }
+}
+
+static int64_t vae_dec_param_count(const LdpVaeConfig& c) {
+  auto conv = [](int64_t k, int64_t ci, int64_t co) { return k * k * ci * co + co; };
+  auto res = [&](int64_t ci, int64_t co) { return 2 * ci + conv(3, ci, co) + 2 * co + conv(3, co, co) + (ci != co ? conv(1, ci, co) : 0); };
+  int64_t ch = c.block_out_channels[c.n_blocks - 1];
+  int64_t n = conv(1, c.latent_channels, c.latent_channels) + conv(3, c.latent_channels, ch);
+  n += res(ch, ch) + 2 * ch + 4 * (ch * ch + ch) + res(ch, ch);
+  for (int i = 0; i < c.n_blocks; ++i) {
+    const int64_t co = c.block_out_channels[c.n_blocks - 1 - i];
+    for (int j = 0; j < c.layers_per_block + 1; ++j) {
+      n += res(ch, co);
+      ch = co;
+    }
+    if (i != c.n_blocks - 1) n += conv(3, co, co);
+  }
+  n += 2 * ch + conv(3, ch, c.in_channels);
+  return n;
+}
+
+static int vae_dec_create_impl(const LdpVaeConfig* cfg, const float* params_host, uint64_t n_params, LdpVae* h) {
+  h->cfg = *cfg;
+  h->is_decoder = true;
+  const LdpVaeConfig& c = h->cfg;
+  const int64_t expect = vae_dec_param_count(c);
+  LDP_CHECK((int64_t)n_params == expect, LDP_ERR_PARAM_COUNT,
+            "VAE decoder weight blob has " + std::to_string(n_params) + " floats, config needs " + std::to_string(expect));
+  LDP_TRY(h->arena.alloc_t(&h->blob, n_params, false));
+  LDP_CUDA_OK(cudaMemcpy(h->blob, params_host, n_params * 4, cudaMemcpyHostToDevice));
+  BlobWalker w{h->blob, 0};
+  int ch = c.block_out_channels[c.n_blocks - 1];
+  h->quant = take_conv(w, 1, c.latent_channels, c.latent_channels);
+  h->conv_in = take_conv(w, 3, c.latent_channels, ch);
+  h->mid0 = take_res(w, ch, ch);
+  h->ag_s = w.take(ch); h->ag_b = w.take(ch);
+  h->aq.w = w.take((uint64_t)ch * ch); h->aq.b = w.take(ch);
+  h->ak.w = w.take((uint64_t)ch * ch); h->ak.b = w.take(ch);
+  h->av.w = w.take((uint64_t)ch * ch); h->av.b = w.take(ch);
+  h->ap = ConvW();
+  h->ap.k = 1; h->ap.cin = ch; h->ap.cout = ch;
+  h->ap.w = w.take((uint64_t)ch * ch); h->ap.b = w.take(ch);
+  h->mid1 = take_res(w, ch, ch);
+  const int c_mid = ch;
+  for (int i = 0; i < c.n_blocks; ++i) {
+    const int co = c.block_out_channels[c.n_blocks - 1 - i];
+    std::vector<ResW> rs;
+    for (int j = 0; j < c.layers_per_block + 1; ++j) {
+      rs.push_back(take_res(w, ch, co));
+      ch = co;
+    }
+    h->blocks.push_back(rs);
+    if (i != c.n_blocks - 1) h->down.push_back(take_conv(w, 3, co, co));
+  }
+  h->nos = w.take(ch); h->nob = w.take(ch);
+  h->conv_out = take_conv(w, 3, ch, c.in_channels);
+  LDP_CHECK((int64_t)w.pos == expect, LDP_ERR_PARAM_COUNT, "internal: decoder blob walk mismatch");
+  LDP_TRY(h->arena.alloc_t(&h->wqkv, (size_t)c_mid * 3 * c_mid));
+  LDP_TRY(h->arena.alloc_t(&h->bqkv, (size_t)3 * c_mid));
+  const float* ws[3] = {h->aq.w, h->ak.w, h->av.w};
+  const float* bs[3] = {h->aq.b, h->ak.b, h->av.b};
+  for (int i = 0; i < 3; ++i) {
+    LDP_CUDA_OK(cudaMemcpy2D(h->wqkv + (size_t)i * c_mid, (size_t)3 * c_mid * 4, ws[i], (size_t)c_mid * 4, (size_t)c_mid * 4, c_mid,
+                             cudaMemcpyDeviceToDevice));
+    LDP_CUDA_OK(cudaMemcpy(h->bqkv + (size_t)i * c_mid, bs[i], (size_t)c_mid * 4, cudaMemcpyDeviceToDevice));
+  }
+  return LDP_OK;
+}
+
+template <typename T>
+static int vae_upsample(const T* in, T* out, int nimg, int S, int C, cudaStream_t s) {
+  const long long total = (long long)nimg * 4 * S * S * (C / (16 / (int)sizeof(T)));
+  vae_upsample2x_kernel<T><<<(int)std::min<long long>((total + 255) / 256, 148 * 16), 256, 0, s>>>(in, out, nimg, S, C);
+  VAE_LAUNCH_OK("vae_upsample2x");
+  return LDP_OK;
+}
+
+// fp32 program (parity instrument)
+static int vae_decode_f32(LdpVae* h, VaeWs* w, const float* z, int nimg, float* out, cudaStream_t s) {
+  const LdpVaeConfig& c = h->cfg;
+  if (!w->Gf) LDP_TRY(w->arena.alloc_t(&w->Gf, (size_t)w->Bc * vae_max_act(h), false));
+  int S = c.image_size >> (c.n_blocks - 1);
+  const int ch = c.block_out_channels[c.n_blocks - 1], L = S * S;
+  LDP_TRY(vae_conv_f32(h->quant, z, nullptr, w->Gf, nimg, S, 1, 0, s));
+  LDP_TRY(vae_conv_f32(h->conv_in, w->Gf, nullptr, w->S, nimg, S, 1, 1, s));
+  LDP_TRY(vae_res_f32(h, w, h->mid0, nimg, S, s));
+  {
+    LDP_TRY(vae_gn(h, w, w->S, nimg, L, ch, h->ag_s, h->ag_b, 0, w->Gf, nullptr, s));
+    GemmF32 g;
+    g.x1 = w->Gf; g.c1 = ch; g.ld1 = ch; g.w = h->wqkv; g.ldw = 3 * ch; g.bias = h->bqkv; g.out = w->qkv; g.ldo = 3 * ch;
+    g.m = nimg * L; g.n = 3 * ch;
+    LDP_TRY(launch_gemm_f32(g, s));
+    vae_attn_kernel<<<nimg, 256, 0, s>>>(w->qkv, w->Gf, nullptr, L, ch);
+    VAE_LAUNCH_OK("vae_attn");
+    g = GemmF32();
+    g.x1 = w->Gf; g.c1 = ch; g.ld1 = ch; g.w = h->ap.w; g.ldw = ch; g.bias = h->ap.b; g.res = w->S; g.ldres = ch;
+    g.out = w->S; g.ldo = ch; g.m = nimg * L; g.n = ch;
+    LDP_TRY(launch_gemm_f32(g, s));
+  }
+  LDP_TRY(vae_res_f32(h, w, h->mid1, nimg, S, s));
+  for (int i = 0; i < c.n_blocks; ++i) {
+    for (auto& r : h->blocks[i]) LDP_TRY(vae_res_f32(h, w, r, nimg, S, s));
+    if (i != c.n_blocks - 1) {
+      const int co = h->down[i].cin;
+      LDP_TRY(vae_upsample<float>(w->S, w->Gf, nimg, S, co, s));
+      S *= 2;
+      LDP_TRY(vae_conv_f32(h->down[i], w->Gf, nullptr, w->S, nimg, S, 1, 1, s));
+    }
+  }
+  const int c0 = h->conv_out.cin;
+  LDP_TRY(vae_gn(h, w, w->S, nimg, S * S, c0, h->nos, h->nob, 1, w->Gf, nullptr, s));
+  return vae_conv_f32(h->conv_out, w->Gf, nullptr, out, nimg, S, 1, 1, s);
+}
+
+// tcgen05 program: same two-phase walk as the encoder (build the ops once, then replay)
+static int vae_dec_walk_tc(LdpVae* h, VaeWs* w, bool build, const float* z, int nimg, float* out, cudaStream_t s) {
+  const LdpVaeConfig& c = h->cfg;
+  VaeBufs b{w->S, w->Hf, w->Sb, w->Gb};
+  size_t oi = 0;
+  int conv_id = 0;
+  static const bool fuse_gn = !(getenv("LDP_VAE_FUSE_GN") && getenv("LDP_VAE_FUSE_GN")[0] == '0');
+  int fused_slabs = 0;
+  auto conv = [&](const ConvW& cw, const __nv_bfloat16* in, int S_in, const float* res, float* of32, __nv_bfloat16* obf,
+                  bool gn_next) -> int {
+    const TileGeo tg = tile_geo(S_in);
+    const int G = c.norm_num_groups, cpg = cw.cout / G;
+    const bool fuse = fuse_gn && gn_next && of32 != nullptr && cw.cout % G == 0 && (cpg == 4 || cpg == 8 || cpg == 16 || cpg == 32) &&
+                      S_in * S_in >= 64 && tg.ib <= 2 && tg.tiles_per_img <= 64;
+    fused_slabs = fuse ? tg.tiles_per_img : 0;
+    if (build) {
+      TcGemm op;
+      LDP_TRY(vae_conv_tc(h, w, conv_id, cw, cw.b, in, S_in, 1, &op));
+      op.res_f32 = res; op.ld_res_f32 = cw.cout;
+      op.out_f32 = of32; op.ld_out_f32 = cw.cout;
+      op.out_bf16 = obf; op.ld_out_bf16 = cw.cout;
+      if (fuse) {
+        op.gn_part = w->part; op.gn_cpg = cpg; op.gn_G = G; op.gn_slabs = tg.tiles_per_img; op.gn_imgs_per_tile = tg.ib;
+      }
+      w->ops.push_back(op);
+    } else {
+      TcGemm op = w->ops[oi];
+      op.M = nimg * S_in * S_in;
+      LDP_TRY(launch_tc_gemm(op, s));
+    }
+    ++oi;
+    ++conv_id;
+    return LDP_OK;
+  };
+  auto gn = [&](const float* x, int P, int C, const float* gs_, const float* gb_, int act, float* yf, __nv_bfloat16* y) -> int {
+    const int slabs = fused_slabs;
+    fused_slabs = 0;
+    if (build) return LDP_OK;
+    return vae_gn(h, w, x, nimg, P, C, gs_, gb_, act, yf, y, s, slabs);
+  };
+  auto resnet = [&](const ResW& r, int S) -> int {
+    const int P = S * S;
+    LDP_TRY(gn(b.S, P, r.c1.cin, r.n1s, r.n1b, 1, nullptr, b.Gb));
+    LDP_TRY(conv(r.c1, b.Gb, S, nullptr, b.Hf, nullptr, true));
+    LDP_TRY(gn(b.Hf, P, r.c1.cout, r.n2s, r.n2b, 1, nullptr, b.Gb));
+    if (r.has_sc) {
+      LDP_TRY(conv(r.sc, b.Sb, S, nullptr, b.Hf, nullptr, false));
+      LDP_TRY(conv(r.c2, b.Gb, S, b.Hf, b.S, b.Sb, true));
+    } else {
+      LDP_TRY(conv(r.c2, b.Gb, S, b.S, b.S, b.Sb, true));
+    }
+    return LDP_OK;
+  };
+  int S = c.image_size >> (c.n_blocks - 1);
+  const int ch = c.block_out_channels[c.n_blocks - 1], L = S * S;
+  if (!build) {
+    // 4-channel head on the SIMT convolution, then the bf16 copy the first resnet's shortcut / the tensor maps read
+    LDP_TRY(vae_conv_f32(h->quant, z, nullptr, b.Hf, nimg, S, 1, 0, s));
+    LDP_TRY(vae_conv_f32(h->conv_in, b.Hf, nullptr, b.S, nimg, S, 1, 1, s));
+    LDP_TRY(launch_cast_bf16(b.S, ch, b.Sb, ch, (long long)nimg * L, ch, 0, s));
+  }
+  LDP_TRY(resnet(h->mid0, S));
+  {
+    LDP_TRY(gn(b.S, L, ch, h->ag_s, h->ag_b, 0, nullptr, b.Gb));
+    ConvW qkv;
+    qkv.k = 1; qkv.cin = ch; qkv.cout = 3 * ch; qkv.w = h->wqkv; qkv.b = h->bqkv;
+    LDP_TRY(conv(qkv, b.Gb, S, nullptr, w->qkv, nullptr, false));
+    if (!build) {
+      vae_attn_kernel<<<nimg, 256, 0, s>>>(w->qkv, nullptr, b.Gb, L, ch);
+      VAE_LAUNCH_OK("vae_attn");
+    }
+    LDP_TRY(conv(h->ap, b.Gb, S, b.S, b.S, b.Sb, true));
+  }
+  LDP_TRY(resnet(h->mid1, S));
+  for (int i = 0; i < c.n_blocks; ++i) {
+    for (auto& r : h->blocks[i]) LDP_TRY(resnet(r, S));
+    if (i != c.n_blocks - 1) {
+      const int co = h->down[i].cin;
+      if (!build) LDP_TRY(vae_upsample<__nv_bfloat16>(b.Sb, b.Gb, nimg, S, co, s));
+      S *= 2;
+      LDP_TRY(conv(h->down[i], b.Gb, S, nullptr, b.S, b.Sb, true));
+    }
+  }
+  const int c0 = h->conv_out.cin;
+  LDP_TRY(gn(b.S, S * S, c0, h->nos, h->nob, 1, b.Hf, nullptr));
+  if (!build) LDP_TRY(vae_conv_f32(h->conv_out, b.Hf, nullptr, out, nimg, S, 1, 1, s));
+  return LDP_OK;
+}
+
+static int vae_dec_prepare_tc(LdpVae* h, VaeWs* w) {
+  if (w->tc_ready) return LDP_OK;
+  LDP_TRY(tc_driver_check());
+  LDP_TRY(tc_gemm_init());
+  const size_t max_act = vae_max_act(h);
+  LDP_TRY(w->arena.alloc_t(&w->Sb, (size_t)w->Bc * max_act));
+  LDP_TRY(w->arena.alloc_t(&w->Gb, (size_t)w->Bc * max_act));
+  w->ops.clear();
+  LDP_TRY(vae_dec_walk_tc(h, w, true, nullptr, w->Bc, nullptr, 0));
   w->tc_ready = true;
   return LDP_OK;
 }
@@ -852,6 +1101,7 @@ int ldp_vae_destroy(LdpVae* h) {
 int ldp_vae_encode(LdpVae* h, int precision, const void* images_dev, int pixel_format, int B, float lat_min, float lat_max,
                    float* latent_dev, void* cuda_stream) {
   LDP_CHECK(h && images_dev && latent_dev, LDP_ERR_INVALID_ARG, "null pointer");
+  LDP_CHECK(!h->is_decoder, LDP_ERR_INVALID_ARG, "handle is a decoder (use ldp_vae_create)");
   LDP_CHECK(B > 0, LDP_ERR_BAD_SHAPE, "B must be positive");
   LDP_CHECK(pixel_format == 0 || pixel_format == 1, LDP_ERR_INVALID_ARG, "pixel_format must be 0 (uint8) or 1 (float32)");
   LDP_CHECK(precision == LDP_PREC_FP32 || precision == LDP_PREC_BF16, LDP_ERR_INVALID_ARG, "unknown precision");
@@ -869,6 +1119,46 @@ int ldp_vae_encode(LdpVae* h, int precision, const void* images_dev, int pixel_f
     float* out = latent_dev + (size_t)b0 * hw * hw * c.latent_channels;
     if (precision == LDP_PREC_FP32) LDP_TRY(vae_forward_f32(h, w, img, pixel_format, n, lat_min, lat_max, out, s));
     else LDP_TRY(vae_walk_tc(h, w, false, img, pixel_format, n, lat_min, lat_max, out, s));
+  }
+  return LDP_OK;
+}
+
+int64_t ldp_vae_decoder_param_count(const LdpVaeConfig* cfg) {
+  if (vae_validate(cfg) != LDP_OK) return -1;
+  return vae_dec_param_count(*cfg);
+}
+
+int ldp_vae_decoder_create(const LdpVaeConfig* cfg, const float* params_host, uint64_t n_params, LdpVae** out) {
+  LDP_CHECK(out != nullptr && params_host != nullptr, LDP_ERR_INVALID_ARG, "null pointer");
+  LDP_TRY(vae_validate(cfg));
+  LdpVae* h = new LdpVae();
+  int st = vae_dec_create_impl(cfg, params_host, n_params, h);
+  if (st != LDP_OK) {
+    delete h;
+    return st;
+  }
+  *out = h;
+  return LDP_OK;
+}
+
+int ldp_vae_decode(LdpVae* h, int precision, const float* latent_dev, int B, float* images_dev, void* cuda_stream) {
+  LDP_CHECK(h && latent_dev && images_dev, LDP_ERR_INVALID_ARG, "null pointer");
+  LDP_CHECK(h->is_decoder, LDP_ERR_INVALID_ARG, "handle is an encoder (use ldp_vae_decoder_create)");
+  LDP_CHECK(B > 0, LDP_ERR_BAD_SHAPE, "B must be positive");
+  LDP_CHECK(precision == LDP_PREC_FP32 || precision == LDP_PREC_BF16, LDP_ERR_INVALID_ARG, "unknown precision");
+  cudaStream_t s = (cudaStream_t)cuda_stream;
+  const LdpVaeConfig& c = h->cfg;
+  const int S = c.image_size, hw = S >> (c.n_blocks - 1);
+  const int chunk = std::min(B, 128);
+  VaeWs* w;
+  LDP_TRY(vae_get_ws(h, chunk, &w));
+  if (precision == LDP_PREC_BF16) LDP_TRY(vae_dec_prepare_tc(h, w));
+  for (int b0 = 0; b0 < B; b0 += chunk) {
+    const int n = std::min(chunk, B - b0);
+    const float* z = latent_dev + (size_t)b0 * hw * hw * c.latent_channels;
+    float* out = images_dev + (size_t)b0 * S * S * c.in_channels;
+    if (precision == LDP_PREC_FP32) LDP_TRY(vae_decode_f32(h, w, z, n, out, s));
+    else LDP_TRY(vae_dec_walk_tc(h, w, false, z, n, out, s));
   }
   return LDP_OK;
 }

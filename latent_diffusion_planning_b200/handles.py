@@ -324,3 +324,41 @@ class VaeEncoder:
         N.check(self.lib.ldp_vae_encode(self._h, _prec(precision), img.data_ptr(), fmt, B, float(lat_min), float(lat_max),
                                         out.data_ptr(), _stream()))
         return out
+
+
+class VaeDecoder:
+    """FlaxAutoencoderKL.decode(z).sample (reference agent/ldp_agent.py:66-85 `vae_decode`; plan_viz of sample_viz :483)."""
+
+    def __init__(self, params: Dict[str, np.ndarray], block_out_channels: Sequence[int] = (128, 256, 512, 512),
+                 out_channels: int = 3, latent_channels: int = 4, layers_per_block: int = 2, norm_num_groups: int = 32,
+                 image_size: int = 64):
+        self.lib = N.load()
+        self.spec = P.vae_decoder_spec(block_out_channels, out_channels, latent_channels, layers_per_block)
+        self.cfg = N.vae_config(block_out_channels, out_channels, latent_channels, layers_per_block, norm_num_groups, image_size)
+        self.latent_channels, self.out_channels, self.image_size = latent_channels, out_channels, image_size
+        self.latent_hw = image_size >> (len(block_out_channels) - 1)
+        blob = P.flatten_params(self.spec, params)
+        self._h = C.c_void_p()
+        N.check(self.lib.ldp_vae_decoder_create(C.byref(self.cfg), blob.ctypes.data, blob.size, C.byref(self._h)))
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            self.lib.ldp_vae_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def decode(self, latents: torch.Tensor, precision="bf16") -> torch.Tensor:
+        """latents: (B,h,w,L) float32 (un-normalised), on the GPU -> (B,S,S,3) float32 NHWC."""
+        if not latents.is_cuda or latents.dim() != 4 or latents.shape[1:] != (self.latent_hw, self.latent_hw, self.latent_channels):
+            raise ValueError(f"latents must be a (B,{self.latent_hw},{self.latent_hw},{self.latent_channels}) CUDA tensor")
+        z = _f32c(latents)
+        B = z.shape[0]
+        out = torch.empty(B, self.image_size, self.image_size, self.out_channels, dtype=torch.float32, device=z.device)
+        N.check(self.lib.ldp_vae_decode(self._h, _prec(precision), z.data_ptr(), B, out.data_ptr(), _stream()))
+        return out
+

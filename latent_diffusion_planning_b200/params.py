@@ -170,6 +170,41 @@ def vae_encoder_spec(block_out_channels: Sequence[int] = (128, 256, 512, 512), i
     return spec
 
 
+def vae_decoder_spec(block_out_channels: Sequence[int] = (128, 256, 512, 512), out_channels: int = 3,
+                     latent_channels: int = 4, layers_per_block: int = 2) -> Spec:
+    """diffusers 0.27.2 FlaxAutoencoderKL.decode: post_quant_conv + FlaxDecoder (un-vendored, restated from its published
+    structure): conv_in (L -> C_last), mid block, up blocks over reversed(block_out_channels) with layers_per_block + 1
+    resnets each and a nearest x2 upsampler + 3x3 conv on all but the last, GroupNorm, swish, conv_out (C_0 -> 3)."""
+    spec: Spec = OrderedDict()
+    spec["post_quant_conv/kernel"] = (1, 1, latent_channels, latent_channels)
+    spec["post_quant_conv/bias"] = (latent_channels,)
+    rev = list(reversed(block_out_channels))
+    c = rev[0]
+    spec["decoder/conv_in/kernel"] = (3, 3, latent_channels, c)
+    spec["decoder/conv_in/bias"] = (c,)
+    _resnet_spec(spec, "decoder/mid_block/resnets_0", c, c)
+    a = "decoder/mid_block/attentions_0"
+    spec[f"{a}/group_norm/scale"] = (c,)
+    spec[f"{a}/group_norm/bias"] = (c,)
+    for name in ("query", "key", "value", "proj_attn"):
+        spec[f"{a}/{name}/kernel"] = (c, c)
+        spec[f"{a}/{name}/bias"] = (c,)
+    _resnet_spec(spec, "decoder/mid_block/resnets_1", c, c)
+    n = len(rev)
+    for i, co in enumerate(rev):
+        for j in range(layers_per_block + 1):
+            _resnet_spec(spec, f"decoder/up_blocks_{i}/resnets_{j}", c, co)
+            c = co
+        if i != n - 1:
+            spec[f"decoder/up_blocks_{i}/upsamplers_0/conv/kernel"] = (3, 3, co, co)
+            spec[f"decoder/up_blocks_{i}/upsamplers_0/conv/bias"] = (co,)
+    spec["decoder/conv_norm_out/scale"] = (c,)
+    spec["decoder/conv_norm_out/bias"] = (c,)
+    spec["decoder/conv_out/kernel"] = (3, 3, c, out_channels)
+    spec["decoder/conv_out/bias"] = (out_channels,)
+    return spec
+
+
 # ----------------------------------------------------------------------------------------------
 # init / flatten
 # ----------------------------------------------------------------------------------------------

@@ -67,3 +67,27 @@ def test_flatten_roundtrip():
         assert np.array_equal(blob[off:off + n].reshape(shp), p[k])
         off += n
     assert P.unnest(P.nest(p)).keys() == p.keys()
+
+
+def test_vae_param_counts_match_specs(lib):
+    """Encoder and decoder (next-row N2) blobs: the C side's parameter walk and params.py's spec agree on the size;
+    SD-VAE [128,256,512,512]: 34.16 M encoder / 49.49 M decoder parameters."""
+    for blocks, lpb in (((128, 256, 512, 512), 2), ((128, 256, 256, 256, 256, 256), 2), ((32, 64), 1)):
+        cfg = N.vae_config(blocks, 3, 4, lpb, 32 if blocks[0] >= 128 else 8, 64 if blocks[0] >= 128 else 16)
+        assert lib.ldp_vae_param_count(C.byref(cfg)) == P.spec_size(P.vae_encoder_spec(blocks, 3, 4, lpb))
+        assert lib.ldp_vae_decoder_param_count(C.byref(cfg)) == P.spec_size(P.vae_decoder_spec(blocks, 3, 4, lpb))
+    assert round(P.spec_size(P.vae_decoder_spec()) / 1e6, 2) == 49.49
+
+
+def test_oracle_decoder_upsample_and_shapes():
+    """Nearest x2 upsampling index map (out[i] = in[i // 2]) and the decoder's output geometry on integer-valued inputs."""
+    import torch
+    x = torch.arange(2 * 3 * 3 * 1, dtype=torch.float64).reshape(2, 3, 3, 1)
+    up = x.repeat_interleave(2, dim=1).repeat_interleave(2, dim=2)
+    for i in range(6):
+        for j in range(6):
+            assert float(up[1, i, j, 0]) == float(x[1, i // 2, j // 2, 0])
+    blocks = (32, 64, 64)
+    p = P.init_params(P.vae_decoder_spec(blocks, 3, 4, 1), seed=0)
+    y = O.vae_decode(p, torch.zeros(1, 4, 4, 4), blocks, 1, 8)
+    assert tuple(y.shape) == (1, 16, 16, 3)

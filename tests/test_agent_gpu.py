@@ -124,3 +124,27 @@ def test_process_sdvae_data_matches_direct_encode(tmp_path):
         lo, hi = float(z["data.attrs/min_z"]), float(z["data.attrs/max_z"])
         allz = np.concatenate([z[k].ravel() for k in z.files if k.startswith("data/")])
         assert lo == min(0.0, float(allz.min())) and hi == max(0.0, float(allz.max())) and int(z["data.attrs/total"]) == 2
+
+
+def test_sample_viz_decodes_the_plan(cuda):
+    """viz=True: plan_viz = vae_decode(plan) (reference agent/ldp_agent.py:66-85, :483): first 16 features of every plan
+    frame -> (2,2,4) latents -> unnormalize_obs -> decoder -> (B, Ha+1, 3, 64, 64)."""
+    from latent_diffusion_planning_b200 import params as P
+    from latent_diffusion_planning_b200.agent import LDPAgent
+    ag = LDPAgent.create(3, None, {"ac_dim": 7, "all_shapes": SHAPES}, planner=dict(down_dims=DIMS),
+                         rgb_obs=["latent_agentview_image"], lowdim_obs=LOWDIM, obs_normalization=_norm(),
+                         vae_feature_dim=16, vae_block_out_channels=VAE_BLOCKS, obs_horizon=1, pred_horizon=8,
+                         action_horizon=4, planner_n_diffusion_steps=2, idm_n_diffusion_steps=2, precision="fp32", viz=True)
+    action, info = ag.sample_viz(_batch(2, seed=4), 7)
+    viz, plan = info["plan_viz"], info["plan"]
+    assert viz.shape == (2, 5, 3, 64, 64) and torch.isfinite(viz).all()
+    dp = P.init_params(P.vae_decoder_spec(VAE_BLOCKS), seed=3 + 3)
+    z = plan[..., :16].reshape(10, 2, 2, 4).cpu().double()
+    z = torch.clamp((z + 1) / 2 * 20.0 - 10.0, -10.0, 10.0)                       # unnormalize_obs with min -10 / max 10
+    ref = O.vae_decode(dp, z, VAE_BLOCKS, 2, 32).permute(0, 3, 1, 2).reshape(2, 5, 3, 64, 64)
+    assert float((viz.cpu().double() - ref).abs().max()) < 1e-4 * max(1.0, float(ref.abs().max()))
+    # without viz the reference-shaped dict still carries the key
+    assert ag.viz and LDPAgent.create(3, None, {"ac_dim": 7, "all_shapes": SHAPES}, planner=dict(down_dims=DIMS),
+                                      rgb_obs=["latent_agentview_image"], lowdim_obs=LOWDIM, obs_normalization=_norm(),
+                                      vae_feature_dim=16, vae_block_out_channels=VAE_BLOCKS, planner_n_diffusion_steps=2,
+                                      idm_n_diffusion_steps=2, precision="fp32").sample_viz(_batch(1), 1)[1]["plan_viz"] is None

@@ -410,3 +410,38 @@ def test_vae_chunking_is_invisible(H):
     whole = vae.encode(img, precision="bf16")
     parts = torch.cat([vae.encode(img[:256], precision="bf16"), vae.encode(img[256:], precision="bf16")])
     assert _maxerr(whole, parts) < 1e-4
+
+
+# ------------------------------------------------------------------------------------------------
+# VAE decoder (next-row N2: plan_viz)
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("blocks,S,B", [((32, 64), 16, 3), ((32, 64, 64), 32, 2)])
+def test_vae_decoder_small_configs(H, blocks, S, B):
+    """decode(z).sample against the oracle: fp32 path at the fp32 gate, bf16 tensor-core path at the stacked-layer gate the
+    encoder uses (relative L2 1e-2, max-abs 2e-2 max|ref|)."""
+    sp = P.vae_decoder_spec(blocks, 3, 4, 1)
+    p = P.init_params(sp, seed=5, perturb=0.1)
+    dec = H.VaeDecoder(p, blocks, 3, 4, 1, 8, S)
+    hw = S >> (len(blocks) - 1)
+    z = torch.randn(B, hw, hw, 4, generator=torch.Generator().manual_seed(9))
+    ref = O.vae_decode(p, z, blocks, 1, 8)
+    out32 = dec.decode(z.cuda(), precision="fp32")
+    assert out32.shape == (B, S, S, 3)
+    assert _maxerr(out32, ref) < 3e-5 * max(1.0, float(ref.abs().max()))
+    out16 = dec.decode(z.cuda(), precision="bf16").cpu().double()
+    rel = float((out16 - ref).norm() / ref.norm())
+    assert rel < 1e-2 and _maxerr(out16, ref) < 2e-2 * max(1.0, float(ref.abs().max()))
+
+
+def test_vae_decoder_benchmark_topology_and_chunking(H):
+    """SD-VAE [128,256,512,512] decoder, 8x8x4 -> 64x64x3: bf16 path vs oracle on 2 frames; a batch equals its pieces."""
+    blocks = (128, 256, 512, 512)
+    p = P.init_params(P.vae_decoder_spec(blocks), seed=6)
+    dec = H.VaeDecoder(p, blocks)
+    z = torch.randn(3, 8, 8, 4, generator=torch.Generator().manual_seed(2))
+    out = dec.decode(z.cuda(), precision="bf16")
+    ref = O.vae_decode(p, z[:2], blocks, 2, 32, dtype=torch.float32).double()
+    rel = float((out[:2].cpu().double() - ref).norm() / ref.norm())
+    assert rel < 1.5e-2
+    one = dec.decode(z[2:].cuda(), precision="bf16")
+    assert torch.equal(one, out[2:])
