@@ -381,6 +381,19 @@ def side_metrics(torch, H, P, rank):
     out["act_plans_per_sec"] = B_PLANS / ms * 1e3
     out["act_config"] = "LDPAgent.act: VAE encode + 100 planner DDPM steps + 100 IDM DDPM steps, B=1024, rm_lift shapes, bf16"
     out["act_ms"] = ms
+    # the two remaining pieces of act(), timed alone: IDM reverse loop (B * Ha = 4096 transition rows) and, for sample_viz
+    # with viz=True, the VAE decoder over the (Ha + 1) frames of every plan
+    idm = agent.idm
+    ssp = (torch.rand(B_PLANS * 4, 2 * D_OBS, generator=g) * 2 - 1).cuda()
+    a_T = torch.randn(B_PLANS * 4, 7, generator=g).cuda()
+    ms = timeit(lambda: idm.sample(ssp, a_T, seed=1, n_steps=N_DIFF, precision="bf16"), 3)
+    out["idm_loop_ms"] = ms
+    out["idm_config"] = "MLPDiffusion reverse loop, 4096 rows (B=1024 x Ha=4), 2D=530, A=7, 100 DDPM steps, bf16"
+    dec = H.VaeDecoder(P.init_params(P.vae_decoder_spec(), seed=7))
+    z = torch.randn(1024, 8, 8, 4, generator=g).cuda()
+    ms = timeit(lambda: dec.decode(z, precision="bf16"), 2)
+    out["vae_decode_frames_per_sec"] = 1024 / ms * 1e3
+    out["vae_decode_config"] = "FlaxAutoencoderKL.decode 8x8x4 -> 64x64x3, SD-VAE [128,256,512,512], B=1024 frames, bf16 (plan_viz path)"
     return out
 
 
