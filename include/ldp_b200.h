@@ -219,6 +219,38 @@ LDP_API int ldp_tc_dense(const float* a_dev, const float* w_host, const float* b
 LDP_API int64_t ldp_launch_count(void);
 LDP_API void ldp_launch_count_reset(void);
 
+/* ---------------------------------------------------------------------------------------------------------
+ * Training objective (next-row N1)  -  LDPAgent.update (agent/ldp_agent.py:229-277)
+ * The caller owns flat float32 device buffers in the canonical spec order (params.unet_spec / params.idm_spec):
+ * parameters, gradients (same layout; the functions ADD into them, zero them first) and the two Adam moments.
+ * The data-parallel exchange is therefore one all-reduce over the gradient buffer (reference: GSPMD mean over the
+ * global batch, train_bc.py:73).  The trainer handle owns activations only.  fp32 arithmetic.
+ * --------------------------------------------------------------------------------------------------------- */
+typedef struct LdpTrainer LdpTrainer;
+
+LDP_API int ldp_unet_trainer_create(const LdpUnetConfig* cfg, LdpTrainer** out);
+LDP_API int ldp_idm_trainer_create(const LdpIdmConfig* cfg, LdpTrainer** out);
+LDP_API int ldp_trainer_destroy(LdpTrainer* h);
+
+/* planner_loss (agent/ldp_agent.py:113-126): noisy = add_noise(x0, noise, t); eps = UNet(noisy, t, cond);
+ * loss = mean((eps - noise)^2).  x0_dev, noise_dev (B,T,D); t_dev (B,) int32; cond_dev (B,Dc).
+ * *loss_dev += loss;  grads_dev += loss_weight * d loss / d params. */
+LDP_API int ldp_unet_loss_grad(LdpTrainer* h, const float* params_dev, float* grads_dev, const float* x0_dev,
+                               const float* noise_dev, const int32_t* t_dev, const float* cond_dev, int B, int T,
+                               float loss_weight, float* loss_dev, void* cuda_stream);
+
+/* idm_loss (agent/ldp_agent.py:128-139): s_dev (N,2D) = [s | s'], a0_dev, noise_dev (N,A), t_dev (N,) int32. */
+LDP_API int ldp_idm_loss_grad(LdpTrainer* h, const float* params_dev, float* grads_dev, const float* s_dev,
+                              const float* a0_dev, const float* noise_dev, const int32_t* t_dev, int N,
+                              float loss_weight, float* loss_dev, void* cuda_stream);
+
+/* optax.adam step (agent/ldp_agent.py:580-600; optax 0.2.2 scale_by_adam, eps outside the square root, eps_root 0):
+ * g = grads * grad_scale; mu = b1 mu + (1-b1) g; nu = b2 nu + (1-b2) g^2;
+ * params -= lr * (mu / (1-b1^count)) / (sqrt(nu / (1-b2^count)) + eps);  count is 1-based. */
+LDP_API int ldp_adam_update(float* params_dev, const float* grads_dev, float* mu_dev, float* nu_dev, uint64_t n,
+                            float lr, float b1, float b2, float eps, int64_t count, float grad_scale,
+                            void* cuda_stream);
+
 #ifdef __cplusplus
 }
 #endif

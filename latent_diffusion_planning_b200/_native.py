@@ -25,6 +25,8 @@ EXPORTS = [
     "ldp_idm_create", "ldp_idm_destroy", "ldp_idm_param_count", "ldp_idm_forward", "ldp_idm_sample",
     "ldp_vae_create", "ldp_vae_destroy", "ldp_vae_param_count", "ldp_vae_encode",
     "ldp_vae_decoder_create", "ldp_vae_decoder_param_count", "ldp_vae_decode",
+    "ldp_unet_trainer_create", "ldp_idm_trainer_create", "ldp_trainer_destroy", "ldp_unet_loss_grad",
+    "ldp_idm_loss_grad", "ldp_adam_update",
     "ldp_tc_dense", "ldp_launch_count", "ldp_launch_count_reset",
 ]
 
@@ -98,6 +100,12 @@ def load() -> C.CDLL:
     lib.ldp_vae_decoder_param_count.argtypes = [C.POINTER(VaeConfig)]
     lib.ldp_vae_decoder_param_count.restype = i64
     lib.ldp_vae_decode.argtypes = [vp, i32, vp, i32, vp, vp]
+    lib.ldp_unet_trainer_create.argtypes = [C.POINTER(UnetConfig), C.POINTER(vp)]
+    lib.ldp_idm_trainer_create.argtypes = [C.POINTER(IdmConfig), C.POINTER(vp)]
+    lib.ldp_trainer_destroy.argtypes = [vp]
+    lib.ldp_unet_loss_grad.argtypes = [vp, vp, vp, vp, vp, vp, vp, i32, i32, f32, vp, vp]
+    lib.ldp_idm_loss_grad.argtypes = [vp, vp, vp, vp, vp, vp, vp, i32, f32, vp, vp]
+    lib.ldp_adam_update.argtypes = [vp, vp, vp, vp, u64, f32, f32, f32, f32, i64, f32, vp]
     lib.ldp_tc_dense.argtypes = [vp, vp, vp, vp, i32, i32, i32, vp]
     lib.ldp_launch_count.restype = i64
     lib.ldp_launch_count_reset.restype = None

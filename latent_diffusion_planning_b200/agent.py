@@ -22,6 +22,7 @@ from . import params as P
 
 # Philox stream ids (disjoint streams for the independent draws of one act())
 STREAM_PLANNER_LOOP, STREAM_IDM_LOOP, STREAM_PLANNER_INIT, STREAM_IDM_INIT = 0, 1, 2, 3
+STREAM_TRAIN_PLANNER, STREAM_TRAIN_IDM = 4, 5
 
 
 # ------------------------------------------------------------------------------------------------
@@ -60,13 +61,36 @@ class LDPAgent:
     def __init__(self, planner: H.Planner, idm: H.Idm, vae: Optional[H.VaeEncoder], obs_normalization: Dict[str, Any],
                  config: Dict[str, Any], planner_params, idm_params, precision: str = "bf16", sampler: str = "ddpm",
                  vae_decoder: Optional["H.VaeDecoder"] = None, viz: bool = False):
-        self.planner, self.idm, self.vae = planner, idm, vae
+        self._planner, self._idm, self.vae = planner, idm, vae
+        self._train: Dict[str, Any] = {}          # name -> train.TrainState, built by the first update()
+        self._stale = set()                       # networks whose inference handle lags the trained parameters
         self.vae_decoder, self.viz = vae_decoder, viz
         self.obs_normalization = obs_normalization
         self.config = config
         self._planner_params, self._idm_params = planner_params, idm_params
         self.precision, self.sampler = precision, sampler
         self.use_planner = self.use_idm = True
+
+    # inference handles; rebuilt from the trained parameters the first time they are used after an update()
+    @property
+    def planner(self) -> H.Planner:
+        if "planner" in self._stale:
+            self._planner_params = self._train["planner"].get_params()
+            old = self._planner
+            self._planner = H.Planner(self._planner_params, *self._net_args["planner"])
+            old.close()
+            self._stale.discard("planner")
+        return self._planner
+
+    @property
+    def idm(self) -> H.Idm:
+        if "idm" in self._stale:
+            self._idm_params = self._train["idm"].get_params()
+            old = self._idm
+            self._idm = H.Idm(self._idm_params, *self._net_args["idm"])
+            old.close()
+            self._stale.discard("idm")
+        return self._idm
 
     # ---------------------------------------------------------------- construction
     @classmethod
@@ -78,7 +102,7 @@ class LDPAgent:
                planner_n_diffusion_steps: int = 100, idm_n_diffusion_steps: int = 100, alpha_planner: float = 1.0,
                alpha_idm: float = 1.0, lr: float = 1e-4, end_lr: float = 1e-6, idm_lr: float = 1e-4, idm_end_lr: float = 1e-6,
                warmup_steps: int = 1000, decay_steps: int = 500000, update_planner_every: int = 1, update_idm_every: int = 1,
-               update_idm_after: int = 0, update_planner_until: int = 10 ** 12, update_planner_after: int = 0, grad_clip=None,
+               update_idm_after: int = -1, update_planner_until: int = -1, update_planner_after: int = -1, grad_clip=None,
                # additions (not in the reference): weights, VAE topology, compute mode
                planner_params: Optional[dict] = None, idm_params: Optional[dict] = None, vae_params: Optional[dict] = None,
                vae_block_out_channels: Sequence[int] = (128, 256, 512, 512), precision: str = "bf16", sampler: str = "ddpm",
@@ -139,12 +163,26 @@ class LDPAgent:
         config = dict(name=name, obs_horizon=obs_horizon, action_dim=action_dim, pred_horizon=pred_horizon,
                       action_horizon=action_horizon, obs_dim=obs_dim, rgb_obs=list(rgb_obs), lowdim_obs=list(lowdim_obs),
                       vae_feature_dim=int(vae_feature_dim), planner_n_diffusion_steps=planner_n_diffusion_steps,
-                      idm_n_diffusion_steps=idm_n_diffusion_steps, data_name=data_name)   # agent/ldp_agent.py:653-665
-        return cls(pl, idm, vae, obs_normalization or {}, config, planner_params, idm_params, precision, sampler, vae_dec, viz)
+                      idm_n_diffusion_steps=idm_n_diffusion_steps, data_name=data_name,   # agent/ldp_agent.py:653-665
+                      update_planner_every=update_planner_every, update_idm_every=update_idm_every,
+                      update_idm_after=update_idm_after, update_planner_until=update_planner_until,
+                      update_planner_after=update_planner_after)
+        agent = cls(pl, idm, vae, obs_normalization or {}, config, planner_params, idm_params, precision, sampler, vae_dec, viz)
+        agent.use_planner, agent.use_idm = bool(use_planner), bool(use_idm)
+        agent.alpha_planner, agent.alpha_idm = float(alpha_planner), float(alpha_idm)
+        agent._net_args = dict(planner=(obs_dim, cond_dim, down_dims, dsed, ksize, n_groups, planner_n_diffusion_steps),
+                               idm=(obs_dim, action_dim, hidden, n_blocks, time_dim, cond_hidden, idm_n_diffusion_steps))
+        agent._opt = dict(lr=lr, end_lr=end_lr, idm_lr=idm_lr, idm_end_lr=idm_end_lr, warmup_steps=warmup_steps,
+                          decay_steps=decay_steps)
+        return agent
 
     # ---------------------------------------------------------------- reference-named pieces
     def get_params(self):
         """`{planner_params, idm_params}` as nested Flax-style trees (agent/ldp_agent.py:508-514)."""
+        if "planner" in self._train:
+            self._planner_params = self._train["planner"].get_params()
+        if "idm" in self._train:
+            self._idm_params = self._train["idm"].get_params()
         return dict(planner_params=P.nest(self._planner_params), idm_params=P.nest(self._idm_params))
 
     def _postprocess_obs(self, obs: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
@@ -276,12 +314,118 @@ class LDPAgent:
             return action, metrics
         return gather_rows(action, B, world), metrics
 
-    # ---------------------------------------------------------------- training (next scope row)
-    def update(self, batch, rng, step):
-        raise NotImplementedError("LDPAgent.update (backward + Adam + gradient all-reduce) is scope row N1 (SURVEY.md 8f); "
-                                  "this build covers the sampling path")
+    # ---------------------------------------------------------------- training (scope row N1)
+    def _train_state(self, name: str):
+        """Lazily build the flat train state (TrainState.create + optax.adam(warmup_cosine), agent/ldp_agent.py:580-631)."""
+        if name not in self._train:
+            from . import train as TR
+            o = self._opt
+            if name == "planner":
+                sched = TR.warmup_cosine_decay_schedule(o["end_lr"], o["lr"], o["warmup_steps"], o["decay_steps"], o["end_lr"])
+                self._train[name] = TR.TrainState("planner", self._planner.spec, self._planner.cfg, self._planner_params, sched)
+            else:
+                sched = TR.warmup_cosine_decay_schedule(o["idm_end_lr"], o["idm_lr"], o["warmup_steps"], o["decay_steps"],
+                                                        o["idm_end_lr"])
+                self._train[name] = TR.TrainState("idm", self._idm.spec, self._idm.cfg, self._idm_params, sched)
+        return self._train[name]
 
-    update_mixed = update
+    def _gates(self, step: int) -> Tuple[bool, bool]:
+        """Which networks this step trains (agent/ldp_agent.py:229-236)."""
+        c = self.config
+        use_planner = bool(self.use_planner) and step % c["update_planner_every"] == 0
+        use_idm = bool(self.use_idm) and step % c["update_idm_every"] == 0 and step >= c["update_idm_after"]
+        upd = (c["update_planner_until"] < 0 or step < c["update_planner_until"]) and step >= c["update_planner_after"]
+        return use_planner and upd, use_idm
+
+    def _train_inputs(self, batch):
+        """postprocess_batch (utils/data_utils.py:70-74) + get_obs_cond: normalised (B,H,D) embeddings and actions."""
+        obs = self.vae_encode(self._postprocess_obs(batch["obs"]))
+        obs_emb = self.get_obs_cond(obs)
+        a = batch["actions"]
+        a = (a if torch.is_tensor(a) else torch.as_tensor(np.asarray(a))).to(obs_emb.device, torch.float32)
+        spec = self.obs_normalization.get("actions")
+        return obs, obs_emb, (normalize_unnormalize(a, spec, True) if spec else a)
+
+    def update(self, batch, rng, step):
+        """agent/ldp_agent.py:229-277.  Returns `(agent, metrics)`; the agent is updated in place (the reference returns
+        a replaced copy).  Under torch.distributed every rank passes its equal shard of the global batch
+        (train_bc.py:73 `batch % n_devices == 0`); losses are means over the global batch."""
+        return self._update_step(batch, batch, rng, int(step), *self._gates(int(step)))
+
+    def update_mixed(self, batch, mixed_batch, rng, step):
+        """agent/ldp_agent.py:279-327: planner on `batch`, IDM on `mixed_batch`."""
+        return self._update_step(batch, mixed_batch, rng, int(step), *self._gates(int(step)))
+
+    def _update_step(self, batch, idm_batch, rng, step: int, use_planner: bool, use_idm: bool):
+        import torch.distributed as dist
+        from . import train as TR
+        seed, cfg = int(rng), self.config
+        oh = cfg["obs_horizon"]
+        world = dist.get_world_size() if (dist.is_available() and dist.is_initialized()) else 1
+        rank = dist.get_rank() if world > 1 else 0
+        obs, obs_emb, action = self._train_inputs(batch)
+        B = obs_emb.shape[0]
+        metrics: Dict[str, Any] = {}
+        plan_loss = idm_loss = torch.zeros((), device=obs_emb.device)
+        states = []
+        if use_planner:
+            ts = self._train_state("planner")
+            ts.zero_grad()
+            target = obs_emb[:, oh:].contiguous()
+            T, D = target.shape[1], target.shape[2]
+            g = torch.Generator().manual_seed(seed * 2 + 0)      # timesteps of the GLOBAL batch, then this rank's slice
+            t = torch.randint(0, cfg["planner_n_diffusion_steps"], (B * world,), generator=g)[rank * B:(rank + 1) * B]
+            noise = H.philox_normal_rows(seed, STREAM_TRAIN_PLANNER, step, rank * B * T, B * T, D).reshape(B, T, D)
+            cond = obs_emb[:, :oh].reshape(B, -1).contiguous()
+            plan_loss = self.alpha_planner * ts.planner_loss_grad(target, noise, t.to(obs_emb.device), cond, self.alpha_planner)
+            states.append(("planner", ts))
+        if use_idm:
+            if idm_batch is not batch:
+                _, emb_i, act_i = self._train_inputs(idm_batch)
+            else:
+                emb_i, act_i = obs_emb, action
+            ts = self._train_state("idm")
+            ts.zero_grad()
+            ssp = torch.cat([emb_i[:, oh - 1:-1], emb_i[:, oh:]], dim=-1)
+            ssp = ssp.reshape(-1, ssp.shape[-1]).contiguous()
+            a0 = act_i[:, :-1].reshape(-1, act_i.shape[-1]).contiguous()
+            n = a0.shape[0]
+            if ssp.shape[0] != n:
+                raise ValueError(f"IDM pairs: {ssp.shape[0]} transitions but {n} actions (obs and actions must share their horizon)")
+            g = torch.Generator().manual_seed(seed * 2 + 1)
+            t = torch.randint(0, cfg["idm_n_diffusion_steps"], (n * world,), generator=g)[rank * n:(rank + 1) * n]
+            noise = H.philox_normal_rows(seed, STREAM_TRAIN_IDM, step, rank * n, n, a0.shape[1])
+            idm_loss = self.alpha_idm * ts.idm_loss_grad(ssp, a0, noise, t.to(obs_emb.device), self.alpha_idm)
+            states.append(("idm", ts))
+        sq = torch.zeros((), device=obs_emb.device)
+        scale = 1.0
+        for _, ts in states:
+            scale = TR.allreduce_grads(ts.grads)
+            sq = sq + (torch.linalg.vector_norm(ts.grads) * scale) ** 2
+        loss = plan_loss + idm_loss
+        if world > 1:
+            packed = torch.stack([plan_loss, idm_loss, loss]) / world
+            dist.all_reduce(packed)
+            plan_loss, idm_loss, loss = packed[0], packed[1], packed[2]
+        metrics.update(plan_loss=plan_loss, idm_loss=idm_loss, loss=loss, emb_min=obs_emb.min(), emb_max=obs_emb.max(),
+                       emb_mean=obs_emb.mean(), emb_std=obs_emb.std(unbiased=False), action_min=action.min(),
+                       action_max=action.max())
+        for k, v in obs.items():
+            metrics[f"{k}_min"], metrics[f"{k}_max"] = v.min(), v.max()
+        metrics["g_norm"] = sq.sqrt()
+        # the reference reports both learning rates through the LAST schedule it built, the IDM's (agent/ldp_agent.py:258,619)
+        report = self._train_state("idm").lr_schedule if self.use_idm else self._train_state("planner").lr_schedule
+        for name in ("planner", "idm"):
+            ts = dict(states).get(name)
+            if ts is None:
+                metrics[f"{name}_lr"], metrics[f"{name}_step"] = 0, 0
+                if name == "planner":
+                    metrics["noise_diff"] = 0
+                continue
+            metrics[f"{name}_lr"], metrics[f"{name}_step"] = report(ts.step), ts.step
+            ts.apply_gradients(grad_scale=scale)
+            self._stale.add(name)
+        return self, metrics
 
 
 def gather_rows(local: torch.Tensor, n_total: int, world: int) -> torch.Tensor:

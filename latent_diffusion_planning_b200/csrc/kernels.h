@@ -35,6 +35,7 @@ struct GemmF32 {
   int t_in = 1, t_out = 1, taps = 1, stride = 1, pad = 0, dil = 1;
   int a_act = 0;                    // 0 none, 1 mish
   const float* w = nullptr; int ldw = 0;
+  int w_mode = 0, w_ctot = 0, w_coff = 0;   // w_mode 1: data-gradient view of a forward kernel (train.cu)
   const float* bias = nullptr;
   const float* tab = nullptr; int ld_tab = 0; StepRef step;
   int act = 0;                      // 0 none, 1 relu

@@ -61,12 +61,28 @@ __global__ void __launch_bounds__(256) gemm_f32_kernel(const GemmF32 p) {
       }
       As[kk][r] = v;
     }
+    if (p.w_mode == 0) {
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      int idx = tid + i * 256;
-      int kk = idx / GN, nn = idx % GN;
-      int k = k0 + kk, n = n0 + nn;
-      Bs[kk][nn] = (k < K && n < p.n) ? p.w[(long long)k * p.ldw + n] : 0.f;
+      for (int i = 0; i < 4; ++i) {
+        int idx = tid + i * 256;
+        int kk = idx / GN, nn = idx % GN;
+        int k = k0 + kk, n = n0 + nn;
+        Bs[kk][nn] = (k < K && n < p.n) ? p.w[(long long)k * p.ldw + n] : 0.f;
+      }
+    } else {
+      // data-gradient view of a forward kernel W[taps][w_ctot][ldw]: B(k = (j', co), n) = W[taps-1-j'][w_coff+n][co]
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        int idx = tid + i * 256;
+        int nn = idx / GK, kk = idx % GK;
+        int k = k0 + kk, n = n0 + nn;
+        float v = 0.f;
+        if (k < K && n < p.n) {
+          int j = k / ctot, co = k - j * ctot;
+          v = p.w[((long long)(p.taps - 1 - j) * p.w_ctot + p.w_coff + n) * p.ldw + co];
+        }
+        Bs[kk][nn] = v;
+      }
     }
     __syncthreads();
 #pragma unroll
@@ -152,7 +168,7 @@ __global__ void __launch_bounds__(256) groupnorm_f32_kernel(const GroupNormF32 p
   const float* trow = nullptr;
   const float* orow = nullptr;
   if (p.film) {
-    trow = p.ttab + (long long)step_of(p.step, b) * p.ld_ttab + p.film_off;
+    trow = p.ttab ? p.ttab + (long long)step_of(p.step, b) * p.ld_ttab + p.film_off : nullptr;
     orow = p.otab + (long long)b * p.ld_otab + p.film_off;
   }
   float* yb = p.y + (long long)b * p.P * p.ldy + g * gw;
@@ -163,7 +179,7 @@ __global__ void __launch_bounds__(256) groupnorm_f32_kernel(const GroupNormF32 p
     float v = (xb[(long long)pos * p.ldx + c] - mean) * rstd * p.gamma[ch] + p.beta[ch];
     if (p.act == 1) v = mish_f<false>(v);
     else if (p.act == 2) v = v / (1.f + expf(-v));
-    if (p.film) v = (trow[ch] + orow[ch]) * v + (trow[p.C + ch] + orow[p.C + ch]);
+    if (p.film) v = ((trow ? trow[ch] : 0.f) + orow[ch]) * v + ((trow ? trow[p.C + ch] : 0.f) + orow[p.C + ch]);
     if (rb) v += rb[(long long)pos * p.ldres + c];
     yb[(long long)pos * p.ldy + c] = v;
   }

@@ -99,8 +99,6 @@ def test_sample_action_and_from_plan(agent):
     nxt = torch.rand(B, Hh, 25, generator=g).cuda() * 2 - 1
     a2 = agent.sample_action_from_plan({"obs": obs}, nxt, 9)
     assert tuple(a2.shape) == (B, Hh, 7) and torch.isfinite(a2).all()
-    with pytest.raises(NotImplementedError):
-        agent.update({}, 0, 0)
 
 
 def test_process_sdvae_data_matches_direct_encode(tmp_path):
