@@ -224,7 +224,10 @@ LDP_API void ldp_launch_count_reset(void);
  * The caller owns flat float32 device buffers in the canonical spec order (params.unet_spec / params.idm_spec):
  * parameters, gradients (same layout; the functions ADD into them, zero them first) and the two Adam moments.
  * The data-parallel exchange is therefore one all-reduce over the gradient buffer (reference: GSPMD mean over the
- * global batch, train_bc.py:73).  The trainer handle owns activations only.  fp32 arithmetic.
+ * global batch, train_bc.py:73).  The trainer handle owns activations only.
+ * precision LDP_PREC_FP32: every contraction in fp32 FFMA (the reference trains in float32; parity gate).
+ * precision LDP_PREC_BF16: forward, data-gradient and weight-gradient contractions on tcgen05 with bf16 operands and
+ * fp32 accumulation (BASELINE config #4 "bf16"); parameters, gradients, norms, activations and Adam stay fp32.
  * --------------------------------------------------------------------------------------------------------- */
 typedef struct LdpTrainer LdpTrainer;
 
@@ -235,12 +238,12 @@ LDP_API int ldp_trainer_destroy(LdpTrainer* h);
 /* planner_loss (agent/ldp_agent.py:113-126): noisy = add_noise(x0, noise, t); eps = UNet(noisy, t, cond);
  * loss = mean((eps - noise)^2).  x0_dev, noise_dev (B,T,D); t_dev (B,) int32; cond_dev (B,Dc).
  * *loss_dev += loss;  grads_dev += loss_weight * d loss / d params. */
-LDP_API int ldp_unet_loss_grad(LdpTrainer* h, const float* params_dev, float* grads_dev, const float* x0_dev,
+LDP_API int ldp_unet_loss_grad(LdpTrainer* h, int precision, const float* params_dev, float* grads_dev, const float* x0_dev,
                                const float* noise_dev, const int32_t* t_dev, const float* cond_dev, int B, int T,
                                float loss_weight, float* loss_dev, void* cuda_stream);
 
 /* idm_loss (agent/ldp_agent.py:128-139): s_dev (N,2D) = [s | s'], a0_dev, noise_dev (N,A), t_dev (N,) int32. */
-LDP_API int ldp_idm_loss_grad(LdpTrainer* h, const float* params_dev, float* grads_dev, const float* s_dev,
+LDP_API int ldp_idm_loss_grad(LdpTrainer* h, int precision, const float* params_dev, float* grads_dev, const float* s_dev,
                               const float* a0_dev, const float* noise_dev, const int32_t* t_dev, int N,
                               float loss_weight, float* loss_dev, void* cuda_stream);
 

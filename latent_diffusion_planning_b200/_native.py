@@ -103,8 +103,8 @@ def load() -> C.CDLL:
     lib.ldp_unet_trainer_create.argtypes = [C.POINTER(UnetConfig), C.POINTER(vp)]
     lib.ldp_idm_trainer_create.argtypes = [C.POINTER(IdmConfig), C.POINTER(vp)]
     lib.ldp_trainer_destroy.argtypes = [vp]
-    lib.ldp_unet_loss_grad.argtypes = [vp, vp, vp, vp, vp, vp, vp, i32, i32, f32, vp, vp]
-    lib.ldp_idm_loss_grad.argtypes = [vp, vp, vp, vp, vp, vp, vp, i32, f32, vp, vp]
+    lib.ldp_unet_loss_grad.argtypes = [vp, i32, vp, vp, vp, vp, vp, vp, i32, i32, f32, vp, vp]
+    lib.ldp_idm_loss_grad.argtypes = [vp, i32, vp, vp, vp, vp, vp, vp, i32, f32, vp, vp]
     lib.ldp_adam_update.argtypes = [vp, vp, vp, vp, u64, f32, f32, f32, f32, i64, f32, vp]
     lib.ldp_tc_dense.argtypes = [vp, vp, vp, vp, i32, i32, i32, vp]
     lib.ldp_launch_count.restype = i64

@@ -322,11 +322,12 @@ class LDPAgent:
             o = self._opt
             if name == "planner":
                 sched = TR.warmup_cosine_decay_schedule(o["end_lr"], o["lr"], o["warmup_steps"], o["decay_steps"], o["end_lr"])
-                self._train[name] = TR.TrainState("planner", self._planner.spec, self._planner.cfg, self._planner_params, sched)
+                self._train[name] = TR.TrainState("planner", self._planner.spec, self._planner.cfg, self._planner_params, sched,
+                                                     precision=self.precision)
             else:
                 sched = TR.warmup_cosine_decay_schedule(o["idm_end_lr"], o["idm_lr"], o["warmup_steps"], o["decay_steps"],
                                                         o["idm_end_lr"])
-                self._train[name] = TR.TrainState("idm", self._idm.spec, self._idm.cfg, self._idm_params, sched)
+                self._train[name] = TR.TrainState("idm", self._idm.spec, self._idm.cfg, self._idm_params, sched, precision=self.precision)
         return self._train[name]
 
     def _gates(self, step: int) -> Tuple[bool, bool]:

@@ -10,6 +10,8 @@
 #include <algorithm>
 #include <cmath>
 #include <deque>
+#include <map>
+#include <tuple>
 
 #include "net_common.h"
 
@@ -387,15 +389,168 @@ __global__ void __launch_bounds__(256) mse_loss_grad_kernel(const float* eps, co
 
 // optax.adam (scale_by_adam + scale(-lr)), count = 1-based step:  mu = b1 mu + (1-b1) g;  nu = b2 nu + (1-b2) g^2;
 // p -= lr * (mu / (1-b1^count)) / (sqrt(nu / (1-b2^count)) + eps)
-__global__ void adam_kernel(float* p, const float* g, float* mu, float* nu, long long n, float lr, float b1, float b2,
-                            float eps, float bc1, float bc2, float gscale) {
-  LDP_GRID_STRIDE(i, n) {
-    float gv = g[i] * gscale;
-    float m = b1 * mu[i] + (1.f - b1) * gv;
-    float v = b2 * nu[i] + (1.f - b2) * gv * gv;
-    mu[i] = m;
-    nu[i] = v;
-    p[i] -= lr * (m / bc1) / (sqrtf(v / bc2) + eps);
+__device__ __forceinline__ void adam_one(float& p, float g, float& mu, float& nu, float lr, float b1, float b2, float eps,
+                                         float bc1, float bc2, float gscale) {
+  float gv = g * gscale;
+  float m = b1 * mu + (1.f - b1) * gv;
+  float v = b2 * nu + (1.f - b2) * gv * gv;
+  mu = m;
+  nu = v;
+  p -= lr * (m / bc1) / (sqrtf(v / bc2) + eps);
+}
+__global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ mu,
+                                                   float* __restrict__ nu, long long n, float lr, float b1, float b2,
+                                                   float eps, float bc1, float bc2, float gscale) {
+  const long long n4 = n >> 2;
+  float4* p4 = reinterpret_cast<float4*>(p);
+  const float4* g4 = reinterpret_cast<const float4*>(g);
+  float4* m4 = reinterpret_cast<float4*>(mu);
+  float4* v4 = reinterpret_cast<float4*>(nu);
+  LDP_GRID_STRIDE(i, n4) {
+    float4 pv = p4[i], gv = __ldcs(g4 + i), mv = m4[i], vv = v4[i];
+    adam_one(pv.x, gv.x, mv.x, vv.x, lr, b1, b2, eps, bc1, bc2, gscale);
+    adam_one(pv.y, gv.y, mv.y, vv.y, lr, b1, b2, eps, bc1, bc2, gscale);
+    adam_one(pv.z, gv.z, mv.z, vv.z, lr, b1, b2, eps, bc1, bc2, gscale);
+    adam_one(pv.w, gv.w, mv.w, vv.w, lr, b1, b2, eps, bc1, bc2, gscale);
+    p4[i] = pv; m4[i] = mv; v4[i] = vv;
+  }
+  for (long long i = (n4 << 2) + blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    adam_one(p[i], g[i], mu[i], nu[i], lr, b1, b2, eps, bc1, bc2, gscale);
+}
+
+// ------------------------------------------------------------------------------------------------
+// bf16 / tcgen05 path: every contraction (forward, data gradient, weight gradient) becomes one dense
+// C[M][N] = A[M][K] W[K][N] on tc_gemm_kernel (PLAIN epilogue, fp32 accumulate and output).  The operands are
+// materialised in bf16 by the kernels below: the implicit-GEMM gather (im2col), its transpose for the weight
+// gradient (the reduction runs over rows there), and the K-major weight packs.
+// ------------------------------------------------------------------------------------------------
+struct Im2col {
+  const float* x1 = nullptr; int c1 = 0, ld1 = 0;
+  const float* x2 = nullptr; int c2 = 0, ld2 = 0;
+  int t_in = 1, t_out = 1, taps = 1, stride = 1, pad = 0, dil = 1;
+  int m = 0;
+};
+__device__ __forceinline__ float im2col_at(const Im2col& p, int m, int k, int ctot) {
+  int j = k / ctot, c = k - j * ctot;
+  int b = m / p.t_out, t = m - b * p.t_out;
+  int num = t * p.stride + j - p.pad;
+  if (num < 0 || (num % p.dil) != 0) return 0.f;
+  int ti = num / p.dil;
+  if (ti >= p.t_in) return 0.f;
+  long long row = (long long)b * p.t_in + ti;
+  return (c < p.c1) ? p.x1[row * p.ld1 + c] : p.x2[row * p.ld2 + (c - p.c1)];
+}
+// A[m][k] for k < kp (zero beyond K)
+__global__ void im2col_bf16_kernel(const Im2col p, __nv_bfloat16* __restrict__ out, int kp) {
+  const int ctot = p.c1 + p.c2, K = p.taps * ctot;
+  LDP_GRID_STRIDE(i, (long long)p.m * kp) {
+    int m = (int)(i / kp), k = (int)(i - (long long)m * kp);
+    out[i] = __float2bfloat16(k < K ? im2col_at(p, m, k, ctot) : 0.f);
+  }
+}
+// same, 8 consecutive k per thread: needs c1, c2, ld1, ld2 multiples of 8 (so a group never straddles a tap or source)
+__global__ void im2col8_bf16_kernel(const Im2col p, __nv_bfloat16* __restrict__ out, int kp) {
+  const int ctot = p.c1 + p.c2, K = p.taps * ctot, kp8 = kp >> 3;
+  LDP_GRID_STRIDE(i, (long long)p.m * kp8) {
+    int m = (int)(i / kp8), k = (int)(i - (long long)m * kp8) << 3;
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
+    if (k < K) {
+      int j = k / ctot, c = k - j * ctot;
+      int bi = m / p.t_out, t = m - bi * p.t_out;
+      int num = t * p.stride + j - p.pad;
+      if (num >= 0 && (num % p.dil) == 0) {
+        int ti = num / p.dil;
+        if (ti < p.t_in) {
+          long long row = (long long)bi * p.t_in + ti;
+          const float* src = (c < p.c1) ? p.x1 + row * p.ld1 + c : p.x2 + row * p.ld2 + (c - p.c1);
+          a = *reinterpret_cast<const float4*>(src);
+          b = *reinterpret_cast<const float4*>(src + 4);
+        }
+      }
+    }
+    __nv_bfloat162 o[4] = {__floats2bfloat162_rn(a.x, a.y), __floats2bfloat162_rn(a.z, a.w),
+                           __floats2bfloat162_rn(b.x, b.y), __floats2bfloat162_rn(b.z, b.w)};
+    *reinterpret_cast<uint4*>(out + (long long)m * kp + k) = *reinterpret_cast<uint4*>(o);
+  }
+}
+static int launch_im2col(const Im2col& q, __nv_bfloat16* out, int kp, cudaStream_t s) {
+  const bool v8 = (q.c1 % 8) == 0 && (q.c2 % 8) == 0 && (q.ld1 % 8) == 0 && (q.c2 == 0 || (q.ld2 % 8) == 0) &&
+                  (((uintptr_t)q.x1 | (uintptr_t)q.x2) & 15) == 0;
+  if (v8) im2col8_bf16_kernel<<<(int)std::min<long long>(((long long)q.m * (kp / 8) + 255) / 256, 148 * 8), 256, 0, s>>>(q, out, kp);
+  else im2col_bf16_kernel<<<(int)std::min<long long>(((long long)q.m * kp + 255) / 256, 148 * 8), 256, 0, s>>>(q, out, kp);
+  LDP_LAUNCH_OK();
+  return LDP_OK;
+}
+// At[k][m] for m < mp (zero beyond M); 32x32 tiles through shared memory so both sides stay coalesced
+__global__ void __launch_bounds__(256) im2col_t_bf16_kernel(const Im2col p, __nv_bfloat16* __restrict__ out, int mp) {
+  __shared__ float tile[32][33];
+  const int ctot = p.c1 + p.c2, K = p.taps * ctot;
+  const int k0 = blockIdx.x * 32, m0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int r = ty; r < 32; r += 8) {
+    int m = m0 + r, k = k0 + tx;
+    tile[r][tx] = (m < p.m && k < K) ? im2col_at(p, m, k, ctot) : 0.f;
+  }
+  __syncthreads();
+  for (int r = ty; r < 32; r += 8) {
+    int k = k0 + r, m = m0 + tx;
+    if (k < K && m < mp) out[(long long)k * mp + m] = __float2bfloat16(tile[tx][r]);
+  }
+}
+// dst[n][k] = bf16(src[k*ld + n]) for n < n_pad, k < kp (zeros outside K x N): the K-major "W^T" operand.
+// colsum, if given, also receives sum_k src[k][n] (the bias gradient when src is dY).
+__global__ void __launch_bounds__(256) pack_t_bf16_kernel(const float* __restrict__ src, int ld, int K, int N,
+                                                          __nv_bfloat16* __restrict__ dst, int kp, int n_pad,
+                                                          float* __restrict__ colsum) {
+  __shared__ float tile[32][33];
+  const int n0 = blockIdx.x * 32, k0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int r = ty; r < 32; r += 8) {
+    int k = k0 + r, n = n0 + tx;
+    tile[r][tx] = (k < K && n < N) ? src[(long long)k * ld + n] : 0.f;
+  }
+  __syncthreads();
+  for (int r = ty; r < 32; r += 8) {
+    int n = n0 + r, k = k0 + tx;
+    if (n < n_pad && k < kp) dst[(long long)n * kp + k] = __float2bfloat16(tile[tx][r]);
+  }
+  if (colsum && ty == 0 && n0 + tx < N) {
+    float acc = 0.f;
+#pragma unroll
+    for (int r = 0; r < 32; ++r) acc += tile[r][tx];
+    atomicAdd(colsum + n0 + tx, acc);
+  }
+}
+// data-gradient operand of a forward kernel W[taps][ctot][cout]:  dst[n = c][k = (j', co)] = W[taps-1-j'][c][co]
+__global__ void pack_dgrad_bf16_kernel(const float* __restrict__ w, int taps, int ctot, int cout,
+                                       __nv_bfloat16* __restrict__ dst, int kp, int n_pad) {
+  const int K = taps * cout;
+  LDP_GRID_STRIDE(i, (long long)n_pad * kp) {
+    int n = (int)(i / kp), k = (int)(i - (long long)n * kp);
+    float v = 0.f;
+    if (n < ctot && k < K) {
+      int j = k / cout, co = k - j * cout;
+      v = w[((long long)(taps - 1 - j) * ctot + n) * cout + co];
+    }
+    dst[i] = __float2bfloat16(v);
+  }
+}
+// same, 8 consecutive k per thread (cout a multiple of 8)
+__global__ void pack_dgrad8_bf16_kernel(const float* __restrict__ w, int taps, int ctot, int cout,
+                                        __nv_bfloat16* __restrict__ dst, int kp, int n_pad) {
+  const int K = taps * cout, kp8 = kp >> 3;
+  LDP_GRID_STRIDE(i, (long long)n_pad * kp8) {
+    int n = (int)(i / kp8), k = (int)(i - (long long)n * kp8) << 3;
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
+    if (n < ctot && k < K) {
+      int j = k / cout, co = k - j * cout;
+      const float* src = w + ((long long)(taps - 1 - j) * ctot + n) * cout + co;
+      a = *reinterpret_cast<const float4*>(src);
+      b = *reinterpret_cast<const float4*>(src + 4);
+    }
+    __nv_bfloat162 o[4] = {__floats2bfloat162_rn(a.x, a.y), __floats2bfloat162_rn(a.z, a.w),
+                           __floats2bfloat162_rn(b.x, b.y), __floats2bfloat162_rn(b.z, b.w)};
+    *reinterpret_cast<uint4*>(dst + (long long)n * kp + k) = *reinterpret_cast<uint4*>(o);
   }
 }
 
@@ -435,13 +590,114 @@ struct TrainWs {
   void reset() { arena.release(); pool.clear(); cursor = 0; }
 };
 
+// growable device scratch (operands of the bf16 path; reused by consecutive GEMMs, stream order keeps that safe)
+struct Scratch {
+  void* p = nullptr;
+  size_t cap = 0;
+  int ensure(size_t bytes) {
+    if (bytes <= cap) return LDP_OK;
+    if (p) { cudaDeviceSynchronize(); cudaFree(p); p = nullptr; cap = 0; }
+    bytes = bytes + bytes / 4;
+    LDP_CUDA_OK(cudaMalloc(&p, bytes));
+    cap = bytes;
+    return LDP_OK;
+  }
+  ~Scratch() { if (p) cudaFree(p); }
+};
+
+// Dense bf16 GEMMs on tc_gemm_kernel.  Ops (two tensor maps each) are cached by their pointers and shapes: the
+// workspace and scratch buffers keep their addresses from step to step.
+struct TcDense {
+  Arena arena;
+  TcStage* kb_dev = nullptr;     // identity stage table, shared by every op
+  int kb_cap = 0;
+  struct Key {
+    const void *a, *w, *out, *res, *bias; int M, kp, N, lda, ldo, relu;
+    bool operator<(const Key& o) const {
+      return std::tie(a, w, out, res, bias, M, kp, N, lda, ldo, relu) <
+             std::tie(o.a, o.w, o.out, o.res, o.bias, o.M, o.kp, o.N, o.lda, o.ldo, o.relu);
+    }
+  };
+  std::map<Key, TcGemm> ops;
+  int init(int max_kb) {
+    if (kb_dev && max_kb <= kb_cap) return LDP_OK;
+    LDP_TRY(tc_driver_check());
+    LDP_TRY(tc_gemm_init());
+    std::vector<TcStage> kb(max_kb);
+    for (int i = 0; i < max_kb; ++i) kb[i] = make_stage(0, 0, 1, i * 64, 0, 0, i);
+    LDP_TRY(arena.alloc_t(&kb_dev, max_kb));
+    LDP_CUDA_OK(cudaMemcpy(kb_dev, kb.data(), kb.size() * sizeof(TcStage), cudaMemcpyHostToDevice));
+    kb_cap = max_kb;
+    ops.clear();
+    return LDP_OK;
+  }
+  // out[M][N] (ldo) = A[M][kp] (lda, bf16) . Wt[n_pad][kp]^T + bias, optional relu, optional + res (may alias out)
+  int gemm(const __nv_bfloat16* a, int lda, int M, int kp, const __nv_bfloat16* wt, int n_pad, int N, const float* bias,
+           int relu, const float* res, int ldres, float* out, int ldo, cudaStream_t s) {
+    LDP_TRY(init(std::max(kp / 64, 256)));
+    Key key{a, wt, out, res, bias, M, kp, N, lda, ldo, relu};
+    auto it = ops.find(key);
+    if (it == ops.end()) {
+      TcGemm op;
+      uint64_t ad[4] = {(uint64_t)kp, 1, 1, (uint64_t)M};
+      uint64_t as[3] = {(uint64_t)lda * 2, (uint64_t)lda * 2, (uint64_t)lda * 2};
+      uint32_t ab[4] = {64, 1, 1, 128};
+      LDP_TRY(make_tmap_bf16(&op.map_a[0], a, 4, ad, as, ab));
+      for (int i = 1; i < 4; ++i) op.map_a[i] = op.map_a[0];
+      uint64_t bd[2] = {(uint64_t)kp, (uint64_t)n_pad};
+      uint64_t bs[1] = {(uint64_t)kp * 2};
+      uint32_t bb[2] = {64, 128};
+      LDP_TRY(make_tmap_bf16(&op.map_b, wt, 2, bd, bs, bb));
+      TcRun run;
+      run.src_acc = make_stage(0, 0, 1, 0, 0, 0, 0).src_acc; run.count = kp / 64;
+      TcRun* run_dev;
+      LDP_TRY(arena.alloc_t(&run_dev, 1));
+      LDP_CUDA_OK(cudaMemcpyAsync(run_dev, &run, sizeof(run), cudaMemcpyHostToDevice, s));
+      op.kb = kb_dev; op.num_kb = kp / 64; op.runs = run_dev; op.num_runs = 1;
+      tc_set_inline_runs(&op, &run, 1);
+      op.M = M; op.N = N; op.block_n = 128; op.items_per_tile = 128; op.rows_per_item = 1;
+      op.mode = TC_EPI_PLAIN; op.bias = bias; op.relu = relu;
+      op.res_f32 = res; op.ld_res_f32 = ldres; op.out_f32 = out; op.ld_out_f32 = ldo;
+      it = ops.emplace(key, op).first;
+    }
+    return launch_tc_gemm(it->second, s);
+  }
+};
+
+struct TrainCtx {
+  cudaStream_t s = 0;
+  int prec = LDP_PREC_FP32;
+  TcDense* tc = nullptr;
+  Scratch *sa = nullptr, *sw = nullptr;   // A-operand and W-operand scratch
+};
+
 #define LDP_TN(var, ws, rows, c, grad)                                                            \
   Tn* var = (ws).get((rows), (c), (grad));                                                        \
   LDP_CHECK(var != nullptr, LDP_ERR_CUDA, "trainer workspace allocation failed")
 
+static Im2col im2col_of(const Tn& x1, const Tn* x2, const Geo& g, int m, bool grad_values = false) {
+  Im2col q;
+  q.x1 = grad_values ? x1.g : x1.v; q.c1 = x1.c; q.ld1 = x1.ld;
+  if (x2) { q.x2 = x2->v; q.c2 = x2->c; q.ld2 = x2->ld; }
+  q.t_in = g.t_in; q.t_out = g.t_out; q.taps = g.taps; q.stride = g.stride; q.pad = g.pad; q.dil = g.dil; q.m = m;
+  return q;
+}
+
 // y = conv(x1 [| x2]) + bias [relu] [+ res]
 static int conv_fwd(const Tn& x1, const Tn* x2, const Geo& g, const float* w, const float* bias, int cout, int act,
-                    const Tn* res, Tn* y, cudaStream_t s) {
+                    const Tn* res, Tn* y, TrainCtx& cx) {
+  cudaStream_t s = cx.s;
+  if (cx.prec == LDP_PREC_BF16) {
+    const int K = g.taps * (x1.c + (x2 ? x2->c : 0)), kp = round_up(K, 64), n_pad = round_up(cout, 128), M = y->rows;
+    LDP_TRY(cx.sa->ensure((size_t)M * kp * 2));
+    LDP_TRY(cx.sw->ensure((size_t)n_pad * kp * 2));
+    __nv_bfloat16* A = (__nv_bfloat16*)cx.sa->p;
+    __nv_bfloat16* W = (__nv_bfloat16*)cx.sw->p;
+    LDP_TRY(launch_im2col(im2col_of(x1, x2, g, M), A, kp, s));
+    pack_t_bf16_kernel<<<dim3(n_pad / 32, kp / 32), 256, 0, s>>>(w, cout, K, cout, W, kp, n_pad, nullptr);
+    LDP_LAUNCH_OK();
+    return cx.tc->gemm(A, kp, M, kp, W, n_pad, cout, bias, act, res ? res->v : nullptr, res ? res->ld : 0, y->v, y->ld, s);
+  }
   GemmF32 p;
   p.x1 = x1.v; p.c1 = x1.c; p.ld1 = x1.ld;
   if (x2) { p.x2 = x2->v; p.c2 = x2->c; p.ld2 = x2->ld; }
@@ -453,29 +709,70 @@ static int conv_fwd(const Tn& x1, const Tn* x2, const Geo& g, const float* w, co
 }
 
 // data gradient of one source: src.g (=|+=) dY (*) W^T restricted to the source's channel range
-static int conv_dgrad(Tn* src, int coff, int ctot, const Geo& g, const float* w, int cout, const Tn& y, cudaStream_t s) {
+static int conv_dgrad(Tn* src, int coff, int ctot, const Geo& g, const float* w, int cout, const Tn& y, TrainCtx& cx) {
   if (!src->g) return LDP_OK;
+  cudaStream_t s = cx.s;
+  Geo gt;                       // the transposed geometry: a convolution over dY
+  gt.t_in = g.t_out; gt.t_out = g.t_in; gt.taps = g.taps; gt.stride = g.dil; gt.dil = g.stride; gt.pad = g.taps - 1 - g.pad;
+  const bool acc = src->gset;
+  src->gset = true;
+  if (cx.prec == LDP_PREC_BF16) {
+    const int K = g.taps * cout, kp = round_up(K, 64), n_pad = round_up(ctot, 128) + 128, M = src->rows;
+    LDP_TRY(cx.sa->ensure((size_t)M * kp * 2));
+    LDP_TRY(cx.sw->ensure((size_t)n_pad * kp * 2));
+    __nv_bfloat16* A = (__nv_bfloat16*)cx.sa->p;
+    __nv_bfloat16* W = (__nv_bfloat16*)cx.sw->p;
+    Tn dy = y;
+    dy.c = cout;
+    LDP_TRY(launch_im2col(im2col_of(dy, nullptr, gt, M, true), A, kp, s));
+    if ((cout % 8) == 0 && ((uintptr_t)w & 15) == 0)
+      pack_dgrad8_bf16_kernel<<<ew_blocks((long long)n_pad * (kp / 8)), 256, 0, s>>>(w, g.taps, ctot, cout, W, kp, n_pad);
+    else
+      pack_dgrad_bf16_kernel<<<ew_blocks((long long)n_pad * kp), 256, 0, s>>>(w, g.taps, ctot, cout, W, kp, n_pad);
+    LDP_LAUNCH_OK();
+    // rows [coff, coff + src->c) of the pack are this source's channels
+    return cx.tc->gemm(A, kp, M, kp, W + (size_t)coff * kp, round_up(src->c, 128), src->c, nullptr, 0,
+                       acc ? src->g : nullptr, src->ld, src->g, src->ld, s);
+  }
   GemmF32 p;
   p.x1 = y.g; p.c1 = cout; p.ld1 = y.ld;
-  p.t_in = g.t_out; p.t_out = g.t_in; p.taps = g.taps; p.stride = g.dil; p.dil = g.stride; p.pad = g.taps - 1 - g.pad;
+  p.t_in = gt.t_in; p.t_out = gt.t_out; p.taps = gt.taps; p.stride = gt.stride; p.dil = gt.dil; p.pad = gt.pad;
   p.w = w; p.ldw = cout; p.w_mode = 1; p.w_ctot = ctot; p.w_coff = coff;
-  if (src->gset) { p.res = src->g; p.ldres = src->ld; }
+  if (acc) { p.res = src->g; p.ldres = src->ld; }
   p.out = src->g; p.ldo = src->ld; p.m = src->rows; p.n = src->c;
-  src->gset = true;
   return launch_gemm_f32(p, s);
 }
 
-static int conv_bwd(Tn* x1, Tn* x2, const Geo& g, const float* w, float* dw, float* db, int cout, const Tn& y,
-                    cudaStream_t s) {
+// weight and bias gradients (added into dw / db), then the data gradients of the sources
+static int conv_wgrad(const Tn& x1, const Tn* x2, const Geo& g, float* dw, float* db, int cout, const Tn& y, TrainCtx& cx) {
+  cudaStream_t s = cx.s;
+  if (cx.prec == LDP_PREC_BF16) {
+    const int K = g.taps * (x1.c + (x2 ? x2->c : 0)), m = y.rows, mp = round_up(m, 64), n_pad = round_up(cout, 128);
+    LDP_TRY(cx.sa->ensure((size_t)K * mp * 2));
+    LDP_TRY(cx.sw->ensure((size_t)n_pad * mp * 2));
+    __nv_bfloat16* At = (__nv_bfloat16*)cx.sa->p;
+    __nv_bfloat16* Yt = (__nv_bfloat16*)cx.sw->p;
+    im2col_t_bf16_kernel<<<dim3(ceil_div(K, 32), mp / 32), 256, 0, s>>>(im2col_of(x1, x2, g, m), At, mp);
+    LDP_LAUNCH_OK();
+    pack_t_bf16_kernel<<<dim3(n_pad / 32, mp / 32), 256, 0, s>>>(y.g, y.ld, m, cout, Yt, mp, n_pad, db);
+    LDP_LAUNCH_OK();
+    LDP_TRY(cx.tc->gemm(At, mp, K, mp, Yt, n_pad, cout, nullptr, 0, dw, cout, dw, cout, s));
+    return LDP_OK;
+  }
   WgradF32 q;
-  q.x1 = x1->v; q.c1 = x1->c; q.ld1 = x1->ld;
+  q.x1 = x1.v; q.c1 = x1.c; q.ld1 = x1.ld;
   if (x2) { q.x2 = x2->v; q.c2 = x2->c; q.ld2 = x2->ld; }
   q.t_in = g.t_in; q.t_out = g.t_out; q.taps = g.taps; q.stride = g.stride; q.pad = g.pad; q.dil = g.dil;
   q.dy = y.g; q.lddy = y.ld; q.dw = dw; q.ldw = cout; q.dbias = db; q.m = y.rows; q.n = cout;
-  LDP_TRY(launch_wgrad_f32(q, s));
+  return launch_wgrad_f32(q, s);
+}
+
+static int conv_bwd(Tn* x1, Tn* x2, const Geo& g, const float* w, float* dw, float* db, int cout, const Tn& y,
+                    TrainCtx& cx) {
+  LDP_TRY(conv_wgrad(*x1, x2, g, dw, db, cout, y, cx));
   const int ctot = x1->c + (x2 ? x2->c : 0);
-  LDP_TRY(conv_dgrad(x1, 0, ctot, g, w, cout, y, s));
-  if (x2) LDP_TRY(conv_dgrad(x2, x1->c, ctot, g, w, cout, y, s));
+  LDP_TRY(conv_dgrad(x1, 0, ctot, g, w, cout, y, cx));
+  if (x2) LDP_TRY(conv_dgrad(x2, x1->c, ctot, g, w, cout, y, cx));
   return LDP_OK;
 }
 
@@ -522,6 +819,8 @@ struct LdpTrainer {
   float* time_table = nullptr;  // sinusoid / Fourier features of every timestep [n_train][dim]
   int64_t n_params = 0;
   TrainWs ws;
+  TcDense tc;
+  Scratch scratch_a, scratch_w;
 };
 
 namespace ldp {
@@ -573,9 +872,10 @@ struct CrbT {
   bool proj;
 };
 
-static int unet_loss_grad(LdpTrainer* h, const float* params, float* grads, const float* x0, const float* noise,
-                          const int32_t* t, const float* cond, int B, int T, float weight, float* loss_dev,
-                          cudaStream_t s) {
+static int unet_loss_grad(LdpTrainer* h, int prec, const float* params, float* grads, const float* x0,
+                          const float* noise, const int32_t* t, const float* cond, int B, int T, float weight,
+                          float* loss_dev, cudaStream_t s) {
+  TrainCtx cx{s, prec, &h->tc, &h->scratch_a, &h->scratch_w};
   const LdpUnetConfig& c = h->ucfg;
   const int nl = c.n_levels, ds = c.step_embed_dim, dc = c.global_cond_dim, cd = ds + dc, D = c.input_dim, G = c.n_groups;
   LDP_CHECK(T > 0 && (T % (1 << (nl - 1))) == 0, LDP_ERR_UNSUPPORTED, "T must be a multiple of 2^(n_levels-1)");
@@ -596,11 +896,11 @@ static int unet_loss_grad(LdpTrainer* h, const float* params, float* grads, cons
   LDP_TN(gbuf, ws, B, cd, true);
   LDP_TN(mg, ws, B, cd, true);
   Geo dense;
-  LDP_TRY(conv_fwd(*sin_in, nullptr, dense, t0w.w, t0b.w, ds * 4, 0, nullptr, hid, s));
+  LDP_TRY(conv_fwd(*sin_in, nullptr, dense, t0w.w, t0b.w, ds * 4, 0, nullptr, hid, cx));
   LDP_TRY(mish_fwd(*hid, hm, s));
   Tn temb = *gbuf;            // view: the first ds columns of g
   temb.c = ds;
-  LDP_TRY(conv_fwd(*hm, nullptr, dense, t1w.w, t1b.w, ds, 0, nullptr, &temb, s));
+  LDP_TRY(conv_fwd(*hm, nullptr, dense, t1w.w, t1b.w, ds, 0, nullptr, &temb, cx));
   LDP_CUDA_OK(cudaMemcpy2DAsync(gbuf->v + ds, (size_t)cd * 4, cond, (size_t)dc * 4, (size_t)dc * 4, B,
                                 cudaMemcpyDeviceToDevice, s));
   LDP_TRY(mish_fwd(*gbuf, mg, s));
@@ -624,15 +924,15 @@ static int unet_loss_grad(LdpTrainer* h, const float* params, float* grads, cons
     LDP_TN(c2, ws, rows, cout, true);
     LDP_TN(o, ws, rows, cout, true);
     b.c1 = c1; b.e = e; b.h1 = h1; b.c2 = c2; b.out = o; b.r = nullptr;
-    LDP_TRY(conv_fwd(*x1, x2, g5, b.c1w.w, b.c1b.w, cout, 0, nullptr, c1, s));
-    LDP_TRY(conv_fwd(*mg, nullptr, dense, b.fw.w, b.fb.w, 2 * cout, 0, nullptr, e, s));
+    LDP_TRY(conv_fwd(*x1, x2, g5, b.c1w.w, b.c1b.w, cout, 0, nullptr, c1, cx));
+    LDP_TRY(conv_fwd(*mg, nullptr, dense, b.fw.w, b.fb.w, 2 * cout, 0, nullptr, e, cx));
     LDP_TRY(gn_fwd(*c1, B, Tl, G, b.g1s, b.g1b, e, nullptr, h1, s));
-    LDP_TRY(conv_fwd(*h1, nullptr, g5, b.c2w.w, b.c2b.w, cout, 0, nullptr, c2, s));
+    LDP_TRY(conv_fwd(*h1, nullptr, g5, b.c2w.w, b.c2b.w, cout, 0, nullptr, c2, cx));
     const Tn* res = x1;
     if (proj) {
       LDP_TN(r, ws, rows, cout, true);
       b.r = r;
-      LDP_TRY(conv_fwd(*x1, x2, g1, b.rw.w, b.rb.w, cout, 0, nullptr, r, s));
+      LDP_TRY(conv_fwd(*x1, x2, g1, b.rw.w, b.rb.w, cout, 0, nullptr, r, cx));
       res = r;
     }
     LDP_TRY(gn_fwd(*c2, B, Tl, G, b.g2s, b.g2b, nullptr, res, o, s));
@@ -677,7 +977,7 @@ static int unet_loss_grad(LdpTrainer* h, const float* params, float* grads, cons
     if (l < nl - 1) {
       Geo g; g.t_in = Tl; g.t_out = Tl / 2; g.taps = 3; g.stride = 2; g.pad = 0;
       LDP_TN(y, ws, B * (Tl / 2), d, true);
-      LDP_TRY(conv_fwd(*cur, nullptr, g, down_w[l].w, down_b[l].w, d, 0, nullptr, y, s));
+      LDP_TRY(conv_fwd(*cur, nullptr, g, down_w[l].w, down_b[l].w, d, 0, nullptr, y, cx));
       resamp.push_back({cur, y, g, down_w[l], down_b[l], d});
       cur = y;
     }
@@ -695,7 +995,7 @@ static int unet_loss_grad(LdpTrainer* h, const float* params, float* grads, cons
     LDP_TRY(crb_fwd(cur, nullptr, d, false, Tl, &cur));
     Geo g; g.t_in = Tl; g.t_out = 2 * Tl; g.taps = 4; g.stride = 1; g.pad = 2; g.dil = 2;
     LDP_TN(y, ws, B * 2 * Tl, d, true);
-    LDP_TRY(conv_fwd(*cur, nullptr, g, up_w[u].w, up_b[u].w, d, 0, nullptr, y, s));
+    LDP_TRY(conv_fwd(*cur, nullptr, g, up_w[u].w, up_b[u].w, d, 0, nullptr, y, cx));
     resamp.push_back({cur, y, g, up_w[u], up_b[u], d});
     cur = y;
   }
@@ -707,16 +1007,16 @@ static int unet_loss_grad(LdpTrainer* h, const float* params, float* grads, cons
   LDP_TN(ff, ws, B * T, (int)d0, true);
   LDP_TN(eps, ws, B * T, D, true);
   Tn* final_in = cur;
-  LDP_TRY(conv_fwd(*final_in, nullptr, g5, fcw.w, fcb.w, (int)d0, 0, nullptr, fc, s));
+  LDP_TRY(conv_fwd(*final_in, nullptr, g5, fcw.w, fcb.w, (int)d0, 0, nullptr, fc, cx));
   LDP_TRY(gn_fwd(*fc, B, T, 8, fgs, fgb, nullptr, nullptr, ff, s));
-  LDP_TRY(conv_fwd(*ff, nullptr, g1, ow.w, ob.w, D, 0, nullptr, eps, s));
+  LDP_TRY(conv_fwd(*ff, nullptr, g1, ow.w, ob.w, D, 0, nullptr, eps, cx));
 
   // ---- loss and backward
   LDP_TRY(mse(*eps, noise, weight, loss_dev, s));
   eps->gset = true;
-  LDP_TRY(conv_bwd(ff, nullptr, g1, ow.w, ow.g, ob.g, D, *eps, s));
+  LDP_TRY(conv_bwd(ff, nullptr, g1, ow.w, ow.g, ob.g, D, *eps, cx));
   LDP_TRY(gn_bwd(fc, B, T, 8, fgs, fgb, nullptr, nullptr, *ff, s));
-  LDP_TRY(conv_bwd(final_in, nullptr, g5, fcw.w, fcw.g, fcb.g, (int)d0, *fc, s));
+  LDP_TRY(conv_bwd(final_in, nullptr, g5, fcw.w, fcw.g, fcb.g, (int)d0, *fc, cx));
 
   auto crb_bwd = [&](CrbT& b) -> int {
     const int Tl = b.Tl, cout = b.cout;
@@ -724,11 +1024,11 @@ static int unet_loss_grad(LdpTrainer* h, const float* params, float* grads, cons
     Geo g1b; g1b.t_in = Tl; g1b.t_out = Tl;
     Tn* res = b.proj ? b.r : b.x1;
     LDP_TRY(gn_bwd(b.c2, B, Tl, G, b.g2s, b.g2b, nullptr, res, *b.out, s));
-    LDP_TRY(conv_bwd(b.h1, nullptr, g5b, b.c2w.w, b.c2w.g, b.c2b.g, cout, *b.c2, s));
+    LDP_TRY(conv_bwd(b.h1, nullptr, g5b, b.c2w.w, b.c2w.g, b.c2b.g, cout, *b.c2, cx));
     LDP_TRY(gn_bwd(b.c1, B, Tl, G, b.g1s, b.g1b, b.e, nullptr, *b.h1, s));
-    LDP_TRY(conv_bwd(b.x1, b.x2, g5b, b.c1w.w, b.c1w.g, b.c1b.g, cout, *b.c1, s));
-    if (b.proj) LDP_TRY(conv_bwd(b.x1, b.x2, g1b, b.rw.w, b.rw.g, b.rb.g, cout, *b.r, s));
-    LDP_TRY(conv_bwd(mg, nullptr, dense, b.fw.w, b.fw.g, b.fb.g, 2 * cout, *b.e, s));
+    LDP_TRY(conv_bwd(b.x1, b.x2, g5b, b.c1w.w, b.c1w.g, b.c1b.g, cout, *b.c1, cx));
+    if (b.proj) LDP_TRY(conv_bwd(b.x1, b.x2, g1b, b.rw.w, b.rw.g, b.rb.g, cout, *b.r, cx));
+    LDP_TRY(conv_bwd(mg, nullptr, dense, b.fw.w, b.fw.g, b.fb.g, 2 * cout, *b.e, cx));
     return LDP_OK;
   };
   // reverse creation order: resampling convs are interleaved with the blocks exactly as in the forward
@@ -737,7 +1037,7 @@ static int unet_loss_grad(LdpTrainer* h, const float* params, float* grads, cons
     int ri = (int)resamp.size() - 1;
     for (int u = nl - 2; u >= 0; --u) {          // up path, last to first
       Resamp& r = resamp[ri--];
-      LDP_TRY(conv_bwd(r.x, nullptr, r.g, r.w.w, r.w.g, r.b.g, r.cout, *r.y, s));
+      LDP_TRY(conv_bwd(r.x, nullptr, r.g, r.w.w, r.w.g, r.b.g, r.cout, *r.y, cx));
       LDP_TRY(crb_bwd(blocks[bi--]));
       LDP_TRY(crb_bwd(blocks[bi--]));
     }
@@ -746,7 +1046,7 @@ static int unet_loss_grad(LdpTrainer* h, const float* params, float* grads, cons
     for (int l = nl - 1; l >= 0; --l) {          // down path
       if (l < nl - 1) {
         Resamp& r = resamp[ri--];
-        LDP_TRY(conv_bwd(r.x, nullptr, r.g, r.w.w, r.w.g, r.b.g, r.cout, *r.y, s));
+        LDP_TRY(conv_bwd(r.x, nullptr, r.g, r.w.w, r.w.g, r.b.g, r.cout, *r.y, cx));
       }
       LDP_TRY(crb_bwd(blocks[bi--]));
       LDP_TRY(crb_bwd(blocks[bi--]));
@@ -756,17 +1056,18 @@ static int unet_loss_grad(LdpTrainer* h, const float* params, float* grads, cons
   LDP_TRY(mish_bwd(gbuf, *mg, s));
   Tn temb_g = *gbuf;
   temb_g.c = ds;
-  LDP_TRY(conv_bwd(hm, nullptr, dense, t1w.w, t1w.g, t1b.g, ds, temb_g, s));
+  LDP_TRY(conv_bwd(hm, nullptr, dense, t1w.w, t1w.g, t1b.g, ds, temb_g, cx));
   LDP_TRY(mish_bwd(hid, *hm, s));
-  LDP_TRY(conv_bwd(sin_in, nullptr, dense, t0w.w, t0w.g, t0b.g, ds * 4, *hid, s));
+  LDP_TRY(conv_bwd(sin_in, nullptr, dense, t0w.w, t0w.g, t0b.g, ds * 4, *hid, cx));
   return LDP_OK;
 }
 
 // ------------------------------------------------------------------------------------------------
 // IDM: loss = mean((MLPDiffusion(s||s', add_noise(a0, noise, t), t) - noise)^2)   (agent/ldp_agent.py:128-139)
 // ------------------------------------------------------------------------------------------------
-static int idm_loss_grad(LdpTrainer* h, const float* params, float* grads, const float* sdev, const float* a0,
+static int idm_loss_grad(LdpTrainer* h, int prec, const float* params, float* grads, const float* sdev, const float* a0,
                          const float* noise, const int32_t* t, int N, float weight, float* loss_dev, cudaStream_t s) {
+  TrainCtx cx{s, prec, &h->tc, &h->scratch_a, &h->scratch_w};
   const LdpIdmConfig& c = h->icfg;
   const int A = c.action_dim, S2 = 2 * c.obs_dim, H = c.hidden_dim, td = c.time_dim;
   TrainWs& ws = h->ws;
@@ -801,12 +1102,12 @@ static int idm_loss_grad(LdpTrainer* h, const float* params, float* grads, const
       const bool last = i + 1 == c.n_cond_layers;
       if (last) {
         L.y = nullptr; L.ym = nullptr;
-        LDP_TRY(conv_fwd(*cur, nullptr, dense, L.w.w, L.b.w, n, 0, nullptr, &cond_view, s));
+        LDP_TRY(conv_fwd(*cur, nullptr, dense, L.w.w, L.b.w, n, 0, nullptr, &cond_view, cx));
       } else {
         LDP_TN(y, ws, N, n, true);
         LDP_TN(ym, ws, N, n, true);
         L.y = y; L.ym = ym;
-        LDP_TRY(conv_fwd(*cur, nullptr, dense, L.w.w, L.b.w, n, 0, nullptr, y, s));
+        LDP_TRY(conv_fwd(*cur, nullptr, dense, L.w.w, L.b.w, n, 0, nullptr, y, cx));
         LDP_TRY(mish_fwd(*y, ym, s));
         cur = ym;
       }
@@ -816,7 +1117,7 @@ static int idm_loss_grad(LdpTrainer* h, const float* params, float* grads, const
   }
   PG w0 = pw.take((int64_t)in_dim * H), b0 = pw.take(H);
   LDP_TN(h0, ws, N, H, true);
-  LDP_TRY(conv_fwd(*xin, nullptr, dense, w0.w, b0.w, H, 0, nullptr, h0, s));
+  LDP_TRY(conv_fwd(*xin, nullptr, dense, w0.w, b0.w, H, 0, nullptr, h0, cx));
   struct BlkT { Tn *hin, *hn, *u, *hout; PG ln_s, ln_b, w1, b1, w2, b2; };
   std::vector<BlkT> blk;
   Tn* hc = h0;
@@ -831,8 +1132,8 @@ static int idm_loss_grad(LdpTrainer* h, const float* params, float* grads, const
     LDP_TN(ho, ws, N, H, true);
     q.hn = hn; q.u = u; q.hout = ho;
     LDP_TRY(launch_layernorm_f32(hc->v, hn->v, N, H, q.ln_s.w, q.ln_b.w, 1e-6f, 0, s));
-    LDP_TRY(conv_fwd(*hn, nullptr, dense, q.w1.w, q.b1.w, 4 * H, 1, nullptr, u, s));
-    LDP_TRY(conv_fwd(*u, nullptr, dense, q.w2.w, q.b2.w, H, 0, hc, ho, s));
+    LDP_TRY(conv_fwd(*hn, nullptr, dense, q.w1.w, q.b1.w, 4 * H, 1, nullptr, u, cx));
+    LDP_TRY(conv_fwd(*u, nullptr, dense, q.w2.w, q.b2.w, H, 0, hc, ho, cx));
     blk.push_back(q);
     hc = ho;
   }
@@ -842,41 +1143,38 @@ static int idm_loss_grad(LdpTrainer* h, const float* params, float* grads, const
   LDP_TN(eps, ws, N, A, true);
   relu_fwd_kernel<<<ew_blocks((long long)N * H), 256, 0, s>>>(hc->v, hr->v, (long long)N * H);
   LDP_LAUNCH_OK();
-  LDP_TRY(conv_fwd(*hr, nullptr, dense, wout.w, bout.w, A, 0, nullptr, eps, s));
+  LDP_TRY(conv_fwd(*hr, nullptr, dense, wout.w, bout.w, A, 0, nullptr, eps, cx));
 
   // ---- loss and backward
   LDP_TRY(mse(*eps, noise, weight, loss_dev, s));
   eps->gset = true;
-  LDP_TRY(conv_bwd(hr, nullptr, dense, wout.w, wout.g, bout.g, A, *eps, s));
+  LDP_TRY(conv_bwd(hr, nullptr, dense, wout.w, wout.g, bout.g, A, *eps, cx));
   relu_bwd_kernel<<<ew_blocks((long long)N * H), 256, 0, s>>>(hc->v, hr->g, hc->g, (long long)N * H, 0);
   LDP_LAUNCH_OK();
   hc->gset = true;
   for (int b = c.n_blocks - 1; b >= 0; --b) {
     BlkT& q = blk[b];
     // hout = Dense_1(u) + hin
-    LDP_TRY(conv_bwd(q.u, nullptr, dense, q.w2.w, q.w2.g, q.b2.g, H, *q.hout, s));
+    LDP_TRY(conv_bwd(q.u, nullptr, dense, q.w2.w, q.w2.g, q.b2.g, H, *q.hout, cx));
     relu_bwd_kernel<<<ew_blocks((long long)N * 4 * H), 256, 0, s>>>(q.u->v, q.u->g, q.u->g, (long long)N * 4 * H, 0);
     LDP_LAUNCH_OK();
-    LDP_TRY(conv_bwd(q.hn, nullptr, dense, q.w1.w, q.w1.g, q.b1.g, 4 * H, *q.u, s));
+    LDP_TRY(conv_bwd(q.hn, nullptr, dense, q.w1.w, q.w1.g, q.b1.g, 4 * H, *q.u, cx));
     LDP_TRY(launch_ln_bwd_f32(q.hin->v, q.hn->g, q.hout->g, q.hin->g, N, H, q.ln_s.w, q.ln_s.g, q.ln_b.g, 1e-6f, s));
     q.hin->gset = true;
   }
   // Dense_0: weight gradient over the whole input, data gradient only for the cond columns
   {
-    WgradF32 q;
-    q.x1 = xin->v; q.c1 = in_dim; q.ld1 = in_dim; q.dy = h0->g; q.lddy = H; q.dw = w0.g; q.ldw = H; q.dbias = b0.g;
-    q.m = N; q.n = H;
-    LDP_TRY(launch_wgrad_f32(q, s));
-    LDP_TRY(conv_dgrad(&cond_view, A + S2, in_dim, dense, w0.w, H, *h0, s));
+    LDP_TRY(conv_wgrad(*xin, nullptr, dense, w0.g, b0.g, H, *h0, cx));
+    LDP_TRY(conv_dgrad(&cond_view, A + S2, in_dim, dense, w0.w, H, *h0, cx));
   }
   for (int i = c.n_cond_layers - 1; i >= 0; --i) {
     CondL& L = cl[i];
     const bool last = i + 1 == c.n_cond_layers;
     if (last) {
-      LDP_TRY(conv_bwd(L.x, nullptr, dense, L.w.w, L.w.g, L.b.g, L.n, cond_view, s));
+      LDP_TRY(conv_bwd(L.x, nullptr, dense, L.w.w, L.w.g, L.b.g, L.n, cond_view, cx));
     } else {
       LDP_TRY(mish_bwd(L.y, *L.ym, s));
-      LDP_TRY(conv_bwd(L.x, nullptr, dense, L.w.w, L.w.g, L.b.g, L.n, *L.y, s));
+      LDP_TRY(conv_bwd(L.x, nullptr, dense, L.w.w, L.w.g, L.b.g, L.n, *L.y, cx));
     }
   }
   return LDP_OK;
@@ -917,23 +1215,25 @@ int ldp_trainer_destroy(LdpTrainer* h) {
   return LDP_OK;
 }
 
-int ldp_unet_loss_grad(LdpTrainer* h, const float* params_dev, float* grads_dev, const float* x0_dev,
+int ldp_unet_loss_grad(LdpTrainer* h, int precision, const float* params_dev, float* grads_dev, const float* x0_dev,
                        const float* noise_dev, const int32_t* t_dev, const float* cond_dev, int B, int T,
                        float loss_weight, float* loss_dev, void* cuda_stream) {
   LDP_CHECK(h && h->kind == 0, LDP_ERR_INVALID_ARG, "not a planner trainer handle");
   LDP_CHECK(params_dev && grads_dev && x0_dev && noise_dev && t_dev && cond_dev && loss_dev && B > 0 && T > 0,
             LDP_ERR_INVALID_ARG, "bad arguments");
-  return unet_loss_grad(h, params_dev, grads_dev, x0_dev, noise_dev, t_dev, cond_dev, B, T, loss_weight, loss_dev,
+  LDP_CHECK(precision == LDP_PREC_FP32 || precision == LDP_PREC_BF16, LDP_ERR_INVALID_ARG, "bad precision");
+  return unet_loss_grad(h, precision, params_dev, grads_dev, x0_dev, noise_dev, t_dev, cond_dev, B, T, loss_weight, loss_dev,
                         (cudaStream_t)cuda_stream);
 }
 
-int ldp_idm_loss_grad(LdpTrainer* h, const float* params_dev, float* grads_dev, const float* s_dev, const float* a0_dev,
+int ldp_idm_loss_grad(LdpTrainer* h, int precision, const float* params_dev, float* grads_dev, const float* s_dev, const float* a0_dev,
                       const float* noise_dev, const int32_t* t_dev, int N, float loss_weight, float* loss_dev,
                       void* cuda_stream) {
   LDP_CHECK(h && h->kind == 1, LDP_ERR_INVALID_ARG, "not an IDM trainer handle");
   LDP_CHECK(params_dev && grads_dev && s_dev && a0_dev && noise_dev && t_dev && loss_dev && N > 0, LDP_ERR_INVALID_ARG,
             "bad arguments");
-  return idm_loss_grad(h, params_dev, grads_dev, s_dev, a0_dev, noise_dev, t_dev, N, loss_weight, loss_dev,
+  LDP_CHECK(precision == LDP_PREC_FP32 || precision == LDP_PREC_BF16, LDP_ERR_INVALID_ARG, "bad precision");
+  return idm_loss_grad(h, precision, params_dev, grads_dev, s_dev, a0_dev, noise_dev, t_dev, N, loss_weight, loss_dev,
                        (cudaStream_t)cuda_stream);
 }
 
@@ -942,7 +1242,9 @@ int ldp_adam_update(float* params_dev, const float* grads_dev, float* mu_dev, fl
   LDP_CHECK(params_dev && grads_dev && mu_dev && nu_dev && n > 0 && count >= 1, LDP_ERR_INVALID_ARG, "bad arguments");
   const float bc1 = (float)(1.0 - std::pow((double)b1, (double)count));
   const float bc2 = (float)(1.0 - std::pow((double)b2, (double)count));
-  adam_kernel<<<ew_blocks((long long)n), 256, 0, (cudaStream_t)cuda_stream>>>(params_dev, grads_dev, mu_dev, nu_dev,
+  LDP_CHECK((((uintptr_t)params_dev | (uintptr_t)grads_dev | (uintptr_t)mu_dev | (uintptr_t)nu_dev) & 15) == 0,
+            LDP_ERR_INVALID_ARG, "adam: buffers must be 16-byte aligned");
+  adam_kernel<<<148 * 8, 256, 0, (cudaStream_t)cuda_stream>>>(params_dev, grads_dev, mu_dev, nu_dev,
                                                                               (long long)n, lr, b1, b2, eps, bc1, bc2,
                                                                               grad_scale);
   LDP_LAUNCH_OK();

@@ -59,9 +59,10 @@ class TrainState:
     plus the 0-based optimiser step `step` (flax TrainState.step)."""
 
     def __init__(self, kind: str, spec, cfg, params: Dict[str, np.ndarray], lr_schedule: Callable[[int], float],
-                 b1: float = 0.9, b2: float = 0.999, eps: float = 1e-8, device="cuda"):
+                 b1: float = 0.9, b2: float = 0.999, eps: float = 1e-8, device="cuda", precision="fp32"):
         self.lib = N.load()
         self.kind, self.spec, self.cfg = kind, spec, cfg
+        self.precision = {"fp32": 0, "bf16": 1}[precision]
         self.lr_schedule, self.b1, self.b2, self.eps = lr_schedule, b1, b2, eps
         self.params = torch.from_numpy(P.flatten_params(spec, params)).to(device)
         self.grads = torch.zeros_like(self.params)
@@ -103,7 +104,7 @@ class TrainState:
         if noise.shape != x0.shape or t.shape != (B,) or cond.shape != (B, self.cfg.global_cond_dim) or D != self.cfg.input_dim:
             raise ValueError("planner_loss_grad: shape mismatch")
         before = self.loss.clone()
-        N.check(self.lib.ldp_unet_loss_grad(self._h, self.params.data_ptr(), self.grads.data_ptr(), x0.data_ptr(),
+        N.check(self.lib.ldp_unet_loss_grad(self._h, self.precision, self.params.data_ptr(), self.grads.data_ptr(), x0.data_ptr(),
                                             noise.data_ptr(), t.data_ptr(), cond.data_ptr(), B, T, float(weight),
                                             self.loss.data_ptr(), self._stream()))
         return (self.loss - before)[0]
@@ -118,7 +119,7 @@ class TrainState:
         if s.shape != (n, 2 * self.cfg.obs_dim) or a0.shape != (n, self.cfg.action_dim) or noise.shape != a0.shape or t.shape != (n,):
             raise ValueError("idm_loss_grad: shape mismatch")
         before = self.loss.clone()
-        N.check(self.lib.ldp_idm_loss_grad(self._h, self.params.data_ptr(), self.grads.data_ptr(), s.data_ptr(),
+        N.check(self.lib.ldp_idm_loss_grad(self._h, self.precision, self.params.data_ptr(), self.grads.data_ptr(), s.data_ptr(),
                                            a0.data_ptr(), noise.data_ptr(), t.data_ptr(), n, float(weight),
                                            self.loss.data_ptr(), self._stream()))
         return (self.loss - before)[0]

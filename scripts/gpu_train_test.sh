@@ -1,6 +1,4 @@
 #!/bin/bash
-# N1 bring-up: compute-sanitizer on one small case, then the training tests
 mkdir -p gpurun_out
-timeout 600 compute-sanitizer --tool memcheck python -m pytest tests/test_train_gpu.py -x -q -m gpu -k "planner_loss_and_grads and 6-dims0" > gpurun_out/train_sanitizer.log 2>&1
-tail -5 gpurun_out/train_sanitizer.log
-timeout 900 python -m pytest tests/test_train_gpu.py -x -q -m gpu 2>&1 | tail -40
+timeout 900 python -m pytest tests/test_train_gpu.py -q -m gpu 2>&1 | tail -5
+timeout 600 python scripts/train_bench.py --steps 5 --warmup 2 2>&1 | tail -3 | tee gpurun_out/train_bench_bf16.json
