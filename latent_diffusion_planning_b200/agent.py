@@ -64,6 +64,7 @@ class LDPAgent:
         self._planner, self._idm, self.vae = planner, idm, vae
         self._train: Dict[str, Any] = {}          # name -> train.TrainState, built by the first update()
         self._stale = set()                       # networks whose inference handle lags the trained parameters
+        self.data_parallel = True                 # update(): all-reduce gradients when a process group is initialised
         self.vae_decoder, self.viz = vae_decoder, viz
         self.obs_normalization = obs_normalization
         self.config = config
@@ -362,7 +363,7 @@ class LDPAgent:
         from . import train as TR
         seed, cfg = int(rng), self.config
         oh = cfg["obs_horizon"]
-        world = dist.get_world_size() if (dist.is_available() and dist.is_initialized()) else 1
+        world = dist.get_world_size() if (self.data_parallel and dist.is_available() and dist.is_initialized()) else 1
         rank = dist.get_rank() if world > 1 else 0
         obs, obs_emb, action = self._train_inputs(batch)
         B = obs_emb.shape[0]
@@ -401,7 +402,7 @@ class LDPAgent:
         sq = torch.zeros((), device=obs_emb.device)
         scale = 1.0
         for _, ts in states:
-            scale = TR.allreduce_grads(ts.grads)
+            scale = TR.allreduce_grads(ts.grads) if world > 1 else 1.0
             sq = sq + (torch.linalg.vector_norm(ts.grads) * scale) ** 2
         loss = plan_loss + idm_loss
         if world > 1:
