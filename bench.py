@@ -394,6 +394,24 @@ def side_metrics(torch, H, P, rank):
     ms = timeit(lambda: dec.decode(z, precision="bf16"), 2)
     out["vae_decode_frames_per_sec"] = 1024 / ms * 1e3
     out["vae_decode_config"] = "FlaxAutoencoderKL.decode 8x8x4 -> 64x64x3, SD-VAE [128,256,512,512], B=1024 frames, bf16 (plan_viz path)"
+    # scope row N1: one LDPAgent.update (planner + IDM losses, gradients, Adam) at the reference's train batch (train_bc.yaml:10)
+    g = torch.Generator().manual_seed(5)
+    tb = {"obs": {"latent_agentview_image": (torch.randn(256, 9, LATENT, generator=g) * 3).cuda()}, "actions": torch.randn(256, 9, 7, generator=g).cuda()}
+    for k in lowdim:
+        tb["obs"][k] = (torch.rand(256, 9, shapes[k][0], generator=g) * 2 - 1).cuda()
+    agent.data_parallel = False          # side metric of rank 0 alone: no gradient all-reduce here (scripts/train_bench.py has it)
+    for i in range(3):
+        agent.update(tb, i, i)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(5):
+        agent.update(tb, 3 + i, 3 + i)
+    e1.record()
+    torch.cuda.synchronize()
+    out["train_step_ms"] = e0.elapsed_time(e1) / 5
+    out["train_samples_per_sec"] = 256 / out["train_step_ms"] * 1e3
+    out["train_config"] = "LDPAgent.update (train_bc.py agent=ldp_agent, rm_lift latent_img shapes), batch 256, bf16 tcgen05 contractions, fp32 master weights + Adam"
     return out
 
 

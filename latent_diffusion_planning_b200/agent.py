@@ -358,7 +358,32 @@ class LDPAgent:
         """agent/ldp_agent.py:279-327: planner on `batch`, IDM on `mixed_batch`."""
         return self._update_step(batch, mixed_batch, rng, int(step), *self._gates(int(step)))
 
-    def _update_step(self, batch, idm_batch, rng, step: int, use_planner: bool, use_idm: bool):
+    def get_metrics(self, batch, rng):
+        """agent/ldp_agent.py:328-348: the loss metrics of `update` on `batch`, without touching the parameters."""
+        _, m = self._update_step(batch, batch, rng, 0, bool(self.use_planner), bool(self.use_idm), apply=False)
+        return {k: v for k, v in m.items() if k not in ("g_norm", "planner_lr", "planner_step", "idm_lr", "idm_step", "noise_diff")}
+
+    def load_params(self, planner_params: Optional[dict] = None, idm_params: Optional[dict] = None):
+        """Replace network weights (checkpoint restore, train_bc.py:204-231): Flax-layout trees, nested or flat."""
+        for name, tree in (("planner", planner_params), ("idm", idm_params)):
+            if tree is None:
+                continue
+            flat = P.canonicalize_flax_names(P.unnest(tree) if _is_nested(tree) else tree)
+            handle = self._planner if name == "planner" else self._idm
+            blob = torch.from_numpy(P.flatten_params(handle.spec, flat))
+            if name in self._train:
+                self._train[name].params.copy_(blob)
+                self._stale.add(name)
+            elif name == "planner":
+                self._planner_params, old = flat, self._planner
+                self._planner = H.Planner(flat, *self._net_args["planner"])
+                old.close()
+            else:
+                self._idm_params, old = flat, self._idm
+                self._idm = H.Idm(flat, *self._net_args["idm"])
+                old.close()
+
+    def _update_step(self, batch, idm_batch, rng, step: int, use_planner: bool, use_idm: bool, apply: bool = True):
         import torch.distributed as dist
         from . import train as TR
         seed, cfg = int(rng), self.config
@@ -425,8 +450,9 @@ class LDPAgent:
                     metrics["noise_diff"] = 0
                 continue
             metrics[f"{name}_lr"], metrics[f"{name}_step"] = report(ts.step), ts.step
-            ts.apply_gradients(grad_scale=scale)
-            self._stale.add(name)
+            if apply:
+                ts.apply_gradients(grad_scale=scale)
+                self._stale.add(name)
         return self, metrics
 
 

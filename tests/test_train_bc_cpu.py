@@ -1,0 +1,76 @@
+"""Host pieces of the training entry point mirror (train_bc.py / utils/py_utils.py / data/robomimic_latent_data.py)."""
+import csv
+
+import numpy as np
+import pytest
+
+from latent_diffusion_planning_b200 import train_bc as TB
+
+
+def test_every_matches_reference_semantics():
+    e = TB.Every(10)
+    assert [s for s in range(1, 31) if e(s)] == [10, 20, 30] and e(0)
+    assert not any(TB.Every(-1)(s) for s in range(5)) and not TB.Every(None)(3)
+    assert [s for s in range(1, 11) if TB.Every(10, action_repeat=2)(s)] == [5, 10]
+
+
+def test_timer_tick_tock():
+    t = TB.Timer()
+    t.tick("a"); t.tock("a"); t.tick("a"); t.tock("a")
+    with pytest.raises(ValueError):
+        t.tock("a")
+    t.tick("b")
+    with pytest.raises(ValueError):
+        t.tick("b")
+    avg = t.get_average_times()
+    assert set(avg) == {"a"} and avg["a"] >= 0 and t.counts == {}
+
+
+def _episodes():
+    eps = {}
+    for d, n in enumerate([5, 3]):
+        base = 100 * (d + 1)
+        eps[f"demo_{d}"] = {"obs": {"z": (base + np.arange(n, dtype=np.float32))[:, None] * np.ones((1, 2), np.float32),
+                                    "q": (base + np.arange(n, dtype=np.float32))[:, None]},
+                            "actions": (base + np.arange(n, dtype=np.float32))[:, None] * np.ones((1, 3), np.float32)}
+    return eps
+
+
+def test_window_sampler_edge_padding():
+    """data/robomimic_latent_data.py:116-147: clip the window to the demo, repeat the first / last frame."""
+    ds = TB.LatentSequenceDataset(_episodes(), ["z", "q"], seq_length=4, n_frame_stack=2)
+    assert len(ds) == 8
+    it = ds.get_item(0)                                   # first step of demo 0: one frame of start padding
+    assert it["obs"]["q"][:, 0].tolist() == [100, 100, 101, 102, 103] and it["actions"][:, 0].tolist() == [100, 101, 102, 103]
+    it = ds.get_item(3)                                   # window runs past the end of demo 0 (length 5)
+    assert it["obs"]["q"][:, 0].tolist() == [102, 103, 104, 104, 104] and it["actions"][:, 0].tolist() == [103, 104, 104, 104]
+    it = ds.get_item(5)                                   # first step of demo 1: never reaches back into demo 0
+    assert it["obs"]["z"][:, 1].tolist() == [200, 200, 201, 202, 202] and it["obs"]["z"].shape == (5, 2)
+    it = ds.get_item(7)                                   # last step of demo 1
+    assert it["actions"][:, 2].tolist() == [202, 202, 202, 202]
+    with pytest.raises(ValueError):
+        bad = _episodes()
+        bad["demo_0"]["obs"]["q"] = bad["demo_0"]["obs"]["q"][:-1]
+        TB.LatentSequenceDataset(bad, ["z", "q"], 4)
+
+
+def test_sample_batch_shards_one_global_draw():
+    ds = TB.LatentSequenceDataset(_episodes(), ["z", "q"], seq_length=3)
+    full = ds.sample_batch(8, np.random.default_rng(5))
+    parts = [ds.sample_batch(8, np.random.default_rng(5), rank=r, world=2) for r in range(2)]
+    assert full["actions"].shape == (8, 3, 3) and parts[0]["obs"]["z"].shape == (4, 3, 2)
+    assert np.array_equal(np.concatenate([p["actions"].numpy() for p in parts]), full["actions"].numpy())
+    with pytest.raises(AssertionError):
+        ds.sample_batch(7, np.random.default_rng(0), 0, 2)
+
+
+def test_csv_logger_averages_between_dumps(tmp_path):
+    lg = TB.CSVLogger(tmp_path)
+    lg.log_metrics({"loss": 2.0, "lr": 1e-3}, 10)
+    lg.log_metrics({"loss": 4.0, "lr": 1e-3, "skip": None}, 20)
+    row = lg.dump(20)
+    assert row["loss"] == 3.0 and row["step"] == 20
+    lg.log_metrics({"loss": 1.0, "extra": 5.0}, 30)
+    lg.dump(30)
+    rows = list(csv.DictReader(open(tmp_path / "train.csv")))
+    assert [r["step"] for r in rows] == ["20", "30"] and rows[1]["extra"] == "5.0" and rows[0]["extra"] == ""

@@ -255,3 +255,44 @@ def test_update_gating(cuda):
     assert m1["planner_lr"] == 0 and m1["noise_diff"] == 0 and float(m1["plan_loss"]) == 0 and float(m1["idm_loss"]) > 0
     _, m2 = ag.update_mixed(_train_batch(2), _train_batch(2, seed=5), 2, 2)
     assert m2["planner_step"] == 1 and m2["idm_step"] == 1
+
+
+def test_workspace_run_logs_saves_and_restores(cuda, tmp_path):
+    """train_bc Workspace mirror: 6 updates on window-sampled latent episodes, the reference's cadence (log / dump /
+    save / eval), then a snapshot restored into a fresh agent reproduces the trained network."""
+    import csv
+    from latent_diffusion_planning_b200 import params as P, train_bc as TB
+    from latent_diffusion_planning_b200.agent import LDPAgent
+    g = np.random.default_rng(0)
+    eps = {}
+    for d, n in enumerate([12, 9, 15]):
+        eps[f"demo_{d}"] = {"obs": {"latent_agentview_image": g.normal(0, 3, (n, 16)).astype(np.float32),
+                                    **{k: g.uniform(-0.4, 0.4, (n, SHAPES[k][0])).astype(np.float32) for k in LOWDIM}},
+                            "actions": g.normal(0, 0.5, (n, 7)).astype(np.float32)}
+    keys = ["latent_agentview_image"] + LOWDIM
+    ds = TB.LatentSequenceDataset(eps, keys, seq_length=9, n_frame_stack=1)
+    mk = lambda: LDPAgent.create(2, None, {"ac_dim": 7, "all_shapes": SHAPES}, planner=dict(down_dims=(256,), diffusion_step_embed_dim=32),
+                                 rgb_obs=["latent_agentview_image"], lowdim_obs=LOWDIM, obs_normalization=_norm(), vae_feature_dim=16,
+                                 vae_block_out_channels=(32,) * 6, planner_n_diffusion_steps=4, idm_n_diffusion_steps=4,
+                                 precision="bf16", lr=1e-3, warmup_steps=2, decay_steps=20)
+    ws = TB.Workspace(mk(), ds, tmp_path, eval_dataset=ds, batch_size=8, n_grad_steps=6, log_every_step=2, dump_every_step=3,
+                      save_every_step=6, eval_every_step=6, n_eval_batches=1)
+    last = ws.run()
+    assert ws.step == 6 and np.isfinite(last["loss"])
+    train_rows = list(csv.DictReader(open(tmp_path / "train.csv")))
+    assert [r["step"] for r in train_rows] == ["3", "6"] and float(train_rows[-1]["planner_step"]) >= 3
+    eval_rows = list(csv.DictReader(open(tmp_path / "eval.csv")))
+    assert len(eval_rows) == 1 and {"evaldata/action_mse", "evaldata/plan_loss", "evaldata/full_action_mse", "evaldata/plan_mse"} <= set(eval_rows[0])
+    ck = tmp_path / "ckpt" / "6.ckpt.npz"
+    assert ck.exists()
+    fresh = TB.Workspace(mk(), ds, tmp_path / "b", batch_size=8)
+    fresh.load_snapshot(ck)
+    assert fresh.step == 6
+    a, b = P.unnest(ws.agent.get_params()["planner_params"]), P.unnest(fresh.agent.get_params()["planner_params"])
+    assert all(np.array_equal(a[k], b[k]) for k in a)
+    batch = ds.sample_batch(4, np.random.default_rng(1))
+    x = ws.agent.sample_action(batch, 3)
+    y = fresh.agent.sample_action(batch, 3)
+    assert torch.equal(x, y)
+    with pytest.raises(TypeError):
+        TB.Workspace(mk(), ds, tmp_path / "c", bogus=1)
