@@ -646,8 +646,12 @@ struct TcDense {
       for (int i = 1; i < 4; ++i) op.map_a[i] = op.map_a[0];
       uint64_t bd[2] = {(uint64_t)kp, (uint64_t)n_pad};
       uint64_t bs[1] = {(uint64_t)kp * 2};
-      uint32_t bb[2] = {64, 128};
+      // 128-wide tiles leave most SMs idle on the small-M layers (batch 256: 16 x 2 tiles): halve the tile there
+      static const int force_bn = getenv("LDP_TRAIN_BN") ? atoi(getenv("LDP_TRAIN_BN")) : 0;
+      const int bn = force_bn ? force_bn : ((ceil_div(M, 128) * ceil_div(N, 128) < 120 && N > 64) ? 64 : 128);
+      uint32_t bb[2] = {64, (uint32_t)bn};
       LDP_TRY(make_tmap_bf16(&op.map_b, wt, 2, bd, bs, bb));
+      op.block_n = bn;
       TcRun run;
       run.src_acc = make_stage(0, 0, 1, 0, 0, 0, 0).src_acc; run.count = kp / 64;
       TcRun* run_dev;
@@ -655,7 +659,7 @@ struct TcDense {
       LDP_CUDA_OK(cudaMemcpyAsync(run_dev, &run, sizeof(run), cudaMemcpyHostToDevice, s));
       op.kb = kb_dev; op.num_kb = kp / 64; op.runs = run_dev; op.num_runs = 1;
       tc_set_inline_runs(&op, &run, 1);
-      op.M = M; op.N = N; op.block_n = 128; op.items_per_tile = 128; op.rows_per_item = 1;
+      op.M = M; op.N = N; op.items_per_tile = 128; op.rows_per_item = 1;
       op.mode = TC_EPI_PLAIN; op.bias = bias; op.relu = relu;
       op.res_f32 = res; op.ld_res_f32 = ldres; op.out_f32 = out; op.ld_out_f32 = ldo;
       it = ops.emplace(key, op).first;
