@@ -673,6 +673,11 @@ struct TrainCtx {
   int prec = LDP_PREC_FP32;
   TcDense* tc = nullptr;
   Scratch *sa = nullptr, *sw = nullptr;   // A-operand and W-operand scratch
+  // bf16 path: weight gradients run on a side stream with their own scratch, next to the data gradients on `s` - the
+  // two only share dY as an input, and most GEMMs at batch 256 fill a fraction of the SMs
+  cudaStream_t s2 = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  Scratch *sa2 = nullptr, *sw2 = nullptr;
 };
 
 #define LDP_TN(var, ws, rows, c, grad)                                                            \
@@ -771,9 +776,35 @@ static int conv_wgrad(const Tn& x1, const Tn* x2, const Geo& g, float* dw, float
   return launch_wgrad_f32(q, s);
 }
 
+// the weight gradient of one layer, on the side stream when there is one (dY is complete on `s` at this point)
+static int conv_wgrad_side(const Tn& x1, const Tn* x2, const Geo& g, float* dw, float* db, int cout, const Tn& y, TrainCtx& cx) {
+  if (cx.prec != LDP_PREC_BF16 || !cx.s2) return conv_wgrad(x1, x2, g, dw, db, cout, y, cx);
+  LDP_CUDA_OK(cudaEventRecord(cx.ev_fork, cx.s));
+  LDP_CUDA_OK(cudaStreamWaitEvent(cx.s2, cx.ev_fork, 0));
+  TrainCtx c2 = cx;
+  c2.s = cx.s2; c2.sa = cx.sa2; c2.sw = cx.sw2; c2.s2 = nullptr;
+  return conv_wgrad(x1, x2, g, dw, db, cout, y, c2);
+}
+// a context on the side stream, ordered after everything issued on `s` so far (falls back to `cx` itself)
+static int fork_side(TrainCtx& cx, TrainCtx* c2) {
+  *c2 = cx;
+  if (cx.prec != LDP_PREC_BF16 || !cx.s2) return LDP_OK;
+  LDP_CUDA_OK(cudaEventRecord(cx.ev_fork, cx.s));
+  LDP_CUDA_OK(cudaStreamWaitEvent(cx.s2, cx.ev_fork, 0));
+  c2->s = cx.s2; c2->sa = cx.sa2; c2->sw = cx.sw2; c2->s2 = nullptr;
+  return LDP_OK;
+}
+// the main stream waits for everything issued on the side stream so far
+static int join_side(TrainCtx& cx) {
+  if (cx.prec != LDP_PREC_BF16 || !cx.s2) return LDP_OK;
+  LDP_CUDA_OK(cudaEventRecord(cx.ev_join, cx.s2));
+  LDP_CUDA_OK(cudaStreamWaitEvent(cx.s, cx.ev_join, 0));
+  return LDP_OK;
+}
+
 static int conv_bwd(Tn* x1, Tn* x2, const Geo& g, const float* w, float* dw, float* db, int cout, const Tn& y,
                     TrainCtx& cx) {
-  LDP_TRY(conv_wgrad(*x1, x2, g, dw, db, cout, y, cx));
+  LDP_TRY(conv_wgrad_side(*x1, x2, g, dw, db, cout, y, cx));
   const int ctot = x1->c + (x2 ? x2->c : 0);
   LDP_TRY(conv_dgrad(x1, 0, ctot, g, w, cout, y, cx));
   if (x2) LDP_TRY(conv_dgrad(x2, x1->c, ctot, g, w, cout, y, cx));
@@ -824,7 +855,22 @@ struct LdpTrainer {
   int64_t n_params = 0;
   TrainWs ws;
   TcDense tc;
-  Scratch scratch_a, scratch_w;
+  Scratch scratch_a, scratch_w, scratch_a2, scratch_w2;
+  cudaStream_t side = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  LdpTrainer() {
+    const char* e = getenv("LDP_TRAIN_STREAMS");
+    if (!(e && e[0] == '1')) {
+      cudaStreamCreateWithFlags(&side, cudaStreamNonBlocking);
+      cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming);
+      cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming);
+    }
+  }
+  ~LdpTrainer() {
+    if (side) { cudaStreamSynchronize(side); cudaStreamDestroy(side); }
+    if (ev_fork) cudaEventDestroy(ev_fork);
+    if (ev_join) cudaEventDestroy(ev_join);
+  }
 };
 
 namespace ldp {
@@ -879,7 +925,7 @@ struct CrbT {
 static int unet_loss_grad(LdpTrainer* h, int prec, const float* params, float* grads, const float* x0,
                           const float* noise, const int32_t* t, const float* cond, int B, int T, float weight,
                           float* loss_dev, cudaStream_t s) {
-  TrainCtx cx{s, prec, &h->tc, &h->scratch_a, &h->scratch_w};
+  TrainCtx cx{s, prec, &h->tc, &h->scratch_a, &h->scratch_w, h->side, h->ev_fork, h->ev_join, &h->scratch_a2, &h->scratch_w2};
   const LdpUnetConfig& c = h->ucfg;
   const int nl = c.n_levels, ds = c.step_embed_dim, dc = c.global_cond_dim, cd = ds + dc, D = c.input_dim, G = c.n_groups;
   LDP_CHECK(T > 0 && (T % (1 << (nl - 1))) == 0, LDP_ERR_UNSUPPORTED, "T must be a multiple of 2^(n_levels-1)");
@@ -928,17 +974,21 @@ static int unet_loss_grad(LdpTrainer* h, int prec, const float* params, float* g
     LDP_TN(c2, ws, rows, cout, true);
     LDP_TN(o, ws, rows, cout, true);
     b.c1 = c1; b.e = e; b.h1 = h1; b.c2 = c2; b.out = o; b.r = nullptr;
-    LDP_TRY(conv_fwd(*x1, x2, g5, b.c1w.w, b.c1b.w, cout, 0, nullptr, c1, cx));
-    LDP_TRY(conv_fwd(*mg, nullptr, dense, b.fw.w, b.fb.w, 2 * cout, 0, nullptr, e, cx));
-    LDP_TRY(gn_fwd(*c1, B, Tl, G, b.g1s, b.g1b, e, nullptr, h1, s));
-    LDP_TRY(conv_fwd(*h1, nullptr, g5, b.c2w.w, b.c2b.w, cout, 0, nullptr, c2, cx));
+    // the FiLM Dense and the residual projection only need the block's inputs: side stream, next to the first conv
+    TrainCtx cside;
+    LDP_TRY(fork_side(cx, &cside));
+    LDP_TRY(conv_fwd(*mg, nullptr, dense, b.fw.w, b.fb.w, 2 * cout, 0, nullptr, e, cside));
     const Tn* res = x1;
     if (proj) {
       LDP_TN(r, ws, rows, cout, true);
       b.r = r;
-      LDP_TRY(conv_fwd(*x1, x2, g1, b.rw.w, b.rb.w, cout, 0, nullptr, r, cx));
+      LDP_TRY(conv_fwd(*x1, x2, g1, b.rw.w, b.rb.w, cout, 0, nullptr, r, cside));
       res = r;
     }
+    LDP_TRY(conv_fwd(*x1, x2, g5, b.c1w.w, b.c1b.w, cout, 0, nullptr, c1, cx));
+    LDP_TRY(join_side(cx));
+    LDP_TRY(gn_fwd(*c1, B, Tl, G, b.g1s, b.g1b, e, nullptr, h1, s));
+    LDP_TRY(conv_fwd(*h1, nullptr, g5, b.c2w.w, b.c2b.w, cout, 0, nullptr, c2, cx));
     LDP_TRY(gn_fwd(*c2, B, Tl, G, b.g2s, b.g2b, nullptr, res, o, s));
     blocks.push_back(b);
     *out = o;
@@ -1030,9 +1080,12 @@ static int unet_loss_grad(LdpTrainer* h, int prec, const float* params, float* g
     LDP_TRY(gn_bwd(b.c2, B, Tl, G, b.g2s, b.g2b, nullptr, res, *b.out, s));
     LDP_TRY(conv_bwd(b.h1, nullptr, g5b, b.c2w.w, b.c2w.g, b.c2b.g, cout, *b.c2, cx));
     LDP_TRY(gn_bwd(b.c1, B, Tl, G, b.g1s, b.g1b, b.e, nullptr, *b.h1, s));
+    // FiLM Dense backward entirely on the side stream: Mish(g)'s gradient is only ever accumulated there (in order)
+    TrainCtx cside;
+    LDP_TRY(fork_side(cx, &cside));
+    LDP_TRY(conv_bwd(mg, nullptr, dense, b.fw.w, b.fw.g, b.fb.g, 2 * cout, *b.e, cside));
     LDP_TRY(conv_bwd(b.x1, b.x2, g5b, b.c1w.w, b.c1w.g, b.c1b.g, cout, *b.c1, cx));
     if (b.proj) LDP_TRY(conv_bwd(b.x1, b.x2, g1b, b.rw.w, b.rw.g, b.rb.g, cout, *b.r, cx));
-    LDP_TRY(conv_bwd(mg, nullptr, dense, b.fw.w, b.fw.g, b.fb.g, 2 * cout, *b.e, cx));
     return LDP_OK;
   };
   // reverse creation order: resampling convs are interleaved with the blocks exactly as in the forward
@@ -1057,13 +1110,14 @@ static int unet_loss_grad(LdpTrainer* h, int prec, const float* params, float* g
     }
   }
   // conditioning path: mg = Mish(g); g[:, :ds] = Dense_1(Mish(Dense_0(sinusoid)))
+  LDP_TRY(join_side(cx));
   LDP_TRY(mish_bwd(gbuf, *mg, s));
   Tn temb_g = *gbuf;
   temb_g.c = ds;
   LDP_TRY(conv_bwd(hm, nullptr, dense, t1w.w, t1w.g, t1b.g, ds, temb_g, cx));
   LDP_TRY(mish_bwd(hid, *hm, s));
   LDP_TRY(conv_bwd(sin_in, nullptr, dense, t0w.w, t0w.g, t0b.g, ds * 4, *hid, cx));
-  return LDP_OK;
+  return join_side(cx);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1071,7 +1125,7 @@ static int unet_loss_grad(LdpTrainer* h, int prec, const float* params, float* g
 // ------------------------------------------------------------------------------------------------
 static int idm_loss_grad(LdpTrainer* h, int prec, const float* params, float* grads, const float* sdev, const float* a0,
                          const float* noise, const int32_t* t, int N, float weight, float* loss_dev, cudaStream_t s) {
-  TrainCtx cx{s, prec, &h->tc, &h->scratch_a, &h->scratch_w};
+  TrainCtx cx{s, prec, &h->tc, &h->scratch_a, &h->scratch_w, h->side, h->ev_fork, h->ev_join, &h->scratch_a2, &h->scratch_w2};
   const LdpIdmConfig& c = h->icfg;
   const int A = c.action_dim, S2 = 2 * c.obs_dim, H = c.hidden_dim, td = c.time_dim;
   TrainWs& ws = h->ws;
@@ -1168,7 +1222,7 @@ static int idm_loss_grad(LdpTrainer* h, int prec, const float* params, float* gr
   }
   // Dense_0: weight gradient over the whole input, data gradient only for the cond columns
   {
-    LDP_TRY(conv_wgrad(*xin, nullptr, dense, w0.g, b0.g, H, *h0, cx));
+    LDP_TRY(conv_wgrad_side(*xin, nullptr, dense, w0.g, b0.g, H, *h0, cx));
     LDP_TRY(conv_dgrad(&cond_view, A + S2, in_dim, dense, w0.w, H, *h0, cx));
   }
   for (int i = c.n_cond_layers - 1; i >= 0; --i) {
@@ -1181,7 +1235,7 @@ static int idm_loss_grad(LdpTrainer* h, int prec, const float* params, float* gr
       LDP_TRY(conv_bwd(L.x, nullptr, dense, L.w.w, L.w.g, L.b.g, L.n, *L.y, cx));
     }
   }
-  return LDP_OK;
+  return join_side(cx);
 }
 
 }  // namespace ldp
