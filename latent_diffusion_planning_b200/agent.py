@@ -65,6 +65,7 @@ class LDPAgent:
         self._train: Dict[str, Any] = {}          # name -> train.TrainState, built by the first update()
         self._stale = set()                       # networks whose inference handle lags the trained parameters
         self.data_parallel = True                 # update(): all-reduce gradients when a process group is initialised
+        self._side_stream = None
         self.vae_decoder, self.viz = vae_decoder, viz
         self.obs_normalization = obs_normalization
         self.config = config
@@ -395,6 +396,34 @@ class LDPAgent:
         metrics: Dict[str, Any] = {}
         plan_loss = idm_loss = torch.zeros((), device=obs_emb.device)
         states = []
+        # The two networks are independent: the (small, launch-bound) IDM step is issued first on a side stream and runs
+        # under the planner's; the streams join before the gradient exchange.
+        main = torch.cuda.current_stream()
+        side = None
+        if use_idm:
+            if use_planner:
+                if self._side_stream is None:
+                    self._side_stream = torch.cuda.Stream()
+                side = self._side_stream
+                side.wait_stream(main)
+            with torch.cuda.stream(side if side is not None else main):
+                if idm_batch is not batch:
+                    _, emb_i, act_i = self._train_inputs(idm_batch)
+                else:
+                    emb_i, act_i = obs_emb, action
+                ts = self._train_state("idm")
+                ts.zero_grad()
+                ssp = torch.cat([emb_i[:, oh - 1:-1], emb_i[:, oh:]], dim=-1)
+                ssp = ssp.reshape(-1, ssp.shape[-1]).contiguous()
+                a0 = act_i[:, :-1].reshape(-1, act_i.shape[-1]).contiguous()
+                n = a0.shape[0]
+                if ssp.shape[0] != n:
+                    raise ValueError(f"IDM pairs: {ssp.shape[0]} transitions but {n} actions (obs and actions must share their horizon)")
+                g = torch.Generator().manual_seed(seed * 2 + 1)
+                t = torch.randint(0, cfg["idm_n_diffusion_steps"], (n * world,), generator=g)[rank * n:(rank + 1) * n]
+                noise = H.philox_normal_rows(seed, STREAM_TRAIN_IDM, step, rank * n, n, a0.shape[1])
+                idm_loss = self.alpha_idm * ts.idm_loss_grad(ssp, a0, noise, t.to(obs_emb.device), self.alpha_idm)
+                states.append(("idm", ts))
         if use_planner:
             ts = self._train_state("planner")
             ts.zero_grad()
@@ -406,24 +435,8 @@ class LDPAgent:
             cond = obs_emb[:, :oh].reshape(B, -1).contiguous()
             plan_loss = self.alpha_planner * ts.planner_loss_grad(target, noise, t.to(obs_emb.device), cond, self.alpha_planner)
             states.append(("planner", ts))
-        if use_idm:
-            if idm_batch is not batch:
-                _, emb_i, act_i = self._train_inputs(idm_batch)
-            else:
-                emb_i, act_i = obs_emb, action
-            ts = self._train_state("idm")
-            ts.zero_grad()
-            ssp = torch.cat([emb_i[:, oh - 1:-1], emb_i[:, oh:]], dim=-1)
-            ssp = ssp.reshape(-1, ssp.shape[-1]).contiguous()
-            a0 = act_i[:, :-1].reshape(-1, act_i.shape[-1]).contiguous()
-            n = a0.shape[0]
-            if ssp.shape[0] != n:
-                raise ValueError(f"IDM pairs: {ssp.shape[0]} transitions but {n} actions (obs and actions must share their horizon)")
-            g = torch.Generator().manual_seed(seed * 2 + 1)
-            t = torch.randint(0, cfg["idm_n_diffusion_steps"], (n * world,), generator=g)[rank * n:(rank + 1) * n]
-            noise = H.philox_normal_rows(seed, STREAM_TRAIN_IDM, step, rank * n, n, a0.shape[1])
-            idm_loss = self.alpha_idm * ts.idm_loss_grad(ssp, a0, noise, t.to(obs_emb.device), self.alpha_idm)
-            states.append(("idm", ts))
+        if side is not None:
+            main.wait_stream(side)
         sq = torch.zeros((), device=obs_emb.device)
         scale = 1.0
         for _, ts in states:

@@ -858,7 +858,27 @@ struct LdpTrainer {
   Scratch scratch_a, scratch_w, scratch_a2, scratch_w2;
   cudaStream_t side = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  // Captured steps (bf16 path).  A step is ~750 launches plus ~120 cross-stream events: issued one by one the host is
+  // the bottleneck, replayed as a graph it is not.  Inputs are staged into fixed buffers so the graph's pointers hold.
+  struct GraphKey {
+    int a, b; const void *params, *grads, *loss; float weight;
+    bool operator<(const GraphKey& o) const {
+      return std::tie(a, b, params, grads, loss, weight) < std::tie(o.a, o.b, o.params, o.grads, o.loss, o.weight);
+    }
+  };
+  struct GraphSlot { int warm = 0; cudaGraphExec_t exec = nullptr; };
+  std::map<GraphKey, GraphSlot> graphs;
+  Scratch stage[4];
+  bool use_graph = true;
+  cudaStream_t cap_stream = nullptr;
+  void drop_graphs() {
+    for (auto& kv : graphs)
+      if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
+    graphs.clear();
+  }
   LdpTrainer() {
+    const char* ge = getenv("LDP_TRAIN_GRAPH");
+    use_graph = !(ge && ge[0] == '0');
     const char* e = getenv("LDP_TRAIN_STREAMS");
     if (!(e && e[0] == '1')) {
       cudaStreamCreateWithFlags(&side, cudaStreamNonBlocking);
@@ -867,6 +887,8 @@ struct LdpTrainer {
     }
   }
   ~LdpTrainer() {
+    drop_graphs();
+    if (cap_stream) cudaStreamDestroy(cap_stream);
     if (side) { cudaStreamSynchronize(side); cudaStreamDestroy(side); }
     if (ev_fork) cudaEventDestroy(ev_fork);
     if (ev_join) cudaEventDestroy(ev_join);
@@ -1240,6 +1262,59 @@ static int idm_loss_grad(LdpTrainer* h, int prec, const float* params, float* gr
 
 }  // namespace ldp
 
+namespace ldp {
+
+// Runs `body` (which only enqueues work on `s` and the trainer's side stream): directly the first time a key is seen
+// (workspace, scratch and tensor-map allocations happen then), captured into a graph the second time, replayed after.
+template <typename F>
+static int run_step(LdpTrainer* h, int prec, const LdpTrainer::GraphKey& key, cudaStream_t s, F&& body) {
+  if (prec != LDP_PREC_BF16 || !h->use_graph) return body(s);
+  // one shape at a time: the workspace is rebuilt when the shape changes, which would leave older graphs dangling
+  if (!h->graphs.empty() && h->graphs.find(key) == h->graphs.end()) h->drop_graphs();
+  LdpTrainer::GraphSlot& slot = h->graphs[key];
+  if (slot.exec) {
+    LDP_CUDA_OK(cudaGraphLaunch(slot.exec, s));
+    return LDP_OK;
+  }
+  // two direct passes first: the first grows the scratch buffers layer by layer (tensor maps built early in it point at
+  // buffers that were reallocated later), the second builds every tensor map against the final addresses
+  if (slot.warm < 2) {
+    ++slot.warm;
+    return body(s);
+  }
+  // capture on a private stream (the caller's may be the legacy default stream, which cannot be captured)
+  if (!h->cap_stream) LDP_CUDA_OK(cudaStreamCreateWithFlags(&h->cap_stream, cudaStreamNonBlocking));
+  cudaGraph_t graph = nullptr;
+  const long long before = launch_count_get();
+  cudaError_t e = cudaStreamBeginCapture(h->cap_stream, cudaStreamCaptureModeThreadLocal);
+  int st = LDP_OK;
+  if (e == cudaSuccess) {
+    st = body(h->cap_stream);
+    e = cudaStreamEndCapture(h->cap_stream, &graph);
+  }
+  count_launch((int)(before - launch_count_get()));     // captured launches did not execute
+  if (st == LDP_OK && e == cudaSuccess && graph) e = cudaGraphInstantiate(&slot.exec, graph, 0);
+  if (graph) cudaGraphDestroy(graph);
+  if (st != LDP_OK || e != cudaSuccess || !slot.exec) {
+    slot.exec = nullptr;
+    cudaGetLastError();
+    h->use_graph = false;                               // fall back to direct launches for good
+    return body(s);
+  }
+  LDP_CUDA_OK(cudaGraphLaunch(slot.exec, s));
+  return LDP_OK;
+}
+
+// copy a caller tensor into the trainer's fixed staging buffer i
+static int stage_in(LdpTrainer* h, int i, const void* src, size_t bytes, cudaStream_t s, const void** out) {
+  LDP_TRY(h->stage[i].ensure(bytes));
+  LDP_CUDA_OK(cudaMemcpyAsync(h->stage[i].p, src, bytes, cudaMemcpyDeviceToDevice, s));
+  *out = h->stage[i].p;
+  return LDP_OK;
+}
+
+}  // namespace ldp
+
 // ================================================================================================
 // C ABI
 // ================================================================================================
@@ -1280,8 +1355,20 @@ int ldp_unet_loss_grad(LdpTrainer* h, int precision, const float* params_dev, fl
   LDP_CHECK(params_dev && grads_dev && x0_dev && noise_dev && t_dev && cond_dev && loss_dev && B > 0 && T > 0,
             LDP_ERR_INVALID_ARG, "bad arguments");
   LDP_CHECK(precision == LDP_PREC_FP32 || precision == LDP_PREC_BF16, LDP_ERR_INVALID_ARG, "bad precision");
-  return unet_loss_grad(h, precision, params_dev, grads_dev, x0_dev, noise_dev, t_dev, cond_dev, B, T, loss_weight, loss_dev,
-                        (cudaStream_t)cuda_stream);
+  cudaStream_t s = (cudaStream_t)cuda_stream;
+  if (precision == LDP_PREC_BF16 && h->use_graph) {
+    const size_t nx = (size_t)B * T * h->ucfg.input_dim * 4;
+    const void *x0s, *zs, *ts, *cs;
+    LDP_TRY(stage_in(h, 0, x0_dev, nx, s, &x0s));
+    LDP_TRY(stage_in(h, 1, noise_dev, nx, s, &zs));
+    LDP_TRY(stage_in(h, 2, t_dev, (size_t)B * 4, s, &ts));
+    LDP_TRY(stage_in(h, 3, cond_dev, (size_t)B * h->ucfg.global_cond_dim * 4, s, &cs));
+    x0_dev = (const float*)x0s; noise_dev = (const float*)zs; t_dev = (const int32_t*)ts; cond_dev = (const float*)cs;
+  }
+  LdpTrainer::GraphKey key{B, T, params_dev, grads_dev, loss_dev, loss_weight};
+  return run_step(h, precision, key, s, [&](cudaStream_t st) {
+    return unet_loss_grad(h, precision, params_dev, grads_dev, x0_dev, noise_dev, t_dev, cond_dev, B, T, loss_weight, loss_dev, st);
+  });
 }
 
 int ldp_idm_loss_grad(LdpTrainer* h, int precision, const float* params_dev, float* grads_dev, const float* s_dev, const float* a0_dev,
@@ -1291,8 +1378,19 @@ int ldp_idm_loss_grad(LdpTrainer* h, int precision, const float* params_dev, flo
   LDP_CHECK(params_dev && grads_dev && s_dev && a0_dev && noise_dev && t_dev && loss_dev && N > 0, LDP_ERR_INVALID_ARG,
             "bad arguments");
   LDP_CHECK(precision == LDP_PREC_FP32 || precision == LDP_PREC_BF16, LDP_ERR_INVALID_ARG, "bad precision");
-  return idm_loss_grad(h, precision, params_dev, grads_dev, s_dev, a0_dev, noise_dev, t_dev, N, loss_weight, loss_dev,
-                       (cudaStream_t)cuda_stream);
+  cudaStream_t s = (cudaStream_t)cuda_stream;
+  if (precision == LDP_PREC_BF16 && h->use_graph) {
+    const void *ss, *as, *zs, *ts;
+    LDP_TRY(stage_in(h, 0, s_dev, (size_t)N * 2 * h->icfg.obs_dim * 4, s, &ss));
+    LDP_TRY(stage_in(h, 1, a0_dev, (size_t)N * h->icfg.action_dim * 4, s, &as));
+    LDP_TRY(stage_in(h, 2, noise_dev, (size_t)N * h->icfg.action_dim * 4, s, &zs));
+    LDP_TRY(stage_in(h, 3, t_dev, (size_t)N * 4, s, &ts));
+    s_dev = (const float*)ss; a0_dev = (const float*)as; noise_dev = (const float*)zs; t_dev = (const int32_t*)ts;
+  }
+  LdpTrainer::GraphKey key{N, 0, params_dev, grads_dev, loss_dev, loss_weight};
+  return run_step(h, precision, key, s, [&](cudaStream_t st) {
+    return idm_loss_grad(h, precision, params_dev, grads_dev, s_dev, a0_dev, noise_dev, t_dev, N, loss_weight, loss_dev, st);
+  });
 }
 
 int ldp_adam_update(float* params_dev, const float* grads_dev, float* mu_dev, float* nu_dev, uint64_t n, float lr,
