@@ -396,51 +396,70 @@ class LDPAgent:
         metrics: Dict[str, Any] = {}
         plan_loss = idm_loss = torch.zeros((), device=obs_emb.device)
         states = []
-        # The two networks are independent: the (small, launch-bound) IDM step is issued first on a side stream and runs
-        # under the planner's; the streams join before the gradient exchange.
-        main = torch.cuda.current_stream()
-        side = None
-        if use_idm:
-            if use_planner:
-                if self._side_stream is None:
-                    self._side_stream = torch.cuda.Stream()
-                side = self._side_stream
-                side.wait_stream(main)
-            with torch.cuda.stream(side if side is not None else main):
-                if idm_batch is not batch:
-                    _, emb_i, act_i = self._train_inputs(idm_batch)
-                else:
-                    emb_i, act_i = obs_emb, action
-                ts = self._train_state("idm")
-                ts.zero_grad()
-                ssp = torch.cat([emb_i[:, oh - 1:-1], emb_i[:, oh:]], dim=-1)
-                ssp = ssp.reshape(-1, ssp.shape[-1]).contiguous()
-                a0 = act_i[:, :-1].reshape(-1, act_i.shape[-1]).contiguous()
-                n = a0.shape[0]
-                if ssp.shape[0] != n:
-                    raise ValueError(f"IDM pairs: {ssp.shape[0]} transitions but {n} actions (obs and actions must share their horizon)")
-                g = torch.Generator().manual_seed(seed * 2 + 1)
-                t = torch.randint(0, cfg["idm_n_diffusion_steps"], (n * world,), generator=g)[rank * n:(rank + 1) * n]
-                noise = H.philox_normal_rows(seed, STREAM_TRAIN_IDM, step, rank * n, n, a0.shape[1])
-                idm_loss = self.alpha_idm * ts.idm_loss_grad(ssp, a0, noise, t.to(obs_emb.device), self.alpha_idm)
-                states.append(("idm", ts))
-        if use_planner:
+        losses = {}
+
+        def run_idm():
+            emb_i, act_i = (obs_emb, action) if idm_batch is batch else self._train_inputs(idm_batch)[1:]
+            ts = self._train_state("idm")
+            ts.zero_grad()
+            ssp = torch.cat([emb_i[:, oh - 1:-1], emb_i[:, oh:]], dim=-1)
+            ssp = ssp.reshape(-1, ssp.shape[-1]).contiguous()
+            a0 = act_i[:, :-1].reshape(-1, act_i.shape[-1]).contiguous()
+            n = a0.shape[0]
+            if ssp.shape[0] != n:
+                raise ValueError(f"IDM pairs: {ssp.shape[0]} transitions but {n} actions (obs and actions must share their horizon)")
+            g = torch.Generator().manual_seed(seed * 2 + 1)      # timesteps of the GLOBAL batch, then this rank's slice
+            t = torch.randint(0, cfg["idm_n_diffusion_steps"], (n * world,), generator=g)[rank * n:(rank + 1) * n]
+            noise = H.philox_normal_rows(seed, STREAM_TRAIN_IDM, step, rank * n, n, a0.shape[1])
+            losses["idm"] = self.alpha_idm * ts.idm_loss_grad(ssp, a0, noise, t.to(obs_emb.device), self.alpha_idm)
+            states.append(("idm", ts))
+            return ts
+
+        def run_planner():
             ts = self._train_state("planner")
             ts.zero_grad()
             target = obs_emb[:, oh:].contiguous()
             T, D = target.shape[1], target.shape[2]
-            g = torch.Generator().manual_seed(seed * 2 + 0)      # timesteps of the GLOBAL batch, then this rank's slice
+            g = torch.Generator().manual_seed(seed * 2 + 0)
             t = torch.randint(0, cfg["planner_n_diffusion_steps"], (B * world,), generator=g)[rank * B:(rank + 1) * B]
             noise = H.philox_normal_rows(seed, STREAM_TRAIN_PLANNER, step, rank * B * T, B * T, D).reshape(B, T, D)
             cond = obs_emb[:, :oh].reshape(B, -1).contiguous()
-            plan_loss = self.alpha_planner * ts.planner_loss_grad(target, noise, t.to(obs_emb.device), cond, self.alpha_planner)
+            losses["planner"] = self.alpha_planner * ts.planner_loss_grad(target, noise, t.to(obs_emb.device), cond, self.alpha_planner)
             states.append(("planner", ts))
-        if side is not None:
-            main.wait_stream(side)
-        sq = torch.zeros((), device=obs_emb.device)
+            return ts
+
         scale = 1.0
+        if world == 1:
+            # The two networks are independent: the (small, launch-bound) IDM step is issued first on a side stream and
+            # runs under the planner's; the streams join before the optimiser.
+            main = torch.cuda.current_stream()
+            side = None
+            if use_idm:
+                if use_planner:
+                    if self._side_stream is None:
+                        self._side_stream = torch.cuda.Stream()
+                    side = self._side_stream
+                    side.wait_stream(main)
+                with torch.cuda.stream(side if side is not None else main):
+                    run_idm()
+            if use_planner:
+                run_planner()
+            if side is not None:
+                main.wait_stream(side)
+        else:
+            # Data parallel: the planner's gradient buffer (278 MB) starts its all-reduce as soon as its backward is done
+            # and the IDM step runs under it; one collective per network, nothing else on the wire but three loss scalars.
+            pending = []
+            if use_planner:
+                pending.append(dist.all_reduce(run_planner().grads, op=dist.ReduceOp.SUM, async_op=True))
+            if use_idm:
+                pending.append(dist.all_reduce(run_idm().grads, op=dist.ReduceOp.SUM, async_op=True))
+            for work in pending:
+                work.wait()
+            scale = 1.0 / world
+        plan_loss, idm_loss = losses.get("planner", plan_loss), losses.get("idm", idm_loss)
+        sq = torch.zeros((), device=obs_emb.device)
         for _, ts in states:
-            scale = TR.allreduce_grads(ts.grads) if world > 1 else 1.0
             sq = sq + (torch.linalg.vector_norm(ts.grads) * scale) ** 2
         loss = plan_loss + idm_loss
         if world > 1:
