@@ -205,6 +205,10 @@ __global__ void __launch_bounds__(256) gn_bwd_f32_kernel(const GnBwdF32 p) {
   const float rstd = rsqrtf(fmaxf(ss / cnt - mean * mean, 0.f) + p.eps);
   const float* frow = p.film ? p.film + (long long)b * 2 * p.C : nullptr;
   float s1 = 0.f, s2 = 0.f;
+  // when the group width divides the block size a thread always sees the same channel: per-channel sums stay in
+  // registers and are combined once; otherwise shared-memory atomics per element
+  const bool fixed_c = (blockDim.x % gw) == 0;
+  float a_dg = 0.f, a_db = 0.f, a_ds = 0.f, a_dh = 0.f;
   for (int i = threadIdx.x; i < cnt; i += blockDim.x) {
     int pos = i / gw, c = i - pos * gw, ch = g * gw + c;
     float xh = (xb[(long long)pos * p.C + c] - mean) * rstd;
@@ -214,13 +218,13 @@ __global__ void __launch_bounds__(256) gn_bwd_f32_kernel(const GnBwdF32 p) {
     float dyv = dyb[(long long)pos * p.C + c];
     float dm = dyv;
     if (frow) {
-      atomicAdd(&s_ch[2 * gw + c], dyv * mv);
-      atomicAdd(&s_ch[3 * gw + c], dyv);
+      if (fixed_c) { a_ds += dyv * mv; a_dh += dyv; }
+      else { atomicAdd(&s_ch[2 * gw + c], dyv * mv); atomicAdd(&s_ch[3 * gw + c], dyv); }
       dm = dyv * frow[ch];
     }
     float dn = dm * md;
-    atomicAdd(&s_ch[c], dn * xh);
-    atomicAdd(&s_ch[gw + c], dn);
+    if (fixed_c) { a_dg += dn * xh; a_db += dn; }
+    else { atomicAdd(&s_ch[c], dn * xh); atomicAdd(&s_ch[gw + c], dn); }
     float dxh = dn * p.gamma[ch];
     s_dxh[i] = dxh;
     s_xh[i] = xh;
@@ -230,6 +234,13 @@ __global__ void __launch_bounds__(256) gn_bwd_f32_kernel(const GnBwdF32 p) {
       float* d = p.dres + base + (long long)pos * p.C + c;
       *d = p.dres_acc ? *d + dyv : dyv;
     }
+  }
+  if (fixed_c && (int)threadIdx.x < cnt + (int)blockDim.x) {
+    // threads c, c + gw, c + 2 gw, ... own channel c: a handful of atomics per channel instead of one per element
+    const int c = threadIdx.x % gw;
+    atomicAdd(&s_ch[c], a_dg);
+    atomicAdd(&s_ch[gw + c], a_db);
+    if (frow) { atomicAdd(&s_ch[2 * gw + c], a_ds); atomicAdd(&s_ch[3 * gw + c], a_dh); }
   }
   s1 = block_sum_t(s1, sh) / cnt;
   s2 = block_sum_t(s2, sh) / cnt;
@@ -407,12 +418,12 @@ __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const 
   float4* m4 = reinterpret_cast<float4*>(mu);
   float4* v4 = reinterpret_cast<float4*>(nu);
   LDP_GRID_STRIDE(i, n4) {
-    float4 pv = p4[i], gv = __ldcs(g4 + i), mv = m4[i], vv = v4[i];
+    float4 pv = __ldcs(p4 + i), gv = __ldcs(g4 + i), mv = __ldcs(m4 + i), vv = __ldcs(v4 + i);   // 286 MB each: no reuse in L2
     adam_one(pv.x, gv.x, mv.x, vv.x, lr, b1, b2, eps, bc1, bc2, gscale);
     adam_one(pv.y, gv.y, mv.y, vv.y, lr, b1, b2, eps, bc1, bc2, gscale);
     adam_one(pv.z, gv.z, mv.z, vv.z, lr, b1, b2, eps, bc1, bc2, gscale);
     adam_one(pv.w, gv.w, mv.w, vv.w, lr, b1, b2, eps, bc1, bc2, gscale);
-    p4[i] = pv; m4[i] = mv; v4[i] = vv;
+    __stcs(p4 + i, pv); __stcs(m4 + i, mv); __stcs(v4 + i, vv);
   }
   for (long long i = (n4 << 2) + blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
     adam_one(p[i], g[i], mu[i], nu[i], lr, b1, b2, eps, bc1, bc2, gscale);
@@ -487,9 +498,26 @@ __global__ void __launch_bounds__(256) im2col_t_bf16_kernel(const Im2col p, __nv
   const int ctot = p.c1 + p.c2, K = p.taps * ctot;
   const int k0 = blockIdx.x * 32, m0 = blockIdx.y * 32;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-  for (int r = ty; r < 32; r += 8) {
-    int m = m0 + r, k = k0 + tx;
-    tile[r][tx] = (m < p.m && k < K) ? im2col_at(p, m, k, ctot) : 0.f;
+  {
+    // this thread's k (tap j, channel c) is fixed; only the row changes
+    const int k = k0 + tx;
+    const bool kok = k < K;
+    const int j = kok ? k / ctot : 0, c = kok ? k - j * ctot : 0;
+    const float* src = (c < p.c1) ? p.x1 + c : p.x2 + (c - p.c1);
+    const int ld = (c < p.c1) ? p.ld1 : p.ld2;
+    for (int r = ty; r < 32; r += 8) {
+      const int m = m0 + r;
+      float v = 0.f;
+      if (kok && m < p.m) {
+        const int b = m / p.t_out, t = m - b * p.t_out;
+        const int num = t * p.stride + j - p.pad;
+        if (num >= 0 && (num % p.dil) == 0) {
+          const int ti = num / p.dil;
+          if (ti < p.t_in) v = src[((long long)b * p.t_in + ti) * ld];
+        }
+      }
+      tile[r][tx] = v;
+    }
   }
   __syncthreads();
   for (int r = ty; r < 32; r += 8) {
