@@ -219,6 +219,13 @@ LDP_API int ldp_tc_dense(const float* a_dev, const float* w_host, const float* b
 LDP_API int64_t ldp_launch_count(void);
 LDP_API void ldp_launch_count_reset(void);
 
+/* jax.random on the device (jax 0.4.26 default threefry2x32 generator; row N4's optional RNG-stream compatibility):
+ * for each of n_keys raw keys (keys_dev: [n_keys][2] uint32) the n values `jax.random.bits(key, (n,), uint32)` (mode 0)
+ * or `jax.random.normal(key, (n,), float32)` (mode 1) -> out_dev [n_keys][n].  With the key threading of
+ * agent/ldp_agent.py:461-503 (restated in latent_diffusion_planning_b200/jax_random.py) the sampling loops can be fed
+ * the noise the reference would draw from the same PRNGKey.  Bits are exact; normal differs from XLA's erf_inv by ~1 ulp. */
+LDP_API int ldp_jax_random(const uint32_t* keys_dev, int n_keys, int64_t n, int mode, void* out_dev, void* cuda_stream);
+
 /* ---------------------------------------------------------------------------------------------------------
  * Training objective (next-row N1)  -  LDPAgent.update (agent/ldp_agent.py:229-277)
  * The caller owns flat float32 device buffers in the canonical spec order (params.unet_spec / params.idm_spec):

@@ -18,6 +18,7 @@ import numpy as np
 import torch
 
 from . import handles as H
+from . import jax_random as JR
 from . import params as P
 
 # Philox stream ids (disjoint streams for the independent draws of one act())
@@ -235,10 +236,16 @@ class LDPAgent:
         return normalize_unnormalize(a, spec, False) if spec else a
 
     # ---------------------------------------------------------------- sampling
-    def _idm_loop(self, ssp: torch.Tensor, seed: int, row_offset: int) -> torch.Tensor:
+    def _idm_loop(self, ssp: torch.Tensor, seed, row_offset: int) -> torch.Tensor:
         n, A = ssp.shape[0], self.config["action_dim"]
+        steps = self.config["idm_n_diffusion_steps"]
+        if JR.is_key(seed):                       # a raw JAX key: the reference's key threading and generator (:488-503)
+            start_key, step_keys, _ = JR.sampling_keys(seed, steps)
+            a_T = JR.normal(start_key, n * A).reshape(n, A)
+            noise = JR.normal(step_keys, n * A).reshape(steps, n, A) if self.sampler == "ddpm" else None
+            return self.idm.sample(ssp, a_T, noise=noise, n_steps=steps, sampler=self.sampler, precision=self.precision)
         a_T = H.philox_normal_rows(seed, STREAM_IDM_INIT, 0, row_offset, n, A)
-        return self.idm.sample(ssp, a_T, seed=seed, row_offset=row_offset, n_steps=self.config["idm_n_diffusion_steps"],
+        return self.idm.sample(ssp, a_T, seed=seed, row_offset=row_offset, n_steps=steps,
                                sampler=self.sampler, precision=self.precision)
 
     def vae_decode(self, feats: torch.Tensor) -> torch.Tensor:
@@ -261,15 +268,26 @@ class LDPAgent:
         """agent/ldp_agent.py:435-506: encode -> planner loop -> plan -> IDM loop -> actions.
         Returns `(action (B, Ha, A), {'plan': (B, Ha+1, D), 'plan_viz': (B, Ha+1, 3, S, S) | None[, 'plan_mse']})`;
         `plan_viz` is decoded when the agent was created with `viz=True` (reference :483 always decodes)."""
-        seed = int(eval_rng)
         cfg = self.config
         obs = self.vae_encode(self._postprocess_obs(batch["obs"]))
         obs_emb = self.get_obs_cond(obs)
         B, oh, T, D = obs_emb.shape[0], cfg["obs_horizon"], cfg["pred_horizon"], cfg["obs_dim"]
         obs_cond = obs_emb[:, :oh].reshape(B, -1).contiguous()
-        x_T = H.philox_normal_rows(seed, STREAM_PLANNER_INIT, 0, row_offset * T, B * T, D).reshape(B, T, D)
-        x0 = self.planner.sample(x_T, obs_cond, seed=seed, row_offset=row_offset, n_steps=cfg["planner_n_diffusion_steps"],
-                                 sampler=self.sampler, precision=self.precision)
+        steps = cfg["planner_n_diffusion_steps"]
+        if JR.is_key(eval_rng):
+            # `eval_rng` is a raw JAX PRNG key: draw what the reference draws (jax.random threefry, its split sequence,
+            # :461-476).  The draws depend on the full batch shape, so this mode is not shard-invariant.
+            if row_offset:
+                raise ValueError("JAX-key noise is drawn for the whole batch: row_offset must be 0")
+            start_key, step_keys, seed = JR.sampling_keys(eval_rng, steps)
+            x_T = JR.normal(start_key, B * T * D).reshape(B, T, D)
+            noise = JR.normal(step_keys, B * T * D).reshape(steps, B, T, D) if self.sampler == "ddpm" else None
+            x0 = self.planner.sample(x_T, obs_cond, noise=noise, n_steps=steps, sampler=self.sampler, precision=self.precision)
+        else:
+            seed = int(eval_rng)
+            x_T = H.philox_normal_rows(seed, STREAM_PLANNER_INIT, 0, row_offset * T, B * T, D).reshape(B, T, D)
+            x0 = self.planner.sample(x_T, obs_cond, seed=seed, row_offset=row_offset, n_steps=steps,
+                                     sampler=self.sampler, precision=self.precision)
         Ha = cfg["action_horizon"]
         plan = torch.cat([obs_emb[:, oh - 1:oh], x0[:, :Ha]], dim=1)
         ssp = torch.cat([plan[:, :-1], plan[:, 1:]], dim=-1).reshape(B * Ha, 2 * D).contiguous()
@@ -291,7 +309,7 @@ class LDPAgent:
         plan = self.get_obs_cond(obs)
         B, Hh, D = plan.shape
         ssp = torch.cat([plan[:, :-1], plan[:, 1:]], dim=-1).reshape(B * (Hh - 1), 2 * D).contiguous()
-        a = self._idm_loop(ssp, int(eval_rng), row_offset * (Hh - 1)).reshape(B, Hh - 1, self.config["action_dim"])
+        a = self._idm_loop(ssp, eval_rng if JR.is_key(eval_rng) else int(eval_rng), row_offset * (Hh - 1)).reshape(B, Hh - 1, self.config["action_dim"])
         return self._unnormalize_actions(a)
 
     def sample_action_from_plan(self, batch, next_plan: torch.Tensor, eval_rng, row_offset: int = 0) -> torch.Tensor:
@@ -300,7 +318,7 @@ class LDPAgent:
         start = self.get_obs_cond(obs)
         B, Hh, D = start.shape
         ssp = torch.cat([start, next_plan.to(start)], dim=-1).reshape(B * Hh, 2 * D).contiguous()
-        a = self._idm_loop(ssp, int(eval_rng), row_offset * Hh).reshape(B, Hh, self.config["action_dim"])
+        a = self._idm_loop(ssp, eval_rng if JR.is_key(eval_rng) else int(eval_rng), row_offset * Hh).reshape(B, Hh, self.config["action_dim"])
         return self._unnormalize_actions(a)
 
     def sample_sharded(self, batch, eval_rng, gather: bool = True):
@@ -387,7 +405,11 @@ class LDPAgent:
     def _update_step(self, batch, idm_batch, rng, step: int, use_planner: bool, use_idm: bool, apply: bool = True):
         import torch.distributed as dist
         from . import train as TR
-        seed, cfg = int(rng), self.config
+        cfg = self.config
+        # `rng`: an integer seed (counter-based Philox draws, shard-invariant) or a raw JAX key (the reference's generator
+        # and key threading, agent/ldp_agent.py:240 / :143-155 / :115 / :133)
+        jax_keys = JR.update_keys(rng, use_planner, use_idm) if JR.is_key(rng) else None
+        seed = 0 if jax_keys is not None else int(rng)
         oh = cfg["obs_horizon"]
         world = dist.get_world_size() if (self.data_parallel and dist.is_available() and dist.is_initialized()) else 1
         rank = dist.get_rank() if world > 1 else 0
@@ -408,9 +430,14 @@ class LDPAgent:
             n = a0.shape[0]
             if ssp.shape[0] != n:
                 raise ValueError(f"IDM pairs: {ssp.shape[0]} transitions but {n} actions (obs and actions must share their horizon)")
-            g = torch.Generator().manual_seed(seed * 2 + 1)      # timesteps of the GLOBAL batch, then this rank's slice
-            t = torch.randint(0, cfg["idm_n_diffusion_steps"], (n * world,), generator=g)[rank * n:(rank + 1) * n]
-            noise = H.philox_normal_rows(seed, STREAM_TRAIN_IDM, step, rank * n, n, a0.shape[1])
+            if jax_keys is not None:                             # the reference's draws, for the GLOBAL batch, sliced
+                t_key, z_key = jax_keys["idm"]
+                t = JR.randint(t_key, n * world, 0, cfg["idm_n_diffusion_steps"])[rank * n:(rank + 1) * n]
+                noise = JR.normal(z_key, n * world * a0.shape[1]).reshape(n * world, -1)[rank * n:(rank + 1) * n]
+            else:
+                g = torch.Generator().manual_seed(seed * 2 + 1)  # timesteps of the GLOBAL batch, then this rank's slice
+                t = torch.randint(0, cfg["idm_n_diffusion_steps"], (n * world,), generator=g)[rank * n:(rank + 1) * n]
+                noise = H.philox_normal_rows(seed, STREAM_TRAIN_IDM, step, rank * n, n, a0.shape[1])
             losses["idm"] = self.alpha_idm * ts.idm_loss_grad(ssp, a0, noise, t.to(obs_emb.device), self.alpha_idm)
             states.append(("idm", ts))
             return ts
@@ -420,9 +447,14 @@ class LDPAgent:
             ts.zero_grad()
             target = obs_emb[:, oh:].contiguous()
             T, D = target.shape[1], target.shape[2]
-            g = torch.Generator().manual_seed(seed * 2 + 0)
-            t = torch.randint(0, cfg["planner_n_diffusion_steps"], (B * world,), generator=g)[rank * B:(rank + 1) * B]
-            noise = H.philox_normal_rows(seed, STREAM_TRAIN_PLANNER, step, rank * B * T, B * T, D).reshape(B, T, D)
+            if jax_keys is not None:
+                t_key, z_key = jax_keys["planner"]
+                t = JR.randint(t_key, B * world, 0, cfg["planner_n_diffusion_steps"])[rank * B:(rank + 1) * B]
+                noise = JR.normal(z_key, B * world * T * D).reshape(B * world, T, D)[rank * B:(rank + 1) * B]
+            else:
+                g = torch.Generator().manual_seed(seed * 2 + 0)
+                t = torch.randint(0, cfg["planner_n_diffusion_steps"], (B * world,), generator=g)[rank * B:(rank + 1) * B]
+                noise = H.philox_normal_rows(seed, STREAM_TRAIN_PLANNER, step, rank * B * T, B * T, D).reshape(B, T, D)
             cond = obs_emb[:, :oh].reshape(B, -1).contiguous()
             losses["planner"] = self.alpha_planner * ts.planner_loss_grad(target, noise, t.to(obs_emb.device), cond, self.alpha_planner)
             states.append(("planner", ts))

@@ -114,6 +114,11 @@ int ldp_philox_normal_rows(uint64_t seed, uint32_t stream_id, uint32_t step, int
   return launch_philox_normal_rows(seed, stream_id, step, row0, rows, row_len, out_dev, (cudaStream_t)cuda_stream);
 }
 
+int ldp_jax_random(const uint32_t* keys_dev, int n_keys, int64_t n, int mode, void* out_dev, void* cuda_stream) {
+  LDP_CHECK(mode == 0 || mode == 1, LDP_ERR_INVALID_ARG, "mode must be 0 (bits) or 1 (normal)");
+  return launch_jax_random(keys_dev, n_keys, n, mode, out_dev, (cudaStream_t)cuda_stream);
+}
+
 int ldp_tc_dense(const float* a_dev, const float* w_host, const float* bias_host, float* c_dev, int M, int K, int N,
                  void* cuda_stream) {
   LDP_CHECK(a_dev && w_host && c_dev && M > 0 && K > 0 && N > 0, LDP_ERR_INVALID_ARG, "bad arguments");

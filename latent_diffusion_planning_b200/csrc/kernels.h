@@ -98,6 +98,8 @@ int launch_philox_normal(unsigned long long seed, uint32_t stream_id, uint32_t s
 // out[r][c] for r < rows, c < row_len: the row-structured normals the sampling loops draw (see DdpmCall)
 int launch_philox_normal_rows(unsigned long long seed, uint32_t stream_id, uint32_t step, long long row0, long long rows,
                               int row_len, float* out, cudaStream_t s);
+// jax.random (threefry2x32) for a batch of keys [n_keys][2]: out[key][n] = random_bits (mode 0, uint32) or normal (mode 1)
+int launch_jax_random(const uint32_t* keys_dev, int n_keys, long long n, int mode, void* out, cudaStream_t s);
 // out[(c / 4) * rows + r] (float4) = in[r * ld + c .. c+3]   (cols a multiple of 4)
 int launch_transpose_quads(const float* in, int ld, float* out, int rows, int cols, cudaStream_t s);
 int launch_add_i32(int32_t* p, int delta, cudaStream_t s);     // *p += delta (advances the device step counter)

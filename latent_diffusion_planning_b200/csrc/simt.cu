@@ -448,3 +448,64 @@ int launch_pack_wt_bf16(const float* src, int ld_src, int n_src, const int32_t* 
 }
 
 }  // namespace ldp
+
+// ------------------------------------------------------------------------------------------------
+// jax.random on the device (jax 0.4.26, threefry2x32, non-partitionable): random_bits / normal for a batch of keys.
+// Counter layout of `threefry_2x32(key, iota(n))`: counters padded to even length with a zero, first half -> x0,
+// second half -> x1, outputs concatenated.  One thread per counter pair.
+// ------------------------------------------------------------------------------------------------
+namespace ldp {
+
+__device__ __forceinline__ void threefry2x32_dev(uint32_t k0, uint32_t k1, uint32_t& x0, uint32_t& x1) {
+  const uint32_t ks[3] = {k0, k1, k0 ^ k1 ^ 0x1BD11BDAu};
+  x0 += ks[0];
+  x1 += ks[1];
+#pragma unroll
+  for (int i = 0; i < 5; ++i) {
+    const int r0 = (i & 1) ? 17 : 13, r1 = (i & 1) ? 29 : 15, r2 = (i & 1) ? 16 : 26, r3 = (i & 1) ? 24 : 6;
+    x0 += x1; x1 = __funnelshift_l(x1, x1, r0); x1 ^= x0;
+    x0 += x1; x1 = __funnelshift_l(x1, x1, r1); x1 ^= x0;
+    x0 += x1; x1 = __funnelshift_l(x1, x1, r2); x1 ^= x0;
+    x0 += x1; x1 = __funnelshift_l(x1, x1, r3); x1 ^= x0;
+    x0 += ks[(i + 1) % 3];
+    x1 += ks[(i + 2) % 3] + (uint32_t)(i + 1);
+  }
+}
+
+// jax.random.normal float32: u = bits -> [0,1); v = max(lo, u * (1 - lo) + lo), lo = nextafter(-1, 0); sqrt(2) erfinv(v)
+__device__ __forceinline__ float jax_normal_from_bits(uint32_t bits) {
+  const float u = __uint_as_float((bits >> 9) | 0x3F800000u) - 1.0f;
+  const float lo = -0.99999994f;
+  const float v = fmaxf(lo, __fadd_rn(__fmul_rn(u, 1.0f - lo), lo));
+  return __fmul_rn(1.41421354f, erfinvf(v));
+}
+
+__global__ void jax_random_kernel(const uint32_t* __restrict__ keys, long long n, int mode, void* __restrict__ out) {
+  const long long half = (n + 1) >> 1;
+  const uint32_t k0 = keys[2 * blockIdx.y], k1 = keys[2 * blockIdx.y + 1];
+  uint32_t* ob = reinterpret_cast<uint32_t*>(out) + (long long)blockIdx.y * n;
+  float* of = reinterpret_cast<float*>(out) + (long long)blockIdx.y * n;
+  for (long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x; p < half; p += (long long)gridDim.x * blockDim.x) {
+    uint32_t x0 = (uint32_t)p;
+    uint32_t x1 = (half + p < n) ? (uint32_t)(half + p) : 0u;     // the pad element of an odd-length counter vector
+    threefry2x32_dev(k0, k1, x0, x1);
+    if (mode == 0) {
+      ob[p] = x0;
+      if (half + p < n) ob[half + p] = x1;
+    } else {
+      of[p] = jax_normal_from_bits(x0);
+      if (half + p < n) of[half + p] = jax_normal_from_bits(x1);
+    }
+  }
+}
+
+int launch_jax_random(const uint32_t* keys_dev, int n_keys, long long n, int mode, void* out, cudaStream_t s) {
+  LDP_CHECK(keys_dev && out && n_keys > 0 && n > 0 && n < (1ll << 32), LDP_ERR_INVALID_ARG, "jax_random: bad arguments");
+  const long long half = (n + 1) >> 1;
+  const int bx = (int)std::min<long long>((half + 255) / 256, 148 * 16);
+  jax_random_kernel<<<dim3(bx, n_keys), 256, 0, s>>>(keys_dev, n, mode, out);
+  LDP_LAUNCH_OK();
+  return LDP_OK;
+}
+
+}  // namespace ldp
