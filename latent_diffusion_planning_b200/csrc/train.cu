@@ -417,8 +417,26 @@ __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const 
   const float4* g4 = reinterpret_cast<const float4*>(g);
   float4* m4 = reinterpret_cast<float4*>(mu);
   float4* v4 = reinterpret_cast<float4*>(nu);
-  LDP_GRID_STRIDE(i, n4) {
-    float4 pv = __ldcs(p4 + i), gv = __ldcs(g4 + i), mv = __ldcs(m4 + i), vv = __ldcs(v4 + i);   // 286 MB each: no reuse in L2
+  // two independent float4 quadruples per iteration: 8 loads of 16 bytes in flight per thread
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  for (; i + stride < n4; i += 2 * stride) {
+    const long long j = i + stride;
+    float4 pa = __ldcs(p4 + i), ga = __ldcs(g4 + i), ma = __ldcs(m4 + i), va = __ldcs(v4 + i);
+    float4 pb = __ldcs(p4 + j), gb = __ldcs(g4 + j), mb = __ldcs(m4 + j), vb = __ldcs(v4 + j);
+    adam_one(pa.x, ga.x, ma.x, va.x, lr, b1, b2, eps, bc1, bc2, gscale);
+    adam_one(pa.y, ga.y, ma.y, va.y, lr, b1, b2, eps, bc1, bc2, gscale);
+    adam_one(pa.z, ga.z, ma.z, va.z, lr, b1, b2, eps, bc1, bc2, gscale);
+    adam_one(pa.w, ga.w, ma.w, va.w, lr, b1, b2, eps, bc1, bc2, gscale);
+    adam_one(pb.x, gb.x, mb.x, vb.x, lr, b1, b2, eps, bc1, bc2, gscale);
+    adam_one(pb.y, gb.y, mb.y, vb.y, lr, b1, b2, eps, bc1, bc2, gscale);
+    adam_one(pb.z, gb.z, mb.z, vb.z, lr, b1, b2, eps, bc1, bc2, gscale);
+    adam_one(pb.w, gb.w, mb.w, vb.w, lr, b1, b2, eps, bc1, bc2, gscale);
+    __stcs(p4 + i, pa); __stcs(m4 + i, ma); __stcs(v4 + i, va);
+    __stcs(p4 + j, pb); __stcs(m4 + j, mb); __stcs(v4 + j, vb);
+  }
+  for (; i < n4; i += stride) {
+    float4 pv = __ldcs(p4 + i), gv = __ldcs(g4 + i), mv = __ldcs(m4 + i), vv = __ldcs(v4 + i);
     adam_one(pv.x, gv.x, mv.x, vv.x, lr, b1, b2, eps, bc1, bc2, gscale);
     adam_one(pv.y, gv.y, mv.y, vv.y, lr, b1, b2, eps, bc1, bc2, gscale);
     adam_one(pv.z, gv.z, mv.z, vv.z, lr, b1, b2, eps, bc1, bc2, gscale);
@@ -1428,7 +1446,7 @@ int ldp_adam_update(float* params_dev, const float* grads_dev, float* mu_dev, fl
   const float bc2 = (float)(1.0 - std::pow((double)b2, (double)count));
   LDP_CHECK((((uintptr_t)params_dev | (uintptr_t)grads_dev | (uintptr_t)mu_dev | (uintptr_t)nu_dev) & 15) == 0,
             LDP_ERR_INVALID_ARG, "adam: buffers must be 16-byte aligned");
-  adam_kernel<<<148 * 8, 256, 0, (cudaStream_t)cuda_stream>>>(params_dev, grads_dev, mu_dev, nu_dev,
+  adam_kernel<<<148 * 16, 256, 0, (cudaStream_t)cuda_stream>>>(params_dev, grads_dev, mu_dev, nu_dev,
                                                                               (long long)n, lr, b1, b2, eps, bc1, bc2,
                                                                               grad_scale);
   LDP_LAUNCH_OK();
