@@ -28,6 +28,34 @@ namespace ldp {
     count_launch();                                                                                         \
   } while (0)
 
+// Programmatic dependent launch for the small operand kernels of the bf16 path: launched with the stream-serialisation
+// attribute they may become resident while their predecessor drains; `pdl_enter()` is the first thing they execute -
+// wait until everything before them in the stream is complete and visible, then let their own dependent (the next
+// operand kernel, or the GEMM, whose producer waits on its own) start its prologue.  Nothing is read or written
+// before the wait, so shared scratch buffers are safe.
+__device__ __forceinline__ void pdl_enter() {
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+static bool train_use_pdl() {
+  static const bool on = !(getenv("LDP_TRAIN_PDL") && getenv("LDP_TRAIN_PDL")[0] == '0');
+  return on;
+}
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, cudaStream_t s, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = 0;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = train_use_pdl() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
 // ------------------------------------------------------------------------------------------------
 // weight gradient: dW[(j,c)][n] += sum_m A(m,(j,c)) dY[m][n];  dbias[n] += sum_m dY[m][n]
 // A is the same implicit-GEMM gather as the forward (kernels.h GemmF32).  64x64 tile of (k, n), m in steps of 16,
@@ -471,6 +499,7 @@ __device__ __forceinline__ float im2col_at(const Im2col& p, int m, int k, int ct
 }
 // A[m][k] for k < kp (zero beyond K)
 __global__ void im2col_bf16_kernel(const Im2col p, __nv_bfloat16* __restrict__ out, int kp) {
+  pdl_enter();
   const int ctot = p.c1 + p.c2, K = p.taps * ctot;
   LDP_GRID_STRIDE(i, (long long)p.m * kp) {
     int m = (int)(i / kp), k = (int)(i - (long long)m * kp);
@@ -479,6 +508,7 @@ __global__ void im2col_bf16_kernel(const Im2col p, __nv_bfloat16* __restrict__ o
 }
 // same, 8 consecutive k per thread: needs c1, c2, ld1, ld2 multiples of 8 (so a group never straddles a tap or source)
 __global__ void im2col8_bf16_kernel(const Im2col p, __nv_bfloat16* __restrict__ out, int kp) {
+  pdl_enter();
   const int ctot = p.c1 + p.c2, K = p.taps * ctot, kp8 = kp >> 3;
   LDP_GRID_STRIDE(i, (long long)p.m * kp8) {
     int m = (int)(i / kp8), k = (int)(i - (long long)m * kp8) << 3;
@@ -505,13 +535,14 @@ __global__ void im2col8_bf16_kernel(const Im2col p, __nv_bfloat16* __restrict__ 
 static int launch_im2col(const Im2col& q, __nv_bfloat16* out, int kp, cudaStream_t s) {
   const bool v8 = (q.c1 % 8) == 0 && (q.c2 % 8) == 0 && (q.ld1 % 8) == 0 && (q.c2 == 0 || (q.ld2 % 8) == 0) &&
                   (((uintptr_t)q.x1 | (uintptr_t)q.x2) & 15) == 0;
-  if (v8) im2col8_bf16_kernel<<<(int)std::min<long long>(((long long)q.m * (kp / 8) + 255) / 256, 148 * 8), 256, 0, s>>>(q, out, kp);
-  else im2col_bf16_kernel<<<(int)std::min<long long>(((long long)q.m * kp + 255) / 256, 148 * 8), 256, 0, s>>>(q, out, kp);
-  LDP_LAUNCH_OK();
+  if (v8) LDP_CUDA_OK(launch_pdl(im2col8_bf16_kernel, dim3((unsigned)std::min<long long>(((long long)q.m * (kp / 8) + 255) / 256, 148 * 8)), dim3(256), s, q, out, kp));
+  else LDP_CUDA_OK(launch_pdl(im2col_bf16_kernel, dim3((unsigned)std::min<long long>(((long long)q.m * kp + 255) / 256, 148 * 8)), dim3(256), s, q, out, kp));
+  count_launch();
   return LDP_OK;
 }
 // At[k][m] for m < mp (zero beyond M); 32x32 tiles through shared memory so both sides stay coalesced
 __global__ void __launch_bounds__(256) im2col_t_bf16_kernel(const Im2col p, __nv_bfloat16* __restrict__ out, int mp) {
+  pdl_enter();
   __shared__ float tile[32][33];
   const int ctot = p.c1 + p.c2, K = p.taps * ctot;
   const int k0 = blockIdx.x * 32, m0 = blockIdx.y * 32;
@@ -548,6 +579,7 @@ __global__ void __launch_bounds__(256) im2col_t_bf16_kernel(const Im2col p, __nv
 __global__ void __launch_bounds__(256) pack_t_bf16_kernel(const float* __restrict__ src, int ld, int K, int N,
                                                           __nv_bfloat16* __restrict__ dst, int kp, int n_pad,
                                                           float* __restrict__ colsum) {
+  pdl_enter();
   __shared__ float tile[32][33];
   const int n0 = blockIdx.x * 32, k0 = blockIdx.y * 32;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
@@ -570,6 +602,7 @@ __global__ void __launch_bounds__(256) pack_t_bf16_kernel(const float* __restric
 // data-gradient operand of a forward kernel W[taps][ctot][cout]:  dst[n = c][k = (j', co)] = W[taps-1-j'][c][co]
 __global__ void pack_dgrad_bf16_kernel(const float* __restrict__ w, int taps, int ctot, int cout,
                                        __nv_bfloat16* __restrict__ dst, int kp, int n_pad) {
+  pdl_enter();
   const int K = taps * cout;
   LDP_GRID_STRIDE(i, (long long)n_pad * kp) {
     int n = (int)(i / kp), k = (int)(i - (long long)n * kp);
@@ -584,6 +617,7 @@ __global__ void pack_dgrad_bf16_kernel(const float* __restrict__ w, int taps, in
 // same, 8 consecutive k per thread (cout a multiple of 8)
 __global__ void pack_dgrad8_bf16_kernel(const float* __restrict__ w, int taps, int ctot, int cout,
                                         __nv_bfloat16* __restrict__ dst, int kp, int n_pad) {
+  pdl_enter();
   const int K = taps * cout, kp8 = kp >> 3;
   LDP_GRID_STRIDE(i, (long long)n_pad * kp8) {
     int n = (int)(i / kp8), k = (int)(i - (long long)n * kp8) << 3;
@@ -749,8 +783,8 @@ static int conv_fwd(const Tn& x1, const Tn* x2, const Geo& g, const float* w, co
     __nv_bfloat16* A = (__nv_bfloat16*)cx.sa->p;
     __nv_bfloat16* W = (__nv_bfloat16*)cx.sw->p;
     LDP_TRY(launch_im2col(im2col_of(x1, x2, g, M), A, kp, s));
-    pack_t_bf16_kernel<<<dim3(n_pad / 32, kp / 32), 256, 0, s>>>(w, cout, K, cout, W, kp, n_pad, nullptr);
-    LDP_LAUNCH_OK();
+    LDP_CUDA_OK(launch_pdl(pack_t_bf16_kernel, dim3(n_pad / 32, kp / 32), dim3(256), s, w, cout, K, cout, W, kp, n_pad, (float*)nullptr));
+    count_launch();
     return cx.tc->gemm(A, kp, M, kp, W, n_pad, cout, bias, act, res ? res->v : nullptr, res ? res->ld : 0, y->v, y->ld, s);
   }
   GemmF32 p;
@@ -781,10 +815,10 @@ static int conv_dgrad(Tn* src, int coff, int ctot, const Geo& g, const float* w,
     dy.c = cout;
     LDP_TRY(launch_im2col(im2col_of(dy, nullptr, gt, M, true), A, kp, s));
     if ((cout % 8) == 0 && ((uintptr_t)w & 15) == 0)
-      pack_dgrad8_bf16_kernel<<<ew_blocks((long long)n_pad * (kp / 8)), 256, 0, s>>>(w, g.taps, ctot, cout, W, kp, n_pad);
+      LDP_CUDA_OK(launch_pdl(pack_dgrad8_bf16_kernel, dim3(ew_blocks((long long)n_pad * (kp / 8))), dim3(256), s, w, g.taps, ctot, cout, W, kp, n_pad));
     else
-      pack_dgrad_bf16_kernel<<<ew_blocks((long long)n_pad * kp), 256, 0, s>>>(w, g.taps, ctot, cout, W, kp, n_pad);
-    LDP_LAUNCH_OK();
+      LDP_CUDA_OK(launch_pdl(pack_dgrad_bf16_kernel, dim3(ew_blocks((long long)n_pad * kp)), dim3(256), s, w, g.taps, ctot, cout, W, kp, n_pad));
+    count_launch();
     // rows [coff, coff + src->c) of the pack are this source's channels
     return cx.tc->gemm(A, kp, M, kp, W + (size_t)coff * kp, round_up(src->c, 128), src->c, nullptr, 0,
                        acc ? src->g : nullptr, src->ld, src->g, src->ld, s);
@@ -807,10 +841,10 @@ static int conv_wgrad(const Tn& x1, const Tn* x2, const Geo& g, float* dw, float
     LDP_TRY(cx.sw->ensure((size_t)n_pad * mp * 2));
     __nv_bfloat16* At = (__nv_bfloat16*)cx.sa->p;
     __nv_bfloat16* Yt = (__nv_bfloat16*)cx.sw->p;
-    im2col_t_bf16_kernel<<<dim3(ceil_div(K, 32), mp / 32), 256, 0, s>>>(im2col_of(x1, x2, g, m), At, mp);
-    LDP_LAUNCH_OK();
-    pack_t_bf16_kernel<<<dim3(n_pad / 32, mp / 32), 256, 0, s>>>(y.g, y.ld, m, cout, Yt, mp, n_pad, db);
-    LDP_LAUNCH_OK();
+    LDP_CUDA_OK(launch_pdl(im2col_t_bf16_kernel, dim3(ceil_div(K, 32), mp / 32), dim3(256), s, im2col_of(x1, x2, g, m), At, mp));
+    count_launch();
+    LDP_CUDA_OK(launch_pdl(pack_t_bf16_kernel, dim3(n_pad / 32, mp / 32), dim3(256), s, (const float*)y.g, y.ld, m, cout, Yt, mp, n_pad, db));
+    count_launch();
     LDP_TRY(cx.tc->gemm(At, mp, K, mp, Yt, n_pad, cout, nullptr, 0, dw, cout, dw, cout, s));
     return LDP_OK;
   }
