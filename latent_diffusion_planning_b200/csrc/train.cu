@@ -497,55 +497,51 @@ __device__ __forceinline__ float im2col_at(const Im2col& p, int m, int k, int ct
   long long row = (long long)b * p.t_in + ti;
   return (c < p.c1) ? p.x1[row * p.ld1 + c] : p.x2[row * p.ld2 + (c - p.c1)];
 }
-// A[m][k] for k < kp (zero beyond K)
-__global__ void im2col_bf16_kernel(const Im2col p, __nv_bfloat16* __restrict__ out, int kp) {
-  pdl_enter();
+// ---- operand builders.  Each GEMM needs two of them (an A part and a W part); both run in ONE launch (`prep_kernel`),
+// the leading blocks on the A part and the rest on the W part - at batch 256 the step is bound by kernel boundaries,
+// not by bytes.  Grid-stride parts take (block id, block count); tiled parts take their 32x32 tile coordinates.
+
+// A[m][k] for k < kp (zero beyond K).  v8: 8 consecutive k per thread - needs c1, c2, ld1, ld2 multiples of 8 (a group
+// never straddles a tap or a source) and 16-byte aligned inputs.
+__device__ __forceinline__ void im2col_body(const Im2col& p, __nv_bfloat16* __restrict__ out, int kp, int v8, long long bid,
+                                            long long nb) {
   const int ctot = p.c1 + p.c2, K = p.taps * ctot;
-  LDP_GRID_STRIDE(i, (long long)p.m * kp) {
-    int m = (int)(i / kp), k = (int)(i - (long long)m * kp);
-    out[i] = __float2bfloat16(k < K ? im2col_at(p, m, k, ctot) : 0.f);
-  }
-}
-// same, 8 consecutive k per thread: needs c1, c2, ld1, ld2 multiples of 8 (so a group never straddles a tap or source)
-__global__ void im2col8_bf16_kernel(const Im2col p, __nv_bfloat16* __restrict__ out, int kp) {
-  pdl_enter();
-  const int ctot = p.c1 + p.c2, K = p.taps * ctot, kp8 = kp >> 3;
-  LDP_GRID_STRIDE(i, (long long)p.m * kp8) {
-    int m = (int)(i / kp8), k = (int)(i - (long long)m * kp8) << 3;
-    float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
-    if (k < K) {
-      int j = k / ctot, c = k - j * ctot;
-      int bi = m / p.t_out, t = m - bi * p.t_out;
-      int num = t * p.stride + j - p.pad;
-      if (num >= 0 && (num % p.dil) == 0) {
-        int ti = num / p.dil;
-        if (ti < p.t_in) {
-          long long row = (long long)bi * p.t_in + ti;
-          const float* src = (c < p.c1) ? p.x1 + row * p.ld1 + c : p.x2 + row * p.ld2 + (c - p.c1);
-          a = *reinterpret_cast<const float4*>(src);
-          b = *reinterpret_cast<const float4*>(src + 4);
+  if (v8) {
+    const int kp8 = kp >> 3;
+    for (long long i = bid * blockDim.x + threadIdx.x; i < (long long)p.m * kp8; i += nb * blockDim.x) {
+      int m = (int)(i / kp8), k = (int)(i - (long long)m * kp8) << 3;
+      float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
+      if (k < K) {
+        int j = k / ctot, c = k - j * ctot;
+        int bi = m / p.t_out, t = m - bi * p.t_out;
+        int num = t * p.stride + j - p.pad;
+        if (num >= 0 && (num % p.dil) == 0) {
+          int ti = num / p.dil;
+          if (ti < p.t_in) {
+            long long row = (long long)bi * p.t_in + ti;
+            const float* src = (c < p.c1) ? p.x1 + row * p.ld1 + c : p.x2 + row * p.ld2 + (c - p.c1);
+            a = *reinterpret_cast<const float4*>(src);
+            b = *reinterpret_cast<const float4*>(src + 4);
+          }
         }
       }
+      __nv_bfloat162 o[4] = {__floats2bfloat162_rn(a.x, a.y), __floats2bfloat162_rn(a.z, a.w),
+                             __floats2bfloat162_rn(b.x, b.y), __floats2bfloat162_rn(b.z, b.w)};
+      *reinterpret_cast<uint4*>(out + (long long)m * kp + k) = *reinterpret_cast<uint4*>(o);
     }
-    __nv_bfloat162 o[4] = {__floats2bfloat162_rn(a.x, a.y), __floats2bfloat162_rn(a.z, a.w),
-                           __floats2bfloat162_rn(b.x, b.y), __floats2bfloat162_rn(b.z, b.w)};
-    *reinterpret_cast<uint4*>(out + (long long)m * kp + k) = *reinterpret_cast<uint4*>(o);
+  } else {
+    for (long long i = bid * blockDim.x + threadIdx.x; i < (long long)p.m * kp; i += nb * blockDim.x) {
+      int m = (int)(i / kp), k = (int)(i - (long long)m * kp);
+      out[i] = __float2bfloat16(k < K ? im2col_at(p, m, k, ctot) : 0.f);
+    }
   }
 }
-static int launch_im2col(const Im2col& q, __nv_bfloat16* out, int kp, cudaStream_t s) {
-  const bool v8 = (q.c1 % 8) == 0 && (q.c2 % 8) == 0 && (q.ld1 % 8) == 0 && (q.c2 == 0 || (q.ld2 % 8) == 0) &&
-                  (((uintptr_t)q.x1 | (uintptr_t)q.x2) & 15) == 0;
-  if (v8) LDP_CUDA_OK(launch_pdl(im2col8_bf16_kernel, dim3((unsigned)std::min<long long>(((long long)q.m * (kp / 8) + 255) / 256, 148 * 8)), dim3(256), s, q, out, kp));
-  else LDP_CUDA_OK(launch_pdl(im2col_bf16_kernel, dim3((unsigned)std::min<long long>(((long long)q.m * kp + 255) / 256, 148 * 8)), dim3(256), s, q, out, kp));
-  count_launch();
-  return LDP_OK;
-}
-// At[k][m] for m < mp (zero beyond M); 32x32 tiles through shared memory so both sides stay coalesced
-__global__ void __launch_bounds__(256) im2col_t_bf16_kernel(const Im2col p, __nv_bfloat16* __restrict__ out, int mp) {
-  pdl_enter();
+
+// At[k][m] for m < mp (zero beyond M): the weight gradient reduces over rows.  32x32 tile (bx over k, by over m)
+__device__ __forceinline__ void im2col_t_body(const Im2col& p, __nv_bfloat16* __restrict__ out, int mp, int bx, int by) {
   __shared__ float tile[32][33];
   const int ctot = p.c1 + p.c2, K = p.taps * ctot;
-  const int k0 = blockIdx.x * 32, m0 = blockIdx.y * 32;
+  const int k0 = bx * 32, m0 = by * 32;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   {
     // this thread's k (tap j, channel c) is fixed; only the row changes
@@ -574,14 +570,13 @@ __global__ void __launch_bounds__(256) im2col_t_bf16_kernel(const Im2col p, __nv
     if (k < K && m < mp) out[(long long)k * mp + m] = __float2bfloat16(tile[tx][r]);
   }
 }
-// dst[n][k] = bf16(src[k*ld + n]) for n < n_pad, k < kp (zeros outside K x N): the K-major "W^T" operand.
-// colsum, if given, also receives sum_k src[k][n] (the bias gradient when src is dY).
-__global__ void __launch_bounds__(256) pack_t_bf16_kernel(const float* __restrict__ src, int ld, int K, int N,
-                                                          __nv_bfloat16* __restrict__ dst, int kp, int n_pad,
-                                                          float* __restrict__ colsum) {
-  pdl_enter();
+
+// dst[n][k] = bf16(src[k*ld + n]) for n < n_pad, k < kp (zeros outside K x N): the K-major "W^T" operand.  colsum, if
+// given, also receives sum_k src[k][n] (the bias gradient when src is dY).  32x32 tile (bx over n, by over k)
+__device__ __forceinline__ void pack_t_body(const float* __restrict__ src, int ld, int K, int N, __nv_bfloat16* __restrict__ dst,
+                                            int kp, int n_pad, float* __restrict__ colsum, int bx, int by) {
   __shared__ float tile[32][33];
-  const int n0 = blockIdx.x * 32, k0 = blockIdx.y * 32;
+  const int n0 = bx * 32, k0 = by * 32;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   for (int r = ty; r < 32; r += 8) {
     int k = k0 + r, n = n0 + tx;
@@ -599,40 +594,78 @@ __global__ void __launch_bounds__(256) pack_t_bf16_kernel(const float* __restric
     atomicAdd(colsum + n0 + tx, acc);
   }
 }
+
 // data-gradient operand of a forward kernel W[taps][ctot][cout]:  dst[n = c][k = (j', co)] = W[taps-1-j'][c][co]
-__global__ void pack_dgrad_bf16_kernel(const float* __restrict__ w, int taps, int ctot, int cout,
-                                       __nv_bfloat16* __restrict__ dst, int kp, int n_pad) {
-  pdl_enter();
+// (v8: 8 consecutive k per thread, cout a multiple of 8)
+__device__ __forceinline__ void pack_dgrad_body(const float* __restrict__ w, int taps, int ctot, int cout,
+                                                __nv_bfloat16* __restrict__ dst, int kp, int n_pad, int v8, long long bid,
+                                                long long nb) {
   const int K = taps * cout;
-  LDP_GRID_STRIDE(i, (long long)n_pad * kp) {
-    int n = (int)(i / kp), k = (int)(i - (long long)n * kp);
-    float v = 0.f;
-    if (n < ctot && k < K) {
-      int j = k / cout, co = k - j * cout;
-      v = w[((long long)(taps - 1 - j) * ctot + n) * cout + co];
+  if (v8) {
+    const int kp8 = kp >> 3;
+    for (long long i = bid * blockDim.x + threadIdx.x; i < (long long)n_pad * kp8; i += nb * blockDim.x) {
+      int n = (int)(i / kp8), k = (int)(i - (long long)n * kp8) << 3;
+      float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
+      if (n < ctot && k < K) {
+        int j = k / cout, co = k - j * cout;
+        const float* src = w + ((long long)(taps - 1 - j) * ctot + n) * cout + co;
+        a = *reinterpret_cast<const float4*>(src);
+        b = *reinterpret_cast<const float4*>(src + 4);
+      }
+      __nv_bfloat162 o[4] = {__floats2bfloat162_rn(a.x, a.y), __floats2bfloat162_rn(a.z, a.w),
+                             __floats2bfloat162_rn(b.x, b.y), __floats2bfloat162_rn(b.z, b.w)};
+      *reinterpret_cast<uint4*>(dst + (long long)n * kp + k) = *reinterpret_cast<uint4*>(o);
     }
-    dst[i] = __float2bfloat16(v);
+  } else {
+    for (long long i = bid * blockDim.x + threadIdx.x; i < (long long)n_pad * kp; i += nb * blockDim.x) {
+      int n = (int)(i / kp), k = (int)(i - (long long)n * kp);
+      float v = 0.f;
+      if (n < ctot && k < K) {
+        int j = k / cout, co = k - j * cout;
+        v = w[((long long)(taps - 1 - j) * ctot + n) * cout + co];
+      }
+      dst[i] = __float2bfloat16(v);
+    }
   }
 }
-// same, 8 consecutive k per thread (cout a multiple of 8)
-__global__ void pack_dgrad8_bf16_kernel(const float* __restrict__ w, int taps, int ctot, int cout,
-                                        __nv_bfloat16* __restrict__ dst, int kp, int n_pad) {
+
+struct PrepArgs {
+  // A part: a_kind 0 row-major im2col (grid-stride over a_blocks), 1 transposed im2col (tiles a_gx x a_gy, a_blocks = product)
+  Im2col q;
+  __nv_bfloat16* a_out = nullptr;
+  int a_kind = 0, a_ld = 0, a_v8 = 0, a_blocks = 0, a_gx = 1;
+  // W part: w_kind 0 transpose-pack of src[K][N] (tiles w_gx x w_gy), 1 data-gradient view of a conv kernel (grid-stride)
+  const float* w_src = nullptr;
+  __nv_bfloat16* w_out = nullptr;
+  int w_kind = 0, w_ld = 0, w_K = 0, w_N = 0, w_kp = 0, w_npad = 0, w_v8 = 0, w_blocks = 0, w_gx = 1;
+  int taps = 1, ctot = 0, cout = 0;
+  float* colsum = nullptr;
+};
+
+__global__ void __launch_bounds__(256) prep_kernel(const PrepArgs a) {
   pdl_enter();
-  const int K = taps * cout, kp8 = kp >> 3;
-  LDP_GRID_STRIDE(i, (long long)n_pad * kp8) {
-    int n = (int)(i / kp8), k = (int)(i - (long long)n * kp8) << 3;
-    float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
-    if (n < ctot && k < K) {
-      int j = k / cout, co = k - j * cout;
-      const float* src = w + ((long long)(taps - 1 - j) * ctot + n) * cout + co;
-      a = *reinterpret_cast<const float4*>(src);
-      b = *reinterpret_cast<const float4*>(src + 4);
-    }
-    __nv_bfloat162 o[4] = {__floats2bfloat162_rn(a.x, a.y), __floats2bfloat162_rn(a.z, a.w),
-                           __floats2bfloat162_rn(b.x, b.y), __floats2bfloat162_rn(b.z, b.w)};
-    *reinterpret_cast<uint4*>(dst + (long long)n * kp + k) = *reinterpret_cast<uint4*>(o);
+  int b = blockIdx.x;
+  if (b < a.a_blocks) {
+    if (a.a_kind == 0) im2col_body(a.q, a.a_out, a.a_ld, a.a_v8, b, a.a_blocks);
+    else im2col_t_body(a.q, a.a_out, a.a_ld, b % a.a_gx, b / a.a_gx);
+  } else {
+    b -= a.a_blocks;
+    if (a.w_kind == 0) pack_t_body(a.w_src, a.w_ld, a.w_K, a.w_N, a.w_out, a.w_kp, a.w_npad, a.colsum, b % a.w_gx, b / a.w_gx);
+    else pack_dgrad_body(a.w_src, a.taps, a.ctot, a.cout, a.w_out, a.w_kp, a.w_npad, a.w_v8, b, a.w_blocks);
   }
 }
+
+static int launch_prep(const PrepArgs& a, cudaStream_t s) {
+  LDP_CUDA_OK(launch_pdl(prep_kernel, dim3((unsigned)(a.a_blocks + a.w_blocks)), dim3(256), s, a));
+  count_launch();
+  return LDP_OK;
+}
+
+static bool im2col_v8(const Im2col& q) {
+  return (q.c1 % 8) == 0 && (q.c2 % 8) == 0 && (q.ld1 % 8) == 0 && (q.c2 == 0 || (q.ld2 % 8) == 0) &&
+         (((uintptr_t)q.x1 | (uintptr_t)q.x2) & 15) == 0;
+}
+static int stride_blocks(long long items) { return (int)std::min<long long>((items + 255) / 256, 148 * 4); }
 
 // ------------------------------------------------------------------------------------------------
 // tensors with gradients
@@ -782,9 +815,12 @@ static int conv_fwd(const Tn& x1, const Tn* x2, const Geo& g, const float* w, co
     LDP_TRY(cx.sw->ensure((size_t)n_pad * kp * 2));
     __nv_bfloat16* A = (__nv_bfloat16*)cx.sa->p;
     __nv_bfloat16* W = (__nv_bfloat16*)cx.sw->p;
-    LDP_TRY(launch_im2col(im2col_of(x1, x2, g, M), A, kp, s));
-    LDP_CUDA_OK(launch_pdl(pack_t_bf16_kernel, dim3(n_pad / 32, kp / 32), dim3(256), s, w, cout, K, cout, W, kp, n_pad, (float*)nullptr));
-    count_launch();
+    PrepArgs pa;
+    pa.q = im2col_of(x1, x2, g, M); pa.a_out = A; pa.a_kind = 0; pa.a_ld = kp; pa.a_v8 = im2col_v8(pa.q) ? 1 : 0;
+    pa.a_blocks = stride_blocks((long long)M * (pa.a_v8 ? kp / 8 : kp));
+    pa.w_kind = 0; pa.w_src = w; pa.w_ld = cout; pa.w_K = K; pa.w_N = cout; pa.w_out = W; pa.w_kp = kp; pa.w_npad = n_pad;
+    pa.w_gx = n_pad / 32; pa.w_blocks = pa.w_gx * (kp / 32);
+    LDP_TRY(launch_prep(pa, s));
     return cx.tc->gemm(A, kp, M, kp, W, n_pad, cout, bias, act, res ? res->v : nullptr, res ? res->ld : 0, y->v, y->ld, s);
   }
   GemmF32 p;
@@ -813,12 +849,13 @@ static int conv_dgrad(Tn* src, int coff, int ctot, const Geo& g, const float* w,
     __nv_bfloat16* W = (__nv_bfloat16*)cx.sw->p;
     Tn dy = y;
     dy.c = cout;
-    LDP_TRY(launch_im2col(im2col_of(dy, nullptr, gt, M, true), A, kp, s));
-    if ((cout % 8) == 0 && ((uintptr_t)w & 15) == 0)
-      LDP_CUDA_OK(launch_pdl(pack_dgrad8_bf16_kernel, dim3(ew_blocks((long long)n_pad * (kp / 8))), dim3(256), s, w, g.taps, ctot, cout, W, kp, n_pad));
-    else
-      LDP_CUDA_OK(launch_pdl(pack_dgrad_bf16_kernel, dim3(ew_blocks((long long)n_pad * kp)), dim3(256), s, w, g.taps, ctot, cout, W, kp, n_pad));
-    count_launch();
+    PrepArgs pa;
+    pa.q = im2col_of(dy, nullptr, gt, M, true); pa.a_out = A; pa.a_kind = 0; pa.a_ld = kp; pa.a_v8 = im2col_v8(pa.q) ? 1 : 0;
+    pa.a_blocks = stride_blocks((long long)M * (pa.a_v8 ? kp / 8 : kp));
+    pa.w_kind = 1; pa.w_src = w; pa.taps = g.taps; pa.ctot = ctot; pa.cout = cout; pa.w_out = W; pa.w_kp = kp; pa.w_npad = n_pad;
+    pa.w_v8 = ((cout % 8) == 0 && ((uintptr_t)w & 15) == 0) ? 1 : 0;
+    pa.w_blocks = stride_blocks((long long)n_pad * (pa.w_v8 ? kp / 8 : kp));
+    LDP_TRY(launch_prep(pa, s));
     // rows [coff, coff + src->c) of the pack are this source's channels
     return cx.tc->gemm(A, kp, M, kp, W + (size_t)coff * kp, round_up(src->c, 128), src->c, nullptr, 0,
                        acc ? src->g : nullptr, src->ld, src->g, src->ld, s);
@@ -841,10 +878,12 @@ static int conv_wgrad(const Tn& x1, const Tn* x2, const Geo& g, float* dw, float
     LDP_TRY(cx.sw->ensure((size_t)n_pad * mp * 2));
     __nv_bfloat16* At = (__nv_bfloat16*)cx.sa->p;
     __nv_bfloat16* Yt = (__nv_bfloat16*)cx.sw->p;
-    LDP_CUDA_OK(launch_pdl(im2col_t_bf16_kernel, dim3(ceil_div(K, 32), mp / 32), dim3(256), s, im2col_of(x1, x2, g, m), At, mp));
-    count_launch();
-    LDP_CUDA_OK(launch_pdl(pack_t_bf16_kernel, dim3(n_pad / 32, mp / 32), dim3(256), s, (const float*)y.g, y.ld, m, cout, Yt, mp, n_pad, db));
-    count_launch();
+    PrepArgs pa;
+    pa.q = im2col_of(x1, x2, g, m); pa.a_out = At; pa.a_kind = 1; pa.a_ld = mp; pa.a_gx = ceil_div(K, 32);
+    pa.a_blocks = pa.a_gx * (mp / 32);
+    pa.w_kind = 0; pa.w_src = y.g; pa.w_ld = y.ld; pa.w_K = m; pa.w_N = cout; pa.w_out = Yt; pa.w_kp = mp; pa.w_npad = n_pad;
+    pa.w_gx = n_pad / 32; pa.w_blocks = pa.w_gx * (mp / 32); pa.colsum = db;
+    LDP_TRY(launch_prep(pa, s));
     LDP_TRY(cx.tc->gemm(At, mp, K, mp, Yt, n_pad, cout, nullptr, 0, dw, cout, dw, cout, s));
     return LDP_OK;
   }
