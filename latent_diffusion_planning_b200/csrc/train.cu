@@ -572,26 +572,54 @@ __device__ __forceinline__ void im2col_t_body(const Im2col& p, __nv_bfloat16* __
 }
 
 // dst[n][k] = bf16(src[k*ld + n]) for n < n_pad, k < kp (zeros outside K x N): the K-major "W^T" operand.  colsum, if
-// given, also receives sum_k src[k][n] (the bias gradient when src is dY).  32x32 tile (bx over n, by over k)
+// given, also receives sum_k src[k][n] (the bias gradient when src is dY).  64x64 tile (bx over n, by over k; kp and
+// n_pad are multiples of 64): float4 reads along n, 16-byte bf16 writes along k.
+constexpr int PT = 64;
 __device__ __forceinline__ void pack_t_body(const float* __restrict__ src, int ld, int K, int N, __nv_bfloat16* __restrict__ dst,
                                             int kp, int n_pad, float* __restrict__ colsum, int bx, int by) {
-  __shared__ float tile[32][33];
-  const int n0 = bx * 32, k0 = by * 32;
-  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-  for (int r = ty; r < 32; r += 8) {
-    int k = k0 + r, n = n0 + tx;
-    tile[r][tx] = (k < K && n < N) ? src[(long long)k * ld + n] : 0.f;
+  __shared__ float tile[PT][PT + 1];
+  const int n0 = bx * PT, k0 = by * PT;
+  const int tid = threadIdx.x;
+  const bool vec = (ld & 3) == 0 && (((uintptr_t)src) & 15) == 0;
+  {
+    const int c4 = (tid & 15) * 4, r0 = tid >> 4;          // 16 threads x float4 cover 64 columns; 16 rows per pass
+#pragma unroll
+    for (int pass = 0; pass < 4; ++pass) {
+      const int r = r0 + pass * 16, k = k0 + r, n = n0 + c4;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (k < K) {
+        const float* sp = src + (long long)k * ld + n;
+        if (vec && n + 3 < N) {
+          v = *reinterpret_cast<const float4*>(sp);
+        } else {
+          if (n < N) v.x = sp[0];
+          if (n + 1 < N) v.y = sp[1];
+          if (n + 2 < N) v.z = sp[2];
+          if (n + 3 < N) v.w = sp[3];
+        }
+      }
+      tile[r][c4] = v.x; tile[r][c4 + 1] = v.y; tile[r][c4 + 2] = v.z; tile[r][c4 + 3] = v.w;
+    }
   }
   __syncthreads();
-  for (int r = ty; r < 32; r += 8) {
-    int n = n0 + r, k = k0 + tx;
-    if (n < n_pad && k < kp) dst[(long long)n * kp + k] = __float2bfloat16(tile[tx][r]);
-  }
-  if (colsum && ty == 0 && n0 + tx < N) {
-    float acc = 0.f;
+  {
+    const int k8 = (tid & 7) * 8, nr0 = tid >> 3;          // 8 threads x 8 bf16 cover 64 k; 32 n rows per pass
 #pragma unroll
-    for (int r = 0; r < 32; ++r) acc += tile[r][tx];
-    atomicAdd(colsum + n0 + tx, acc);
+    for (int pass = 0; pass < 2; ++pass) {
+      const int nr = nr0 + pass * 32, n = n0 + nr;
+      if (n < n_pad) {
+        __nv_bfloat162 o[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) o[i] = __floats2bfloat162_rn(tile[k8 + 2 * i][nr], tile[k8 + 2 * i + 1][nr]);
+        *reinterpret_cast<uint4*>(dst + (long long)n * kp + k0 + k8) = *reinterpret_cast<uint4*>(o);
+      }
+    }
+  }
+  if (colsum && tid < PT && n0 + tid < N) {
+    float acc = 0.f;
+#pragma unroll 8
+    for (int r = 0; r < PT; ++r) acc += tile[r][tid];
+    atomicAdd(colsum + n0 + tid, acc);
   }
 }
 
@@ -819,7 +847,7 @@ static int conv_fwd(const Tn& x1, const Tn* x2, const Geo& g, const float* w, co
     pa.q = im2col_of(x1, x2, g, M); pa.a_out = A; pa.a_kind = 0; pa.a_ld = kp; pa.a_v8 = im2col_v8(pa.q) ? 1 : 0;
     pa.a_blocks = stride_blocks((long long)M * (pa.a_v8 ? kp / 8 : kp));
     pa.w_kind = 0; pa.w_src = w; pa.w_ld = cout; pa.w_K = K; pa.w_N = cout; pa.w_out = W; pa.w_kp = kp; pa.w_npad = n_pad;
-    pa.w_gx = n_pad / 32; pa.w_blocks = pa.w_gx * (kp / 32);
+    pa.w_gx = n_pad / PT; pa.w_blocks = pa.w_gx * (kp / PT);
     LDP_TRY(launch_prep(pa, s));
     return cx.tc->gemm(A, kp, M, kp, W, n_pad, cout, bias, act, res ? res->v : nullptr, res ? res->ld : 0, y->v, y->ld, s);
   }
@@ -882,7 +910,7 @@ static int conv_wgrad(const Tn& x1, const Tn* x2, const Geo& g, float* dw, float
     pa.q = im2col_of(x1, x2, g, m); pa.a_out = At; pa.a_kind = 1; pa.a_ld = mp; pa.a_gx = ceil_div(K, 32);
     pa.a_blocks = pa.a_gx * (mp / 32);
     pa.w_kind = 0; pa.w_src = y.g; pa.w_ld = y.ld; pa.w_K = m; pa.w_N = cout; pa.w_out = Yt; pa.w_kp = mp; pa.w_npad = n_pad;
-    pa.w_gx = n_pad / 32; pa.w_blocks = pa.w_gx * (mp / 32); pa.colsum = db;
+    pa.w_gx = n_pad / PT; pa.w_blocks = pa.w_gx * (mp / PT); pa.colsum = db;
     LDP_TRY(launch_prep(pa, s));
     LDP_TRY(cx.tc->gemm(At, mp, K, mp, Yt, n_pad, cout, nullptr, 0, dw, cout, dw, cout, s));
     return LDP_OK;
