@@ -91,3 +91,16 @@ def test_oracle_decoder_upsample_and_shapes():
     p = P.init_params(P.vae_decoder_spec(blocks, 3, 4, 1), seed=0)
     y = O.vae_decode(p, torch.zeros(1, 4, 4, 4), blocks, 1, 8)
     assert tuple(y.shape) == (1, 16, 16, 3)
+
+
+def test_training_and_rng_entry_points_reject_bad_arguments(lib):
+    """Row N1 / N4 exports: argument checks fire before any CUDA call, so they are testable without a GPU."""
+    assert lib.ldp_adam_update(None, None, None, None, 0, 1e-3, 0.9, 0.999, 1e-8, 1, 1.0, None) == -1
+    assert b"bad arguments" in lib.ldp_last_error()
+    assert lib.ldp_unet_loss_grad(None, 0, None, None, None, None, None, None, 1, 8, 1.0, None, None) == -1
+    assert b"trainer handle" in lib.ldp_last_error()
+    assert lib.ldp_idm_loss_grad(None, 0, None, None, None, None, None, None, 1, 1.0, None, None) == -1
+    assert lib.ldp_unet_trainer_create(None, None) == -1
+    assert lib.ldp_jax_random(None, 1, 4, 1, None, None) == -1
+    assert lib.ldp_jax_random(None, 1, 4, 7, None, None) == -1 and b"mode" in lib.ldp_last_error()
+    assert lib.ldp_trainer_destroy(None) == 0
