@@ -106,6 +106,39 @@ class LatentSequenceDataset:
             return np.concatenate([seq[:1]] * pad0 + [seq] + [seq[-1:]] * pad1, axis=0)
         return {"actions": window("actions")[self.n_frame_stack - 1:], "obs": {k: window(k) for k in self.obs_keys}}
 
+    # ---- vectorised path: the whole dataset lives on one device and a batch is one gather per key -------------------
+    def to(self, device) -> "LatentSequenceDataset":
+        """Keep the flat arrays as tensors on `device` (a latent dataset is small: 8x8x4 floats per frame)."""
+        self._dev = {k: torch.as_tensor(v).to(device) for k, v in self.data.items()}
+        self._starts_t = torch.as_tensor(np.asarray(self._starts, dtype=np.int64)).to(device)
+        self._lengths_t = torch.as_tensor(np.asarray(self._lengths, dtype=np.int64)).to(device)
+        self._demo_of_t = torch.as_tensor(np.asarray(self._index_to_demo, dtype=np.int64)).to(device)
+        return self
+
+    def gather_batch(self, indices) -> Dict[str, Any]:
+        """`get_item` for a vector of indices at once: row r of the window of sample i is the flat row
+        clamp(i - (n_frame_stack - 1) + r, demo_start, demo_end - 1) - clamping IS the reference's edge padding
+        (repeat the first / last frame of the demo)."""
+        if not hasattr(self, "_dev"):
+            self.to("cpu")
+        idx = torch.as_tensor(indices, dtype=torch.int64, device=self._starts_t.device)
+        demo = self._demo_of_t[idx]
+        lo = self._starts_t[demo]
+        hi = lo + self._lengths_t[demo] - 1
+        fs = self.n_frame_stack
+        r = torch.arange(fs - 1 + self.seq_length, device=idx.device)
+        rows = torch.minimum(torch.maximum(idx[:, None] - (fs - 1) + r[None, :], lo[:, None]), hi[:, None])
+        return {"actions": self._dev["actions"][rows[:, fs - 1:]],
+                "obs": {k: self._dev[k][rows] for k in self.obs_keys}}
+
+    def sample_batch_fast(self, batch_size: int, rng: np.random.Generator, rank: int = 0, world: int = 1) -> Dict[str, Any]:
+        """Same draw and same result as `sample_batch`, gathered on the dataset's device."""
+        if batch_size % world:
+            raise AssertionError("batch_size % n_devices != 0 (train_bc.py:73)")
+        idx = rng.integers(0, self.total_n_sequences, size=batch_size)
+        per = batch_size // world
+        return self.gather_batch(idx[rank * per:(rank + 1) * per])
+
     def sample_batch(self, batch_size: int, rng: np.random.Generator, rank: int = 0, world: int = 1) -> Dict[str, Any]:
         """One GLOBAL batch of `batch_size` windows drawn from `rng` (identical on every rank); returns rank's shard."""
         if batch_size % world:
@@ -179,7 +212,8 @@ class Workspace:
         metrics: Dict[str, Any] = {}
         while self.step < c["n_grad_steps"]:
             self.timer.tick("time/update_loop")
-            batch = self.dataset.sample_batch(c["batch_size"], rng, self.rank, self.world)
+            sample = self.dataset.sample_batch_fast if hasattr(self.dataset, "_dev") else self.dataset.sample_batch
+            batch = sample(c["batch_size"], rng, self.rank, self.world)
             update_seed = int(rng.integers(0, 2 ** 31 - 1))
             self.agent, metrics = self.agent.update(batch, update_seed, self.step)
             self.step += 1

@@ -25,6 +25,7 @@ def main():
     ap.add_argument("--batch", type=int, default=256)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--workspace", action="store_true", help="time the train_bc.Workspace loop (on-device window sampling + update + logging cadence), wall clock")
     a = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -37,6 +38,32 @@ def main():
         norm["obs"][k] = {"min": np.full(SHAPES[k][0], -1.0, np.float32), "max": np.full(SHAPES[k][0], 1.0, np.float32)}
     ag = LDPAgent.create(0, None, {"ac_dim": 7, "all_shapes": SHAPES}, rgb_obs=["latent_agentview_image"], lowdim_obs=LOWDIM,
                          obs_normalization=norm, vae_feature_dim=256, obs_horizon=1, pred_horizon=8, action_horizon=4)
+    if a.workspace:
+        import tempfile
+        import time
+        from latent_diffusion_planning_b200 import train_bc as TB
+        rs = np.random.default_rng(0)
+        eps = {f"demo_{i}": {"obs": {"latent_agentview_image": rs.normal(0, 3, (120, 256)).astype(np.float32),
+                                     **{k: rs.uniform(-1, 1, (120, SHAPES[k][0])).astype(np.float32) for k in LOWDIM}},
+                             "actions": rs.uniform(-1, 1, (120, 7)).astype(np.float32)} for i in range(50)}
+        ds = TB.LatentSequenceDataset(eps, ["latent_agentview_image"] + LOWDIM, seq_length=9).to("cuda")
+        with tempfile.TemporaryDirectory() as d:
+            ws = TB.Workspace(ag, ds, d, batch_size=a.batch * world, n_grad_steps=a.warmup, log_every_step=10, dump_every_step=-1,
+                              save_every_step=-1, eval_every_step=-1)
+            ws.run()
+            torch.cuda.synchronize()
+            ws.cfg["n_grad_steps"] = a.warmup + a.steps
+            t0 = time.time()
+            ws.run()
+            torch.cuda.synchronize()
+            ms = (time.time() - t0) / a.steps * 1e3
+        if rank == 0:
+            print(json.dumps({"workspace_loop_ms_per_step": ms, "batch_per_gpu": a.batch, "n_gpus": world,
+                              "samples_per_sec": a.batch * world / ms * 1e3,
+                              "config": "train_bc.Workspace.run: on-device window sampling + LDPAgent.update + metrics every 10 steps, wall clock"}))
+        if world > 1:
+            dist.destroy_process_group()
+        return
     g = torch.Generator().manual_seed(rank)
     B = a.batch
     batch = {"obs": {"latent_agentview_image": (torch.randn(B, 9, 256, generator=g) * 3).cuda()},

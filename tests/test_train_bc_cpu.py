@@ -74,3 +74,19 @@ def test_csv_logger_averages_between_dumps(tmp_path):
     lg.dump(30)
     rows = list(csv.DictReader(open(tmp_path / "train.csv")))
     assert [r["step"] for r in rows] == ["20", "30"] and rows[1]["extra"] == "5.0" and rows[0]["extra"] == ""
+
+
+@pytest.mark.parametrize("fs,seq", [(1, 4), (2, 4), (3, 2), (1, 9)])
+def test_vectorised_gather_equals_per_item_windows(fs, seq):
+    """The one-gather-per-key batch (clamped row indices) is exactly the reference's clip + edge padding, for every
+    sample of every demo, including windows longer than the demo."""
+    ds = TB.LatentSequenceDataset(_episodes(), ["z", "q"], seq_length=seq, n_frame_stack=fs)
+    got = ds.gather_batch(np.arange(len(ds)))
+    for i in range(len(ds)):
+        it = ds.get_item(i)
+        assert np.array_equal(got["actions"][i].numpy(), it["actions"])
+        for k in ("z", "q"):
+            assert np.array_equal(got["obs"][k][i].numpy(), it["obs"][k])
+    a = ds.sample_batch(6, np.random.default_rng(3), rank=1, world=2)
+    b = ds.to("cpu").sample_batch_fast(6, np.random.default_rng(3), rank=1, world=2)
+    assert np.array_equal(a["actions"].numpy(), b["actions"].numpy()) and np.array_equal(a["obs"]["z"].numpy(), b["obs"]["z"].numpy())

@@ -275,7 +275,10 @@ def test_workspace_run_logs_saves_and_restores(cuda, tmp_path):
                                  rgb_obs=["latent_agentview_image"], lowdim_obs=LOWDIM, obs_normalization=_norm(), vae_feature_dim=16,
                                  vae_block_out_channels=(32,) * 6, planner_n_diffusion_steps=4, idm_n_diffusion_steps=4,
                                  precision="bf16", lr=1e-3, warmup_steps=2, decay_steps=20)
-    ws = TB.Workspace(mk(), ds, tmp_path, eval_dataset=ds, batch_size=8, n_grad_steps=6, log_every_step=2, dump_every_step=3,
+    ds_gpu = TB.LatentSequenceDataset(eps, keys, seq_length=9, n_frame_stack=1).to("cuda")      # one gather per key on the device
+    b0, b1 = ds.sample_batch(8, np.random.default_rng(4)), ds_gpu.sample_batch_fast(8, np.random.default_rng(4))
+    assert torch.equal(b0["obs"]["latent_agentview_image"], b1["obs"]["latent_agentview_image"].cpu()) and torch.equal(b0["actions"], b1["actions"].cpu())
+    ws = TB.Workspace(mk(), ds_gpu, tmp_path, eval_dataset=ds, batch_size=8, n_grad_steps=6, log_every_step=2, dump_every_step=3,
                       save_every_step=6, eval_every_step=6, n_eval_batches=1)
     last = ws.run()
     assert ws.step == 6 and np.isfinite(last["loss"])
