@@ -93,6 +93,40 @@ class LatentSequenceDataset:
     def __len__(self):
         return self.total_n_sequences
 
+    @classmethod
+    def from_latent_file(cls, latent_path, episodes: Dict[str, Dict[str, Any]], rgb_keys: Sequence[str],
+                         lowdim_keys: Sequence[str], seq_length: int, n_frame_stack: int = 1,
+                         data_name: str = "rm_lift") -> "LatentSequenceDataset":
+        """The reference's dataset assembly (data/robomimic_latent_data.py:85-110): image observations come from the
+        latent file `process_sdvae_data` wrote (`data/<demo>/latent/<rgb_key>`, flattened to h*w*c per frame under the
+        key `latent_<rgb_key>`), low-dim observations from the demonstration itself with the last `next_obs` row
+        appended (robomimic), actions with the last action repeated - so every key has T_ep + 1 rows."""
+        path = Path(latent_path)
+        if path.suffix == ".npz":
+            z = np.load(path)
+            read = lambda demo, key: z[f"data/{demo}/latent/{key}"]
+        else:
+            import h5py  # type: ignore
+            f = h5py.File(path, "r")
+            read = lambda demo, key: f["data"][demo]["latent"][key][:]
+        out: Dict[str, Dict[str, Any]] = {}
+        for demo, ep in episodes.items():
+            obs: Dict[str, np.ndarray] = {}
+            for k in rgb_keys:
+                lat = np.asarray(read(demo, k), dtype=np.float32)
+                obs[f"latent_{k}"] = lat.reshape(lat.shape[0], -1)
+            actions = np.asarray(ep["actions"], dtype=np.float32)
+            if "rm" in data_name:
+                for k in lowdim_keys:
+                    o = np.asarray(ep["obs"][k], dtype=np.float32)
+                    obs[k] = np.concatenate([o, np.asarray(ep["next_obs"][k], dtype=np.float32)[-1:]], axis=0)
+                actions = np.concatenate([actions, actions[-1:]], axis=0)
+            else:
+                for k in lowdim_keys:
+                    obs[k] = np.asarray(ep["obs"][k], dtype=np.float32)
+            out[demo] = {"obs": obs, "actions": actions}
+        return cls(out, [f"latent_{k}" for k in rgb_keys] + list(lowdim_keys), seq_length, n_frame_stack)
+
     def get_item(self, index: int) -> Dict[str, Any]:
         d = self._index_to_demo[index]
         lo, hi = self._starts[d], self._starts[d] + self._lengths[d]

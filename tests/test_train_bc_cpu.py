@@ -90,3 +90,24 @@ def test_vectorised_gather_equals_per_item_windows(fs, seq):
     a = ds.sample_batch(6, np.random.default_rng(3), rank=1, world=2)
     b = ds.to("cpu").sample_batch_fast(6, np.random.default_rng(3), rank=1, world=2)
     assert np.array_equal(a["actions"].numpy(), b["actions"].numpy()) and np.array_equal(a["obs"]["z"].numpy(), b["obs"]["z"].numpy())
+
+
+def test_dataset_from_latent_file_roundtrip(tmp_path):
+    """process_sdvae_data writer -> training dataset reader: latents flattened per frame, low-dim keys and actions
+    extended to T_ep + 1 rows the way the reference does (data/robomimic_latent_data.py:95-110)."""
+    from latent_diffusion_planning_b200 import process_sdvae_data as PS
+    g = np.random.default_rng(0)
+    eps, tables = {}, {}
+    for d, n in enumerate([4, 6]):
+        eps[f"demo_{d}"] = {"obs": {"q": g.normal(size=(n, 3)).astype(np.float32)}, "next_obs": {"q": g.normal(size=(n, 3)).astype(np.float32)},
+                            "actions": g.normal(size=(n, 2)).astype(np.float32)}
+        tables[f"data/demo_{d}/latent/cam"] = g.normal(size=(n + 1, 2, 2, 4)).astype(np.float32)
+    tables.update({"data.attrs/total": np.asarray(2), "data.attrs/min_z": np.asarray(-1.0), "data.attrs/max_z": np.asarray(1.0)})
+    path = PS.write_latents(tables, tmp_path, prefer_hdf5=False)
+    ds = TB.LatentSequenceDataset.from_latent_file(path, eps, ["cam"], ["q"], seq_length=3)
+    assert len(ds) == 5 + 7 and ds.obs_keys == ["latent_cam", "q"]
+    it = ds.get_item(4)                                     # last row of demo_0: the appended next_obs / repeated action
+    assert np.array_equal(it["obs"]["q"][0], eps["demo_0"]["next_obs"]["q"][-1])
+    assert np.array_equal(it["actions"][0], eps["demo_0"]["actions"][-1])
+    assert np.array_equal(it["obs"]["latent_cam"][0], tables["data/demo_0/latent/cam"][4].reshape(-1))
+    assert it["obs"]["latent_cam"].shape == (3, 16)
