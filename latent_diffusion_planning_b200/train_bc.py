@@ -318,3 +318,63 @@ class Workspace:
             self.step = int(z["step"])
         self.agent.load_params(trees.get("planner_params") or None, trees.get("idm_params") or None)
         return self.agent
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# command line (the reference's entry point is Hydra-driven: `python train_bc.py agent=ldp_agent data=cfg/rm_lift/latent_img`)
+# ---------------------------------------------------------------------------------------------------------------------
+RM_LIFT_LOWDIM = ["robot0_eef_pos", "robot0_eef_quat", "robot0_gripper_qpos"]      # data/cfg/rm_lift/latent_img.yaml:20-24
+RM_LIFT_SHAPES = {"robot0_eef_pos": [3], "robot0_eef_quat": [4], "robot0_gripper_qpos": [2]}
+
+
+def synthetic_rm_lift_episodes(n_demos: int = 50, length: int = 120, latent_dim: int = 256, seed: int = 0):
+    """Stand-in for a robomimic-lift latent dataset (there is no dataset in this image): same keys and shapes."""
+    rs = np.random.default_rng(seed)
+    return {f"demo_{i}": {"obs": {"latent_agentview_image": rs.normal(0, 3, (length, latent_dim)).astype(np.float32),
+                                  **{k: rs.uniform(-1, 1, (length, RM_LIFT_SHAPES[k][0])).astype(np.float32) for k in RM_LIFT_LOWDIM}},
+                          "actions": rs.uniform(-1, 1, (length, 7)).astype(np.float32)} for i in range(n_demos)}
+
+
+def main(argv=None):
+    import argparse
+    import os
+    import torch.distributed as dist
+    from .agent import LDPAgent
+    ap = argparse.ArgumentParser(description="LDP training loop on the B200-native kernels (rm_lift latent_img shapes)")
+    ap.add_argument("--work-dir", default="exp_local/train_bc")
+    ap.add_argument("--steps", type=int, default=200, help="n_grad_steps")
+    ap.add_argument("--batch-size", type=int, default=256, help="GLOBAL batch (train_bc.yaml:10); divided over ranks")
+    ap.add_argument("--seed", type=int, default=0)
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--latent-dim", type=int, default=256)
+    ap.add_argument("--log-every", type=int, default=10)
+    ap.add_argument("--save-every", type=int, default=-1)
+    a = ap.parse_args(argv)
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
+    if world > 1:
+        dist.init_process_group("nccl")
+    shapes = {**RM_LIFT_SHAPES, "latent_agentview_image": [a.latent_dim]}
+    norm = {"obs": {"latent_agentview_image": {"min": np.full(a.latent_dim, -10.0, np.float32), "max": np.full(a.latent_dim, 10.0, np.float32)},
+                    **{k: {"min": -np.ones(n[0], np.float32), "max": np.ones(n[0], np.float32)} for k, n in RM_LIFT_SHAPES.items()}},
+            "actions": {"clip_min": -np.ones(7, np.float32), "clip_max": np.ones(7, np.float32)}}   # data/cfg/rm_lift/latent_img.yaml:53-61
+    agent = LDPAgent.create(a.seed, None, {"ac_dim": 7, "all_shapes": shapes}, rgb_obs=["latent_agentview_image"],
+                            lowdim_obs=RM_LIFT_LOWDIM, obs_normalization=norm, vae_feature_dim=a.latent_dim, precision=a.precision,
+                            decay_steps=max(a.steps, 1001))
+    ds = LatentSequenceDataset(synthetic_rm_lift_episodes(latent_dim=a.latent_dim, seed=a.seed),
+                               ["latent_agentview_image"] + RM_LIFT_LOWDIM, seq_length=9).to("cuda")
+    ws = Workspace(agent, ds, a.work_dir, seed=a.seed, batch_size=a.batch_size, n_grad_steps=a.steps, log_every_step=a.log_every,
+                   dump_every_step=a.log_every, save_every_step=a.save_every, eval_every_step=-1)
+    t0 = time.time()
+    last = ws.run()
+    torch.cuda.synchronize()
+    if ws.rank == 0:
+        dt = time.time() - t0
+        print(json.dumps({"steps": ws.step, "loss": float(last.get("loss", float("nan"))), "seconds": dt,
+                          "samples_per_sec": ws.step * a.batch_size / dt, "log": str(ws.work_dir / "train.csv")}))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
