@@ -147,3 +147,24 @@ def test_unflatten_roundtrip():
     p = P.init_params(spec, seed=0)
     back = TR.unflatten_params(spec, P.flatten_params(spec, p))
     assert all(np.array_equal(back[k], p[k]) for k in spec)
+
+
+def test_update_gating_follows_the_reference_rules():
+    """LDPAgent._gates == the boolean algebra of `update` (agent/ldp_agent.py:229-236), checked without a GPU handle."""
+    from latent_diffusion_planning_b200.agent import LDPAgent
+    ag = LDPAgent.__new__(LDPAgent)
+    ag.use_planner, ag.use_idm = True, True
+    ag.config = dict(update_planner_every=2, update_idm_every=3, update_idm_after=4, update_planner_until=9, update_planner_after=2)
+
+    def ref(step, c):
+        use_planner = step % c["update_planner_every"] == 0
+        use_idm = step % c["update_idm_every"] == 0 and step >= c["update_idm_after"]
+        upd = (c["update_planner_until"] < 0 or step < c["update_planner_until"]) and step >= c["update_planner_after"]
+        return use_planner and upd, use_idm
+    for step in range(14):
+        assert ag._gates(step) == ref(step, ag.config)
+    assert ag._gates(0) == (False, False) and ag._gates(2) == (True, False) and ag._gates(6) == (True, True) and ag._gates(10) == (False, False)
+    ag.config.update(update_planner_until=-1, update_planner_after=-1, update_idm_after=-1, update_planner_every=1, update_idm_every=1)
+    assert all(ag._gates(s) == (True, True) for s in range(5))          # the yaml defaults (agent/ldp_agent.yaml:56-60)
+    ag.use_idm = False
+    assert ag._gates(3) == (True, False)
