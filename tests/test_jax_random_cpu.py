@@ -67,3 +67,13 @@ def test_update_key_threading_matches_oracle():
         assert set(a) == set(b) and all(np.array_equal(a[n][i], b[n][i]) for n in a for i in (0, 1))
     # the IDM's keys depend on whether the planner consumed a split before it
     assert not np.array_equal(JR.update_keys(k, True, True)["idm"][0], JR.update_keys(k, False, True)["idm"][0])
+
+
+def test_two_threefry_implementations_agree_on_random_blocks():
+    """numpy-vectorised oracle vs the product's pure-integer host implementation, 200 random (key, counter) blocks."""
+    rs = np.random.default_rng(0)
+    ks, cs = rs.integers(0, 2 ** 32, (200, 2), dtype=np.uint64), rs.integers(0, 2 ** 32, (200, 2), dtype=np.uint64)
+    for (k0, k1), (c0, c1) in zip(ks, cs):
+        with np.errstate(over="ignore"):
+            y0, y1 = O.threefry2x32(int(k0), int(k1), np.array([c0], np.uint32), np.array([c1], np.uint32))
+        assert JR.threefry2x32(int(k0), int(k1), int(c0), int(c1)) == (int(y0[0]), int(y1[0]))
