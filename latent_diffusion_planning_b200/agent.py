@@ -143,6 +143,13 @@ class LDPAgent:
         pl = H.Planner(planner_params, obs_dim, cond_dim, down_dims, dsed, ksize, n_groups, planner_n_diffusion_steps)
         idm = H.Idm(idm_params, obs_dim, action_dim, hidden, n_blocks, time_dim, cond_hidden, idm_n_diffusion_steps)
         vae = None
+        if vae_pretrain_path is not None and vae_params is None and len(rgb_obs) > 0:
+            # a Flax msgpack file / directory (e.g. the HF `diffusion_flax_model.msgpack`); the reference restores an orbax
+            # directory here (agent/ldp_agent.py:553, model/stable_vae_model.py:119-120), which is not restated
+            from . import checkpoints as CK
+            vae_params, dec_from_file = CK.load_vae_flax(vae_pretrain_path, vae_block_out_channels)
+            if vae_decoder_params is None:
+                vae_decoder_params = dec_from_file
         if len(rgb_obs) > 0:
             vspec = P.vae_encoder_spec(vae_block_out_channels)
             if vae_params is None:
