@@ -5,7 +5,9 @@ Same method names and argument meaning as the reference (`create`, `sample`, `sa
 name BASELINE.json uses).  Batches are dicts of tensors exactly like the reference's:
 `{'obs': {key: (B, H, ...)}, ['actions': (B, H, A)]}` with raw pixels 0..255.  Everything numerical runs in
 libldp_b200 (VAE encoder, planner loop, IDM loop); this file only does the reference's glue: normalisation constants,
-concatenations, reshapes.  Training (`update`, `update_mixed`) is the next scope row and raises.
+concatenations, reshapes.  Training (`update`, `update_mixed`, `get_metrics`) runs through
+`train.TrainState` on the same library (csrc/train.cu); under torch.distributed the gradients are all-reduced in
+buckets that start as the backward pass finishes them.
 
 `rng` replaces the JAX PRNG key: an int seed (or anything `int()` accepts).  Noise is counter-based Philox keyed by
 (seed, stream, step, GLOBAL row), so a batch sharded over ranks (`row_offset`) reproduces the unsharded result.
@@ -109,7 +111,8 @@ class LDPAgent:
                # additions (not in the reference): weights, VAE topology, compute mode
                planner_params: Optional[dict] = None, idm_params: Optional[dict] = None, vae_params: Optional[dict] = None,
                vae_block_out_channels: Sequence[int] = (128, 256, 512, 512), precision: str = "bf16", sampler: str = "ddpm",
-               vae_decoder_params: Optional[dict] = None, viz: bool = False):
+               vae_decoder_params: Optional[dict] = None, viz: bool = False, vae_image_size: int = 64,
+               vae_layers_per_block: int = 2, vae_norm_num_groups: int = 32):
         """Keyword surface of the reference's `LDPAgent.create` (agent/ldp_agent.py:516-532).  `shape_meta` is the data
         config's `{'ac_dim': A, 'all_shapes': {key: [...]}}`.  Weights: pass Flax-layout trees (flat 'a/b/kernel' dicts or
         nested), otherwise they are drawn with the reference's initialisers from `rng` (no checkpoints without network)."""
@@ -132,7 +135,16 @@ class LDPAgent:
             planner_params = P.canonicalize_flax_names(P.unnest(planner_params) if _is_nested(planner_params) else planner_params)
         idm_net = dict(idm_net or {})
         hidden = int(idm_net.get("hidden_dim", 256))
-        n_blocks = int(idm_net.get("num_blocks", 3))
+        # reference key: idm_net.n_blocks (agent/ldp_agent.yaml:19, MLPResNet.n_blocks); `num_blocks` accepted as an alias
+        n_blocks = int(idm_net.get("n_blocks", idm_net.get("num_blocks", 3)))
+        # options of the reference networks that the kernels do not implement are rejected, never silently ignored
+        if not idm_net.get("use_layer_norm", True):
+            raise NotImplementedError("idm_net.use_layer_norm=False: the IDM kernels implement the LayerNorm variant "
+                                      "(agent/ldp_agent.yaml:21) only")
+        if float(idm_net.get("dropout_rate") or 0.0) > 0.0:
+            raise NotImplementedError("idm_net.dropout_rate > 0 is not implemented (the reference yaml leaves it unset)")
+        if not planner.get("downsample", True):
+            raise NotImplementedError("planner.downsample=False is not implemented (networks/diffusion_nets_v2.py:112 default True)")
         time_dim = int((preprocess_time or {}).get("output_size", 256))
         cond_hidden = tuple((cond_encoder or {}).get("hidden_dims", (256, 256)))
         ispec = P.idm_spec(obs_dim, action_dim, hidden, n_blocks, time_dim, cond_hidden)
@@ -151,12 +163,13 @@ class LDPAgent:
             if vae_decoder_params is None:
                 vae_decoder_params = dec_from_file
         if len(rgb_obs) > 0:
-            vspec = P.vae_encoder_spec(vae_block_out_channels)
+            vspec = P.vae_encoder_spec(vae_block_out_channels, layers_per_block=vae_layers_per_block)
             if vae_params is None:
                 vae_params = P.init_params(vspec, seed=seed + 2)
             else:
                 vae_params = P.unnest(vae_params) if _is_nested(vae_params) else vae_params
-            vae = H.VaeEncoder(vae_params, vae_block_out_channels)
+            vae = H.VaeEncoder(vae_params, vae_block_out_channels, layers_per_block=vae_layers_per_block,
+                               norm_num_groups=vae_norm_num_groups, image_size=vae_image_size)
             lat = vae.latent_hw * vae.latent_hw * vae.latent_channels
             if lat != int(vae_feature_dim):
                 raise ValueError(f"vae_feature_dim={vae_feature_dim} but the encoder produces {lat} features per frame")
@@ -164,12 +177,13 @@ class LDPAgent:
         # decodes inside sample_viz; here it is a flag because decoding Ha+1 frames per plan costs more than the plan.
         vae_dec = None
         if viz and len(rgb_obs) > 0:
-            dspec = P.vae_decoder_spec(vae_block_out_channels)
+            dspec = P.vae_decoder_spec(vae_block_out_channels, layers_per_block=vae_layers_per_block)
             if vae_decoder_params is None:
                 vae_decoder_params = P.init_params(dspec, seed=seed + 3)
             else:
                 vae_decoder_params = P.unnest(vae_decoder_params) if _is_nested(vae_decoder_params) else vae_decoder_params
-            vae_dec = H.VaeDecoder(vae_decoder_params, vae_block_out_channels)
+            vae_dec = H.VaeDecoder(vae_decoder_params, vae_block_out_channels, layers_per_block=vae_layers_per_block,
+                                   norm_num_groups=vae_norm_num_groups, image_size=vae_image_size)
         config = dict(name=name, obs_horizon=obs_horizon, action_dim=action_dim, pred_horizon=pred_horizon,
                       action_horizon=action_horizon, obs_dim=obs_dim, rgb_obs=list(rgb_obs), lowdim_obs=list(lowdim_obs),
                       vae_feature_dim=int(vae_feature_dim), planner_n_diffusion_steps=planner_n_diffusion_steps,
@@ -224,10 +238,15 @@ class LDPAgent:
             if img.dtype != torch.uint8:                 # float pixels 0..255 -> [-1, 1] with the key's own constants
                 spec = norm.get(k, {"min": 0, "max": 255})
                 img = normalize_unnormalize(img.to(torch.float32), spec, True)
+            # latent normalisation (:62): fused into the encoder when the spec is one scalar pair; a per-dimension
+            # min/max (or a clip spec) is applied on the raw latents with the same code the training path uses
             lspec = norm.get(lk)
-            lo, hi = (float(np.min(lspec["min"])), float(np.max(lspec["max"]))) if lspec and "min" in lspec else (0.0, 0.0)
-            z = self.vae.encode(img.contiguous(), lat_min=lo, lat_max=hi, precision=self.precision)
-            out[lk] = z.reshape(B, Hh, -1)
+            scalar = bool(lspec) and "min" in lspec and np.ptp(np.asarray(lspec["min"])) == 0 and np.ptp(np.asarray(lspec["max"])) == 0
+            lo, hi = (float(np.min(lspec["min"])), float(np.max(lspec["max"]))) if scalar else (0.0, 0.0)
+            z = self.vae.encode(img.contiguous(), lat_min=lo, lat_max=hi, precision=self.precision).reshape(B, Hh, -1)
+            if lspec and not scalar:
+                z = normalize_unnormalize(z, lspec, True)
+            out[lk] = z
         return out
 
     def get_obs_cond(self, obs: Dict[str, torch.Tensor]) -> torch.Tensor:

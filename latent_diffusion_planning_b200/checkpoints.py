@@ -45,7 +45,10 @@ def _unchunk(tree):
         if tree.get("__msgpack_chunked_array__"):
             chunks = tree["chunks"]
             flat = np.concatenate([np.asarray(chunks[str(i)]).reshape(-1) for i in range(len(chunks))])
-            return flat.reshape(tree["shape"])
+            shape = tree["shape"]               # flax stores tuples as {'0': d0, '1': d1, ...} (_tuple_to_dict)
+            if isinstance(shape, dict):
+                shape = tuple(int(shape[str(i)]) for i in range(len(shape)))
+            return flat.reshape(tuple(shape))
         return {k: _unchunk(v) for k, v in tree.items()}
     return tree
 

@@ -242,8 +242,17 @@ def init_params(spec: Spec, seed: int = 0, perturb: float = 0.02, xavier_dense: 
     return out
 
 
-def flatten_params(spec: Spec, params: Dict[str, np.ndarray]) -> np.ndarray:
-    """Concatenate tensors in canonical (spec) order into the float32 blob the C ABI takes."""
+def flatten_params(spec: Spec, params: Dict[str, np.ndarray], strict: bool = True) -> np.ndarray:
+    """Concatenate tensors in canonical (spec) order into the float32 blob the C ABI takes.  `strict`: a tree with
+    tensors the spec does not know (e.g. a 4-block IDM handed to a 3-block spec) is an error, not silently truncated."""
+    missing = [k for k in spec if k not in params]
+    if missing:
+        raise KeyError(f"parameter tree lacks {len(missing)} tensors of the spec, first: {missing[:3]}")
+    if strict:
+        extra = [k for k in params if k not in spec]
+        if extra:
+            raise ValueError(f"parameter tree has {len(extra)} tensors that the network spec does not contain "
+                             f"(wrong n_blocks / down_dims / block_out_channels?), first: {extra[:3]}")
     chunks = []
     for path, shape in spec.items():
         a = np.asarray(params[path], dtype=np.float32)

@@ -10,6 +10,13 @@ JAX); h5py is not installed, so the default container is an `.npz` whose keys ar
 the same function writes `latent.hdf5` in the reference's layout.  The reference pads the last shard of an episode
 with zero images so that XLA sees one shape (lines 95-107); our kernels take any batch size, so no padding is done
 (images are independent: same latents).  Hydra/wandb/orbax plumbing is out of scope.
+
+Resize: with `pretrain_path` set the reference bilinearly resizes every frame to 3x256x256 before encoding
+(`jax.image.resize(..., method="bilinear")`, lines 66-69 / 91-92).  `resize_to=S` does the same here (`resize_bilinear`:
+half-pixel centres, no antialiasing when upsampling - jax.image.resize's semantics) on the normalised float frames.  The
+sm_100a encoder kernels take square inputs up to 128 pixels, so `resize_to=256` raises instead of silently producing latents
+of a different geometry; latents of a 64-pixel encode (8x8x4) are NOT interchangeable with the reference's 256-pixel
+ones (32x32x4) and `LDPAgent.create(vae_pretrain_path=...)` says so.
 """
 from __future__ import annotations
 
@@ -95,14 +102,33 @@ def read_latent_stats(path) -> Dict[str, float]:
         return {k: f["data"].attrs[k].item() for k in ("total", "min_z", "max_z")}
 
 
-def process_sdvae_data(episodes: Mapping[str, Mapping], rgb_keys: Sequence[str], vae, out_dir, data_name: str = "rm_lift",
-                       shard: int = 256, precision: str = "bf16", device: str = "cuda") -> Path:
-    """The reference's entry point on our encoder: `vae` is a `handles.VaeEncoder` (raises if the CUDA library or a GPU
-    is missing - there is no CPU fallback)."""
+def resize_bilinear(frames, size: int):
+    """`jax.vmap(jax.image.resize(obs, (3, S, S), "bilinear"))` of the reference (process_sdvae_data.py:66-69): separable
+    triangle kernel on half-pixel centres; jax antialiases only when DOWN-sampling, which torch's `antialias=True` matches.
+    frames: float tensor (n, H, W, 3) NHWC -> (n, S, S, 3)."""
     import torch
+    import torch.nn.functional as F
+    x = frames.permute(0, 3, 1, 2)
+    down = size < x.shape[-1] or size < x.shape[-2]
+    y = F.interpolate(x, size=(size, size), mode="bilinear", align_corners=False, antialias=down)
+    return y.permute(0, 2, 3, 1).contiguous()
+
+
+def process_sdvae_data(episodes: Mapping[str, Mapping], rgb_keys: Sequence[str], vae, out_dir, data_name: str = "rm_lift",
+                       shard: int = 256, precision: str = "bf16", device: str = "cuda", resize_to: Optional[int] = None) -> Path:
+    """The reference's entry point on our encoder: `vae` is a `handles.VaeEncoder` (raises if the CUDA library or a GPU
+    is missing - there is no CPU fallback).  `resize_to`: the reference's pretrain_path resize (see the module docstring)."""
+    import torch
+    if resize_to is not None and int(resize_to) != vae.image_size:
+        raise ValueError(f"resize_to={resize_to} but the encoder handle was built for {vae.image_size}-pixel inputs "
+                         f"(the kernels support square inputs up to 128 pixels; the reference's 256 is not available)")
 
     def encode(frames: np.ndarray) -> np.ndarray:
         img = torch.from_numpy(np.ascontiguousarray(frames)).to(device)
+        if resize_to is not None and img.shape[1] != resize_to:
+            img = resize_bilinear((img.to(torch.float32) / 255 - 0.5) / 0.5, int(resize_to))   # lines 89-92
+        elif img.shape[1] != vae.image_size:
+            raise ValueError(f"frames are {img.shape[1]} pixels, the encoder takes {vae.image_size}: pass resize_to=")
         return vae.encode(img, precision=precision).cpu().numpy()          # raw latent_dist.mean, no min/max normalisation
 
     return write_latents(encode_dataset(episodes, rgb_keys, encode, data_name, shard), out_dir)

@@ -101,7 +101,7 @@ def test_sample_action_and_from_plan(agent):
     assert tuple(a2.shape) == (B, Hh, 7) and torch.isfinite(a2).all()
 
 
-def test_process_sdvae_data_matches_direct_encode(tmp_path):
+def test_process_sdvae_data_matches_direct_encode(cuda, tmp_path):
     """process_sdvae_data mirror (reference process_sdvae_data.py:52-118): the latent file holds exactly what
     VaeEncoder.encode returns for the assembled episode frames, in shards, with the reference's min/max attributes."""
     import numpy as np

@@ -35,6 +35,11 @@ def test_roundtrip_nested_tree_and_dtypes(tmp_path):
     chunked = {"__msgpack_chunked_array__": True, "shape": [2, 3], "chunks": {"0": np.arange(4, dtype=np.float32), "1": np.arange(4, 6, dtype=np.float32)}}
     raw = msgpack.packb({"big": CK._encode(chunked) | {"__msgpack_chunked_array__": True, "shape": [2, 3]}}, use_bin_type=True)
     assert np.array_equal(CK.load_flax_msgpack(raw)["big"], np.arange(6, dtype=np.float32).reshape(2, 3))
+    # the layout flax.serialization._chunk really writes: the shape tuple goes through _tuple_to_dict -> {'0': 2, '1': 3}
+    flax_chunked = {"__msgpack_chunked_array__": True, "shape": {"0": 2, "1": 3},
+                    "chunks": CK._encode({"0": np.arange(4, dtype=np.float32), "1": np.arange(4, 6, dtype=np.float32)})}
+    raw = msgpack.packb({"big": flax_chunked}, use_bin_type=True)
+    assert np.array_equal(CK.load_flax_msgpack(raw)["big"], np.arange(6, dtype=np.float32).reshape(2, 3))
 
 
 def test_vae_file_splits_into_encoder_and_decoder_specs(tmp_path):
