@@ -10,6 +10,16 @@ A "step" is one pass of the hot path over one batch: 100 DDPM reverse steps of t
 update fused into the last GEMM, in-kernel Philox noise.  Weak scaling: every rank runs its own 1024 plans
 (independent units, no data-path collective); `value` = plans of all ranks / max-over-ranks device time.
 
+Besides the headline the same line carries first-class blocks, each timed on every rank and max-reduced over ranks:
+  strong    the SAME 1024 plans split over the N ranks (B/N per rank, global-row Philox noise), planner loop, and BASELINE
+            config #5 end to end (aloha act(): VAE encode + planner + IDM, B = 512 total, T = 16, 100 DDIM steps, actions
+            all-gathered over NCCL) - the split north_star names;
+  train_dp  LDPAgent.update with the gradient all-reduce ON: 256 per rank (global 256 N) and fixed global 256, the
+            all-reduce timed alone (bus bandwidth) and the same step with the exchange switched off;
+  vae       BASELINE config #3: VAE encode at B = 4096 per GPU with its own roofline, host-buffer e2e and CPU baseline;
+  parity    the measured abs / max-normalised errors of the benchmarked configurations (profiles/parity_r2.json,
+            written from the -m gpu test run of tests/test_bench_config_parity_gpu.py).
+
 One JSON line on stdout (rank 0).  See DESIGN.md "Measurement" for how each field is produced.
 """
 from __future__ import annotations
@@ -171,7 +181,7 @@ def run_reference(args) -> None:
     if rank != 0:
         return
     threads = os.cpu_count() or 1
-    n_rev = 2
+    n_rev = 8
     times = _oracle_reverse_steps(n_rev, reps=args.steps, warm=min(args.warmup, 1), threads=threads)
     t_step = sum(times) / len(times)
     value = B_PLANS / (t_step / n_rev * N_DIFF)
@@ -195,7 +205,65 @@ def run_reference(args) -> None:
 # ----------------------------------------------------------------------------------------------------
 # our arm
 # ----------------------------------------------------------------------------------------------------
+VAE_GFLOP_PER_IMG = 16.92            # 4-block SD-VAE encoder, 64x64x3 -> 8x8x4, useful = nominal
+VAE_B = 4096
+RM_LOWDIM = ["robot0_eef_pos", "robot0_eef_quat", "robot0_gripper_qpos"]
+RM_SHAPES = {"robot0_eef_pos": [3], "robot0_eef_quat": [4], "robot0_gripper_qpos": [2], "latent_agentview_image": [LATENT]}
+
+
+class Ctx:
+    """torch / torch.distributed plumbing shared by the blocks: barrier + sync, per-step CUDA events on the launching
+    stream, L2 flush between timed steps, MAX over ranks."""
+
+    def __init__(self, torch, dist, world, rank, local):
+        self.torch, self.dist, self.world, self.rank, self.local = torch, dist, world, rank, local
+        self.flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")      # > 126 MB L2
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def max_over_ranks(self, v: float) -> float:
+        t = self.torch.tensor([v], dtype=self.torch.float64, device="cuda")
+        if self.world > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def timed(self, fn, k, warm=0, flush=True):
+        """ms per step: `warm` untimed then k timed steps, each bracketed by its own CUDA events, max over ranks of the sum."""
+        torch = self.torch
+        for i in range(warm):
+            fn(-1 - i)
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(k)]
+        self.barrier()
+        for i in range(k):
+            if flush:
+                self.flush.zero_()
+            ev[i][0].record()
+            fn(i)
+            ev[i][1].record()
+        self.barrier()
+        return self.max_over_ranks(sum(a.elapsed_time(b) for a, b in ev)) / k
+
+
+def _peaks():
+    pk = ROOT / "MEASURED_PEAKS.json"
+    peaks = json.loads(pk.read_text()) if pk.exists() else {}
+    if "bf16_tflops_sustained" in peaks:
+        return float(peaks["bf16_tflops_sustained"]), "MEASURED_PEAKS.json bf16_tflops_sustained (of measured)", peaks
+    return 1400.0, "fallback 1.4 PF/s sustained (B200_PROFILING.md) (of fallback)", peaks
+
+
+def _rm_norm(np):
+    return {"obs": {"agentview_image": {"min": 0, "max": 255},
+                    "latent_agentview_image": {"min": np.full(LATENT, -10.0, np.float32), "max": np.full(LATENT, 10.0, np.float32)},
+                    **{k: {"min": -np.ones(RM_SHAPES[k][0], np.float32), "max": np.ones(RM_SHAPES[k][0], np.float32)} for k in RM_LOWDIM}},
+            "actions": {"clip_min": -np.ones(7, np.float32), "clip_max": np.ones(7, np.float32)}}
+
+
 def run_ours(args) -> None:
+    import numpy as np
     import torch
     import torch.distributed as dist
     from latent_diffusion_planning_b200 import _native, handles as H, params as P
@@ -212,6 +280,7 @@ def run_ours(args) -> None:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     lib = _native.load()
     _native.check(lib.ldp_device_check())
+    ctx = Ctx(torch, dist, world, rank, local)
 
     p = P.init_params(P.unet_spec(D_OBS, D_OBS), seed=0)
     planner = H.Planner(p, D_OBS, D_OBS)
@@ -220,32 +289,10 @@ def run_ours(args) -> None:
     c_host = (torch.rand(B_PLANS, D_OBS, generator=g) * 2 - 1).pin_memory()
     out_host = torch.empty_like(x_host).pin_memory()
     x_dev, c_dev = x_host.cuda(), c_host.cuda()
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")      # > 126 MB L2
     row_offset = rank * B_PLANS
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
 
     def one_step(seed):
         return planner.sample(x_dev, c_dev, seed=seed, row_offset=row_offset, n_steps=N_DIFF, sampler="ddpm", precision="bf16")
-
-    def timed(fn, k):
-        """k steps, each bracketed by its own CUDA events on the launching stream, L2 flushed between steps."""
-        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(k)]
-        barrier()
-        for i in range(k):
-            flush.zero_()
-            ev[i][0].record()
-            fn(i)
-            ev[i][1].record()
-        barrier()
-        ms = sum(a.elapsed_time(b) for a, b in ev)
-        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
 
     sampler = ClockSampler(local) if rank == 0 else None
     if sampler:
@@ -258,37 +305,40 @@ def run_ours(args) -> None:
         one_step(2000)
         torch.cuda.synchronize()
     lib.ldp_launch_count_reset()
-    ms_total = timed(lambda i: one_step(i), args.steps)
+    ms_per_step = ctx.timed(lambda i: one_step(max(i, 0)), args.steps)
     launches = int(lib.ldp_launch_count())
     clocks = sampler.stop() if sampler else None
 
     # end to end through the public host-buffer call: pinned host -> device, sample, device -> pinned host
     def e2e_step(i):
-        planner.sample_host(x_host, c_host, out_host, seed=i, row_offset=row_offset, n_steps=N_DIFF, sampler="ddpm",
+        planner.sample_host(x_host, c_host, out_host, seed=max(i, 0), row_offset=row_offset, n_steps=N_DIFF, sampler="ddpm",
                             precision="bf16")
-    for i in range(2):
-        e2e_step(i)
-    ms_e2e = timed(e2e_step, args.steps)
+    ms_e2e = ctx.timed(e2e_step, args.steps, warm=2)
+
+    blocks = {}
+    if not args.no_extras:
+        for name, fn in (("strong", strong_block), ("vae", vae_block), ("act", act_block), ("train_dp", train_block)):
+            try:
+                blocks[name] = fn(ctx, args, planner, x_host, c_host)
+            except Exception as e:                                          # a side block never breaks the headline line
+                import traceback
+                blocks[name] = {"error": f"{type(e).__name__}: {e}", "trace": traceback.format_exc(limit=3)}
+                ctx.barrier()
 
     if rank == 0:
-        peaks = {}
-        pk = ROOT / "MEASURED_PEAKS.json"
-        if pk.exists():
-            peaks = json.loads(pk.read_text())
-        peak_tf = float(peaks.get("bf16_tflops_sustained", 1400.0))
-        peak_src = "MEASURED_PEAKS.json bf16_tflops_sustained" if "bf16_tflops_sustained" in peaks else "fallback 1.4 PF/s sustained (B200_PROFILING.md)"
-        ms_per_step = ms_total / args.steps
+        peak_tf, peak_src, _ = _peaks()
         plans_total = B_PLANS * world
         value = plans_total / (ms_per_step / 1e3)
         flops_step = unet_useful_flops(D_OBS, T_PRED) * B_PLANS * N_DIFF      # per rank per bench step
         launches_per_step = launches / args.steps
         avg_launch_us = ms_per_step * 1e3 / launches_per_step
         achieved_tf = flops_step / (ms_per_step / 1e3) / 1e12
-        traffic = None
+        traffic, traffic_src = None, None
         tf = ROOT / "profiles" / "traffic.json"
         if tf.exists():
             try:
-                traffic = json.loads(tf.read_text()).get("dram_bytes_per_launch")
+                tj = json.loads(tf.read_text())
+                traffic, traffic_src = tj.get("dram_bytes_per_launch"), "profiles/traffic.json: " + str(tj.get("source", "ncu --set full capture"))
             except Exception:
                 traffic = None
         per_op = None
@@ -301,40 +351,46 @@ def run_ours(args) -> None:
                                         key=lambda o: -o["us"])[:3]}
         except Exception as e:                                              # diagnostics only
             per_op = {"error": str(e)}
-        extras = None
-        if not args.no_extras:
-            try:
-                extras = side_metrics(torch, H, P, rank)
-            except Exception as e:                                          # side numbers never break the headline line
-                extras = {"error": str(e)}
         cpu = cpu_baseline_leg() if world == 1 and not args.no_cpu_baseline else None
+        parity = None
+        pf = ROOT / "profiles" / "parity_r2.json"
+        if pf.exists():
+            try:
+                pj = json.loads(pf.read_text())
+                keys = ("planner_b1024_eps_k50", "planner_b1024_eps_k99", "planner_b1024_eps_k0", "planner_b1024_xprev_k50")
+                parity = {"source": "profiles/parity_r2.json (tests/test_bench_config_parity_gpu.py, B=1024 T=8 D=265 bf16 vs float64 oracle)",
+                          "abs": max(pj[k]["abs"] for k in keys if k in pj), "rel": max(pj[k]["rel"] for k in keys if k in pj),
+                          "tolerance": "north_star 1e-2 gated on rel = abs / max(1, max|ref|); abs is reported, gated at 5e-2",
+                          "cases": {k: {"abs": v["abs"], "rel": v["rel"]} for k, v in pj.items()}}
+            except Exception:
+                parity = None
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16", "data": "synthetic",
             "config": {"workload": "planner denoising loop 100 DDPM steps, B=1024 H=9 (T=8) latent=8x8x4 (D=265), bf16, per GPU",
-                       "B_per_gpu": B_PLANS, "T": T_PRED, "D": D_OBS, "n_diffusion_steps": N_DIFF, "sampler": "ddpm",
+                       "B": B_PLANS, "B_per_gpu": B_PLANS, "T": T_PRED, "D": D_OBS, "n_diffusion_steps": N_DIFF, "sampler": "ddpm",
                        "noise": "in-kernel Philox4x32-10", "weights": "random init (seed 0), 69.5 M params",
                        "l2": "256 MB buffer written between timed steps (L2 flush); per-step working set (139 MB bf16 "
                              "weights + activations) also exceeds the 126 MB L2",
                        "parallelism": f"dp{world} (independent plans, no collective)"},
             "denoise_steps_per_sec": value * N_DIFF,
             "roofline": {"bound": "tensor", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
-                         "frac": achieved_tf / peak_tf, "traffic": traffic,
+                         "frac": achieved_tf / peak_tf, "traffic": traffic, "traffic_source": traffic_src,
                          "kernel": "tc_gemm_kernel<BN,EPI> (tcgen05 implicit-GEMM conv + fused GN/Mish/FiLM/DDPM epilogues)",
                          "launches_per_step": launches_per_step, "avg_launch_us": avg_launch_us,
                          "algorithmic_flops_per_launch": flops_step / launches_per_step,
-                         "peak_source": peak_src + " (of measured)" if "MEASURED" in peak_src else peak_src,
-                         "isolated": per_op},
-            "e2e": {"value": plans_total / (ms_e2e / args.steps / 1e3), "unit": UNIT,
+                         "peak_source": peak_src, "isolated": per_op},
+            "e2e": {"value": plans_total / (ms_e2e / 1e3), "unit": UNIT,
                     "h2d_bytes_per_step": x_host.numel() * 4 + c_host.numel() * 4, "d2h_bytes_per_step": out_host.numel() * 4,
-                    "ms_per_step": ms_e2e / args.steps, "api": "handles.Planner.sample_host (pinned host buffers)"},
+                    "ms_per_step": ms_e2e, "api": "handles.Planner.sample_host (pinned host buffers)"},
             "gpu_launches": launches,
             "clocks": clocks,
             "host_cores": os.cpu_count(),
         }
-        if extras is not None:
-            line["extras"] = extras
+        line.update(blocks)
+        if parity is not None:
+            line["parity"] = parity
         if cpu is not None:
             line["cpu_baseline"] = cpu
         print(json.dumps(line), flush=True)
@@ -343,75 +399,208 @@ def run_ours(args) -> None:
         dist.destroy_process_group()
 
 
-def side_metrics(torch, H, P, rank):
-    """Per-GPU side numbers for the other BASELINE configs (not the headline): VAE-encode img/s at B=4096 (config #3),
-    IDM loop and full act() = encode + planner + IDM at B=1024 (rm_lift shapes).  Device-resident inputs, CUDA events."""
+def strong_block(ctx, args, planner, x_host, c_host):
+    """Strong scaling of sampling (the split north_star names; reference call site hands ONE batch: utils/rm_env_utils.py:168-185):
+    the same B = 1024 plans sharded over the ranks by rows, no data-path collective, global-row Philox noise so any N draws the
+    same numbers.  Then BASELINE config #5: aloha act() end to end, B = 512 total, T = 16, D = 270, A = 14, 100 DDIM steps,
+    `LDPAgent.sample_sharded` with the (B, Ha, A) actions all-gathered over NCCL."""
+    import numpy as np
+    torch = ctx.torch
+    from latent_diffusion_planning_b200.agent import LDPAgent, shard_rows
+    out = {}
+    lo, hi = shard_rows(B_PLANS, ctx.rank, ctx.world)
+    g = torch.Generator().manual_seed(1)                         # the SAME global batch on every rank; each takes its rows
+    x = torch.randn(B_PLANS, T_PRED, D_OBS, generator=g)[lo:hi].cuda()
+    c = (torch.rand(B_PLANS, D_OBS, generator=g) * 2 - 1)[lo:hi].cuda()
+    steps = max(3, min(args.steps, 10))
+    ms = ctx.timed(lambda i: planner.sample(x, c, seed=max(i, 0), row_offset=lo, n_steps=N_DIFF, sampler="ddpm", precision="bf16"),
+                   steps, warm=3)
+    fl = unet_useful_flops(D_OBS, T_PRED) * B_PLANS * N_DIFF
+    peak_tf, _, _ = _peaks()
+    out["planner"] = {"workload": f"planner loop, B={B_PLANS} TOTAL split by rows over {ctx.world} ranks ({hi - lo} per rank), T=8, D=265, 100 DDPM steps, bf16",
+                      "ms_per_step": ms, "plans_per_sec": B_PLANS / ms * 1e3, "rows_per_rank": (hi - lo) * T_PRED,
+                      "frac_of_n_gpu_tensor_peak": fl / (ms / 1e3) / 1e12 / (peak_tf * ctx.world),
+                      "collective": "none (independent plans)",
+                      "limit": "M = rows per rank: below ~2048 rows a layer is fewer CTAs than SMs and its fixed cost "
+                               "(launch gap + prologue + epilogue) dominates"}
+    # config #5
+    lat, A, Ha, T5, B5 = 256, 14, 4, 16, 512
+    shapes = {"qpos": [14], "latent_wrist64_image": [lat]}
+    norm = {"obs": {"wrist64_image": {"min": 0, "max": 255},
+                    "latent_wrist64_image": {"min": np.full(lat, -5.5, np.float32), "max": np.full(lat, 5.5, np.float32)},
+                    "qpos": {"min": -np.ones(14, np.float32) * 2, "max": np.ones(14, np.float32) * 2}},
+            "actions": {"min": -np.ones(A, np.float32) * 1.5, "max": np.ones(A, np.float32) * 1.5}}
+    agent = LDPAgent.create(0, None, {"ac_dim": A, "all_shapes": shapes}, rgb_obs=["latent_wrist64_image"], lowdim_obs=["qpos"],
+                            obs_normalization=norm, vae_feature_dim=lat, obs_horizon=1, pred_horizon=T5, action_horizon=Ha,
+                            sampler="ddim", data_name="aloha_cube")
+    g = torch.Generator().manual_seed(9)
+    img_host = torch.randint(0, 256, (B5, 1, 64, 64, 3), generator=g, dtype=torch.int32).to(torch.uint8).pin_memory()
+    qpos_host = (torch.rand(B5, 1, 14, generator=g) * 2 - 1).pin_memory()
+    res = {}
+
+    def act5(i):
+        batch = {"obs": {"wrist64_image": img_host.cuda(non_blocking=True), "qpos": qpos_host.cuda(non_blocking=True)}}
+        a, _ = agent.sample_sharded(batch, max(i, 0) + 1, gather=True)
+        res["a"] = a.to("cpu", non_blocking=True)
+    ms = ctx.timed(act5, steps, warm=2)
+    out["aloha_act_config5"] = {"workload": f"LDPAgent.sample_sharded: VAE encode + planner + IDM, aloha shapes B={B5} TOTAL over {ctx.world} ranks, "
+                                            f"T={T5}, D=270, A={A}, 100 DDIM steps each, bf16; host uint8 frames in, actions all-gathered and read back",
+                                "ms_per_act": ms, "plans_per_sec": B5 / ms * 1e3,
+                                "collective": "all_gather of (B,Ha,A) actions, %d bytes" % (B5 * Ha * A * 4) if ctx.world > 1 else "none",
+                                "actions_finite": bool(torch.isfinite(res["a"]).all()), "actions_shape": list(res["a"].shape)}
+    del agent
+    return out
+
+
+def vae_block(ctx, args, planner, x_host, c_host):
+    """BASELINE config #3: stable_vae_model.encode over 64x64x3 frames, B = 4096 per GPU (process_sdvae_data path)."""
+    torch = ctx.torch
+    from latent_diffusion_planning_b200 import handles as H, params as P
+    vp = P.init_params(P.vae_encoder_spec(), seed=2)
+    vae = H.VaeEncoder(vp)
+    g = torch.Generator().manual_seed(4 + ctx.rank)
+    img_host = torch.randint(0, 256, (VAE_B, 64, 64, 3), generator=g, dtype=torch.int32).to(torch.uint8).pin_memory()
+    img = img_host.cuda()
+    lat_host = torch.empty(VAE_B, 8, 8, 4, dtype=torch.float32).pin_memory()
+    steps = max(3, min(args.steps, 5))
+    lib = vae.lib
+    lib.ldp_launch_count_reset()
+    ms = ctx.timed(lambda i: vae.encode(img, lat_min=-10.0, lat_max=10.0, precision="bf16"), steps, warm=3)
+    launches = int(lib.ldp_launch_count()) / (steps + 3)
+
+    def e2e(i):
+        z = vae.encode(img_host.cuda(non_blocking=True), lat_min=-10.0, lat_max=10.0, precision="bf16")
+        lat_host.copy_(z, non_blocking=True)
+    ms_e2e = ctx.timed(e2e, steps, warm=1)
+    peak_tf, peak_src, _ = _peaks()
+    ach = VAE_B * VAE_GFLOP_PER_IMG / ms                       # GF / ms = TF/s
+    out = {"metric": "vae_encode_imgs_per_sec", "value": VAE_B * ctx.world / ms * 1e3, "unit": "img/s", "ms_per_step": ms,
+           "config": {"workload": "stable_vae_model.encode 64x64x3 uint8 agentview images, B=4096 per GPU, SD-VAE [128,256,512,512] "
+                                  "-> 8x8x4 latents (+ fused latent normalisation), bf16 tensor-core path, chunks of 256 images",
+                      "B_per_gpu": VAE_B, "l2": "256 MB L2 flush between steps; inputs (50 MB) + activations exceed L2"},
+           "roofline": {"bound": "tensor", "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf,
+                        "algorithmic_gflop_per_image": VAE_GFLOP_PER_IMG, "launches_per_step": launches, "peak_source": peak_src,
+                        "kernel": "tc_gemm_kernel<*, PLAIN, persistent> (3x3 / 1x1 / stride-2 implicit-GEMM convolutions)"},
+           "e2e": {"value": VAE_B * ctx.world / ms_e2e * 1e3, "unit": "img/s", "ms_per_step": ms_e2e,
+                   "h2d_bytes_per_step": img_host.numel(), "d2h_bytes_per_step": lat_host.numel() * 4,
+                   "api": "handles.VaeEncoder.encode on pinned uint8 host frames, latents copied back"}}
+    if ctx.world == 1 and not args.no_cpu_baseline:
+        import time as _t
+        from oracle import ldp_oracle as O                     # CPU baseline leg (B = 64, fp32)
+        torch.set_num_threads(os.cpu_count() or 1)
+        sub = img_host[:64].float() / 255 * 2 - 1
+        with torch.no_grad():
+            O.vae_encode_mean(vp, sub[:8], dtype=torch.float32)
+            t0 = _t.perf_counter()
+            O.vae_encode_mean(vp, sub, dtype=torch.float32)
+            dt = _t.perf_counter() - t0
+        out["cpu_baseline"] = {"value": 64 / dt, "unit": "img/s", "cores": os.cpu_count(), "kind": "port",
+                               "sample": f"64 of the 4096 images, fp32 PyTorch-CPU oracle ({dt:.1f} s)"}
+    vae.close()
+    return out
+
+
+def act_block(ctx, args, planner, x_host, c_host):
+    """LDPAgent.act at B = 1024 per GPU (rm_lift shapes): VAE encode + 100 planner steps + 100 IDM steps; IDM loop and VAE
+    decoder timed alone.  Weak scaling (every rank its own batch)."""
+    import numpy as np
+    torch = ctx.torch
+    from latent_diffusion_planning_b200 import handles as H, params as P
     from latent_diffusion_planning_b200.agent import LDPAgent
     out = {}
+    agent = LDPAgent.create(0, None, {"ac_dim": 7, "all_shapes": RM_SHAPES}, rgb_obs=["latent_agentview_image"], lowdim_obs=RM_LOWDIM,
+                            obs_normalization=_rm_norm(np), vae_feature_dim=LATENT, obs_horizon=1, pred_horizon=T_PRED, action_horizon=4)
+    g = torch.Generator().manual_seed(4 + ctx.rank)
+    img_host = torch.randint(0, 256, (B_PLANS, 1, 64, 64, 3), generator=g, dtype=torch.int32).to(torch.uint8).pin_memory()
+    low_host = {k: (torch.rand(B_PLANS, 1, RM_SHAPES[k][0], generator=g) * 2 - 1).pin_memory() for k in RM_LOWDIM}
+    res = {}
 
-    def timeit(fn, reps):
-        fn()
-        torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(reps):
-            fn()
-        e1.record()
-        torch.cuda.synchronize()
-        return e0.elapsed_time(e1) / reps
-
-    lowdim = ["robot0_eef_pos", "robot0_eef_quat", "robot0_gripper_qpos"]
-    shapes = {"robot0_eef_pos": [3], "robot0_eef_quat": [4], "robot0_gripper_qpos": [2], "latent_agentview_image": [LATENT]}
-    import numpy as np
-    norm = {"obs": {"agentview_image": {"min": 0, "max": 255},
-                    "latent_agentview_image": {"min": np.full(LATENT, -10.0, np.float32), "max": np.full(LATENT, 10.0, np.float32)},
-                    **{k: {"min": -np.ones(shapes[k][0], np.float32), "max": np.ones(shapes[k][0], np.float32)} for k in lowdim}},
-            "actions": {"clip_min": -np.ones(7, np.float32), "clip_max": np.ones(7, np.float32)}}
-    agent = LDPAgent.create(0, None, {"ac_dim": 7, "all_shapes": shapes}, rgb_obs=["latent_agentview_image"], lowdim_obs=lowdim,
-                            obs_normalization=norm, vae_feature_dim=LATENT, obs_horizon=1, pred_horizon=T_PRED, action_horizon=4)
-    g = torch.Generator().manual_seed(4 + rank)
-    img = torch.randint(0, 256, (4096, 64, 64, 3), generator=g, dtype=torch.int32).to(torch.uint8).cuda()
-    ms = timeit(lambda: agent.vae.encode(img, lat_min=-10.0, lat_max=10.0, precision="bf16"), 2)
-    out["vae_encode_imgs_per_sec"] = 4096 / ms * 1e3
-    out["vae_encode_config"] = "stable_vae_model.encode 64x64x3 uint8, B=4096, SD-VAE [128,256,512,512] -> 8x8x4, bf16"
-    out["vae_tflops_useful"] = 4096 * 16.92 / ms
-    batch = {"obs": {"agentview_image": img[:B_PLANS].reshape(B_PLANS, 1, 64, 64, 3),
-                     **{k: torch.rand(B_PLANS, 1, shapes[k][0], generator=g).cuda() * 2 - 1 for k in lowdim}}}
-    ms = timeit(lambda: agent.act(batch, 1), 2)
-    out["act_plans_per_sec"] = B_PLANS / ms * 1e3
-    out["act_config"] = "LDPAgent.act: VAE encode + 100 planner DDPM steps + 100 IDM DDPM steps, B=1024, rm_lift shapes, bf16"
+    def act(i):
+        batch = {"obs": {"agentview_image": img_host.cuda(non_blocking=True), **{k: v.cuda(non_blocking=True) for k, v in low_host.items()}}}
+        a, _ = agent.act(batch, max(i, 0) + 1, row_offset=ctx.rank * B_PLANS)
+        res["a"] = a.to("cpu", non_blocking=True)
+    steps = max(3, min(args.steps, 5))
+    ms = ctx.timed(act, steps, warm=2)
     out["act_ms"] = ms
-    # the two remaining pieces of act(), timed alone: IDM reverse loop (B * Ha = 4096 transition rows) and, for sample_viz
-    # with viz=True, the VAE decoder over the (Ha + 1) frames of every plan
+    out["act_plans_per_sec"] = B_PLANS * ctx.world / ms * 1e3
+    out["act_config"] = ("LDPAgent.act end to end: pinned host uint8 frames + low-dim -> VAE encode + 100 planner DDPM steps + 100 IDM "
+                         "DDPM steps -> actions read back, B=1024 per GPU, rm_lift shapes, bf16")
     idm = agent.idm
     ssp = (torch.rand(B_PLANS * 4, 2 * D_OBS, generator=g) * 2 - 1).cuda()
     a_T = torch.randn(B_PLANS * 4, 7, generator=g).cuda()
-    ms = timeit(lambda: idm.sample(ssp, a_T, seed=1, n_steps=N_DIFF, precision="bf16"), 3)
+    ms = ctx.timed(lambda i: idm.sample(ssp, a_T, seed=1, n_steps=N_DIFF, precision="bf16"), steps, warm=2)
+    peak_tf, _, _ = _peaks()
     out["idm_loop_ms"] = ms
-    out["idm_config"] = "MLPDiffusion reverse loop, 4096 rows (B=1024 x Ha=4), 2D=530, A=7, 100 DDPM steps, bf16"
+    out["idm_roofline_frac"] = 3.153e6 * B_PLANS * 4 * N_DIFF / (ms / 1e3) / 1e12 / peak_tf
+    out["idm_config"] = "MLPDiffusion reverse loop, 4096 rows (B=1024 x Ha=4), 2D=530, A=7, 100 DDPM steps, bf16; 3.153 MF useful per row-step"
     dec = H.VaeDecoder(P.init_params(P.vae_decoder_spec(), seed=7))
     z = torch.randn(1024, 8, 8, 4, generator=g).cuda()
-    ms = timeit(lambda: dec.decode(z, precision="bf16"), 2)
+    ms = ctx.timed(lambda i: dec.decode(z, precision="bf16"), 3, warm=1)
     out["vae_decode_frames_per_sec"] = 1024 / ms * 1e3
     out["vae_decode_config"] = "FlaxAutoencoderKL.decode 8x8x4 -> 64x64x3, SD-VAE [128,256,512,512], B=1024 frames, bf16 (plan_viz path)"
-    # scope row N1: one LDPAgent.update (planner + IDM losses, gradients, Adam) at the reference's train batch (train_bc.yaml:10)
-    g = torch.Generator().manual_seed(5)
-    tb = {"obs": {"latent_agentview_image": (torch.randn(256, 9, LATENT, generator=g) * 3).cuda()}, "actions": torch.randn(256, 9, 7, generator=g).cuda()}
-    for k in lowdim:
-        tb["obs"][k] = (torch.rand(256, 9, shapes[k][0], generator=g) * 2 - 1).cuda()
-    agent.data_parallel = False          # side metric of rank 0 alone: no gradient all-reduce here (scripts/train_bench.py has it)
-    for i in range(3):
-        agent.update(tb, i, i)
-    torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for i in range(5):
-        agent.update(tb, 3 + i, 3 + i)
-    e1.record()
-    torch.cuda.synchronize()
-    out["train_step_ms"] = e0.elapsed_time(e1) / 5
-    out["train_samples_per_sec"] = 256 / out["train_step_ms"] * 1e3
-    out["train_config"] = "LDPAgent.update (train_bc.py agent=ldp_agent, rm_lift latent_img shapes), batch 256, bf16 tcgen05 contractions, fp32 master weights + Adam"
+    dec.close()
+    del agent
+    return out
+
+
+def train_block(ctx, args, planner, x_host, c_host):
+    """BASELINE config #4: LDPAgent.update (train_bc.py agent=ldp_agent data=cfg/rm_lift/latent_img), bf16 contractions, fp32 master
+    weights + Adam, data-parallel gradient all-reduce over NCCL (reference train_bc.py:70-78: the global batch is sharded over devices)."""
+    import numpy as np
+    torch, dist, world = ctx.torch, ctx.dist, ctx.world
+    from latent_diffusion_planning_b200.agent import LDPAgent
+    shapes = dict(RM_SHAPES)
+    agent = LDPAgent.create(0, None, {"ac_dim": 7, "all_shapes": shapes}, rgb_obs=["latent_agentview_image"], lowdim_obs=RM_LOWDIM,
+                            obs_normalization={k: v for k, v in _rm_norm(np).items()}, vae_feature_dim=LATENT, obs_horizon=1,
+                            pred_horizon=T_PRED, action_horizon=4, vae_params=None)
+    agent.vae = None                                      # latents are read from the latent dataset (latent_img config)
+
+    def make_batch(b, seed):
+        g = torch.Generator().manual_seed(seed)
+        tb = {"obs": {"latent_agentview_image": (torch.randn(b, 9, LATENT, generator=g) * 3).cuda()}, "actions": torch.randn(b, 9, 7, generator=g).cuda()}
+        for k in RM_LOWDIM:
+            tb["obs"][k] = (torch.rand(b, 9, RM_SHAPES[k][0], generator=g) * 2 - 1).cuda()
+        return tb
+    out = {}
+    step_no = [0]
+
+    def upd(tb):
+        def f(i):
+            agent.update(tb, step_no[0], step_no[0])
+            step_no[0] += 1
+        return f
+    steps = max(3, min(args.steps, 10))
+    n_param = None
+    cases = [("weak_256_per_gpu", 256)]
+    if world > 1 and 256 % world == 0:
+        cases.append(("strong_global_256", 256 // world))
+    for label, b_rank in cases:
+        tb = make_batch(b_rank, 5 + ctx.rank)
+        agent.data_parallel = True
+        ms = ctx.timed(upd(tb), steps, warm=4, flush=False)
+        entry = {"batch_per_gpu": b_rank, "global_batch": b_rank * world, "ms_per_step": ms, "samples_per_sec": b_rank * world / ms * 1e3,
+                 "allreduce": "on" if world > 1 else "n/a (1 rank)"}
+        if world > 1:
+            agent.data_parallel = False                   # same per-rank work without the exchange: the exposed communication time
+            ms_off = ctx.timed(upd(tb), steps, warm=2, flush=False)
+            entry["ms_per_step_allreduce_off"] = ms_off
+            entry["exposed_comm_ms"] = ms - ms_off
+            agent.data_parallel = True
+        out[label] = entry
+    grads = [agent._train[n].grads for n in ("planner", "idm") if n in agent._train]
+    n_bytes = sum(gr.numel() * 4 for gr in grads)
+    out["gradient_bytes"] = n_bytes
+    if world > 1:
+        def ar(i):
+            for gr in grads:
+                dist.all_reduce(gr, op=dist.ReduceOp.SUM)
+        ms_ar = ctx.timed(ar, 10, warm=3, flush=False)
+        out["allreduce_alone_ms"] = ms_ar
+        out["allreduce_busbw_gbs"] = 2 * (world - 1) / world * n_bytes / (ms_ar / 1e3) / 1e9
+        out["allreduce_busbw_reference_gbs"] = "725 GB/s (8 ranks, 1 GiB; B200_PROFILING.md)"
+    out["config"] = ("LDPAgent.update: planner (69.5 M) + IDM (1.9 M) losses, backward, Adam; rm_lift latent_img shapes (D=265, T=8, A=7); bf16 "
+                     "tcgen05 contractions, fp32 master weights / moments / gradients; one flat fp32 gradient buffer per network all-reduced (NCCL)")
+    del agent
     return out
 
 

@@ -129,6 +129,14 @@ LDP_API int ldp_planner_sample(LdpPlanner* h, int precision, int sampler, const 
                                const float* noise_dev, uint64_t seed, int64_t row_offset, int B, int T, int n_steps,
                                float* x0_dev, void* cuda_stream);
 
+/* Diagnostics for per-layer parity (SURVEY.md 8c protocol; no reference counterpart - in the reference these are the
+ * values of `x` between the statements of ConditionalUnet1D.__call__, networks/diffusion_nets_v2.py:137-167): after a
+ * bf16 ldp_unet_forward at (B, T), copies one intermediate activation to out_dev as float32 (rows, cols) row-major.
+ * tap_id: i in [0, n_blocks) = output of ConditionalResidualBlock1D_i; 100 + l = Downsample1d_l; 200 + u =
+ * Upsample1d_u; 300 = the final Conv1dBlock. */
+LDP_API int ldp_planner_read_activation(LdpPlanner* h, int B, int T, int tap_id, float* out_dev, int64_t max_elems,
+                                        int32_t* rows_out, int32_t* cols_out, void* cuda_stream);
+
 /* Diagnostics (no reference counterpart): times every kernel of one bf16 denoising step in isolation - `reps`
  * back-to-back launches between two CUDA events per kernel.  us_host[i] = microseconds per launch of kernel i;
  * meta_host[4i..4i+3] = {M, N, K/64, block_n | epilogue << 16 | aux << 24 | accumulators << 25}.  phases_host (may

@@ -21,7 +21,7 @@ EXPORTS = [
     "ldp_last_error", "ldp_version", "ldp_device_check",
     "ldp_ddpm_schedule", "ldp_ddpm_step", "ldp_ddpm_add_noise", "ldp_philox_normal", "ldp_philox_normal_rows",
     "ldp_planner_create", "ldp_planner_destroy", "ldp_unet_param_count", "ldp_unet_forward", "ldp_planner_sample",
-    "ldp_planner_profile_step",
+    "ldp_planner_profile_step", "ldp_planner_read_activation",
     "ldp_idm_create", "ldp_idm_destroy", "ldp_idm_param_count", "ldp_idm_forward", "ldp_idm_sample",
     "ldp_vae_create", "ldp_vae_destroy", "ldp_vae_param_count", "ldp_vae_encode",
     "ldp_vae_decoder_create", "ldp_vae_decoder_param_count", "ldp_vae_decode",
@@ -86,6 +86,7 @@ def load() -> C.CDLL:
     lib.ldp_unet_forward.argtypes = [vp, i32, vp, vp, i32, vp, i32, i32, vp, vp]
     lib.ldp_planner_sample.argtypes = [vp, i32, i32, vp, vp, vp, u64, i64, i32, i32, i32, vp, vp]
     lib.ldp_planner_profile_step.argtypes = [vp, i32, i32, i32, vp, vp, vp, i32, vp, vp]
+    lib.ldp_planner_read_activation.argtypes = [vp, i32, i32, i32, vp, i64, vp, vp, vp]
     lib.ldp_idm_create.argtypes = [C.POINTER(IdmConfig), vp, u64, C.POINTER(vp)]
     lib.ldp_idm_destroy.argtypes = [vp]
     lib.ldp_idm_param_count.argtypes = [C.POINTER(IdmConfig)]

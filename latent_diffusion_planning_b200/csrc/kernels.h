@@ -108,6 +108,8 @@ int launch_set_i32(int32_t* p, int v, cudaStream_t s);
 // f32 (rows, cols) -> bf16 (rows, ld_out) with optional Mish; pad columns [cols, ld_out) are zeroed.
 int launch_cast_bf16(const float* in, int ld_in, __nv_bfloat16* out, int ld_out, long long rows, int cols, int mish,
                      cudaStream_t s);
+int launch_cast_f32_from_bf16(const __nv_bfloat16* in, int ld_in, float* out, int ld_out, long long rows, int cols,
+                              cudaStream_t s);
 // dst[n][kp] = map[kp] >= 0 ? bf16(src[map[kp]*ld_src + n]) : 0  for n < n_src, zeros for n in [n_src, n_pad)
 // (dst has row pitch ld_dst elements; this call fills columns [k_off, k_off+kp) of rows [0, n_pad))
 int launch_pack_wt_bf16(const float* src, int ld_src, int n_src, const int32_t* map, int kp, __nv_bfloat16* dst,

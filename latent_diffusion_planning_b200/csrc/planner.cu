@@ -98,6 +98,8 @@ struct PlanWs {
   __nv_bfloat16* x_bf16 = nullptr;
   int ld_xb = 0;
   std::vector<TcGemm> ops;         // one denoising step; last op = final 1x1 with the DDPM epilogue
+  struct Tap { int id; ActBf16 act; long long rows; };
+  std::vector<Tap> taps;           // named intermediates for per-layer parity tests (ldp_planner_read_activation)
   cudaGraphExec_t graph = nullptr;
   cudaGraph_t graph_src = nullptr;
   // persistent loop kernel (planner_loop.cu)
@@ -740,6 +742,7 @@ static int prepare_bf16(LdpPlanner* h, PlanWs* w) {
       ActBf16 o;
       LDP_TRY(new_act(Tl, h->crb[bi].cout, &o));
       LDP_TRY(crb_tc(h, w, bi, &cur, 1, Tl, h1buf, o.p));
+      w->taps.push_back({bi, o, (long long)B * Tl});
       cur = o; ++bi;
     }
     skips.push_back(cur);
@@ -754,6 +757,7 @@ static int prepare_bf16(LdpPlanner* h, PlanWs* w) {
       LDP_TRY(conv_tc(h, w, 1000 + l, cd, &op));
       op.mode = TC_EPI_PLAIN; op.bias = h->down_b[l]; op.out_bf16 = o.p; op.ld_out_bf16 = d;
       w->ops.push_back(op);
+      w->taps.push_back({100 + l, o, (long long)B * (Tl / 2)});
       cur = o;
     }
   }
@@ -763,6 +767,7 @@ static int prepare_bf16(LdpPlanner* h, PlanWs* w) {
       ActBf16 o;
       LDP_TRY(new_act(Tl, h->crb[bi].cout, &o));
       LDP_TRY(crb_tc(h, w, bi, &cur, 1, Tl, h1buf, o.p));
+      w->taps.push_back({bi, o, (long long)B * Tl});
       cur = o; ++bi;
     }
   }
@@ -774,9 +779,11 @@ static int prepare_bf16(LdpPlanner* h, PlanWs* w) {
     ActBf16 o;
     LDP_TRY(new_act(Tl, h->crb[bi].cout, &o));
     LDP_TRY(crb_tc(h, w, bi, srcs, 2, Tl, h1buf, o.p));
+    w->taps.push_back({bi, o, (long long)B * Tl});
     cur = o; ++bi;
     LDP_TRY(new_act(Tl, h->crb[bi].cout, &o));
     LDP_TRY(crb_tc(h, w, bi, &cur, 1, Tl, h1buf, o.p));
+    w->taps.push_back({bi, o, (long long)B * Tl});
     cur = o; ++bi;
     const int d = c.down_dims[lvl - 1];
     LDP_TRY(new_act(2 * Tl, d, &o));
@@ -787,6 +794,7 @@ static int prepare_bf16(LdpPlanner* h, PlanWs* w) {
     LDP_TRY(conv_tc(h, w, 2000 + u, cd, &op));
     op.mode = TC_EPI_PLAIN; op.bias = h->up_bias2[u]; op.out_bf16 = o.p; op.ld_out_bf16 = 2 * d;
     w->ops.push_back(op);
+    w->taps.push_back({200 + u, o, (long long)B * 2 * Tl});
     cur = o;
   }
   const int d0 = c.down_dims[0];
@@ -799,6 +807,7 @@ static int prepare_bf16(LdpPlanner* h, PlanWs* w) {
   LDP_TRY(conv_tc(h, w, 3000, cd, &op));
   set_gn(&op, h->fcb, h->fgs, h->fgb, d0, 8, f.p);
   w->ops.push_back(op);
+  w->taps.push_back({300, f, (long long)B * T});
   cd = ConvDesc();
   cd.kind = CONV_K; cd.taps_k = 1; cd.srcs = &f; cd.nsrc = 1; cd.t_in = T; cd.wgt = h->ow; cd.cout = c.input_dim;
   cd.no_pair = true;                                   // the DDPM epilogue kernel is single-CTA
@@ -1025,6 +1034,23 @@ int ldp_planner_sample(LdpPlanner* h, int precision, int sampler, const float* x
   return LDP_OK;
 }
 
+
+// Diagnostics for per-layer parity: the bf16 activation `tap_id` left behind by the last bf16 forward at (B, T), as f32.
+int ldp_planner_read_activation(LdpPlanner* h, int B, int T, int tap_id, float* out_dev, int64_t max_elems, int32_t* rows_out,
+                                int32_t* cols_out, void* cuda_stream) {
+  LDP_CHECK(h && out_dev && rows_out && cols_out, LDP_ERR_INVALID_ARG, "null pointer");
+  auto it = h->ws.find(std::make_pair(B, T));
+  LDP_CHECK(it != h->ws.end() && it->second->bf16_ready, LDP_ERR_INVALID_ARG, "no bf16 forward has run at this (B, T)");
+  for (const PlanWs::Tap& t : it->second->taps) {
+    if (t.id != tap_id) continue;
+    LDP_CHECK(t.rows * t.act.c <= max_elems, LDP_ERR_INVALID_ARG, "output buffer too small");
+    *rows_out = (int32_t)t.rows;
+    *cols_out = t.act.c;
+    return launch_cast_f32_from_bf16(t.act.p, t.act.ld, out_dev, t.act.c, t.rows, t.act.c, (cudaStream_t)cuda_stream);
+  }
+  set_last_error("unknown activation id " + std::to_string(tap_id));
+  return LDP_ERR_INVALID_ARG;
+}
 
 // Diagnostics: time every kernel of one bf16 denoising step in isolation (reps back-to-back launches, CUDA events).
 int ldp_planner_profile_step(LdpPlanner* h, int B, int T, int reps, float* us_host, int32_t* meta_host, float* phases_host,

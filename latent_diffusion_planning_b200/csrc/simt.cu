@@ -418,6 +418,25 @@ int launch_cast_bf16(const float* in, int ld_in, __nv_bfloat16* out, int ld_out,
   return LDP_OK;
 }
 
+__global__ void cast_f32_from_bf16_kernel(const __nv_bfloat16* in, int ld_in, float* out, int ld_out, long long rows, int cols) {
+  long long n = rows * cols;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    long long r = i / cols;
+    int c = (int)(i - r * cols);
+    out[r * ld_out + c] = __bfloat162float(in[r * ld_in + c]);
+  }
+}
+
+int launch_cast_f32_from_bf16(const __nv_bfloat16* in, int ld_in, float* out, int ld_out, long long rows, int cols,
+                              cudaStream_t s) {
+  long long n = rows * cols;
+  int blocks = (int)((n + 255) / 256);
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  cast_f32_from_bf16_kernel<<<blocks, 256, 0, s>>>(in, ld_in, out, ld_out, rows, cols);
+  LDP_LAUNCH_OK();
+  return LDP_OK;
+}
+
 // Weight packing for the tcgen05 path: W^T as [n_pad][kp] bf16 (K contiguous), K gathered through `map`.
 __global__ void pack_wt_bf16_kernel(const float* src, int ld_src, int n_src, const int32_t* map, int kp,
                                     __nv_bfloat16* dst, int ld_dst, int k_off, int n_pad) {

@@ -202,6 +202,15 @@ class Planner:
         out_host.copy_(out, non_blocking=True)
         return out_host
 
+    def read_activation(self, B: int, T: int, tap_id: int) -> torch.Tensor:
+        """Per-layer parity hook: the bf16 activation `tap_id` of the last bf16 `forward` at (B, T) as float32 (rows, C).
+        tap_id: i = ConditionalResidualBlock1D_i output, 100+l = Downsample1d_l, 200+u = Upsample1d_u, 300 = final block."""
+        buf = torch.empty(B * T * 2048, dtype=torch.float32, device="cuda")
+        rows, cols = C.c_int32(0), C.c_int32(0)
+        N.check(self.lib.ldp_planner_read_activation(self._h, B, T, tap_id, buf.data_ptr(), buf.numel(), C.byref(rows),
+                                                     C.byref(cols), _stream()))
+        return buf[:rows.value * cols.value].reshape(rows.value, cols.value).clone()
+
     def profile_step(self, B: int, T: int, reps: int = 20):
         """Per-kernel timing of one bf16 denoising step (diagnostics): list of dicts with us, M, N, K, block_n, epilogue."""
         us = np.zeros(128, np.float32)
