@@ -153,6 +153,12 @@ struct TcGemm {
   CUtensorMap map_a[4];
   CUtensorMap map_b;                // W^T tiles: box {64, BN}; in pair mode {64, BN/2} (see `pair`)
   int pair = 0;                     // 1: map_b was built with the half-width box -> eligible for the cta_group::2 kernel
+  // DDPM epilogue, N = tiles * BN + (1..16) (the planner's last 1x1 convolution: N = 265 = 2 * 128 + 9): instead of a third,
+  // almost empty N tile (192 CTAs = two waves on 148 SMs) the LAST N tile is widened by n_tail = 16 columns - one MMA of
+  // N = BN + 16, the extra 16 W rows fetched through map_b_tail (box {64, 16}) behind the regular W tile.
+  CUtensorMap map_b_tail;
+  int allow_tail = 1;               // 0: never widen (the persistent loop kernel does not implement it)
+  int n_tail = 0;                   // filled by tc_gemm_geometry
   const TcStage* kb = nullptr;      // device table of pipeline stages
   const TcRun* runs = nullptr;      // the same table run-length encoded (what the producer of tc_gemm_kernel reads)
   int num_runs = 0;
@@ -178,6 +184,11 @@ struct TcGemm {
   int epi_skip = 0;                 // diagnostics (LDP_EPI_SKIP): 1 stores, 2 FiLM loads, 4 residual, 8 activation, 16 tap shuffles
   long long* dbg_stage = nullptr;   // diagnostics: CTA (0,0)'s first 24 stage-arrival times
   long long* dbg = nullptr;         // diagnostics: per-CTA phase timestamps [ctas][8] (clock64 deltas)
+  // L2 prefetch of the NEXT layer's packed weights (139 MB of weights stream through a 126 MB L2 once per denoising step, so
+  // every layer's W tiles would otherwise come from HBM at ~2x the L2 latency, which the 6-stage ring does not cover): each
+  // CTA asks for its 1/grid slice with cp.async.bulk.prefetch.L2 from an otherwise idle epilogue thread at kernel start.
+  const void* l2_prefetch = nullptr;
+  unsigned int l2_prefetch_bytes = 0;
   int k_pad = 0;                    // host-side bookkeeping: padded K of the packed weights
   const void* wt_host_ref = nullptr; int n_pad = 0;   // host-side bookkeeping: packed weights [n_pad][k_pad] (to rebuild map_b)
   int M = 0, N = 0;                 // logical output size

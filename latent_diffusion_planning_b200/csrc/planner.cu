@@ -83,6 +83,10 @@ struct PlanWs {
   Arena arena;
   float* otab = nullptr;
   float* otab_q = nullptr;       // quad-transposed copy for the tcgen05 epilogues
+  __nv_bfloat16* cond_bf16 = nullptr;   // Mish(cond) in bf16: A operand of the observation-part FiLM GEMM (bf16 path)
+  int ld_cb = 0;
+  TcGemm otab_op;
+  bool otab_ready = false;
   float* x_state = nullptr;
   float* eps_buf = nullptr;
   int32_t* step_dev = nullptr;
@@ -133,6 +137,8 @@ struct LdpPlanner {
   float* coef = nullptr;     // [n_train][8]
   std::map<std::pair<int, int>, std::unique_ptr<PlanWs>> ws;
   std::map<std::pair<int, int>, ConvPack> packed;   // (op id * 2 + layout, T_in)
+  PackedW pw_otab;                  // wc_all^T packed K-major in bf16 (observation part of every FiLM Dense)
+  bool otab_packed = false;
   bool use_graph = true;
 };
 
@@ -287,6 +293,8 @@ static int planner_create_impl(const LdpUnetConfig* cfg, const float* params_hos
   return planner_build_tables(h);
 }
 
+static bool env_off(const char* name);
+
 // ------------------------------- workspace -------------------------------------------------------
 static int level_len(int T, int level) { return T >> level; }
 
@@ -315,11 +323,63 @@ static int get_ws(LdpPlanner* h, int B, int T, PlanWs** out) {
   return LDP_OK;
 }
 
-static int compute_otab(LdpPlanner* h, PlanWs* w, const float* cond, cudaStream_t s) {
-  GemmF32 g;
-  g.x1 = cond; g.c1 = h->cfg.global_cond_dim; g.ld1 = h->cfg.global_cond_dim; g.a_act = 1;
-  g.w = h->wc_all; g.ldw = h->sum_c2; g.out = w->otab; g.ldo = h->sum_c2; g.m = w->B; g.n = h->sum_c2;
-  LDP_TRY(launch_gemm_f32(g, s));
+// Observation part of every block's FiLM Dense, once per act(): otab[b] = Mish(cond[b]) Wc  (B x Dc x sum_c2).
+// fp32 path: SIMT FFMA GEMM (the 1e-5 parity instrument).  bf16 path: one tcgen05 GEMM (persistent tile loop, fp32
+// accumulation and fp32 output) - on SIMT this contraction alone was 1 ms of a 41 ms sampling loop.
+static int compute_otab(LdpPlanner* h, PlanWs* w, const float* cond, int precision, cudaStream_t s) {
+  const int dc = h->cfg.global_cond_dim;
+  if (precision == LDP_PREC_FP32 || env_off("LDP_OTAB_TC")) {
+    GemmF32 g;
+    g.x1 = cond; g.c1 = dc; g.ld1 = dc; g.a_act = 1;
+    g.w = h->wc_all; g.ldw = h->sum_c2; g.out = w->otab; g.ldo = h->sum_c2; g.m = w->B; g.n = h->sum_c2;
+    LDP_TRY(launch_gemm_f32(g, s));
+    return launch_transpose_quads(w->otab, h->sum_c2, w->otab_q, w->B, h->sum_c2, s);
+  }
+  if (!h->otab_packed) {
+    PackedW& pw = h->pw_otab;
+    pw.kp = round_up(dc, 64);
+    pw.n_pad = round_up(h->sum_c2, 128);
+    LDP_TRY(h->arena.alloc_t(&pw.wt, (size_t)pw.n_pad * pw.kp));
+    std::vector<int32_t> kmap(pw.kp);
+    std::vector<TcStage> st(pw.kp / 64);
+    for (int k = 0; k < pw.kp; ++k) kmap[k] = k < dc ? k : -1;
+    for (int i = 0; i < pw.kp / 64; ++i) st[i] = make_stage(0, 0, 1, i * 64, 0, 0, i);
+    Arena tmp;
+    int32_t* map_dev;
+    LDP_TRY(tmp.alloc_t(&map_dev, pw.kp));
+    LDP_CUDA_OK(cudaMemcpy(map_dev, kmap.data(), (size_t)pw.kp * 4, cudaMemcpyHostToDevice));
+    LDP_TRY(upload_stage_table(h->arena, st, &pw));
+    LDP_TRY(launch_pack_wt_bf16(h->wc_all, h->sum_c2, h->sum_c2, map_dev, pw.kp, pw.wt, pw.kp, 0, pw.n_pad, 0));
+    LDP_CUDA_OK(cudaDeviceSynchronize());
+    h->otab_packed = true;
+  }
+  if (!w->otab_ready) {
+    LDP_TRY(tc_driver_check());
+    LDP_TRY(tc_gemm_init());
+    const PackedW& pw = h->pw_otab;
+    w->ld_cb = round_up(dc, 8);
+    LDP_TRY(w->arena.alloc_t(&w->cond_bf16, (size_t)w->B * w->ld_cb));
+    TcGemm& op = w->otab_op;
+    op = TcGemm();
+    uint64_t ad[4] = {(uint64_t)dc, 1, 1, (uint64_t)w->B};
+    uint64_t as[3] = {(uint64_t)w->ld_cb * 2, (uint64_t)w->ld_cb * 2, (uint64_t)w->ld_cb * 2};
+    uint32_t ab[4] = {64, 1, 1, 128};
+    LDP_TRY(make_tmap_bf16(&op.map_a[0], w->cond_bf16, 4, ad, as, ab));
+    for (int i = 1; i < 4; ++i) op.map_a[i] = op.map_a[0];
+    uint64_t bd[2] = {(uint64_t)pw.kp, (uint64_t)pw.n_pad};
+    uint64_t bs[1] = {(uint64_t)pw.kp * 2};
+    uint32_t bb[2] = {64, 128};
+    LDP_TRY(make_tmap_bf16(&op.map_b, pw.wt, 2, bd, bs, bb));
+    op.kb = pw.kb_dev; op.num_kb = pw.num_kb; op.runs = pw.runs_dev; op.num_runs = pw.num_runs;
+    tc_set_inline_runs(&op, pw.runs_host.data(), pw.num_runs);
+    op.M = w->B; op.N = h->sum_c2; op.block_n = 128;
+    op.items_per_tile = 128; op.rows_per_item = 1;
+    op.mode = TC_EPI_PLAIN;
+    op.out_f32 = w->otab; op.ld_out_f32 = h->sum_c2;
+    w->otab_ready = true;
+  }
+  LDP_TRY(launch_cast_bf16(cond, dc, w->cond_bf16, w->ld_cb, w->B, dc, /*mish=*/1, s));
+  LDP_TRY(launch_tc_gemm(w->otab_op, s));
   return launch_transpose_quads(w->otab, h->sum_c2, w->otab_q, w->B, h->sum_c2, s);
 }
 
@@ -651,6 +711,10 @@ static int conv_tc(LdpPlanner* h, PlanWs* w, int op_id, const ConvDesc& d, TcGem
   const bool pair = !d.no_pair && !(pe && pe[0] == '0') && (tapacc || (pe && pe[0] == '2'));
   uint32_t bb[2] = {64, (uint32_t)(pair ? bn / 2 : bn)};
   LDP_TRY(make_tmap_bf16(&op->map_b, pw->wt, 2, bd, bs, bb));
+  {
+    uint32_t bt[2] = {64, 16};                       // extra W rows of a widened last N tile (DDPM epilogue; see TcGemm)
+    LDP_TRY(make_tmap_bf16(&op->map_b_tail, pw->wt, 2, bd, bs, bt));
+  }
   op->pair = pair ? 1 : 0;
   op->kb = pw->kb_dev;
   op->num_kb = pw->num_kb;
@@ -820,6 +884,15 @@ static int prepare_bf16(LdpPlanner* h, PlanWs* w) {
   op.out_bf16 = w->x_bf16; op.ld_out_bf16 = w->ld_xb;
   op.step_dec = w->step_dev; op.done_counter = w->done_counter;      // the step counter advances inside this kernel
   w->ops.push_back(op);
+  if (!env_off("LDP_L2PF")) {
+    // every layer prefetches the next layer's packed weights into L2 (the last one: the first layer's, for the next step)
+    const size_t n = w->ops.size();
+    for (size_t i = 0; i < n; ++i) {
+      const TcGemm& nx = w->ops[(i + 1) % n];
+      w->ops[i].l2_prefetch = nx.wt_host_ref;
+      w->ops[i].l2_prefetch_bytes = (unsigned)std::min<size_t>((size_t)nx.n_pad * nx.k_pad * 2, (size_t)64 << 20);
+    }
+  }
   w->bf16_ready = true;
   return LDP_OK;
 }
@@ -864,6 +937,7 @@ static int prepare_loop(LdpPlanner* h, PlanWs* w) {
     if (op.mode != TC_EPI_PLAIN && op.mode != TC_EPI_GN && op.mode != TC_EPI_DDPM) return LDP_OK;
     if (op.block_n != 64 && op.block_n != 128) return LDP_OK;
     if (op.mode == TC_EPI_DDPM && op.block_n != 128) return LDP_OK;
+    op.allow_tail = 0;
     if (op.num_kb > 256 || op.tiles_per_item != 1) return LDP_OK;
     if ((spc * op.rows_per_item) % 128 != 0) return LDP_OK;
     if (op.pair) {
@@ -928,7 +1002,8 @@ int ldp_unet_forward(LdpPlanner* h, int precision, const float* sample_dev, cons
   cudaStream_t s = (cudaStream_t)cuda_stream;
   PlanWs* w;
   LDP_TRY(get_ws(h, B, T, &w));
-  LDP_TRY(compute_otab(h, w, cond_dev, s));
+  LDP_CHECK(precision == LDP_PREC_FP32 || precision == LDP_PREC_BF16, LDP_ERR_INVALID_ARG, "unknown precision");
+  LDP_TRY(compute_otab(h, w, cond_dev, precision, s));
   StepRef step;
   step.rows = timesteps_dev;
   step.scalar = timestep;
@@ -952,7 +1027,7 @@ int ldp_planner_sample(LdpPlanner* h, int precision, int sampler, const float* x
   PlanWs* w;
   LDP_TRY(get_ws(h, B, T, &w));
   const size_t n = (size_t)B * T * D;
-  LDP_TRY(compute_otab(h, w, cond_dev, s));
+  LDP_TRY(compute_otab(h, w, cond_dev, precision, s));
   LDP_CUDA_OK(cudaMemcpyAsync(w->x_state, x_T_dev, n * 4, cudaMemcpyDeviceToDevice, s));
   DdpmCall call;
   call.noise = noise_dev;

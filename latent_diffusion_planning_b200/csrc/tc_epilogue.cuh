@@ -548,9 +548,10 @@ __device__ __forceinline__ void epilogue_gn(const TcGemm& p, EpiSmem<BN>& es, ui
 // are accessed coalesced and one Philox call serves four elements (row-structured quads, see DdpmCall).
 template <int BN>
 __device__ __forceinline__ void epilogue_ddpm(const TcGemm& p, EpiSmem<BN>& es, uint32_t taddr, float* tile, int tile_m,
-                                              int n0, int c_begin, int row, int et, int lane, int t_override = -1, long long* dbg = nullptr) {
+                                              int n0, int c_begin, int row, int et, int lane, int t_override = -1, long long* dbg = nullptr,
+                                              int n_tail = 0) {
   constexpr int CPP = TcGeo<BN>::CPP;
-  constexpr int TS = BN + 1;
+  const int TS = BN + n_tail + 1;            // odd row pitch of the transposition tile (n_tail: widened last N tile, 0 or 16)
 #pragma unroll 1
   for (int cc = 0; cc < CPP; ++cc) {
     const int c = c_begin + cc;
@@ -562,6 +563,16 @@ __device__ __forceinline__ void epilogue_ddpm(const TcGemm& p, EpiSmem<BN>& es, 
 #pragma unroll
     for (int i = 0; i < 32; ++i) trow[i] = v[i];
   }
+  if (n_tail > 0 && c_begin == 0) {            // uniform per warp: the first column slice also drains the 16 extra columns
+    float v[32];
+    tmem_ld_32x32(taddr + BN, v);              // columns [BN, BN + 32) lie inside the power-of-two TMEM allocation
+    float* trow = tile + row * TS + BN;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const int n = n0 + BN + i;
+      trow[i] = v[i] + ((n < p.N && p.bias) ? __ldg(p.bias + n) : 0.f);
+    }
+  }
   epi_bar<BN>();
   const int t = t_override >= 0 ? t_override : step_of(p.step, 0);
   const float* cf = p.coef + t * 8;
@@ -570,14 +581,18 @@ __device__ __forceinline__ void epilogue_ddpm(const TcGemm& p, EpiSmem<BN>& es, 
   const float* noise = call.noise ? call.noise + (long long)(call.n_steps - 1 - t) * call.noise_step_stride : nullptr;
   const bool ddim = call.sampler == LDP_SAMPLER_DDIM;
   const bool add_noise = !ddim && t > 0;
-  const int nv = min(BN, p.N - n0);
+  const int nv = min(BN + n_tail, p.N - n0);
   const int nq = (nv + 3) >> 2;                                  // column quads of this tile (n0 is a multiple of 4)
   const int rows_here = min(TC_BM, p.M - tile_m * TC_BM);
   const int total = rows_here * nq;
   const bool vb = p.out_bf16 != nullptr && (p.ld_out_bf16 & 3) == 0;
+  // The loop below is issue-bound (Philox + Box-Muller + index arithmetic: ~250 instructions per quad, 9 quads per thread),
+  // not load-bound - prefetching x ahead of the accumulator barrier changed nothing - so the index division is a multiply:
+  // floor(idx / nq) = (idx * ceil(2^20 / nq)) >> 20 exactly for idx < 4608, nq <= 36.
+  const uint32_t nq_inv = ((1u << 20) + (uint32_t)nq - 1u) / (uint32_t)nq;
 #pragma unroll 1
   for (int idx = et; idx < total; idx += TcGeo<BN>::EPI_THREADS) {
-    const int r = idx / nq, g = idx - r * nq;
+    const int r = (int)(((uint32_t)idx * nq_inv) >> 20), g = idx - r * nq;
     const int m = tile_m * TC_BM + r;
     const int cb = g * 4;
     const int cnt = min(4, nv - cb);

@@ -63,7 +63,9 @@ __global__ void __launch_bounds__(TcGeo<BN>::THREADS, 1) tc_gemm_kernel(const __
   const uint32_t cta_rank = PAIR ? cluster_ctarank() : 0u;
   const bool leader = cta_rank == 0;
   const int STAGES = p.num_stages;
-  const uint32_t stage_bytes = TC_A_BYTES + (uint32_t)p.w_max * B_BYTES;
+  const uint32_t stage_bytes = TC_A_BYTES + (uint32_t)p.w_max * B_BYTES + (MODE == TC_EPI_DDPM ? (uint32_t)p.n_tail * (TC_BK * 2) : 0u);
+  // DDPM: this CTA owns the widened last N tile (BN + n_tail columns)
+  const bool tail_tile = MODE == TC_EPI_DDPM && p.n_tail > 0 && blockIdx.y + 1 == gridDim.y;
   __shared__ __align__(8) uint64_t bar_full[TC_MAX_STAGES];
   __shared__ __align__(8) uint64_t bar_empty[TC_MAX_STAGES];
   __shared__ __align__(8) uint64_t bar_tfull[2];              // accumulator buffer b complete (MMA -> epilogue)
@@ -148,7 +150,7 @@ __global__ void __launch_bounds__(TcGeo<BN>::THREADS, 1) tc_gemm_kernel(const __
         const uint32_t nw = (uint32_t)(r_src_acc >> 16) & 0xffu;
         const int d1 = (int)(short)(r_d12 & 0xffff), c2 = c2_base + (r_d12 >> 16);
         const CUtensorMap* map_a = &p.map_a[r_src_acc & 0xff];
-        const uint32_t tx = (PAIR ? 2u : 1u) * (TC_A_BYTES + nw * (uint32_t)B_BYTES);
+        const uint32_t tx = (PAIR ? 2u : 1u) * (TC_A_BYTES + nw * (uint32_t)B_BYTES) + (tail_tile ? (uint32_t)p.n_tail * (TC_BK * 2) : 0u);
         int c0 = r_c0, wkc = r_wk * TC_BK;
         for (int i = 0; i < r_count; ++i) {
           mbar_wait(empty0 + 8u * stage, phase ^ 1u);
@@ -165,6 +167,7 @@ __global__ void __launch_bounds__(TcGeo<BN>::THREADS, 1) tc_gemm_kernel(const __
             tma_load_4d(sa, map_a, bar, c0, d1, c2, c3);
             if (nw == 1) {
               tma_load_2d(sa + TC_A_BYTES, &p.map_b, bar, wkc, n0);
+              if (MODE == TC_EPI_DDPM && tail_tile) tma_load_2d(sa + TC_A_BYTES + B_BYTES, &p.map_b_tail, bar, wkc, n0 + BN);
             } else {
               for (uint32_t j = 0; j < nw; ++j) tma_load_2d(sa + TC_A_BYTES + j * B_BYTES, &p.map_b, bar, wkc + (int)j * TC_BK, n0);
             }
@@ -194,7 +197,8 @@ __global__ void __launch_bounds__(TcGeo<BN>::THREADS, 1) tc_gemm_kernel(const __
     // segments: kb_main stages of nw_main W tiles, then the aux stages), keeps barrier addresses and the descriptor
     // words in registers and advances them by adds.
     if (leader && elect_one()) {
-      constexpr uint32_t idesc = umma_idesc_bf16(PAIR ? 2 * TC_BM : TC_BM, BN);
+      constexpr uint32_t idesc_full = umma_idesc_bf16(PAIR ? 2 * TC_BM : TC_BM, BN);
+      const uint32_t idesc = (MODE == TC_EPI_DDPM && tail_tile) ? umma_idesc_bf16(TC_BM, BN + p.n_tail) : idesc_full;
       constexpr uint32_t DESC_HI = (uint32_t)(1024 >> 4) | (1u << 14) | (2u << 29);   // SBO 1024 B, version 1, SWIZZLE_128B
       constexpr uint32_t B_STEP = (uint32_t)B_BYTES >> 4;
       const uint32_t stage_step = stage_bytes >> 4;
@@ -288,6 +292,17 @@ __global__ void __launch_bounds__(TcGeo<BN>::THREADS, 1) tc_gemm_kernel(const __
   } else {
     // ===================== epilogue warps (2..9) =====================
     const int ew = warp - 2;
+    if (p.l2_prefetch_bytes != 0 && threadIdx.x == 64) {
+      // weights never depend on earlier kernels: issued ahead of griddepcontrol.wait
+      const unsigned nctas = gridDim.x * gridDim.y, cta = blockIdx.y * gridDim.x + blockIdx.x;
+      const unsigned chunk = (((p.l2_prefetch_bytes + nctas - 1) / nctas) + 4095u) & ~4095u;
+      const unsigned lo = cta * chunk, hi = min(p.l2_prefetch_bytes, lo + chunk);
+      const char* base = reinterpret_cast<const char*>(p.l2_prefetch);
+      for (unsigned off = lo; off < hi; off += 4096u) {
+        const unsigned n = min(4096u, hi - off) & ~15u;
+        if (n) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(base + off), "r"(n) : "memory");
+      }
+    }
     const int quarter = warp & 3;                        // TMEM lane quarter this warp may access
     const int part = ew >> 2;                            // which column slice of the tile
     const int row = quarter * 32 + lane;
@@ -329,7 +344,7 @@ __global__ void __launch_bounds__(TcGeo<BN>::THREADS, 1) tc_gemm_kernel(const __
     else if constexpr (MODE == TC_EPI_GN) epilogue_gn<BN>(p, es, taddr, m, n0, c_begin, row, lane, pf);
     else if constexpr (MODE == TC_EPI_DDPM)
       epilogue_ddpm<BN>(p, es, taddr, reinterpret_cast<float*>(smem_raw + (smem_base - smem_u32(smem_raw))), tile_m, n0,
-                        c_begin, row, (int)threadIdx.x - 64, lane);
+                        c_begin, row, (int)threadIdx.x - 64, lane, -1, nullptr, tail_tile ? p.n_tail : 0);
     else epilogue_ln<BN>(p, es, taddr, m, n0, c_begin, row, part, lane);
     if (!PERSIST) break;
     tc_fence_before();                                   // hand the accumulator buffer back, protect `es`
@@ -471,13 +486,19 @@ int tc_gemm_geometry(TcGemm* p) {
   const int tm = ceil_div(p->M, TC_BM);
   p->tiles_m = p->pair ? round_up(tm, 2) : tm;
   p->tiles_n = ceil_div(p->N, bn);
+  p->n_tail = 0;
+  if (p->mode == TC_EPI_DDPM && p->allow_tail && !p->pair && p->tiles_n >= 2 && p->n_acc == 1 && !p->use_aux &&
+      p->N - (p->tiles_n - 1) * bn <= 16 && p->w_max == 1) {
+    p->tiles_n -= 1;                 // the last N tile takes the remaining <= 16 columns as well
+    p->n_tail = 16;
+  }
   const int tiles = p->tiles_m * p->tiles_n;
   static int persist = -1;
   if (persist < 0) { const char* e = getenv("LDP_PERSIST"); persist = (e && e[0] == '0') ? 0 : 1; }
   const bool persistent = persist && tiles > 148 && !p->pair && p->mode == TC_EPI_PLAIN;
   p->grid_ctas = persistent ? 148 : tiles;
   p->persistent = persistent ? 1 : 0;
-  p->acc_stride = n_acc_total * bn;
+  p->acc_stride = n_acc_total * bn + p->n_tail;
   p->acc_bufs = (persistent && 2 * p->acc_stride <= 512) ? 2 : 1;
   int cols = 32;
   while (cols < p->acc_bufs * p->acc_stride) cols <<= 1;
@@ -501,11 +522,11 @@ static int launch_tc_gemm_inst(const TcGemm& p_in, cudaStream_t s) {
     if (skip < 0) { const char* e = getenv("LDP_EPI_SKIP"); skip = e ? atoi(e) : 0; }
     p.epi_skip = skip;
   }
-  const int stage_bytes = PAIR ? TC_A_BYTES + p.w_max * (BN / 2) * TC_BK * 2 : tc_stage_bytes(BN, p.w_max);
+  const int stage_bytes = (PAIR ? TC_A_BYTES + p.w_max * (BN / 2) * TC_BK * 2 : tc_stage_bytes(BN, p.w_max)) + p.n_tail * TC_BK * 2;
   p.num_stages = std::min(TC_MAX_STAGES, TC_SMEM_RING / stage_bytes);
   LDP_CHECK(p.num_stages >= 2, LDP_ERR_UNSUPPORTED, "tc_gemm: stage does not fit the shared-memory ring twice");
   if (MODE == TC_EPI_DDPM)
-    LDP_CHECK(p.num_stages * stage_bytes >= TC_BM * (BN + 1) * 4, LDP_ERR_UNSUPPORTED,
+    LDP_CHECK(p.num_stages * stage_bytes >= TC_BM * (BN + p.n_tail + 1) * 4, LDP_ERR_UNSUPPORTED,
               "tc_gemm DDPM epilogue: transposition tile does not fit the ring");
   if (p.n_acc > 1 || p.shift[0] != 0)
     LDP_CHECK(p.rows_per_item >= 1 && p.rows_per_item <= 32 && (p.rows_per_item & (p.rows_per_item - 1)) == 0,
