@@ -97,6 +97,10 @@ struct LdpIdm {
   std::vector<PackedW> pw1, pw2;
   PackedW pwout;
   bool use_graph = true;
+  // persistent loop kernel (idm_loop.cu)
+  bool loop_ready = false;
+  IdmLoop loop;
+  float* bsum = nullptr;     // [n_blocks][H] running sums of the down-projection biases
 };
 
 namespace ldp {
@@ -332,6 +336,46 @@ static int idm_prepare_bf16(LdpIdm* h, IdmWs* w) {
   return LDP_OK;
 }
 
+// Weight-side arguments of the persistent loop kernel (maps over the packed weights, bias sums); built once per handle.
+static int idm_prepare_loop(LdpIdm* h) {
+  if (h->loop_ready) return LDP_OK;
+  const int H = h->cfg.hidden_dim, A = h->cfg.action_dim, nb = h->cfg.n_blocks;
+  IdmLoop& lp = h->loop;
+  lp = IdmLoop();
+  std::vector<float> sums((size_t)nb * H, 0.f), tmp(H);
+  for (int b = 0; b < nb; ++b) {
+    LDP_CUDA_OK(cudaMemcpy(tmp.data(), h->blk[b].b2, (size_t)H * 4, cudaMemcpyDeviceToHost));
+    for (int i = 0; i < H; ++i) sums[(size_t)b * H + i] = (b ? sums[(size_t)(b - 1) * H + i] : 0.f) + tmp[i];
+  }
+  LDP_TRY(h->arena.alloc_t(&h->bsum, sums.size()));
+  LDP_CUDA_OK(cudaMemcpy(h->bsum, sums.data(), sums.size() * 4, cudaMemcpyHostToDevice));
+  for (int b = 0; b < nb; ++b) {
+    uint64_t d1[2] = {(uint64_t)h->pw1[b].kp, (uint64_t)h->pw1[b].n_pad};
+    uint64_t s1[1] = {(uint64_t)h->pw1[b].kp * 2};
+    uint32_t b1[2] = {64, 128};
+    LDP_TRY(make_tmap_bf16(&lp.map_w1[b], h->pw1[b].wt, 2, d1, s1, b1));
+    uint64_t d2[2] = {(uint64_t)h->pw2[b].kp, (uint64_t)h->pw2[b].n_pad};
+    uint64_t s2[1] = {(uint64_t)h->pw2[b].kp * 2};
+    uint32_t b2[2] = {64, 256};
+    LDP_TRY(make_tmap_bf16(&lp.map_w2[b], h->pw2[b].wt, 2, d2, s2, b2));
+    lp.b1[b] = h->blk[b].b1;
+    lp.bsum[b] = h->bsum + (size_t)b * H;
+    lp.ln_g[b] = h->blk[b].ln_s;
+    lp.ln_b[b] = h->blk[b].ln_b;
+  }
+  for (int b = nb; b < 4; ++b) { lp.map_w1[b] = lp.map_w1[0]; lp.map_w2[b] = lp.map_w2[0]; }
+  uint64_t d3[2] = {(uint64_t)h->pwout.kp, (uint64_t)h->pwout.n_pad};
+  uint64_t s3[1] = {(uint64_t)h->pwout.kp * 2};
+  uint32_t b3[2] = {64, 16};
+  LDP_TRY(make_tmap_bf16(&lp.map_wout, h->pwout.wt, 2, d3, s3, b3));
+  static unsigned long long gen = 0;
+  lp.const_gen = ++gen;                       // a new handle may reuse a freed handle's addresses
+  lp.n_blocks = nb; lp.A = A;
+  lp.ctab_h = h->ctab_h; lp.wa = h->w0; lp.bout = h->bout; lp.coef = h->coef;
+  h->loop_ready = true;
+  return LDP_OK;
+}
+
 static int idm_run_bf16(LdpIdm* h, IdmWs* w, const float* a, StepRef step, bool final_plain, float* eps_out, cudaStream_t s) {
   LDP_TRY(idm_input(h, w, a, step, true, s));
   for (size_t i = 0; i < w->ops.size(); ++i) {
@@ -433,6 +477,30 @@ int ldp_idm_sample(LdpIdm* h, int precision, int sampler, const float* s_dev, co
     }
   } else {
     LDP_TRY(idm_prepare_bf16(h, w));
+    const char* le = getenv("LDP_IDM_LOOP");
+    if (!(le && le[0] == '0') && h->cfg.hidden_dim == 256 && A <= 16 && h->cfg.n_blocks <= 4) {
+      // the whole reverse loop in one persistent launch (idm_loop.cu)
+      LDP_TRY(idm_prepare_loop(h));
+      IdmLoop lp = h->loop;
+      lp.N = N; lp.n_steps = n_steps; lp.t_first = n_steps - 1;
+      lp.spre = w->spre; lp.a_state = w->a_state; lp.call = call;
+      const char* de = getenv("LDP_IDM_LOOP_DBG");
+      long long* dbg_dev = nullptr;
+      Arena dbg_arena;
+      if (de && de[0] == '1') { LDP_TRY(dbg_arena.alloc_t(&dbg_dev, 16)); lp.dbg = dbg_dev; }
+      LDP_TRY(launch_idm_loop(lp, s));
+      count_launch();
+      if (dbg_dev) {
+        long long hb[16];
+        LDP_CUDA_OK(cudaStreamSynchronize(s));
+        LDP_CUDA_OK(cudaMemcpy(hb, dbg_dev, sizeof(hb), cudaMemcpyDeviceToHost));
+        fprintf(stderr, "idm loop (CTA 0, %d steps): MMA thread total %lld cycles, waiting: weights %lld, U drained %lld, operand chunk %lld, "
+                "LayerNorm %lld | epilogue thread: input %lld, LayerNorm %lld, chunk drain work %lld, wait chunk %lld, wait block %lld, output+step %lld\n",
+                n_steps, hb[4], hb[0], hb[1], hb[2], hb[3], hb[8], hb[9], hb[10], hb[11], hb[12], hb[13]);
+      }
+      LDP_CUDA_OK(cudaMemcpyAsync(a0_dev, w->a_state, n * 4, cudaMemcpyDeviceToDevice, s));
+      return LDP_OK;
+    }
     if (h->use_graph && !w->graph) {
       cudaStream_t cs;
       LDP_CUDA_OK(cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));

@@ -248,6 +248,28 @@ int upload_planner_loop_layers(const TcGemm* layers_host, int n_layers, cudaStre
 int launch_planner_loop(const PlannerLoop& lp, int n_groups, cudaStream_t s);
 int tc_gemm_geometry(TcGemm* p);   // fills tiles_m/n, grid_ctas, acc_bufs, acc_stride, tmem_cols
 
+// The whole IDM reverse-diffusion loop as one persistent kernel (idm_loop.cu); hidden_dim 256, action_dim <= 16, <= 4 blocks.
+struct IdmLoop {
+  CUtensorMap map_w1[4];            // per block: W1^T [1024][256] bf16 K-major, box {64, 128}
+  CUtensorMap map_w2[4];            // per block: W2^T [256][1024] bf16 K-major, box {64, 256}
+  CUtensorMap map_wout;             // Wout^T [>=16][256] bf16 K-major (rows >= action_dim zero), box {64, 16}
+  int n_blocks = 0, N = 0, A = 0, n_steps = 0, t_first = 0;
+  const float* spre = nullptr;      // [N][256]  (s||s') Ws, once per act()
+  const float* ctab_h = nullptr;    // [n_train][256]  cond(t) Wc + b0
+  const float* wa = nullptr;        // [A][256]  action rows of the first Dense
+  const float* b1[4] = {nullptr, nullptr, nullptr, nullptr};     // [1024] up-projection bias
+  const float* bsum[4] = {nullptr, nullptr, nullptr, nullptr};   // [256] b2_0 + ... + b2_b (the TMEM residual stream carries no bias)
+  const float* ln_g[4] = {nullptr, nullptr, nullptr, nullptr};
+  const float* ln_b[4] = {nullptr, nullptr, nullptr, nullptr};
+  const float* bout = nullptr;      // [A]
+  const float* coef = nullptr;      // [n_train][8] scheduler coefficients
+  DdpmCall call;
+  float* a_state = nullptr;         // [N][A] in: a_T, out: a_0
+  unsigned long long const_gen = 0; // identifies the handle whose constants (biases, LayerNorm, Wa) are in the kernel's constant memory
+  long long* dbg = nullptr;         // diagnostics (LDP_IDM_LOOP_DBG=1): CTA 0's cycles spent waiting per barrier class
+};
+int launch_idm_loop(const IdmLoop& p, cudaStream_t s);
+
 // cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time libcuda dependency).
 // bf16 tensor, up to 4-D, dims/strides innermost-first (strides in BYTES for dims 1..rank-1), SWIZZLE_128B.
 int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
