@@ -72,6 +72,43 @@ __global__ void __launch_bounds__(256) vae_conv_in_kernel(const PixT* __restrict
   }
 }
 
+// conv_in on the tensor cores (bf16 path): im2col of the 3x3xCin input window into a K-major bf16 matrix [pixels][64] that the
+// tcgen05 GEMM reads through TMA like any dense operand.  uint8 pixels are written as x - 128 - integers -128..127 are exact in
+// bf16 - and the reference's x/255*2-1 (utils/data_utils.py:11, process_sdvae_data.py:89-90) is folded into the packed weights:
+//   sum_taps w (x/127.5 - 1) = sum_taps (w/127.5) (x - 128)  +  sum_{valid taps} (0.5/127.5) sum_ci w
+// where the second term needs "is this tap inside the image" (zero padding pads the NORMALISED image): columns [9 Cin, 9 Cin + 9)
+// hold those nine indicators.  (Centring keeps the operand in [-1, 1] like the normalised pixel: with raw 0..255 the two terms
+// are each ~3x the result and their bf16 weight rounding does not cancel.)  float32 input (already normalised) is written as
+// is and the indicator weights are zero.
+template <typename PixT>
+__global__ void __launch_bounds__(256) vae_im2col_in_kernel(const PixT* __restrict__ img, __nv_bfloat16* __restrict__ out,
+                                                            long long npix, int S, int cin) {
+  for (long long pix = blockIdx.x * (long long)blockDim.x + threadIdx.x; pix < npix; pix += (long long)gridDim.x * blockDim.x) {
+    const int x = (int)(pix % S), y = (int)((pix / S) % S);
+    const long long b = pix / ((long long)S * S);
+    __align__(16) __nv_bfloat16 row[64];
+#pragma unroll
+    for (int i = 0; i < 64; ++i) row[i] = __float2bfloat16(0.f);
+    for (int dy = 0; dy < 3; ++dy) {
+      const int yy = y + dy - 1;
+      for (int dx = 0; dx < 3; ++dx) {
+        const int xx = x + dx - 1;
+        const bool ok = yy >= 0 && yy < S && xx >= 0 && xx < S;
+        const int tap = dy * 3 + dx;
+        if (ok) {
+          const PixT* ip = img + ((b * S + yy) * S + xx) * cin;
+          for (int ci = 0; ci < cin; ++ci) row[tap * cin + ci] = __float2bfloat16(sizeof(PixT) == 1 ? (float)ip[ci] - 128.f : (float)ip[ci]);
+          row[9 * cin + tap] = __float2bfloat16(1.f);
+        }
+      }
+    }
+    uint4* dst = reinterpret_cast<uint4*>(out + pix * 64);
+    const uint4* src = reinterpret_cast<const uint4*>(row);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) dst[i] = src[i];
+  }
+}
+
 // Direct NHWC convolution in fp32 (parity path): out[b,y,x,co] = bias[co] + sum in[b, y*s+dy-pad, x*s+dx-pad, ci] w[dy,dx,ci,co]
 // (+ res).  One thread per (8 consecutive output pixels of a row, output channel); weights are read coalesced over co.
 __global__ void __launch_bounds__(128) vae_conv_f32_kernel(const float* __restrict__ in, const float* __restrict__ w,
@@ -360,6 +397,9 @@ struct VaeWs {
   __nv_bfloat16 *Sb = nullptr, *Gb = nullptr;        // tc path
   bool tc_ready = false;
   std::vector<TcGemm> ops;
+  TcGemm op_in[2];                                   // conv_in as a dense tcgen05 GEMM over the im2col matrix (uint8 / float pixels)
+  bool op_in_ok = false;
+  __nv_bfloat16* cols = nullptr;                     // im2col matrix [Bc * S * S][64]: Gb when that is large enough, else its own buffer
 };
 
 }  // namespace ldp
@@ -379,6 +419,8 @@ struct LdpVae {
   float* wqkv = nullptr; float* bqkv = nullptr;      // [C][3C], [3C] concatenated projections
   std::map<int, std::unique_ptr<VaeWs>> ws;
   std::map<int, PackedW> packed;                     // conv id -> packed weights (tc path)
+  PackedW pw_in[2];                                  // conv_in as a K = 64 dense GEMM: [0] uint8 pixels (normalisation folded in), [1] float pixels
+  bool pw_in_ready[2] = {false, false};
   int64_t n_params = 0;
   bool is_decoder = false;                           // decoder handle: blocks = up blocks, down = upsampler convs, quant = post_quant_conv
 };
@@ -708,6 +750,85 @@ static int vae_conv_tc(LdpVae* h, VaeWs* w, int id, const ConvW& cw, const float
   return LDP_OK;
 }
 
+// conv_in as a dense K = 64 GEMM (see vae_im2col_in_kernel): packed weights [n_pad][64] bf16 for uint8 (fmt 0) or float (fmt 1) pixels
+static int vae_pack_conv_in(LdpVae* h, int fmt) {
+  if (h->pw_in_ready[fmt]) return LDP_OK;
+  const int cin = h->cfg.in_channels, c0 = h->cfg.block_out_channels[0], kc = 9 * cin;
+  std::vector<float> w((size_t)kc * c0), full((size_t)64 * c0, 0.f);
+  LDP_CUDA_OK(cudaMemcpy(w.data(), h->conv_in.w, w.size() * 4, cudaMemcpyDeviceToHost));
+  for (int k = 0; k < kc; ++k)
+    for (int n = 0; n < c0; ++n) full[(size_t)k * c0 + n] = fmt == 0 ? w[(size_t)k * c0 + n] / 127.5f : w[(size_t)k * c0 + n];
+  if (fmt == 0)
+    for (int tap = 0; tap < 9; ++tap)
+      for (int n = 0; n < c0; ++n) {
+        float sum = 0.f;
+        for (int ci = 0; ci < cin; ++ci) sum += w[(size_t)(tap * cin + ci) * c0 + n];
+        full[(size_t)(kc + tap) * c0 + n] = sum * (0.5f / 127.5f);
+      }
+  PackedW& pw = h->pw_in[fmt];
+  pw.kp = 64;
+  pw.n_pad = round_up(c0, 128);
+  LDP_TRY(h->arena.alloc_t(&pw.wt, (size_t)pw.n_pad * pw.kp));
+  std::vector<TcStage> st(1, make_stage(0, 0, 1, 0, 0, 0, 0));
+  LDP_TRY(upload_stage_table(h->arena, st, &pw));
+  Arena tmp;
+  float* full_dev;
+  int32_t* map_dev;
+  std::vector<int32_t> kmap(64);
+  for (int k = 0; k < 64; ++k) kmap[k] = k;
+  LDP_TRY(tmp.alloc_t(&full_dev, full.size()));
+  LDP_TRY(tmp.alloc_t(&map_dev, 64));
+  LDP_CUDA_OK(cudaMemcpy(full_dev, full.data(), full.size() * 4, cudaMemcpyHostToDevice));
+  LDP_CUDA_OK(cudaMemcpy(map_dev, kmap.data(), 64 * 4, cudaMemcpyHostToDevice));
+  LDP_TRY(launch_pack_wt_bf16(full_dev, c0, c0, map_dev, 64, pw.wt, 64, 0, pw.n_pad, 0));
+  LDP_CUDA_OK(cudaDeviceSynchronize());
+  h->pw_in_ready[fmt] = true;
+  return LDP_OK;
+}
+
+static int vae_conv_in_op(LdpVae* h, VaeWs* w, int fmt, const __nv_bfloat16* cols, float* of32, __nv_bfloat16* obf, TcGemm* op) {
+  LDP_TRY(vae_pack_conv_in(h, fmt));
+  const PackedW& pw = h->pw_in[fmt];
+  const LdpVaeConfig& c = h->cfg;
+  const int S = c.image_size, c0 = c.block_out_channels[0], G = c.norm_num_groups, cpg = c0 / G;
+  const TileGeo g = tile_geo(S);
+  const int P = S * S;
+  *op = TcGemm();
+  if (g.ib == 1) {                  // a tile = 128 consecutive pixels of one image
+    uint64_t dims[4] = {64, 128, (uint64_t)g.tiles_per_img, (uint64_t)w->Bc};
+    uint64_t str[3] = {128, 128 * 128, (uint64_t)P * 128};
+    uint32_t box[4] = {64, 128, 1, 1};
+    LDP_TRY(make_tmap_bf16(&op->map_a[0], cols, 4, dims, str, box));
+    op->tiles_per_item = g.tiles_per_img; op->rows_step = 1; op->items_per_tile = 1;
+  } else {                          // a tile = all P pixels of ib images
+    uint64_t dims[4] = {64, (uint64_t)P, 1, (uint64_t)w->Bc};
+    uint64_t str[3] = {128, (uint64_t)P * 128, (uint64_t)P * 128};
+    uint32_t box[4] = {64, (uint32_t)P, 1, (uint32_t)g.ib};
+    LDP_TRY(make_tmap_bf16(&op->map_a[0], cols, 4, dims, str, box));
+    op->tiles_per_item = 1; op->rows_step = 0; op->items_per_tile = g.ib;
+  }
+  for (int i = 1; i < 4; ++i) op->map_a[i] = op->map_a[0];
+  const int bn = c0 > 64 ? 128 : 64;
+  uint64_t bd[2] = {(uint64_t)pw.kp, (uint64_t)pw.n_pad};
+  uint64_t bs[1] = {(uint64_t)pw.kp * 2};
+  uint32_t bb[2] = {64, (uint32_t)bn};
+  LDP_TRY(make_tmap_bf16(&op->map_b, pw.wt, 2, bd, bs, bb));
+  op->kb = pw.kb_dev; op->num_kb = pw.num_kb; op->runs = pw.runs_dev; op->num_runs = pw.num_runs;
+  tc_set_inline_runs(op, pw.runs_host.data(), pw.num_runs);
+  op->w_max = 1; op->k_pad = pw.kp;
+  op->M = w->Bc * P; op->N = c0; op->block_n = bn;
+  op->rows_per_item = 1;
+  op->mode = TC_EPI_PLAIN;
+  op->bias = h->conv_in.b;
+  op->out_f32 = of32; op->ld_out_f32 = c0;
+  op->out_bf16 = obf; op->ld_out_bf16 = c0;
+  const bool fuse = c0 % G == 0 && (cpg == 4 || cpg == 8 || cpg == 16 || cpg == 32) && P >= 64 && g.ib <= 2 && g.tiles_per_img <= 64;
+  if (fuse) {                       // partial GroupNorm sums of the first resnet's norm1 come out of this epilogue too
+    op->gn_part = w->part; op->gn_cpg = cpg; op->gn_G = G; op->gn_slabs = g.tiles_per_img; op->gn_imgs_per_tile = g.ib;
+  }
+  return LDP_OK;
+}
+
 struct VaeBufs { float *S, *Hf; __nv_bfloat16 *Sb, *Gb; };
 
 // Walks the encoder once.  build = true: creates the TcGemm ops (tensor maps bound to the workspace buffers) in
@@ -770,7 +891,29 @@ static int vae_walk_tc(LdpVae* h, VaeWs* w, bool build, const void* images, int 
   };
   int S = c.image_size;
   const int c0 = c.block_out_channels[0];
-  if (!build) {
+  static const bool in_tc = !(getenv("LDP_VAE_IN_TC") && getenv("LDP_VAE_IN_TC")[0] == '0');
+  const bool conv_in_tc = in_tc && 9 * c.in_channels + 9 <= 64 && ((S * S) % 128 == 0 || 128 % (S * S) == 0);
+  if (build) {
+    w->op_in_ok = false;
+    if (conv_in_tc) {
+      // the im2col matrix lives in Gb (which the first GroupNorm overwrites only after this GEMM has read it) when Gb holds 64
+      // values per pixel, i.e. for c0 >= 64; narrow test encoders get their own buffer
+      if (vae_max_act(h) >= (size_t)S * S * 64) w->cols = b.Gb;
+      else LDP_TRY(w->arena.alloc_t(&w->cols, (size_t)w->Bc * S * S * 64));
+      for (int f = 0; f < 2; ++f) LDP_TRY(vae_conv_in_op(h, w, f, w->cols, b.S, b.Sb, &w->op_in[f]));
+      w->op_in_ok = true;
+    }
+  } else if (w->op_in_ok) {
+    const long long npix = (long long)nimg * S * S;
+    const int blocks = (int)std::min<long long>((npix + 255) / 256, 148 * 16);
+    if (fmt == 0) vae_im2col_in_kernel<uint8_t><<<blocks, 256, 0, s>>>((const uint8_t*)images, w->cols, npix, S, c.in_channels);
+    else vae_im2col_in_kernel<float><<<blocks, 256, 0, s>>>((const float*)images, w->cols, npix, S, c.in_channels);
+    VAE_LAUNCH_OK("vae_im2col_in");
+    TcGemm op = w->op_in[fmt];
+    op.M = (int)npix;
+    LDP_TRY(launch_tc_gemm(op, s));
+    fused_slabs = op.gn_part ? op.gn_slabs : 0;
+  } else {
     const size_t smem = (size_t)9 * c.in_channels * c0 * 4;
     const long long tot = (long long)nimg * S * S * c0 / 4;
     const int blocks = (int)std::min<long long>((tot + 255) / 256, 148 * 8);
@@ -1109,7 +1252,8 @@ int ldp_vae_encode(LdpVae* h, int precision, const void* images_dev, int pixel_f
   const LdpVaeConfig& c = h->cfg;
   const int S = c.image_size, hw = S >> (c.n_blocks - 1);
   const size_t px_bytes = pixel_format == 0 ? 1 : 4;
-  const int chunk = std::min(B, 256);
+  static const int chunk_max = []() { const char* e = getenv("LDP_VAE_CHUNK"); const int v = e ? atoi(e) : 0; return v > 0 ? v : 256; }();
+  const int chunk = std::min(B, chunk_max);
   VaeWs* w;
   LDP_TRY(vae_get_ws(h, chunk, &w));
   if (precision == LDP_PREC_BF16) LDP_TRY(vae_prepare_tc(h, w));
