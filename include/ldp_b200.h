@@ -262,6 +262,17 @@ LDP_API int ldp_idm_loss_grad(LdpTrainer* h, int precision, const float* params_
                               const float* a0_dev, const float* noise_dev, const int32_t* t_dev, int N,
                               float loss_weight, float* loss_dev, void* cuda_stream);
 
+/* Data-parallel exchange of `update` (reference train_bc.py:70-78: the global batch is sharded over devices and jax.grad's
+ * result is averaged by GSPMD; here every rank holds an equal shard and all-reduces the flat gradient buffer).  The backward
+ * pass finishes the gradient buffer range by range, in reverse layer order: ldp_trainer_grad_buckets returns those ranges
+ * (float offsets / lengths into grads_dev) for the LAST ldp_*_loss_grad call on this handle, in completion order;
+ * has_event[i] = 1: the range is complete as soon as the event the step records for it has fired - ldp_trainer_wait_bucket
+ * makes `cuda_stream` wait for exactly that (cudaStreamWaitEvent), so a communication stream can start the bucket's
+ * all-reduce while the rest of the backward pass still runs; has_event[i] = 0: complete when the call itself is. */
+LDP_API int ldp_trainer_grad_buckets(LdpTrainer* h, int64_t* offsets, int64_t* lengths, int32_t* has_event, int max_buckets,
+                                     int* n_buckets);
+LDP_API int ldp_trainer_wait_bucket(LdpTrainer* h, int bucket, void* cuda_stream);
+
 /* optax.adam step (agent/ldp_agent.py:580-600; optax 0.2.2 scale_by_adam, eps outside the square root, eps_root 0):
  * g = grads * grad_scale; mu = b1 mu + (1-b1) g; nu = b2 nu + (1-b2) g^2;
  * params -= lr * (mu / (1-b1^count)) / (sqrt(nu / (1-b2^count)) + eps);  count is 1-based. */

@@ -26,7 +26,7 @@ EXPORTS = [
     "ldp_vae_create", "ldp_vae_destroy", "ldp_vae_param_count", "ldp_vae_encode",
     "ldp_vae_decoder_create", "ldp_vae_decoder_param_count", "ldp_vae_decode",
     "ldp_unet_trainer_create", "ldp_idm_trainer_create", "ldp_trainer_destroy", "ldp_unet_loss_grad",
-    "ldp_idm_loss_grad", "ldp_adam_update",
+    "ldp_idm_loss_grad", "ldp_adam_update", "ldp_trainer_grad_buckets", "ldp_trainer_wait_bucket",
     "ldp_jax_random",
     "ldp_tc_dense", "ldp_launch_count", "ldp_launch_count_reset",
 ]
@@ -107,6 +107,8 @@ def load() -> C.CDLL:
     lib.ldp_trainer_destroy.argtypes = [vp]
     lib.ldp_unet_loss_grad.argtypes = [vp, i32, vp, vp, vp, vp, vp, vp, i32, i32, f32, vp, vp]
     lib.ldp_idm_loss_grad.argtypes = [vp, i32, vp, vp, vp, vp, vp, vp, i32, f32, vp, vp]
+    lib.ldp_trainer_grad_buckets.argtypes = [vp, vp, vp, vp, i32, vp]
+    lib.ldp_trainer_wait_bucket.argtypes = [vp, i32, vp]
     lib.ldp_adam_update.argtypes = [vp, vp, vp, vp, u64, f32, f32, f32, f32, i64, f32, vp]
     lib.ldp_jax_random.argtypes = [vp, i32, i64, i32, vp, vp]
     lib.ldp_tc_dense.argtypes = [vp, vp, vp, vp, i32, i32, i32, vp]

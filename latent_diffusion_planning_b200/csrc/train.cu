@@ -1018,6 +1018,14 @@ struct LdpTrainer {
   Scratch stage[4];
   bool use_graph = true;
   cudaStream_t cap_stream = nullptr;
+  // Gradient buckets for the data-parallel exchange: contiguous ranges of the flat gradient buffer in the order the backward
+  // pass completes them (reverse layer order).  A bucket with ev >= 0 has its own event, recorded inside the step (an external
+  // event-record node when the step is a captured graph) once every kernel that writes the range - data gradients on the main
+  // stream, weight gradients on the side stream - has been issued; ev = -1: complete when the whole call is (stream order).
+  struct Bucket { int64_t off, len; int ev; };
+  std::vector<Bucket> buckets;
+  std::vector<cudaEvent_t> bucket_ev;
+  int64_t bucket_floats = 6 << 20;                    // close a bucket every ~24 MB (LDP_BUCKET_MB)
   void drop_graphs() {
     for (auto& kv : graphs)
       if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
@@ -1026,6 +1034,7 @@ struct LdpTrainer {
   LdpTrainer() {
     const char* ge = getenv("LDP_TRAIN_GRAPH");
     use_graph = !(ge && ge[0] == '0');
+    if (const char* be = getenv("LDP_BUCKET_MB")) bucket_floats = std::max<int64_t>(1024, (int64_t)(atof(be) * (1 << 18)));
     const char* e = getenv("LDP_TRAIN_STREAMS");
     if (!(e && e[0] == '1')) {
       cudaStreamCreateWithFlags(&side, cudaStreamNonBlocking);
@@ -1039,6 +1048,7 @@ struct LdpTrainer {
     if (side) { cudaStreamSynchronize(side); cudaStreamDestroy(side); }
     if (ev_fork) cudaEventDestroy(ev_fork);
     if (ev_join) cudaEventDestroy(ev_join);
+    for (cudaEvent_t e : bucket_ev) cudaEventDestroy(e);
   }
 };
 
@@ -1257,6 +1267,30 @@ static int unet_loss_grad(LdpTrainer* h, int prec, const float* params, float* g
     if (b.proj) LDP_TRY(conv_bwd(b.x1, b.x2, g1b, b.rw.w, b.rw.g, b.rb.g, cout, *b.r, cx));
     return LDP_OK;
   };
+  // Gradient buckets (data-parallel all-reduce overlapped with the rest of the backward pass): the CRB parameters lie in the
+  // blob in forward order and are finished in reverse, so "the blocks finished since the last bucket" is one contiguous range.
+  h->buckets.clear();
+  int n_ev = 0;
+  int64_t bucket_hi = head + crb_total;               // end of the open bucket
+  auto block_off = [&](int bi) { return (int64_t)(blocks[bi].c1w.g - grads); };
+  auto close_bucket = [&](int bi) -> int {             // called after crb_bwd(blocks[bi]); closes [offset of block bi, bucket_hi)
+    const int64_t lo = block_off(bi);
+    if (bi == 0 || bucket_hi - lo < h->bucket_floats) return LDP_OK;
+    LDP_TRY(join_side(cx));                            // weight gradients of these layers run on the side stream
+    if ((int)h->bucket_ev.size() <= n_ev) {
+      cudaEvent_t e;
+      LDP_CUDA_OK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+      h->bucket_ev.push_back(e);
+    }
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    LDP_CUDA_OK(cudaStreamIsCapturing(s, &cs));
+    if (cs == cudaStreamCaptureStatusActive) LDP_CUDA_OK(cudaEventRecordWithFlags(h->bucket_ev[n_ev], s, cudaEventRecordExternal));
+    else LDP_CUDA_OK(cudaEventRecord(h->bucket_ev[n_ev], s));
+    h->buckets.push_back({lo, bucket_hi - lo, n_ev});
+    ++n_ev;
+    bucket_hi = lo;
+    return LDP_OK;
+  };
   // reverse creation order: resampling convs are interleaved with the blocks exactly as in the forward
   {
     int bi = (int)blocks.size() - 1;
@@ -1264,20 +1298,23 @@ static int unet_loss_grad(LdpTrainer* h, int prec, const float* params, float* g
     for (int u = nl - 2; u >= 0; --u) {          // up path, last to first
       Resamp& r = resamp[ri--];
       LDP_TRY(conv_bwd(r.x, nullptr, r.g, r.w.w, r.w.g, r.b.g, r.cout, *r.y, cx));
-      LDP_TRY(crb_bwd(blocks[bi--]));
-      LDP_TRY(crb_bwd(blocks[bi--]));
+      LDP_TRY(crb_bwd(blocks[bi])); LDP_TRY(close_bucket(bi--));
+      LDP_TRY(crb_bwd(blocks[bi])); LDP_TRY(close_bucket(bi--));
     }
-    LDP_TRY(crb_bwd(blocks[bi--]));              // mid
-    LDP_TRY(crb_bwd(blocks[bi--]));
+    LDP_TRY(crb_bwd(blocks[bi])); LDP_TRY(close_bucket(bi--));              // mid
+    LDP_TRY(crb_bwd(blocks[bi])); LDP_TRY(close_bucket(bi--));
     for (int l = nl - 1; l >= 0; --l) {          // down path
       if (l < nl - 1) {
         Resamp& r = resamp[ri--];
         LDP_TRY(conv_bwd(r.x, nullptr, r.g, r.w.w, r.w.g, r.b.g, r.cout, *r.y, cx));
       }
-      LDP_TRY(crb_bwd(blocks[bi--]));
-      LDP_TRY(crb_bwd(blocks[bi--]));
+      LDP_TRY(crb_bwd(blocks[bi])); LDP_TRY(close_bucket(bi--));
+      LDP_TRY(crb_bwd(blocks[bi])); LDP_TRY(close_bucket(bi--));
     }
   }
+  // what is left completes with the call: the time MLP + the first blocks, and the resampling / final convolutions behind the CRBs
+  h->buckets.push_back({0, bucket_hi, -1});
+  h->buckets.push_back({head + crb_total, h->n_params - (head + crb_total), -1});
   // conditioning path: mg = Mish(g); g[:, :ds] = Dense_1(Mish(Dense_0(sinusoid)))
   LDP_TRY(join_side(cx));
   LDP_TRY(mish_bwd(gbuf, *mg, s));
@@ -1292,7 +1329,14 @@ static int unet_loss_grad(LdpTrainer* h, int prec, const float* params, float* g
 // ------------------------------------------------------------------------------------------------
 // IDM: loss = mean((MLPDiffusion(s||s', add_noise(a0, noise, t), t) - noise)^2)   (agent/ldp_agent.py:128-139)
 // ------------------------------------------------------------------------------------------------
+static int idm_loss_grad_impl(LdpTrainer* h, int prec, const float* params, float* grads, const float* sdev, const float* a0,
+                              const float* noise, const int32_t* t, int N, float weight, float* loss_dev, cudaStream_t s);
 static int idm_loss_grad(LdpTrainer* h, int prec, const float* params, float* grads, const float* sdev, const float* a0,
+                         const float* noise, const int32_t* t, int N, float weight, float* loss_dev, cudaStream_t s) {
+  h->buckets.assign(1, LdpTrainer::Bucket{0, h->n_params, -1});      // 7.6 MB: one exchange
+  return idm_loss_grad_impl(h, prec, params, grads, sdev, a0, noise, t, N, weight, loss_dev, s);
+}
+static int idm_loss_grad_impl(LdpTrainer* h, int prec, const float* params, float* grads, const float* sdev, const float* a0,
                          const float* noise, const int32_t* t, int N, float weight, float* loss_dev, cudaStream_t s) {
   TrainCtx cx{s, prec, &h->tc, &h->scratch_a, &h->scratch_w, h->side, h->ev_fork, h->ev_join, &h->scratch_a2, &h->scratch_w2};
   const LdpIdmConfig& c = h->icfg;
@@ -1538,6 +1582,25 @@ int ldp_idm_loss_grad(LdpTrainer* h, int precision, const float* params_dev, flo
   return run_step(h, precision, key, s, [&](cudaStream_t st) {
     return idm_loss_grad(h, precision, params_dev, grads_dev, s_dev, a0_dev, noise_dev, t_dev, N, loss_weight, loss_dev, st);
   });
+}
+
+int ldp_trainer_grad_buckets(LdpTrainer* h, int64_t* offsets, int64_t* lengths, int32_t* has_event, int max_buckets, int* n_buckets) {
+  LDP_CHECK(h && offsets && lengths && has_event && n_buckets, LDP_ERR_INVALID_ARG, "null pointer");
+  LDP_CHECK((int)h->buckets.size() <= max_buckets, LDP_ERR_INVALID_ARG, "output arrays too small");
+  for (size_t i = 0; i < h->buckets.size(); ++i) {
+    offsets[i] = h->buckets[i].off;
+    lengths[i] = h->buckets[i].len;
+    has_event[i] = h->buckets[i].ev >= 0 ? 1 : 0;
+  }
+  *n_buckets = (int)h->buckets.size();
+  return LDP_OK;
+}
+
+int ldp_trainer_wait_bucket(LdpTrainer* h, int bucket, void* cuda_stream) {
+  LDP_CHECK(h && bucket >= 0 && bucket < (int)h->buckets.size() && h->buckets[bucket].ev >= 0, LDP_ERR_INVALID_ARG,
+            "bucket has no event (it completes with the loss/gradient call itself)");
+  LDP_CUDA_OK(cudaStreamWaitEvent((cudaStream_t)cuda_stream, h->bucket_ev[h->buckets[bucket].ev], 0));
+  return LDP_OK;
 }
 
 int ldp_adam_update(float* params_dev, const float* grads_dev, float* mu_dev, float* nu_dev, uint64_t n, float lr,

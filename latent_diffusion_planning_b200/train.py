@@ -137,5 +137,33 @@ class TrainState:
     def get_params(self) -> Dict[str, np.ndarray]:
         return unflatten_params(self.spec, self.params.detach().cpu().numpy())
 
+    def grad_buckets(self):
+        """Ranges of `grads` in the order the last loss/gradient call completes them: [(offset, length, has_event)]."""
+        off = np.zeros(64, np.int64)
+        ln = np.zeros(64, np.int64)
+        ev = np.zeros(64, np.int32)
+        n = C.c_int(0)
+        N.check(self.lib.ldp_trainer_grad_buckets(self._h, off.ctypes.data, ln.ctypes.data, ev.ctypes.data, 64, C.byref(n)))
+        return [(int(off[i]), int(ln[i]), bool(ev[i])) for i in range(n.value)]
+
+    def allreduce_grads_bucketed(self, comm_stream: "torch.cuda.Stream", group=None):
+        """Start the all-reduce of every gradient bucket on `comm_stream` as soon as the backward pass has finished it (the
+        step records one event per bucket; buckets without an event wait for the whole call).  Returns the pending works -
+        `wait()` them before the optimiser - and the 1/world factor for `apply_gradients`."""
+        import torch.distributed as dist
+        world = dist.get_world_size(group)
+        main = torch.cuda.current_stream()
+        works = []
+        for k, (off, ln, has_ev) in enumerate(self.grad_buckets()):
+            if ln == 0:
+                continue
+            if has_ev:
+                N.check(self.lib.ldp_trainer_wait_bucket(self._h, k, comm_stream.cuda_stream))
+            else:
+                comm_stream.wait_stream(main)
+            with torch.cuda.stream(comm_stream):
+                works.append(dist.all_reduce(self.grads[off:off + ln], op=dist.ReduceOp.SUM, group=group, async_op=True))
+        return works, 1.0 / world
+
     def grads_dict(self) -> Dict[str, np.ndarray]:
         return unflatten_params(self.spec, self.grads.detach().cpu().numpy())

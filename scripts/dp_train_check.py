@@ -30,6 +30,7 @@ def make(precision):
 
 
 def main():
+    os.environ.setdefault("LDP_BUCKET_MB", "0.05")        # tiny networks: force many gradient buckets so the per-bucket events are exercised
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
     torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
     dist.init_process_group("nccl")
@@ -38,7 +39,7 @@ def main():
         dp, full = make(precision), make(precision)
         full.data_parallel = False
         Bg = 8 * world
-        for step in range(2):
+        for step in range(4):          # steps 3 and 4 replay the captured graph (bf16 path), bucket events included
             g = torch.Generator().manual_seed(step)
             batch = {"obs": {"latent_agentview_image": torch.randn(Bg, 9, 16, generator=g) * 3}, "actions": torch.randn(Bg, 9, 7, generator=g)}
             for k in LOWDIM:
@@ -50,7 +51,9 @@ def main():
         dl = abs(float(m_dp["loss"]) - float(m_full["loss"]))
         dg = abs(float(m_dp["g_norm"]) - float(m_full["g_norm"]))
         dparam = max(float((dp._train[n].params - full._train[n].params).abs().max()) for n in ("planner", "idm"))
-        out[precision] = dict(loss_diff=dl, g_norm_diff=dg, param_diff=dparam, loss=float(m_full["loss"]))
+        nb = dp._train["planner"].grad_buckets()
+        out[precision] = dict(loss_diff=dl, g_norm_diff=dg, param_diff=dparam, loss=float(m_full["loss"]),
+                              planner_buckets=len(nb), buckets_with_event=sum(1 for b in nb if b[2]))
     ok = out["fp32"]["param_diff"] < 2e-5 and out["fp32"]["loss_diff"] < 1e-5 and out["bf16"]["param_diff"] < 2e-3
     flag = torch.tensor([1.0 if ok else 0.0], device="cuda")
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
