@@ -120,6 +120,7 @@ __global__ void __launch_bounds__(TcGeo<BN>::THREADS, 1) tc_gemm_kernel(const __
   if (PAIR) {
     __syncwarp();
     cluster_sync_all();
+    __syncthreads();          // implied by the cluster barrier; spelled out because compute-sanitizer's racecheck does not model barrier.cluster
   } else {
     __syncthreads();
   }

@@ -6,7 +6,7 @@ timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --mas
 tail -5 gpurun_out/bench_${TAG}_n$N.err
 python - <<PY
 import json
-d=json.load(open("gpurun_out/bench_${TAG}_n$N.json"))
+d=[json.loads(l) for l in open("gpurun_out/bench_${TAG}_n$N.json") if l.startswith("{")][-1]
 print("value", d["value"], "ms", d["ms_per_step"])
 for k in ("strong","train_dp"):
     print(k, json.dumps(d.get(k))[:1800])
