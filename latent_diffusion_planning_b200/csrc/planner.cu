@@ -106,6 +106,9 @@ struct PlanWs {
   std::vector<Tap> taps;           // named intermediates for per-layer parity tests (ldp_planner_read_activation)
   cudaGraphExec_t graph = nullptr;
   cudaGraph_t graph_src = nullptr;
+  // the whole n-step loop as ONE graph (keyed by the step count): consecutive launches of the per-step graph are ordered by the
+  // stream, i.e. by a full kernel boundary, while inside a graph every layer-to-layer edge is a programmatic (PDL) edge
+  std::map<int, cudaGraphExec_t> loop_graphs;
   // persistent loop kernel (planner_loop.cu)
   int loop_state = 0;              // 0 not prepared, 1 ready, -1 unsupported for this shape
   std::vector<TcGemm> loop_ops;    // host copy of the loop kernel's layer table
@@ -115,6 +118,8 @@ struct PlanWs {
   ~PlanWs() {
     if (graph) cudaGraphExecDestroy(graph);
     if (graph_src) cudaGraphDestroy(graph_src);
+    for (auto& kv : loop_graphs)
+      if (kv.second) cudaGraphExecDestroy(kv.second);
   }
 };
 
@@ -1095,6 +1100,36 @@ int ldp_planner_sample(LdpPlanner* h, int precision, int sampler, const float* x
       LDP_CUDA_OK(e);
       LDP_CUDA_OK(cudaGraphInstantiate(&w->graph, w->graph_src, 0));
       LDP_CUDA_OK(cudaStreamDestroy(cs));
+    }
+    static const bool whole_loop_graph = !env_off("LDP_LOOP_GRAPH");
+    if (w->loop_state != 1 && h->use_graph && whole_loop_graph && n_steps >= 4) {
+      auto it = w->loop_graphs.find(n_steps);
+      if (it == w->loop_graphs.end()) {
+        cudaStream_t cs;
+        LDP_CUDA_OK(cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));
+        const long long before = launch_count_get();
+        cudaGraph_t g = nullptr;
+        cudaError_t e = cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal);
+        int st = LDP_OK;
+        if (e == cudaSuccess) {
+          for (int i = 0; i < n_steps && st == LDP_OK; ++i) st = run_ops_bf16(w, step, false, nullptr, D, cs);
+          e = cudaStreamEndCapture(cs, &g);
+        }
+        count_launch((int)(before - launch_count_get()));
+        cudaGraphExec_t ex = nullptr;
+        if (st == LDP_OK && e == cudaSuccess && g) e = cudaGraphInstantiate(&ex, g, 0);
+        if (g) cudaGraphDestroy(g);
+        cudaStreamDestroy(cs);
+        if (st != LDP_OK) return st;
+        if (e != cudaSuccess) { cudaGetLastError(); ex = nullptr; }      // fall back to per-step graphs below
+        it = w->loop_graphs.emplace(n_steps, ex).first;
+      }
+      if (it->second) {
+        LDP_CUDA_OK(cudaGraphLaunch(it->second, s));
+        count_launch((int)w->ops.size() * n_steps);
+        LDP_CUDA_OK(cudaMemcpyAsync(x0_dev, w->x_state, n * 4, cudaMemcpyDeviceToDevice, s));
+        return LDP_OK;
+      }
     }
     for (int i = 0; i < n_steps && w->loop_state != 1; ++i) {
       if (w->graph) {
