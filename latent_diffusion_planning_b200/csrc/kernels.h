@@ -102,6 +102,9 @@ int launch_philox_normal_rows(unsigned long long seed, uint32_t stream_id, uint3
 int launch_jax_random(const uint32_t* keys_dev, int n_keys, long long n, int mode, void* out, cudaStream_t s);
 // out[(c / 4) * rows + r] (float4) = in[r * ld + c .. c+3]   (cols a multiple of 4)
 int launch_transpose_quads(const float* in, int ld, float* out, int rows, int cols, cudaStream_t s);
+// FiLM (scale, shift) pairs of every residual block, half2, quad-transposed [pair / 4][sample] (see film_pack_kernel)
+struct FilmBlocks { int n = 0; int pair_off[16]; int film_off[16]; int C[16]; };
+int launch_film_pack(const float* in, int ld, void* out, int rows, const FilmBlocks& fb, cudaStream_t s);
 int launch_add_i32(int32_t* p, int delta, cudaStream_t s);     // *p += delta (advances the device step counter)
 int launch_set_i32(int32_t* p, int v, cudaStream_t s);
 
@@ -181,6 +184,7 @@ struct TcGemm {
   int shift[5] = {0, 0, 0, 0, 0};
   int num_stages = 0, tmem_cols = 0; // filled by launch_tc_gemm (tc_gemm_geometry)
   int tiles_m = 0, tiles_n = 0, grid_ctas = 0, acc_bufs = 1, acc_stride = 0, persistent = 0;
+  unsigned epi_sleep_ns = 0;        // GN epilogue warps sleep this long before staging / prefetching (LDP_EPI_SLEEP, default 1000)
   int epi_skip = 0;                 // diagnostics (LDP_EPI_SKIP): 1 stores, 2 FiLM loads, 4 residual, 8 activation, 16 tap shuffles
   long long* dbg_stage = nullptr;   // diagnostics: CTA (0,0)'s first 24 stage-arrival times
   long long* dbg = nullptr;         // diagnostics: per-CTA phase timestamps [ctas][8] (clock64 deltas)
@@ -211,7 +215,7 @@ struct TcGemm {
   int group_width = 32;             // C/G
   const float* gamma = nullptr; const float* beta = nullptr; float eps = 1e-6f;
   int film = 0; const float* ttab = nullptr; int ld_ttab = 0;
-  const float* otab_q = nullptr; int otab_B = 0;   // observation part, quad-transposed: [column / 4][sample] float4
+  const void* otab_q = nullptr; int otab_B = 0;    // observation part: half2 (scale, shift) pairs, quad-transposed [pair / 4][sample] uint4; pair = film_off / 2 + column
   int film_off = 0; int film_c = 0;
   StepRef step;
   // LN: out_f32 <- h = acc + bias + res_f32;  out_bf16 <- LN(h) gamma + beta  (or relu(h) if relu)

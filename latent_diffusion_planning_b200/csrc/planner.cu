@@ -82,7 +82,7 @@ struct PlanWs {
   int B = 0, T = 0;
   Arena arena;
   float* otab = nullptr;
-  float* otab_q = nullptr;       // quad-transposed copy for the tcgen05 epilogues
+  float* otab_q = nullptr;       // half2 (scale, shift) pairs, quad-transposed, for the tcgen05 epilogues (film_pack_kernel)
   __nv_bfloat16* cond_bf16 = nullptr;   // Mish(cond) in bf16: A operand of the observation-part FiLM GEMM (bf16 path)
   int ld_cb = 0;
   TcGemm otab_op;
@@ -279,6 +279,7 @@ static int planner_create_impl(const LdpUnetConfig* cfg, const float* params_hos
     h->crb.push_back(b);
   }
   h->sum_c2 = film_off;
+  LDP_CHECK(h->crb.size() <= 16, LDP_ERR_UNSUPPORTED, "at most 16 residual blocks (FilmBlocks table)");
   for (int i = 0; i < c.n_levels - 1; ++i) {
     int64_t d = c.down_dims[i];
     h->down_w.push_back(w.take(3 * d * d));
@@ -328,6 +329,17 @@ static int get_ws(LdpPlanner* h, int B, int T, PlanWs** out) {
   return LDP_OK;
 }
 
+static FilmBlocks film_blocks(const LdpPlanner* h) {
+  FilmBlocks fb;
+  fb.n = (int)h->crb.size();
+  for (int i = 0; i < fb.n; ++i) {
+    fb.film_off[i] = h->crb[i].film_off;
+    fb.pair_off[i] = h->crb[i].film_off / 2;
+    fb.C[i] = h->crb[i].cout;
+  }
+  return fb;
+}
+
 // Observation part of every block's FiLM Dense, once per act(): otab[b] = Mish(cond[b]) Wc  (B x Dc x sum_c2).
 // fp32 path: SIMT FFMA GEMM (the 1e-5 parity instrument).  bf16 path: one tcgen05 GEMM (persistent tile loop, fp32
 // accumulation and fp32 output) - on SIMT this contraction alone was 1 ms of a 41 ms sampling loop.
@@ -338,7 +350,7 @@ static int compute_otab(LdpPlanner* h, PlanWs* w, const float* cond, int precisi
     g.x1 = cond; g.c1 = dc; g.ld1 = dc; g.a_act = 1;
     g.w = h->wc_all; g.ldw = h->sum_c2; g.out = w->otab; g.ldo = h->sum_c2; g.m = w->B; g.n = h->sum_c2;
     LDP_TRY(launch_gemm_f32(g, s));
-    return launch_transpose_quads(w->otab, h->sum_c2, w->otab_q, w->B, h->sum_c2, s);
+    return launch_film_pack(w->otab, h->sum_c2, w->otab_q, w->B, film_blocks(h), s);
   }
   if (!h->otab_packed) {
     PackedW& pw = h->pw_otab;
@@ -385,7 +397,7 @@ static int compute_otab(LdpPlanner* h, PlanWs* w, const float* cond, int precisi
   }
   LDP_TRY(launch_cast_bf16(cond, dc, w->cond_bf16, w->ld_cb, w->B, dc, /*mish=*/1, s));
   LDP_TRY(launch_tc_gemm(w->otab_op, s));
-  return launch_transpose_quads(w->otab, h->sum_c2, w->otab_q, w->B, h->sum_c2, s);
+  return launch_film_pack(w->otab, h->sum_c2, w->otab_q, w->B, film_blocks(h), s);
 }
 
 // ------------------------------- fp32 program -------------------------------------------------------

@@ -98,6 +98,8 @@ __device__ __noinline__ void epilogue_tile(int layer, uint8_t* es_raw, uint32_t 
         es.beta[i] = (ok && p.beta) ? __ldg(p.beta + n) : 0.f;
         es.fscale[i] = (ok && trow) ? __ldg(trow + n) : 0.f;
         es.fshift[i] = (ok && trow) ? __ldg(trow + p.film_c + n) : 0.f;
+        const __half2 ft = __floats2half2_rn(es.fscale[i], es.fshift[i]);
+        es.film_t[i] = *reinterpret_cast<const uint32_t*>(&ft);
       }
     }
     epi_bar<BN>();

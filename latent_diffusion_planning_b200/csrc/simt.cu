@@ -1,5 +1,7 @@
 // fp32 SIMT kernels: the exact-arithmetic path (parity gate 1e-5 vs the fp64 oracle) and the small
 // elementwise / table / packing kernels both precisions share.
+#include <cuda_fp16.h>
+
 #include "kernels.h"
 
 namespace ldp {
@@ -373,6 +375,42 @@ int launch_transpose_quads(const float* in, int ld, float* out, int rows, int co
   const int nq = cols / 4;
   dim3 grid((rows + 31) / 32, (nq + 31) / 32), block(32, 8);
   transpose_quads_kernel<<<grid, block, 0, s>>>(in, ld, reinterpret_cast<float4*>(out), rows, nq);
+  LDP_LAUNCH_OK();
+  return LDP_OK;
+}
+
+// FiLM observation part for the tcgen05 epilogues: out[(pair / 4) * rows + r] = 4 x half2(scale, shift) of pairs pair .. pair+3, where
+// pair = blk.pair_off + c pairs scale = in[r][blk.film_off + c] with shift = in[r][blk.film_off + blk.C + c] (c < blk.C, C % 4 == 0).
+// Half the bytes and a third of the instructions of the float4 (scale quad | shift quad) form the epilogue prefetch used to read.
+__global__ void film_pack_kernel(const float* __restrict__ in, int ld, uint4* __restrict__ out, int rows, int nq, FilmBlocks fb) {
+  __shared__ uint4 t[32][33];
+  const int r0 = blockIdx.x * 32, q0 = blockIdx.y * 32;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int r = r0 + i, q = q0 + threadIdx.x;
+    if (r < rows && q < nq) {
+      const int pair = 4 * q;
+      int b = 0;
+      while (b + 1 < fb.n && fb.pair_off[b + 1] <= pair) ++b;
+      const int c = pair - fb.pair_off[b];
+      const float4 sc = *reinterpret_cast<const float4*>(in + (long long)r * ld + fb.film_off[b] + c);
+      const float4 sh = *reinterpret_cast<const float4*>(in + (long long)r * ld + fb.film_off[b] + fb.C[b] + c);
+      __half2 h0 = __floats2half2_rn(sc.x, sh.x), h1 = __floats2half2_rn(sc.y, sh.y);
+      __half2 h2 = __floats2half2_rn(sc.z, sh.z), h3 = __floats2half2_rn(sc.w, sh.w);
+      t[i][threadIdx.x] = make_uint4(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1),
+                                     *reinterpret_cast<uint32_t*>(&h2), *reinterpret_cast<uint32_t*>(&h3));
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int q = q0 + i, r = r0 + threadIdx.x;
+    if (r < rows && q < nq) out[(long long)q * rows + r] = t[threadIdx.x][i];
+  }
+}
+
+int launch_film_pack(const float* in, int ld, void* out, int rows, const FilmBlocks& fb, cudaStream_t s) {
+  const int nq = (fb.pair_off[fb.n - 1] + fb.C[fb.n - 1]) / 4;
+  dim3 grid((rows + 31) / 32, (nq + 31) / 32), block(32, 8);
+  film_pack_kernel<<<grid, block, 0, s>>>(in, ld, reinterpret_cast<uint4*>(out), rows, nq, fb);
   LDP_LAUNCH_OK();
   return LDP_OK;
 }

@@ -51,6 +51,7 @@ struct EpiSmem {
   float beta[BN];
   float fscale[BN];     // FiLM scale / shift, time part (valid when the whole launch shares one timestep)
   float fshift[BN];
+  uint32_t film_t[BN];  // the same as half2(scale, shift): what the prefetch adds to the observation part
   float2 part[TC_BM][BN / 32];   // per-row, per-32-column-chunk (sum, sum of squares)
 };
 
@@ -360,10 +361,11 @@ __device__ __forceinline__ void gn_prefetch(const TcGemm& p, const EpiSmem<BN>& 
   const bool row_ok = m < p.M;
   const int mm = row_ok ? m : 0;
   const int b = mm / p.rows_per_item;
-  // observation part of the FiLM embedding, quad-transposed [column quad][sample] float4: the lanes of a warp are
-  // consecutive rows = consecutive (or equal) samples, so one load instruction touches one or two 128-byte lines
-  // instead of one line per lane (which made this the most expensive piece of the epilogue)
-  const float4* oq = reinterpret_cast<const float4*>(p.otab_q);
+  // observation part of the FiLM embedding: half2 (scale, shift) pairs, quad-transposed [pair quad][sample] uint4 - the lanes of a
+  // warp are consecutive rows = consecutive (or equal) samples, so one load instruction touches one or two 64-byte runs instead
+  // of one line per lane; the time part is added in half2 (staged as half2 in shared memory, or per row for per-row timesteps).
+  // One LDG.128 + one LDS.128 + four HADD2 per four columns: the prefetch runs while the MMA issuer needs the issue slots.
+  const uint4* oq = reinterpret_cast<const uint4*>(p.otab_q);
   const float* trow = (p.film && p.step.rows) ? p.ttab + (long long)step_of(p.step, mm) * p.ld_ttab + p.film_off : nullptr;
   const bool film = p.film && !(p.epi_skip & 2);
 #pragma unroll
@@ -371,28 +373,28 @@ __device__ __forceinline__ void gn_prefetch(const TcGemm& p, const EpiSmem<BN>& 
     const int c = c_begin + cc;
     const int nb = n0 + c * 32;
     if (film && c < nchunks) {
-      const float4* fs4 = reinterpret_cast<const float4*>(es.fscale + c * 32);
-      const float4* fb4 = reinterpret_cast<const float4*>(es.fshift + c * 32);
-      const float4* os4 = oq + (long long)((p.film_off + nb) >> 2) * p.otab_B + b;
-      const float4* ob4 = oq + (long long)((p.film_off + p.film_c + nb) >> 2) * p.otab_B + b;
+      const uint4* o4 = oq + (long long)(((p.film_off >> 1) + nb) >> 2) * p.otab_B + b;
+      const uint4* t4 = reinterpret_cast<const uint4*>(es.film_t + c * 32);
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        float4 sc = fs4[j], sh = fb4[j];
-        const float4 o1 = __ldg(os4 + (long long)j * p.otab_B), o2 = __ldg(ob4 + (long long)j * p.otab_B);
-        sc.x += o1.x; sc.y += o1.y; sc.z += o1.z; sc.w += o1.w;
-        sh.x += o2.x; sh.y += o2.y; sh.z += o2.z; sh.w += o2.w;
+        const uint4 o = __ldg(o4 + (long long)j * p.otab_B);
+        uint4 t;
         if (trow) {
           const float4 t1 = __ldg(reinterpret_cast<const float4*>(trow + nb) + j);
           const float4 t2 = __ldg(reinterpret_cast<const float4*>(trow + p.film_c + nb) + j);
-          sc.x += t1.x; sc.y += t1.y; sc.z += t1.z; sc.w += t1.w;
-          sh.x += t2.x; sh.y += t2.y; sh.z += t2.z; sh.w += t2.w;
+          __half2 h0 = __floats2half2_rn(t1.x, t2.x), h1 = __floats2half2_rn(t1.y, t2.y);
+          __half2 h2 = __floats2half2_rn(t1.z, t2.z), h3 = __floats2half2_rn(t1.w, t2.w);
+          t = make_uint4(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1), *reinterpret_cast<uint32_t*>(&h2),
+                         *reinterpret_cast<uint32_t*>(&h3));
+        } else {
+          t = t4[j];
         }
-        __half2 h0 = __floats2half2_rn(sc.x, sh.x), h1 = __floats2half2_rn(sc.y, sh.y);
-        __half2 h2 = __floats2half2_rn(sc.z, sh.z), h3 = __floats2half2_rn(sc.w, sh.w);
-        pf.film[cc][4 * j + 0] = *reinterpret_cast<uint32_t*>(&h0);
-        pf.film[cc][4 * j + 1] = *reinterpret_cast<uint32_t*>(&h1);
-        pf.film[cc][4 * j + 2] = *reinterpret_cast<uint32_t*>(&h2);
-        pf.film[cc][4 * j + 3] = *reinterpret_cast<uint32_t*>(&h3);
+        const uint32_t ov[4] = {o.x, o.y, o.z, o.w}, tv[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const __half2 sum = __hadd2(*reinterpret_cast<const __half2*>(&ov[q]), *reinterpret_cast<const __half2*>(&tv[q]));
+          pf.film[cc][4 * j + q] = *reinterpret_cast<const uint32_t*>(&sum);
+        }
       }
     } else {
 #pragma unroll

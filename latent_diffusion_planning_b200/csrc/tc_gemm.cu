@@ -308,6 +308,11 @@ __global__ void __launch_bounds__(TcGeo<BN>::THREADS, 1) tc_gemm_kernel(const __
     const int part = ew >> 2;                            // which column slice of the tile
     const int row = quarter * 32 + lane;
     griddep_wait();                                      // the step counter / residuals / x belong to earlier kernels
+    // The epilogue warps have nothing to do until the accumulators are complete except staging per-column vectors and prefetching
+    // FiLM pairs (~200 instructions each).  Doing that right away competes with the TMA producer and the MMA issuer - single
+    // threads whose every instruction is on the critical path while the ring fills - for issue slots (measured: the FiLM
+    // prefetch alone stretched the main loop of a conv1 layer by 1.5 - 1.9 k cycles).  Sleep through the pipeline fill instead.
+    if (MODE == TC_EPI_GN && p.epi_sleep_ns > 0) __nanosleep(p.epi_sleep_ns);
     int it = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
     const int tile_m = PERSIST ? tile % p.tiles_m : (int)blockIdx.x;
@@ -330,6 +335,8 @@ __global__ void __launch_bounds__(TcGeo<BN>::THREADS, 1) tc_gemm_kernel(const __
           es.beta[i] = (ok && p.beta) ? __ldg(p.beta + n) : 0.f;
           es.fscale[i] = (ok && trow) ? __ldg(trow + n) : 0.f;
           es.fshift[i] = (ok && trow) ? __ldg(trow + p.film_c + n) : 0.f;
+          const __half2 ft = __floats2half2_rn(es.fscale[i], es.fshift[i]);
+          es.film_t[i] = *reinterpret_cast<const uint32_t*>(&ft);
         }
       }
       epi_bar<BN>();
@@ -522,6 +529,10 @@ static int launch_tc_gemm_inst(const TcGemm& p_in, cudaStream_t s) {
     static int skip = -1;                      // diagnostics: LDP_EPI_SKIP bit mask disables parts of the GN epilogue
     if (skip < 0) { const char* e = getenv("LDP_EPI_SKIP"); skip = e ? atoi(e) : 0; }
     p.epi_skip = skip;
+    static int sleep_ns = -1;
+    if (sleep_ns < 0) { const char* e = getenv("LDP_EPI_SLEEP"); sleep_ns = e ? atoi(e) : 1000; }
+    p.epi_sleep_ns = (unsigned)sleep_ns;
+
   }
   const int stage_bytes = (PAIR ? TC_A_BYTES + p.w_max * (BN / 2) * TC_BK * 2 : tc_stage_bytes(BN, p.w_max)) + p.n_tail * TC_BK * 2;
   p.num_stages = std::min(TC_MAX_STAGES, TC_SMEM_RING / stage_bytes);
