@@ -285,6 +285,31 @@ __device__ __forceinline__ void chunk_group_sums(const float (&v)[32], bool row_
   }
 }
 
+// combine the lane quarters of each image in a fixed order and publish this tile's partial GroupNorm sums
+template <int BN>
+__device__ __forceinline__ void gn_part_publish(const TcGemm& p, EpiSmem<BN>& es, int n0, int tile_m) {
+  constexpr int NC = BN / 32;
+  float2* gscr = &es.part[0][0];
+  epi_bar<BN>();
+  const int ngr = 32 / p.gn_cpg, ipt = p.gn_imgs_per_tile, qpi = 4 / ipt;      // groups per chunk, images per tile, quarters per image
+  const int nchunks = min(NC, (p.N - n0 + 31) >> 5);
+  const int q = tile_m / p.tiles_per_item, r = tile_m - q * p.tiles_per_item;
+  for (int t = (int)threadIdx.x - 64; t < nchunks * ngr * ipt; t += TcGeo<BN>::EPI_THREADS) {
+    const int img = t / (nchunks * ngr), cg = t - img * (nchunks * ngr);
+    const int c = cg / ngr, g = cg - c * ngr;
+    float a = 0.f, a2 = 0.f;
+    for (int qq = img * qpi; qq < (img + 1) * qpi; ++qq) {
+      const float2 f = gscr[(qq * NC + c) * 8 + g];
+      a += f.x;
+      a2 += f.y;
+    }
+    const long long b = (long long)q * ipt + img;
+    float* dst = p.gn_part + ((b * p.gn_slabs + r) * p.gn_G + (n0 + c * 32) / p.gn_cpg + g) * 2;
+    dst[0] = a;
+    dst[1] = a2;
+  }
+}
+
 template <int BN>
 __device__ __forceinline__ void epilogue_plain(const TcGemm& p, EpiSmem<BN>& es, uint32_t taddr, int m, int n0,
                                                int c_begin, int lane, int tile_m = 0, int quarter = 0) {
@@ -306,11 +331,116 @@ __device__ __forceinline__ void epilogue_plain(const TcGemm& p, EpiSmem<BN>& es,
 #pragma unroll
       for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
     }
-    if (row_ok) {
+    if (row_ok && !(p.epi_skip & 1)) {
       if (p.res_f32) add_f32x32(v, p.res_f32 + (long long)m * p.ld_res_f32 + nb, vrf, nvalid);
       if (p.res_bf16) add_bf16x32(v, p.res_bf16 + (long long)m * p.ld_res_bf16 + nb, vrb, nvalid);
       if (p.out_f32) store_f32x32(p.out_f32 + (long long)m * p.ld_out_f32 + nb, v, vf, nvalid);
       if (p.out_bf16) store_bf16x32(p.out_bf16 + (long long)m * p.ld_out_bf16 + nb, v, vb, nvalid);
+    }
+    if (p.gn_part && !(p.epi_skip & 2)) {                      // uniform
+      float2* o = gscr + (quarter * NC + c) * 8;
+      if (p.gn_cpg == 4) chunk_group_sums<8>(v, row_ok, o, lane);
+      else if (p.gn_cpg == 8) chunk_group_sums<4>(v, row_ok, o, lane);
+      else if (p.gn_cpg == 16) chunk_group_sums<2>(v, row_ok, o, lane);
+      else chunk_group_sums<1>(v, row_ok, o, lane);
+    }
+  }
+  if (p.gn_part) gn_part_publish<BN>(p, es, n0, tile_m);
+}
+
+// ---- PLAIN epilogue through TMA (TcGemm::epi_tma) ------------------------------------------------------------------
+__device__ __forceinline__ void tma_store_2d(const void* map, uint32_t src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(map), "r"(src), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ float4 lds_128(uint32_t a) {
+  float4 f;
+  asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(f.x), "=f"(f.y), "=f"(f.z), "=f"(f.w) : "r"(a) : "memory");
+  return f;
+}
+__device__ __forceinline__ void sts_128(uint32_t a, uint32_t x, uint32_t y, uint32_t z, uint32_t w) {
+  asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(a), "r"(x), "r"(y), "r"(z), "r"(w) : "memory");
+}
+
+constexpr int TC_EPI_BUF = 4096;     // per epilogue warp: 32 rows x 128 bytes
+
+// The warp (lane quarter `quarter`, chunks [c_begin, c_begin + CPP)) handles 32 rows x 32 columns at a time in `buf`:
+//   [res_f32 box arrives by TMA (issued by the caller for the first chunk, before the accumulator wait)] -> v = acc + bias (+ res)
+//   -> v to buf (f32, 128B swizzle: 16-byte unit u of row r sits at u ^ (r & 7), conflict-free for st.shared.v4) -> TMA store
+//   -> bf16(v) to buf (64B swizzle: unit u of row r at u ^ ((r >> 1) & 3)) -> TMA store.
+// Lane 0 owns the bulk groups: before the buffer is rewritten it waits until the previous store has READ it.  Rows beyond M are
+// written too (they exist: the maps cover the workspace's full chunk) but stay out of the GroupNorm sums.
+template <int BN>
+__device__ __forceinline__ void epilogue_plain_tma(const TcGemm& p, EpiSmem<BN>& es, uint32_t taddr, int m, int n0, int c_begin,
+                                                   int lane, int tile_m, int quarter, uint32_t buf, uint32_t bar_res,
+                                                   uint32_t& res_phase) {
+  constexpr int CPP = TcGeo<BN>::CPP, NC = BN / 32;
+  const bool row_ok = m < p.M;
+  const int row0 = tile_m * TC_BM + quarter * 32;
+  const bool vf = (p.ld_out_f32 & 3) == 0, vb = (p.ld_out_bf16 & 7) == 0, vrf = (p.ld_res_f32 & 3) == 0;
+  float2* gscr = &es.part[0][0];
+  const uint32_t rowf = buf + (uint32_t)lane * 128u, swf = (uint32_t)(lane & 7);
+  const uint32_t rowb = buf + (uint32_t)lane * 64u, swb = (uint32_t)((lane >> 1) & 3);
+#pragma unroll 1
+  for (int cc = 0; cc < CPP; ++cc) {
+    const int c = c_begin + cc;
+    const int nb = n0 + c * 32;
+    if (nb >= p.N) continue;             // uniform across the warp (N is a multiple of 32 here)
+    float v[32];
+    tmem_ld_32x32(taddr + c * 32, v);
+    add_smem32(v, es.bias + c * 32);
+    if (p.relu) {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
+    }
+    if (p.epi_tma & 4) {
+      if (cc > 0 && lane == 0) {
+        bulk_wait_read0();
+        mbar_arrive_expect_tx(bar_res, TC_EPI_BUF);
+        tma_load_2d(buf, &p.epi_maps[2], bar_res, nb, row0);
+      }
+      mbar_wait(bar_res, res_phase);
+      res_phase ^= 1u;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float4 f = lds_128(rowf + (((uint32_t)j ^ swf) << 4));
+        v[4 * j] += f.x; v[4 * j + 1] += f.y; v[4 * j + 2] += f.z; v[4 * j + 3] += f.w;
+      }
+    } else if (p.res_f32 && row_ok) {
+      add_f32x32(v, p.res_f32 + (long long)m * p.ld_res_f32 + nb, vrf, 32);
+    }
+    if (p.epi_tma & 1) {
+      if (!(p.epi_tma & 4) && lane == 0) bulk_wait_read0();
+      __syncwarp();
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        sts_128(rowf + (((uint32_t)j ^ swf) << 4), __float_as_uint(v[4 * j]), __float_as_uint(v[4 * j + 1]), __float_as_uint(v[4 * j + 2]),
+                __float_as_uint(v[4 * j + 3]));
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) {
+        tma_store_2d(&p.epi_maps[0], buf, nb, row0);
+        bulk_commit();
+      }
+    } else if (p.out_f32 && row_ok) {
+      store_f32x32(p.out_f32 + (long long)m * p.ld_out_f32 + nb, v, vf, 32);
+    }
+    if (p.epi_tma & 2) {
+      if (lane == 0) bulk_wait_read0();
+      __syncwarp();
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        sts_128(rowb + (((uint32_t)j ^ swb) << 4), pack_bf16x2(v[8 * j], v[8 * j + 1]), pack_bf16x2(v[8 * j + 2], v[8 * j + 3]),
+                pack_bf16x2(v[8 * j + 4], v[8 * j + 5]), pack_bf16x2(v[8 * j + 6], v[8 * j + 7]));
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) {
+        tma_store_2d(&p.epi_maps[1], buf, nb, row0);
+        bulk_commit();
+      }
+    } else if (p.out_bf16 && row_ok) {
+      store_bf16x32(p.out_bf16 + (long long)m * p.ld_out_bf16 + nb, v, vb, 32);
     }
     if (p.gn_part) {                      // uniform
       float2* o = gscr + (quarter * NC + c) * 8;
@@ -320,27 +450,7 @@ __device__ __forceinline__ void epilogue_plain(const TcGemm& p, EpiSmem<BN>& es,
       else chunk_group_sums<1>(v, row_ok, o, lane);
     }
   }
-  if (p.gn_part) {
-    // combine the lane quarters of each image in a fixed order and publish this tile's partial sums
-    epi_bar<BN>();
-    const int ngr = 32 / p.gn_cpg, ipt = p.gn_imgs_per_tile, qpi = 4 / ipt;      // groups per chunk, images per tile, quarters per image
-    const int nchunks = min(NC, (p.N - n0 + 31) >> 5);
-    const int q = tile_m / p.tiles_per_item, r = tile_m - q * p.tiles_per_item;
-    for (int t = (int)threadIdx.x - 64; t < nchunks * ngr * ipt; t += TcGeo<BN>::EPI_THREADS) {
-      const int img = t / (nchunks * ngr), cg = t - img * (nchunks * ngr);
-      const int c = cg / ngr, g = cg - c * ngr;
-      float a = 0.f, a2 = 0.f;
-      for (int qq = img * qpi; qq < (img + 1) * qpi; ++qq) {
-        const float2 f = gscr[(qq * NC + c) * 8 + g];
-        a += f.x;
-        a2 += f.y;
-      }
-      const long long b = (long long)q * ipt + img;
-      float* dst = p.gn_part + ((b * p.gn_slabs + r) * p.gn_G + (n0 + c * 32) / p.gn_cpg + g) * 2;
-      dst[0] = a;
-      dst[1] = a2;
-    }
-  }
+  if (p.gn_part) gn_part_publish<BN>(p, es, n0, tile_m);
 }
 
 // Operands of the GN epilogue that do not depend on the accumulator - the FiLM scale/shift of this thread's sample and

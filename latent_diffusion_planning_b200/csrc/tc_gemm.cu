@@ -70,13 +70,14 @@ __global__ void __launch_bounds__(TcGeo<BN>::THREADS, 1) tc_gemm_kernel(const __
   __shared__ __align__(8) uint64_t bar_empty[TC_MAX_STAGES];
   __shared__ __align__(8) uint64_t bar_tfull[2];              // accumulator buffer b complete (MMA -> epilogue)
   __shared__ __align__(8) uint64_t bar_tempty[2];             // accumulator buffer b drained (epilogue -> MMA)
+  __shared__ __align__(8) uint64_t bar_res[16];               // TMA epilogue: residual box of epilogue warp w landed
   __shared__ uint32_t tmem_holder;
   __shared__ __align__(16) TcRun runs_s[TC_MAX_RUNS];         // run-length stage table staged once per CTA
   __shared__ __align__(16) EpiSmem<BN> es;
-  __shared__ long long ts[8];                                 // phase timestamps (diagnostics, only when p.dbg != nullptr)
+  __shared__ long long ts[12];                                // phase timestamps / wait-cycle sums (diagnostics, only when p.dbg != nullptr)
   __shared__ long long tk[24];                                // arrival time of the first 24 stages at the MMA issuer
   if (p.dbg && threadIdx.x == 0) {
-    for (int i = 0; i < 8; ++i) ts[i] = 0;
+    for (int i = 0; i < 12; ++i) ts[i] = 0;
     for (int i = 0; i < 24; ++i) tk[i] = 0;
     ts[0] = clock64();
   }
@@ -88,7 +89,13 @@ __global__ void __launch_bounds__(TcGeo<BN>::THREADS, 1) tc_gemm_kernel(const __
   // PERSIST (launches with more tiles than SMs, i.e. the VAE convolutions): 1-D grid of one CTA per SM, CTA c walks
   // tiles c, c + gridDim.x, ... (tile t -> (t % tiles_m, t / tiles_m)); with two accumulator buffers in TMEM the
   // epilogue of one tile overlaps the main loop of the next, and the smem ring simply keeps running across tiles.
-  const int num_tiles = p.tiles_m * p.tiles_n;
+  // PAIR + PERSIST: the cluster (CTA pair) is the scheduling unit: pair c walks tile pairs c, c + gridDim.x / 2, ...; tile pair t ->
+  // M tiles (2 (t % (tiles_m / 2)), + 1) of N tile t / (tiles_m / 2); tiles_m is even (tc_gemm_geometry).
+  constexpr bool PP = PAIR && PERSIST;
+  const int tiles_m_s = PP ? p.tiles_m >> 1 : p.tiles_m;     // M extent of the tile index the loops walk
+  const int num_tiles = tiles_m_s * p.tiles_n;
+  const int tile_first = PP ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int tile_step = PP ? (int)(gridDim.x >> 1) : (int)gridDim.x;
   const uint32_t ncols = (uint32_t)p.tmem_cols;        // power of two in [32, 512] covering acc_bufs * (n_acc + aux) * BN columns
 
   // ---- prologue: touches only constants, shared memory and TMEM -> may overlap the previous kernel (PDL) ----
@@ -99,8 +106,11 @@ __global__ void __launch_bounds__(TcGeo<BN>::THREADS, 1) tc_gemm_kernel(const __
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(smem_u32(&bar_tfull[b]), 1);
-      mbar_init(smem_u32(&bar_tempty[b]), TcGeo<BN>::EPI_THREADS);
+      // PAIR + PERSIST: one arrival per epilogue warp of both CTAs, all on the leader's barrier (the issuer lives there)
+      mbar_init(smem_u32(&bar_tempty[b]), PP ? 2 * TcGeo<BN>::EPI_WARPS : TcGeo<BN>::EPI_THREADS);
     }
+    if (MODE == TC_EPI_PLAIN)
+      for (int w = 0; w < 16; ++w) mbar_init(smem_u32(&bar_res[w]), 1);
     fence_mbar_init();
     tma_prefetch_desc(&p.map_b);
     tma_prefetch_desc(&p.map_a[0]);
@@ -137,9 +147,9 @@ __global__ void __launch_bounds__(TcGeo<BN>::THREADS, 1) tc_gemm_kernel(const __
       asm volatile("" : "+r"(full0), "+r"(empty0));
       griddep_wait();                                   // activations of the previous layer are complete from here on
       if (p.dbg) ts[2] = clock64();                     // dependency resolved
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const int tile_m = PERSIST ? tile % p.tiles_m : (int)blockIdx.x;
-      const int n0 = (PERSIST ? tile / p.tiles_m : (int)blockIdx.y) * BN;
+      for (int tile = tile_first; tile < num_tiles; tile += tile_step) {
+      const int tile_m = PERSIST ? (PP ? 2 * (tile % tiles_m_s) + (int)cta_rank : tile % tiles_m_s) : (int)blockIdx.x;
+      const int n0 = (PERSIST ? tile / tiles_m_s : (int)blockIdx.y) * BN;
       const int q = tile_m / p.tiles_per_item, r = tile_m - q * p.tiles_per_item;
       const int c2_base = r * p.rows_step, c3 = q * p.items_per_tile;
       // Runs of stages that differ only by their channel block: the per-stage work is a barrier wait, the byte-count
@@ -154,7 +164,13 @@ __global__ void __launch_bounds__(TcGeo<BN>::THREADS, 1) tc_gemm_kernel(const __
         const uint32_t tx = (PAIR ? 2u : 1u) * (TC_A_BYTES + nw * (uint32_t)B_BYTES) + (tail_tile ? (uint32_t)p.n_tail * (TC_BK * 2) : 0u);
         int c0 = r_c0, wkc = r_wk * TC_BK;
         for (int i = 0; i < r_count; ++i) {
-          mbar_wait(empty0 + 8u * stage, phase ^ 1u);
+          if (PERSIST && p.dbg) {
+            const long long t = clock64();
+            mbar_wait(empty0 + 8u * stage, phase ^ 1u);
+            ts[7] += clock64() - t;                     // producer: cycles waiting for a free stage
+          } else {
+            mbar_wait(empty0 + 8u * stage, phase ^ 1u);
+          }
           const uint32_t bar = full0 + 8u * stage;
           const uint32_t sa = smem_base + stage * stage_bytes;
           if (PAIR) {
@@ -211,11 +227,14 @@ __global__ void __launch_bounds__(TcGeo<BN>::THREADS, 1) tc_gemm_kernel(const __
       const int kb_aux = p.num_kb - kb_main;
       uint32_t stage = 0, phase = 0;
       int it = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      for (int tile = tile_first; tile < num_tiles; tile += tile_step, ++it) {
       const int buf = PERSIST ? it % p.acc_bufs : 0;
       const uint32_t use = PERSIST ? (uint32_t)(it / p.acc_bufs) : 0u;
       if (PERSIST) {
-        mbar_wait(smem_u32(&bar_tempty[buf]), (use & 1u) ^ 1u);     // epilogue drained this buffer (first use: passes)
+        const long long tw = p.dbg ? clock64() : 0;
+        if (PP) mbar_wait_cluster(smem_u32(&bar_tempty[buf]), (use & 1u) ^ 1u);   // both CTAs' epilogues drained this buffer
+        else mbar_wait(smem_u32(&bar_tempty[buf]), (use & 1u) ^ 1u);              // epilogue drained this buffer (first use: passes)
+        if (p.dbg) ts[8] += clock64() - tw;                                       // issuer: cycles waiting for an accumulator buffer
         tc_fence_after();
       }
       const uint32_t acc_base = tmem_base + (uint32_t)buf * (uint32_t)p.acc_stride;
@@ -228,7 +247,13 @@ __global__ void __launch_bounds__(TcGeo<BN>::THREADS, 1) tc_gemm_kernel(const __
         const uint64_t da_wrap = (uint64_t)((uint32_t)STAGES * stage_step);
         const bool dbg_on = p.dbg != nullptr;
         for (int kb = 0; kb < kb_main; ++kb) {
-          mbar_wait(fb, phase);
+          if (PERSIST && dbg_on) {
+            const long long t = clock64();
+            mbar_wait(fb, phase);
+            ts[9] += clock64() - t;                       // issuer: cycles waiting for operands
+          } else {
+            mbar_wait(fb, phase);
+          }
           tc_fence_after();
           if (dbg_on && kb == 0) ts[3] = clock64();
           const uint64_t db = da + (TC_A_BYTES >> 4);
@@ -314,9 +339,12 @@ __global__ void __launch_bounds__(TcGeo<BN>::THREADS, 1) tc_gemm_kernel(const __
     // prefetch alone stretched the main loop of a conv1 layer by 1.5 - 1.9 k cycles).  Sleep through the pipeline fill instead.
     if (MODE == TC_EPI_GN && p.epi_sleep_ns > 0) __nanosleep(p.epi_sleep_ns);
     int it = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
-    const int tile_m = PERSIST ? tile % p.tiles_m : (int)blockIdx.x;
-    const int n0 = (PERSIST ? tile / p.tiles_m : (int)blockIdx.y) * BN;
+    const uint32_t epi_buf = smem_base + (uint32_t)STAGES * stage_bytes + (uint32_t)ew * TC_EPI_BUF;    // TMA epilogue: behind the ring
+    const uint32_t my_bar_res = smem_u32(&bar_res[ew & 15]);
+    uint32_t res_phase = 0;
+    for (int tile = tile_first; tile < num_tiles; tile += tile_step, ++it) {
+    const int tile_m = PERSIST ? (PP ? 2 * (tile % tiles_m_s) + (int)cta_rank : tile % tiles_m_s) : (int)blockIdx.x;
+    const int n0 = (PERSIST ? tile / tiles_m_s : (int)blockIdx.y) * BN;
     const int buf = PERSIST ? it % p.acc_bufs : 0;
     const uint32_t use = PERSIST ? (uint32_t)(it / p.acc_bufs) : 0u;
     const int m = tile_m * TC_BM + row;
@@ -342,23 +370,45 @@ __global__ void __launch_bounds__(TcGeo<BN>::THREADS, 1) tc_gemm_kernel(const __
       epi_bar<BN>();
     }
     const int c_begin = part * TcGeo<BN>::CPP;
+    if (MODE == TC_EPI_PLAIN && (p.epi_tma & 4) && lane == 0 && n0 + c_begin * 32 < p.N) {
+      // the residual box of this warp's first chunk: in flight while the main loop runs
+      bulk_wait_read0();                                 // the previous tile's stores have read the buffer
+      mbar_arrive_expect_tx(my_bar_res, TC_EPI_BUF);
+      tma_load_2d(epi_buf, &p.epi_maps[2], my_bar_res, n0 + c_begin * 32, tile_m * TC_BM + quarter * 32);
+    }
     GnPrefetch<MODE == TC_EPI_GN ? BN : 64> pf;
     if constexpr (MODE == TC_EPI_GN) gn_prefetch<BN>(p, es, m, n0, c_begin, pf);
-    mbar_wait(smem_u32(&bar_tfull[buf]), use & 1u);
+    {
+      const long long tw = (PERSIST && p.dbg) ? clock64() : 0;
+      mbar_wait(smem_u32(&bar_tfull[buf]), use & 1u);
+      if (PERSIST && p.dbg && threadIdx.x == 64) ts[10] += clock64() - tw;   // epilogue: cycles waiting for accumulators
+    }
     tc_fence_after();
     if (p.dbg && threadIdx.x == 64 && it == 0) ts[5] = clock64();   // accumulators complete
     const uint32_t taddr = tmem_base + (uint32_t)buf * (uint32_t)p.acc_stride + ((uint32_t)(quarter * 32) << 16);
-    if constexpr (MODE == TC_EPI_PLAIN) epilogue_plain<BN>(p, es, taddr, m, n0, c_begin, lane, tile_m, quarter);
+    if constexpr (MODE == TC_EPI_PLAIN) {
+      if (p.epi_tma) epilogue_plain_tma<BN>(p, es, taddr, m, n0, c_begin, lane, tile_m, quarter, epi_buf, my_bar_res, res_phase);
+      else epilogue_plain<BN>(p, es, taddr, m, n0, c_begin, lane, tile_m, quarter);
+    }
     else if constexpr (MODE == TC_EPI_GN) epilogue_gn<BN>(p, es, taddr, m, n0, c_begin, row, lane, pf);
     else if constexpr (MODE == TC_EPI_DDPM)
       epilogue_ddpm<BN>(p, es, taddr, reinterpret_cast<float*>(smem_raw + (smem_base - smem_u32(smem_raw))), tile_m, n0,
                         c_begin, row, (int)threadIdx.x - 64, lane, -1, nullptr, tail_tile ? p.n_tail : 0);
     else epilogue_ln<BN>(p, es, taddr, m, n0, c_begin, row, part, lane);
-    if (!PERSIST) break;
+    if (!PERSIST) {
+      if (MODE == TC_EPI_PLAIN && p.epi_tma && lane == 0) bulk_wait_read0();
+      break;
+    }
     tc_fence_before();                                   // hand the accumulator buffer back, protect `es`
-    mbar_arrive(smem_u32(&bar_tempty[buf]));
+    if (PP) {
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(mapa_shared(smem_u32(&bar_tempty[buf]), 0));
+    } else {
+      mbar_arrive(smem_u32(&bar_tempty[buf]));
+    }
     epi_bar<BN>();
     }
+    if (PERSIST && MODE == TC_EPI_PLAIN && p.epi_tma && lane == 0) bulk_wait_read0();   // shared memory must outlive the last store's read
   }
 
   if (p.dbg && threadIdx.x == 64) ts[6] = clock64();     // this warp's epilogue done
@@ -389,6 +439,7 @@ __global__ void __launch_bounds__(TcGeo<BN>::THREADS, 1) tc_gemm_kernel(const __
     const long long t0 = ts[0];
     for (int i = 1; i < 7; ++i) d[i] = ts[i] ? ts[i] - t0 : 0;
     d[7] = clock64() - t0;
+    if (PERSIST) { d[2] = ts[7]; d[3] = ts[8]; d[4] = ts[9]; d[5] = ts[10]; }    // wait-cycle sums instead of first-tile stamps
     if (p.dbg_stage && blockIdx.x == 0 && blockIdx.y == 0)
       for (int i = 0; i < 23; ++i) p.dbg_stage[i] = tk[i] ? tk[i] - t0 : 0;
     d[0] = (long long)(__cvta_generic_to_shared(&ts[0]) & 0) + (long long)blockIdx.x;   // tile id
@@ -453,6 +504,25 @@ int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t*
   return make_tmap_bf16_strided(out, base, rank, dims, strides_bytes, box, nullptr);
 }
 
+int make_tmap_epi(CUtensorMap* out, const void* base, bool f32, uint64_t cols, uint64_t rows, uint64_t ld) {
+  PFN_encodeTiled fn = get_encode_fn();
+  LDP_CHECK(fn != nullptr, LDP_ERR_NO_DEVICE, "cuTensorMapEncodeTiled driver entry point not available");
+  const uint64_t es = f32 ? 4 : 2;
+  LDP_CHECK((reinterpret_cast<uintptr_t>(base) & 15) == 0 && (ld * es) % 16 == 0 && cols % 32 == 0, LDP_ERR_INVALID_ARG,
+            "epilogue tensor map: base / leading dimension must be 16-byte aligned, columns a multiple of 32");
+  cuuint64_t gdim[2] = {cols, rows};
+  cuuint64_t gstr[1] = {ld * es};
+  cuuint32_t bx[2] = {32, 32}, estr[2] = {1, 1};
+  CUresult r = fn(out, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstr, bx,
+                  estr, CU_TENSOR_MAP_INTERLEAVE_NONE, f32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_last_error("cuTensorMapEncodeTiled (epilogue map) failed with CUresult " + std::to_string((int)r));
+    return LDP_ERR_CUDA;
+  }
+  return LDP_OK;
+}
+
 template <int BN, int MODE>
 static int set_smem_attr() {
   LDP_CUDA_OK(cudaFuncSetAttribute(tc_gemm_kernel<BN, MODE, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -464,6 +534,10 @@ static int set_smem_attr() {
   constexpr bool kPersistable = MODE == TC_EPI_PLAIN;
   if (kPersistable)
     LDP_CUDA_OK(cudaFuncSetAttribute(tc_gemm_kernel<BN, MODE, false, kPersistable>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     TC_SMEM_RING + 1024));
+  constexpr bool kPairPersist = MODE == TC_EPI_PLAIN && BN >= 128;
+  if (kPairPersist)
+    LDP_CUDA_OK(cudaFuncSetAttribute(tc_gemm_kernel<BN, MODE, kPairPersist, kPairPersist>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      TC_SMEM_RING + 1024));
   return LDP_OK;
 }
@@ -503,7 +577,8 @@ int tc_gemm_geometry(TcGemm* p) {
   const int tiles = p->tiles_m * p->tiles_n;
   static int persist = -1;
   if (persist < 0) { const char* e = getenv("LDP_PERSIST"); persist = (e && e[0] == '0') ? 0 : 1; }
-  const bool persistent = persist && tiles > 148 && !p->pair && p->mode == TC_EPI_PLAIN;
+  // pairs + persistence (the VAE convolutions): PLAIN epilogue, BN >= 128; a paired launch that is not persistent needs BN <= 128
+  const bool persistent = persist && tiles > 148 && p->mode == TC_EPI_PLAIN && (!p->pair || bn >= 128);
   p->grid_ctas = persistent ? 148 : tiles;
   p->persistent = persistent ? 1 : 0;
   p->acc_stride = n_acc_total * bn + p->n_tail;
@@ -535,7 +610,11 @@ static int launch_tc_gemm_inst(const TcGemm& p_in, cudaStream_t s) {
 
   }
   const int stage_bytes = (PAIR ? TC_A_BYTES + p.w_max * (BN / 2) * TC_BK * 2 : tc_stage_bytes(BN, p.w_max)) + p.n_tail * TC_BK * 2;
-  p.num_stages = std::min(TC_MAX_STAGES, TC_SMEM_RING / stage_bytes);
+  const int epi_bytes = p.epi_tma ? TcGeo<BN>::EPI_WARPS * TC_EPI_BUF : 0;
+  if (p.epi_tma)
+    LDP_CHECK(MODE == TC_EPI_PLAIN && p.epi_maps && p.N % 32 == 0 && p.n_acc == 1 && p.shift[0] == 0 && !p.use_aux, LDP_ERR_INVALID_ARG,
+              "tc_gemm: the TMA epilogue needs the PLAIN epilogue, one accumulator and N % 32 == 0");
+  p.num_stages = std::min(TC_MAX_STAGES, (TC_SMEM_RING - epi_bytes) / stage_bytes);
   LDP_CHECK(p.num_stages >= 2, LDP_ERR_UNSUPPORTED, "tc_gemm: stage does not fit the shared-memory ring twice");
   if (MODE == TC_EPI_DDPM)
     LDP_CHECK(p.num_stages * stage_bytes >= TC_BM * (BN + p.n_tail + 1) * 4, LDP_ERR_UNSUPPORTED,
@@ -546,7 +625,7 @@ static int launch_tc_gemm_inst(const TcGemm& p_in, cudaStream_t s) {
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = PERSIST ? dim3(p.grid_ctas, 1, 1) : dim3(p.tiles_m, p.tiles_n, 1);
   cfg.blockDim = dim3(TcGeo<BN>::THREADS, 1, 1);
-  cfg.dynamicSmemBytes = p.num_stages * stage_bytes + 1024;
+  cfg.dynamicSmemBytes = p.num_stages * stage_bytes + epi_bytes + 1024;
   cfg.stream = s;
   cudaLaunchAttribute attr[2];
   int na = 0;
@@ -564,6 +643,23 @@ static int launch_tc_gemm_inst(const TcGemm& p_in, cudaStream_t s) {
   }
   cfg.attrs = attr;
   cfg.numAttrs = na;
+  if (PAIR && PERSIST) {
+    // one CTA pair per TPC: ask how many clusters fit (74 on a full B200) instead of assuming it
+    static int max_clusters = 0;
+    if (max_clusters == 0) {
+      cudaLaunchConfig_t q = cfg;
+      q.gridDim = dim3(148, 1, 1);
+      q.attrs = attr + (g_use_pdl ? 1 : 0);
+      q.numAttrs = 1;
+      int n = 0;
+      if (cudaOccupancyMaxActiveClusters(&n, tc_gemm_kernel<BN, MODE, PAIR, PERSIST>, &q) != cudaSuccess || n <= 0) {
+        (void)cudaGetLastError();
+        n = 74;
+      }
+      max_clusters = std::min(n, 74);
+    }
+    cfg.gridDim = dim3(2 * std::min(max_clusters, p.tiles_m / 2 * p.tiles_n), 1, 1);
+  }
   cudaError_t e = cudaLaunchKernelEx(&cfg, tc_gemm_kernel<BN, MODE, PAIR, PERSIST>, p);
   if (e != cudaSuccess) {
     set_last_error(std::string("tc_gemm launch failed: ") + cudaGetErrorString(e));
@@ -595,12 +691,18 @@ int launch_tc_gemm(const TcGemm& p, cudaStream_t s) {
   if (p.mode == TC_EPI_LN) LDP_CHECK(p.N == p.block_n && p.out_f32 && p.bias, LDP_ERR_UNSUPPORTED, "tc_gemm LN epilogue: N must equal block_n");
   if (p.mode == TC_EPI_DDPM) LDP_CHECK(p.x_io && p.coef, LDP_ERR_INVALID_ARG, "tc_gemm DDPM epilogue: x / coefficient table required");
   const bool pair = p.pair != 0;
-  if (pair) LDP_CHECK((p.mode == TC_EPI_PLAIN || p.mode == TC_EPI_GN) && p.block_n <= 128, LDP_ERR_UNSUPPORTED,
-                      "tc_gemm: pair mode exists for the PLAIN / GN epilogues at BN <= 128");
   TcGemm g = p;
   LDP_TRY(tc_gemm_geometry(&g));
+  if (pair) LDP_CHECK((p.mode == TC_EPI_PLAIN || p.mode == TC_EPI_GN) && (p.block_n <= 128 || g.persistent), LDP_ERR_UNSUPPORTED,
+                      "tc_gemm: pair mode exists for the PLAIN / GN epilogues at BN <= 128 (BN 256: persistent PLAIN launches only)");
   const int key = p.block_n * 8 + p.mode;
-  if (pair) {
+  if (pair && g.persistent) {
+    switch (key) {
+      case 128 * 8 + TC_EPI_PLAIN: return launch_tc_gemm_inst<128, TC_EPI_PLAIN, true, true>(p, s);
+      case 256 * 8 + TC_EPI_PLAIN: return launch_tc_gemm_inst<256, TC_EPI_PLAIN, true, true>(p, s);
+      default: break;
+    }
+  } else if (pair) {
     switch (key) {
       case 64 * 8 + TC_EPI_PLAIN:  return launch_tc_gemm_inst<64, TC_EPI_PLAIN, true, false>(p, s);
       case 64 * 8 + TC_EPI_GN:     return launch_tc_gemm_inst<64, TC_EPI_GN, true, false>(p, s);

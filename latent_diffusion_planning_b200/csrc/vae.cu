@@ -717,6 +717,26 @@ static int vae_pack(LdpVae* h, int id, const float* wgt, int k, int pad, int cin
   return LDP_OK;
 }
 
+// Outputs and the f32 residual of a PLAIN-epilogue op as TMA boxes (TcGemm::epi_tma): maps live in device memory.
+// LDP_VAE_EPI_TMA=0 keeps the row-per-thread vector accesses.
+static int vae_epi_maps(Arena& arena, TcGemm* op, size_t rows) {
+  static const bool on = !(getenv("LDP_VAE_EPI_TMA") && getenv("LDP_VAE_EPI_TMA")[0] == '0');
+  if (!on || op->mode != TC_EPI_PLAIN || op->N % 32 != 0) return LDP_OK;
+  CUtensorMap host[3];
+  memset(host, 0, sizeof(host));
+  int bits = 0;
+  if (op->out_f32 && op->ld_out_f32 % 4 == 0) { LDP_TRY(make_tmap_epi(&host[0], op->out_f32, true, op->N, rows, op->ld_out_f32)); bits |= 1; }
+  if (op->out_bf16 && op->ld_out_bf16 % 8 == 0) { LDP_TRY(make_tmap_epi(&host[1], op->out_bf16, false, op->N, rows, op->ld_out_bf16)); bits |= 2; }
+  if (op->res_f32 && op->ld_res_f32 % 4 == 0) { LDP_TRY(make_tmap_epi(&host[2], op->res_f32, true, op->N, rows, op->ld_res_f32)); bits |= 4; }
+  if (!bits) return LDP_OK;
+  CUtensorMap* dev;
+  LDP_TRY(arena.alloc_t(&dev, 3));
+  LDP_CUDA_OK(cudaMemcpy(dev, host, sizeof(host), cudaMemcpyHostToDevice));
+  op->epi_maps = dev;
+  op->epi_tma = bits;
+  return LDP_OK;
+}
+
 // conv on `in` (bf16, NHWC at resolution S_in) -> PLAIN epilogue.  stride 2 = the Downsample conv: taps address
 // (2x + dx, 2y + dy) with dx, dy >= 0 (pad low 0), the row/column beyond the high edge is TMA out-of-bounds zero fill.
 static int vae_conv_tc(LdpVae* h, VaeWs* w, int id, const ConvW& cw, const float* bias, const __nv_bfloat16* in, int S_in,
@@ -739,8 +759,14 @@ static int vae_conv_tc(LdpVae* h, VaeWs* w, int id, const ConvW& cw, const float
   const int bn = (bn256 && cw.cout % 256 == 0) ? 256 : (cw.cout > 64 ? 128 : 64);
   uint64_t bd[2] = {(uint64_t)pw->kp, (uint64_t)pw->n_pad};
   uint64_t bs[1] = {(uint64_t)pw->kp * 2};
-  uint32_t bb[2] = {64, (uint32_t)bn};
+  // CTA pairs (cta_group::2) where the launch is persistent: the convolutions are bound by L2 -> SM operand delivery, and in a
+  // pair each CTA fetches only half of every W tile (LDP_VAE_PAIR=0: single CTAs)
+  static const bool pair_ok = !(getenv("LDP_VAE_PAIR") && getenv("LDP_VAE_PAIR")[0] == '0');
+  const int tiles_m = ceil_div(w->Bc * S_out * S_out, 128), tiles_n = ceil_div(cw.cout, bn);
+  const bool pair = pair_ok && bn >= 128 && tiles_m % 2 == 0 && tiles_m * tiles_n > 148;
+  uint32_t bb[2] = {64, (uint32_t)(pair ? bn / 2 : bn)};
   LDP_TRY(make_tmap_bf16(&op->map_b, pw->wt, 2, bd, bs, bb));
+  op->pair = pair ? 1 : 0;
   op->kb = pw->kb_dev; op->num_kb = pw->num_kb; op->runs = pw->runs_dev; op->num_runs = pw->num_runs; tc_set_inline_runs(op, pw->runs_host.data(), pw->num_runs); op->w_max = 1; op->k_pad = pw->kp;
   op->M = w->Bc * S_out * S_out; op->N = cw.cout; op->block_n = bn;
   op->tiles_per_item = g.tiles_per_img; op->rows_step = g.hb * stride; op->items_per_tile = g.ib;
@@ -826,6 +852,7 @@ static int vae_conv_in_op(LdpVae* h, VaeWs* w, int fmt, const __nv_bfloat16* col
   if (fuse) {                       // partial GroupNorm sums of the first resnet's norm1 come out of this epilogue too
     op->gn_part = w->part; op->gn_cpg = cpg; op->gn_G = G; op->gn_slabs = g.tiles_per_img; op->gn_imgs_per_tile = g.ib;
   }
+  LDP_TRY(vae_epi_maps(w->arena, op, (size_t)w->Bc * P));
   return LDP_OK;
 }
 
@@ -837,6 +864,15 @@ static int vae_walk_tc(LdpVae* h, VaeWs* w, bool build, const void* images, int 
                        float* out, cudaStream_t s) {
   const LdpVaeConfig& c = h->cfg;
   VaeBufs b{w->S, w->Hf, w->Sb, w->Gb};
+  // LDP_VAE_DBG=1: per-CTA wait-cycle sums of every persistent convolution of the third replay, printed to stderr
+  static long long* dbg_store = nullptr;
+  static int dbg_calls = 0;
+  long long* dbg_buf = nullptr;
+  if (!build && getenv("LDP_VAE_DBG") && ++dbg_calls == 3) {
+    if (!dbg_store) LDP_CUDA_OK(cudaMalloc(&dbg_store, (size_t)64 * 148 * 8 * sizeof(long long)));
+    LDP_CUDA_OK(cudaMemsetAsync(dbg_store, 0, (size_t)64 * 148 * 8 * sizeof(long long), s));
+    dbg_buf = dbg_store;
+  }
   size_t oi = 0;
   int conv_id = 0;
   // emit(op builder) / run(op)
@@ -860,10 +896,12 @@ static int vae_walk_tc(LdpVae* h, VaeWs* w, bool build, const void* images, int 
       if (fuse) {
         op.gn_part = w->part; op.gn_cpg = cpg; op.gn_G = G; op.gn_slabs = tg.tiles_per_img; op.gn_imgs_per_tile = tg.ib;
       }
+      LDP_TRY(vae_epi_maps(w->arena, &op, (size_t)w->Bc * S_out * S_out));
       w->ops.push_back(op);
     } else {
       TcGemm op = w->ops[oi];
       op.M = nimg * S_out * S_out;
+      if (dbg_buf && oi < 64) op.dbg = dbg_buf + (size_t)oi * 148 * 8;
       LDP_TRY(launch_tc_gemm(op, s));
     }
     ++oi;
@@ -955,6 +993,26 @@ static int vae_walk_tc(LdpVae* h, VaeWs* w, bool build, const void* images, int 
     vae_post_kernel<<<(int)std::min<long long>((npix * c.latent_channels + 255) / 256, 4096), 256, 0, s>>>(
         b.Hf, h->quant.w, h->quant.b, out, npix, 2 * c.latent_channels, c.latent_channels, lat_min, lat_max);
     VAE_LAUNCH_OK("vae_post");
+  }
+  if (dbg_buf) {
+    LDP_CUDA_OK(cudaStreamSynchronize(s));
+    std::vector<long long> d((size_t)64 * 148 * 8);
+    LDP_CUDA_OK(cudaMemcpy(d.data(), dbg_buf, d.size() * sizeof(long long), cudaMemcpyDeviceToHost));
+    fprintf(stderr, "# op M N kb bn pair | per-CTA mean cycles: total producer_wait_empty issuer_wait_acc issuer_wait_operands epilogue_wait_acc\n");
+    for (int o = 0; o < (int)std::min<size_t>((size_t)oi, 64); ++o) {
+      const TcGemm& op = w->ops[o];
+      double sum[8] = {0};
+      int n = 0;
+      for (int cta = 0; cta < 148; ++cta) {
+        const long long* r = &d[((size_t)o * 148 + cta) * 8];
+        if (r[7] == 0) continue;
+        ++n;
+        for (int i = 0; i < 8; ++i) sum[i] += (double)r[i];
+      }
+      if (n == 0) continue;
+      fprintf(stderr, "%2d %8d %4d %3d %3d %d | %9.0f %9.0f %9.0f %9.0f %9.0f  (%d ctas)\n", o, nimg * 0 + op.M, op.N, op.num_kb, op.block_n, op.pair,
+              sum[7] / n, sum[2] / n, sum[3] / n, sum[4] / n, sum[5] / n, n);
+    }
   }
   return LDP_OK;
 }
@@ -1134,6 +1192,7 @@ static int vae_dec_walk_tc(LdpVae* h, VaeWs* w, bool build, const float* z, int 
       if (fuse) {
         op.gn_part = w->part; op.gn_cpg = cpg; op.gn_G = G; op.gn_slabs = tg.tiles_per_img; op.gn_imgs_per_tile = tg.ib;
       }
+      LDP_TRY(vae_epi_maps(w->arena, &op, (size_t)w->Bc * S_in * S_in));
       w->ops.push_back(op);
     } else {
       TcGemm op = w->ops[oi];
