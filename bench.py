@@ -476,7 +476,7 @@ def vae_block(ctx, args, planner, x_host, c_host):
     ach = VAE_B * VAE_GFLOP_PER_IMG / ms                       # GF / ms = TF/s
     out = {"metric": "vae_encode_imgs_per_sec", "value": VAE_B * ctx.world / ms * 1e3, "unit": "img/s", "ms_per_step": ms,
            "config": {"workload": "stable_vae_model.encode 64x64x3 uint8 agentview images, B=4096 per GPU, SD-VAE [128,256,512,512] "
-                                  "-> 8x8x4 latents (+ fused latent normalisation), bf16 tensor-core path, chunks of 256 images",
+                                  "-> 8x8x4 latents (+ fused latent normalisation), bf16 tensor-core path, chunks of 592 images",
                       "B_per_gpu": VAE_B, "l2": "256 MB L2 flush between steps; inputs (50 MB) + activations exceed L2"},
            "roofline": {"bound": "tensor", "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf,
                         "algorithmic_gflop_per_image": VAE_GFLOP_PER_IMG, "launches_per_step": launches, "peak_source": peak_src,

@@ -402,13 +402,13 @@ def test_vae_reference_topology_bf16(H):
 
 
 def test_vae_chunking_is_invisible(H):
-    """B > the 256-image chunk: images are independent, so a big batch equals its pieces."""
+    """B > the 592-image chunk: images are independent, so a big batch equals its pieces."""
     blocks = (32, 64)
     p = P.init_params(P.vae_encoder_spec(blocks, 3, 4, 1), seed=5, perturb=0.1)
     vae = H.VaeEncoder(p, blocks, 3, 4, 1, 8, 16)
-    img = _images(300, 16, seed=11).cuda()
+    img = _images(700, 16, seed=11).cuda()
     whole = vae.encode(img, precision="bf16")
-    parts = torch.cat([vae.encode(img[:256], precision="bf16"), vae.encode(img[256:], precision="bf16")])
+    parts = torch.cat([vae.encode(img[:592], precision="bf16"), vae.encode(img[592:], precision="bf16")])
     assert _maxerr(whole, parts) < 1e-4
 
 
