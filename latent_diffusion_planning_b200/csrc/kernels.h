@@ -289,6 +289,7 @@ int make_tmap_bf16_strided(CUtensorMap* out, const void* base, int rank, const u
                            const uint64_t* strides_bytes, const uint32_t* box, const uint32_t* elem_strides);
 // 2-D map over a row-major [rows][ld] f32 / bf16 matrix with a 32-column x 32-row box (SWIZZLE_128B / SWIZZLE_64B): TcGemm::epi_maps
 int make_tmap_epi(CUtensorMap* out, const void* base, bool f32, uint64_t cols, uint64_t rows, uint64_t ld);
+int tc_build_epi_maps(const TcGemm& op, size_t rows, CUtensorMap host[3], int* bits);
 int tc_driver_check();
 int tc_gemm_init();   // opt the kernels into their dynamic shared memory size (call outside stream capture)
 

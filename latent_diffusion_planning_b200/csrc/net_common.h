@@ -23,7 +23,11 @@ class Arena {
       return LDP_ERR_CUDA;
     }
     if (zero) {
+      // The fill runs on the legacy stream and is asynchronous to the host; work queued afterwards on a NON-BLOCKING stream (the trainer's
+      // side stream, the capture streams) is not ordered behind it, so wait for it here.  (Found as a 1-in-4 `illegal instruction`: a
+      // tensor map copied on the side stream was zeroed by the fill of its own allocation.)  Allocations are create-time / first-step events.
       e = cudaMemset(p, 0, bytes);
+      if (e == cudaSuccess) e = cudaStreamSynchronize(cudaStreamLegacy);
       if (e != cudaSuccess) {
         set_last_error(std::string("cudaMemset failed: ") + cudaGetErrorString(e));
         return LDP_ERR_CUDA;

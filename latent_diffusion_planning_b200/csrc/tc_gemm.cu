@@ -523,6 +523,19 @@ int make_tmap_epi(CUtensorMap* out, const void* base, bool f32, uint64_t cols, u
   return LDP_OK;
 }
 
+// Host side of TcGemm::epi_tma: which of out_f32 / out_bf16 / res_f32 can move as 32 x 32 boxes, and their maps (the caller copies the
+// three maps to device memory and sets op->epi_maps / op->epi_tma = *bits).
+int tc_build_epi_maps(const TcGemm& op, size_t rows, CUtensorMap host[3], int* bits) {
+  *bits = 0;
+  memset(host, 0, 3 * sizeof(CUtensorMap));
+  if (op.mode != TC_EPI_PLAIN || op.N % 32 != 0 || op.n_acc != 1 || op.shift[0] != 0 || op.use_aux) return LDP_OK;
+  auto ok = [](const void* p) { return p != nullptr && (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+  if (ok(op.out_f32) && op.ld_out_f32 % 4 == 0) { LDP_TRY(make_tmap_epi(&host[0], op.out_f32, true, op.N, rows, op.ld_out_f32)); *bits |= 1; }
+  if (ok(op.out_bf16) && op.ld_out_bf16 % 8 == 0) { LDP_TRY(make_tmap_epi(&host[1], op.out_bf16, false, op.N, rows, op.ld_out_bf16)); *bits |= 2; }
+  if (ok(op.res_f32) && op.ld_res_f32 % 4 == 0) { LDP_TRY(make_tmap_epi(&host[2], op.res_f32, true, op.N, rows, op.ld_res_f32)); *bits |= 4; }
+  return LDP_OK;
+}
+
 template <int BN, int MODE>
 static int set_smem_attr() {
   LDP_CUDA_OK(cudaFuncSetAttribute(tc_gemm_kernel<BN, MODE, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,

@@ -760,6 +760,9 @@ struct TcDense {
     }
   };
   std::map<Key, TcGemm> ops;
+  struct EpiMaps { CUtensorMap m[3]; };
+  std::deque<EpiMaps> epi_host;
+  std::deque<TcRun> run_host;
   int init(int max_kb) {
     if (kb_dev && max_kb <= kb_cap) return LDP_OK;
     LDP_TRY(tc_driver_check());
@@ -793,16 +796,36 @@ struct TcDense {
       uint32_t bb[2] = {64, (uint32_t)bn};
       LDP_TRY(make_tmap_bf16(&op.map_b, wt, 2, bd, bs, bb));
       op.block_n = bn;
-      TcRun run;
+      run_host.emplace_back();           // stable address: under graph capture the copy below is a node that re-reads its source
+      TcRun& run = run_host.back();
       run.src_acc = make_stage(0, 0, 1, 0, 0, 0, 0).src_acc; run.count = kp / 64;
       TcRun* run_dev;
-      LDP_TRY(arena.alloc_t(&run_dev, 1));
+      LDP_TRY(arena.alloc_t(&run_dev, 1, false));      // (no legacy-stream memset racing the copy on `s`)
       LDP_CUDA_OK(cudaMemcpyAsync(run_dev, &run, sizeof(run), cudaMemcpyHostToDevice, s));
       op.kb = kb_dev; op.num_kb = kp / 64; op.runs = run_dev; op.num_runs = 1;
       tc_set_inline_runs(&op, &run, 1);
       op.M = M; op.N = N; op.items_per_tile = 128; op.rows_per_item = 1;
       op.mode = TC_EPI_PLAIN; op.bias = bias; op.relu = relu;
       op.res_f32 = res; op.ld_res_f32 = ldres; op.out_f32 = out; op.ld_out_f32 = ldo;
+      // output / residual as TMA boxes (TcGemm::epi_tma) where the shapes allow: LDP_TRAIN_EPI_TMA=0 keeps the row-per-thread accesses
+      static const bool epi_tma = !(getenv("LDP_TRAIN_EPI_TMA") && getenv("LDP_TRAIN_EPI_TMA")[0] == '0');
+      if (epi_tma) {
+        // ops may be created while the step is being captured into a graph: the copy node then reads its source at every replay, so
+        // the host copies of the maps live as long as this object
+        epi_host.emplace_back();
+        CUtensorMap* host = epi_host.back().m;
+        int bits = 0;
+        LDP_TRY(tc_build_epi_maps(op, (size_t)M, host, &bits));
+        if (bits) {
+          CUtensorMap* dev;
+          // no zero fill: Arena's cudaMemset runs on the legacy stream, which a non-blocking `s` does not order against - it could land
+          // after the copy below
+          LDP_TRY(arena.alloc_t(&dev, 3, false));
+          LDP_CUDA_OK(cudaMemcpyAsync(dev, host, 3 * sizeof(CUtensorMap), cudaMemcpyHostToDevice, s));
+          op.epi_maps = dev;
+          op.epi_tma = bits;
+        }
+      }
       it = ops.emplace(key, op).first;
     }
     return launch_tc_gemm(it->second, s);

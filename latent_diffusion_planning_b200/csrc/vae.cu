@@ -779,13 +779,10 @@ static int vae_pack(LdpVae* h, int id, const float* wgt, int k, int pad, int cin
 // LDP_VAE_EPI_TMA=0 keeps the row-per-thread vector accesses.
 static int vae_epi_maps(Arena& arena, TcGemm* op, size_t rows) {
   static const bool on = !(getenv("LDP_VAE_EPI_TMA") && getenv("LDP_VAE_EPI_TMA")[0] == '0');
-  if (!on || op->mode != TC_EPI_PLAIN || op->N % 32 != 0) return LDP_OK;
+  if (!on) return LDP_OK;
   CUtensorMap host[3];
-  memset(host, 0, sizeof(host));
   int bits = 0;
-  if (op->out_f32 && op->ld_out_f32 % 4 == 0) { LDP_TRY(make_tmap_epi(&host[0], op->out_f32, true, op->N, rows, op->ld_out_f32)); bits |= 1; }
-  if (op->out_bf16 && op->ld_out_bf16 % 8 == 0) { LDP_TRY(make_tmap_epi(&host[1], op->out_bf16, false, op->N, rows, op->ld_out_bf16)); bits |= 2; }
-  if (op->res_f32 && op->ld_res_f32 % 4 == 0) { LDP_TRY(make_tmap_epi(&host[2], op->res_f32, true, op->N, rows, op->ld_res_f32)); bits |= 4; }
+  LDP_TRY(tc_build_epi_maps(*op, rows, host, &bits));
   if (!bits) return LDP_OK;
   CUtensorMap* dev;
   LDP_TRY(arena.alloc_t(&dev, 3));
