@@ -969,16 +969,19 @@ static int vae_walk_tc(LdpVae* h, VaeWs* w, bool build, const void* images, int 
     if (build) return LDP_OK;
     return vae_gn(h, w, x, nimg, P, C, gs_, gb_, act, nullptr, y, s, slabs);
   };
-  auto resnet = [&](const ResW& r, int S) -> int {
+  // sb_out: the bf16 copy of the block's output is read only by a shortcut convolution or the Downsample convolution; everywhere
+  // else (the next consumer is a GroupNorm, which reads the f32 stream) it is not written
+  auto resnet = [&](const ResW& r, int S, bool sb_out) -> int {
     const int P = S * S;
+    __nv_bfloat16* sb = sb_out ? b.Sb : nullptr;
     LDP_TRY(gn(b.S, P, r.c1.cin, r.n1s, r.n1b, 1, b.Gb));
     LDP_TRY(conv(r.c1, b.Gb, S, 1, nullptr, b.Hf, nullptr, true));
     LDP_TRY(gn(b.Hf, P, r.c1.cout, r.n2s, r.n2b, 1, b.Gb));
     if (r.has_sc) {
       LDP_TRY(conv(r.sc, b.Sb, S, 1, nullptr, b.Hf, nullptr));            // Hf is free again after the second GroupNorm
-      LDP_TRY(conv(r.c2, b.Gb, S, 1, b.Hf, b.S, b.Sb, true));
+      LDP_TRY(conv(r.c2, b.Gb, S, 1, b.Hf, b.S, sb, true));
     } else {
-      LDP_TRY(conv(r.c2, b.Gb, S, 1, b.S, b.S, b.Sb, true));               // in place: a thread reads its residual row, then writes it
+      LDP_TRY(conv(r.c2, b.Gb, S, 1, b.S, b.S, sb, true));                 // in place: a thread reads its residual row, then writes it
     }
     return LDP_OK;
   };
@@ -993,7 +996,9 @@ static int vae_walk_tc(LdpVae* h, VaeWs* w, bool build, const void* images, int 
       // values per pixel, i.e. for c0 >= 64; narrow test encoders get their own buffer
       if (vae_max_act(h) >= (size_t)S * S * 64) w->cols = b.Gb;
       else LDP_TRY(w->arena.alloc_t(&w->cols, (size_t)w->Bc * S * S * 64));
-      for (int f = 0; f < 2; ++f) LDP_TRY(vae_conv_in_op(h, w, f, w->cols, b.S, b.Sb, &w->op_in[f]));
+      // (the bf16 copy of conv_in's output would only feed a shortcut convolution of the first resnet)
+      __nv_bfloat16* in_sb = (!h->blocks[0].empty() && h->blocks[0][0].has_sc) ? b.Sb : nullptr;
+      for (int f = 0; f < 2; ++f) LDP_TRY(vae_conv_in_op(h, w, f, w->cols, b.S, in_sb, &w->op_in[f]));
       w->op_in_ok = true;
     }
   } else if (w->op_in_ok) {
@@ -1019,16 +1024,22 @@ static int vae_walk_tc(LdpVae* h, VaeWs* w, bool build, const void* images, int 
     VAE_LAUNCH_OK("vae_conv_in");
   }
   for (int i = 0; i < c.n_blocks; ++i) {
-    for (auto& r : h->blocks[i]) LDP_TRY(resnet(r, S));
+    const size_t nres = h->blocks[i].size();
+    for (size_t j = 0; j < nres; ++j) {
+      const bool last = j + 1 == nres;
+      const bool sb_out = last ? (i != c.n_blocks - 1) : h->blocks[i][j + 1].has_sc;
+      LDP_TRY(resnet(h->blocks[i][j], S, sb_out));
+    }
     if (i != c.n_blocks - 1) {
-      LDP_TRY(conv(h->down[i], b.Sb, S, 2, nullptr, b.Hf, b.Gb, true));
+      const bool next_sc = !h->blocks[i + 1].empty() && h->blocks[i + 1][0].has_sc;
+      LDP_TRY(conv(h->down[i], b.Sb, S, 2, nullptr, b.Hf, next_sc ? b.Gb : nullptr, true));
       std::swap(b.S, b.Hf);
       std::swap(b.Sb, b.Gb);
       S /= 2;
     }
   }
   const int ch = c.block_out_channels[c.n_blocks - 1], L = S * S;
-  LDP_TRY(resnet(h->mid0, S));
+  LDP_TRY(resnet(h->mid0, S, false));
   {
     LDP_TRY(gn(b.S, L, ch, h->ag_s, h->ag_b, 0, b.Gb));
     ConvW qkv;
@@ -1038,9 +1049,9 @@ static int vae_walk_tc(LdpVae* h, VaeWs* w, bool build, const void* images, int 
       vae_attn_kernel<<<nimg, 256, 0, s>>>(w->qkv, nullptr, b.Gb, L, ch);
       VAE_LAUNCH_OK("vae_attn");
     }
-    LDP_TRY(conv(h->ap, b.Gb, S, 1, b.S, b.S, b.Sb, true));
+    LDP_TRY(conv(h->ap, b.Gb, S, 1, b.S, b.S, nullptr, true));
   }
-  LDP_TRY(resnet(h->mid1, S));
+  LDP_TRY(resnet(h->mid1, S, false));
   LDP_TRY(gn(b.S, L, ch, h->nos, h->nob, 1, b.Gb));
   LDP_TRY(conv(h->conv_out, b.Gb, S, 1, nullptr, b.Hf, nullptr));
   if (!build) {
