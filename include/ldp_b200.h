@@ -222,6 +222,11 @@ LDP_API int ldp_vae_decode(LdpVae* h, int precision, const float* latent_dev, in
 LDP_API int ldp_tc_dense(const float* a_dev, const float* w_host, const float* bias_host, float* c_dev, int M, int K,
                          int N, void* cuda_stream);
 
+/* Host-only: the tile / grid / tensor-memory geometry a tcgen05 launch of this shape gets (no device needed; the CPU test suite checks the
+ * decisions for the benchmarked shapes).  epilogue: 0 plain, 1 GroupNorm, 2 DDPM, 3 LayerNorm; pair: 1 = cta_group::2 CTA pairs;
+ * n_acc: tap accumulators (1..5).  out[8] = {tiles_m, tiles_n, grid_ctas, persistent, acc_bufs, tmem_cols, n_tail, acc_stride}. */
+LDP_API int ldp_tc_geometry(int M, int N, int block_n, int epilogue, int pair, int n_acc, int32_t* out);
+
 /* Counters: number of kernels this library launched on the calling thread since the last reset (bench.py's
  * gpu_launches; graph replays count the kernels inside the graph). */
 LDP_API int64_t ldp_launch_count(void);

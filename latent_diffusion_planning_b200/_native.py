@@ -28,7 +28,7 @@ EXPORTS = [
     "ldp_unet_trainer_create", "ldp_idm_trainer_create", "ldp_trainer_destroy", "ldp_unet_loss_grad",
     "ldp_idm_loss_grad", "ldp_adam_update", "ldp_trainer_grad_buckets", "ldp_trainer_wait_bucket",
     "ldp_jax_random",
-    "ldp_tc_dense", "ldp_launch_count", "ldp_launch_count_reset",
+    "ldp_tc_dense", "ldp_tc_geometry", "ldp_launch_count", "ldp_launch_count_reset",
 ]
 
 
@@ -112,6 +112,7 @@ def load() -> C.CDLL:
     lib.ldp_adam_update.argtypes = [vp, vp, vp, vp, u64, f32, f32, f32, f32, i64, f32, vp]
     lib.ldp_jax_random.argtypes = [vp, i32, i64, i32, vp, vp]
     lib.ldp_tc_dense.argtypes = [vp, vp, vp, vp, i32, i32, i32, vp]
+    lib.ldp_tc_geometry.argtypes = [i32, i32, i32, i32, i32, i32, vp]
     lib.ldp_launch_count.restype = i64
     lib.ldp_launch_count_reset.restype = None
     for name in EXPORTS:

@@ -119,6 +119,18 @@ int ldp_jax_random(const uint32_t* keys_dev, int n_keys, int64_t n, int mode, vo
   return launch_jax_random(keys_dev, n_keys, n, mode, out_dev, (cudaStream_t)cuda_stream);
 }
 
+int ldp_tc_geometry(int M, int N, int block_n, int epilogue, int pair, int n_acc, int32_t* out) {
+  LDP_CHECK(out != nullptr && M > 0 && N > 0, LDP_ERR_INVALID_ARG, "bad arguments");
+  LDP_CHECK(block_n == 64 || block_n == 128 || block_n == 256, LDP_ERR_INVALID_ARG, "block_n must be 64, 128 or 256");
+  LDP_CHECK(epilogue >= TC_EPI_PLAIN && epilogue <= TC_EPI_LN && n_acc >= 1 && n_acc <= 5, LDP_ERR_INVALID_ARG, "bad epilogue / n_acc");
+  TcGemm p;
+  p.M = M; p.N = N; p.block_n = block_n; p.mode = epilogue; p.pair = pair ? 1 : 0; p.n_acc = n_acc; p.w_max = n_acc;
+  LDP_TRY(tc_gemm_geometry(&p));
+  const int32_t v[8] = {p.tiles_m, p.tiles_n, p.grid_ctas, p.persistent, p.acc_bufs, p.tmem_cols, p.n_tail, p.acc_stride};
+  for (int i = 0; i < 8; ++i) out[i] = v[i];
+  return LDP_OK;
+}
+
 int ldp_tc_dense(const float* a_dev, const float* w_host, const float* bias_host, float* c_dev, int M, int K, int N,
                  void* cuda_stream) {
   LDP_CHECK(a_dev && w_host && c_dev && M > 0 && K > 0 && N > 0, LDP_ERR_INVALID_ARG, "bad arguments");
