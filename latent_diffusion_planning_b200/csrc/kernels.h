@@ -191,7 +191,7 @@ struct TcGemm {
   // of the level-1 convolutions (profiles/r2c_vae_epilogue.md).  With these bits set the warp's 32 x 32 block goes through
   // a 4 KB swizzled shared-memory buffer and moves as ONE bulk tensor copy (store: out_f32 / out_bf16, load: res_f32).
   const CUtensorMap* epi_maps = nullptr;   // device memory: [0] out_f32, [1] out_bf16, [2] res_f32; boxes of 32 columns x 32 rows
-  int epi_tma = 0;                         // bit 0: out_f32, bit 1: out_bf16, bit 2: res_f32 go through TMA
+  int epi_tma = 0;                         // bit 0: out_f32, bit 1: out_bf16, bit 2: res_f32 go through TMA; bit 3: f32 boxes are 16 columns (2 KB buffers)
   long long* dbg_stage = nullptr;   // diagnostics: CTA (0,0)'s first 24 stage-arrival times
   long long* dbg = nullptr;         // diagnostics: per-CTA phase timestamps [ctas][8] (clock64 deltas)
   // L2 prefetch of the NEXT layer's packed weights (139 MB of weights stream through a 126 MB L2 once per denoising step, so
@@ -288,8 +288,8 @@ int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t*
 int make_tmap_bf16_strided(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
                            const uint64_t* strides_bytes, const uint32_t* box, const uint32_t* elem_strides);
 // 2-D map over a row-major [rows][ld] f32 / bf16 matrix with a 32-column x 32-row box (SWIZZLE_128B / SWIZZLE_64B): TcGemm::epi_maps
-int make_tmap_epi(CUtensorMap* out, const void* base, bool f32, uint64_t cols, uint64_t rows, uint64_t ld);
-int tc_build_epi_maps(const TcGemm& op, size_t rows, CUtensorMap host[3], int* bits);
+int make_tmap_epi(CUtensorMap* out, const void* base, bool f32, uint64_t cols, uint64_t rows, uint64_t ld, int box_cols);
+int tc_build_epi_maps(const TcGemm& op, size_t rows, CUtensorMap host[3], int* bits, bool half = false);
 int tc_driver_check();
 int tc_gemm_init();   // opt the kernels into their dynamic shared memory size (call outside stream capture)
 

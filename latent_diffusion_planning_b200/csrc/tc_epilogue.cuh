@@ -363,25 +363,30 @@ __device__ __forceinline__ void sts_128(uint32_t a, uint32_t x, uint32_t y, uint
   asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(a), "r"(x), "r"(y), "r"(z), "r"(w) : "memory");
 }
 
-constexpr int TC_EPI_BUF = 4096;     // per epilogue warp: 32 rows x 128 bytes
+constexpr int TC_EPI_BUF = 4096;     // per epilogue warp: 32 rows x 128 bytes (TcGemm::epi_tma bit 3: 2048 = 32 rows x 64 bytes)
 
-// The warp (lane quarter `quarter`, chunks [c_begin, c_begin + CPP)) handles 32 rows x 32 columns at a time in `buf`:
-//   [res_f32 box arrives by TMA (issued by the caller for the first chunk, before the accumulator wait)] -> v = acc + bias (+ res)
+// The warp (lane quarter `quarter`, chunks [c_begin, c_begin + CPP)) handles 32 rows x 32 columns at a time through `buf`:
+//   [res_f32 box arrives by TMA (issued by the caller for the first box of the tile, before the accumulator wait)] -> v = acc + bias (+ res)
 //   -> v to buf (f32, 128B swizzle: 16-byte unit u of row r sits at u ^ (r & 7), conflict-free for st.shared.v4) -> TMA store
 //   -> bf16(v) to buf (64B swizzle: unit u of row r at u ^ ((r >> 1) & 3)) -> TMA store.
+// HALF: the f32 boxes are 16 columns wide (64-byte rows, 64B swizzle, two per chunk) so that a warp's buffer is 2 KB: the 32 KB that
+// gives back to the operand ring are a whole stage for the BN = 256 pairs.
 // Lane 0 owns the bulk groups: before the buffer is rewritten it waits until the previous store has READ it.  Rows beyond M are
 // written too (they exist: the maps cover the workspace's full chunk) but stay out of the GroupNorm sums.
-template <int BN>
+template <int BN, bool HALF>
 __device__ __forceinline__ void epilogue_plain_tma(const TcGemm& p, EpiSmem<BN>& es, uint32_t taddr, int m, int n0, int c_begin,
                                                    int lane, int tile_m, int quarter, uint32_t buf, uint32_t bar_res,
                                                    uint32_t& res_phase) {
   constexpr int CPP = TcGeo<BN>::CPP, NC = BN / 32;
+  constexpr int NH = HALF ? 2 : 1, UNITS = HALF ? 4 : 8;          // f32 boxes per chunk, 16-byte units per box row
+  constexpr uint32_t BOX_BYTES = HALF ? 2048u : 4096u;
   const bool row_ok = m < p.M;
   const int row0 = tile_m * TC_BM + quarter * 32;
   const bool vf = (p.ld_out_f32 & 3) == 0, vb = (p.ld_out_bf16 & 7) == 0, vrf = (p.ld_res_f32 & 3) == 0;
   float2* gscr = &es.part[0][0];
-  const uint32_t rowf = buf + (uint32_t)lane * 128u, swf = (uint32_t)(lane & 7);
   const uint32_t rowb = buf + (uint32_t)lane * 64u, swb = (uint32_t)((lane >> 1) & 3);
+  const uint32_t rowf = HALF ? rowb : buf + (uint32_t)lane * 128u, swf = HALF ? swb : (uint32_t)(lane & 7);
+  bool first_box = true;                 // its residual was requested by the caller
 #pragma unroll 1
   for (int cc = 0; cc < CPP; ++cc) {
     const int c = c_begin + cc;
@@ -394,38 +399,44 @@ __device__ __forceinline__ void epilogue_plain_tma(const TcGemm& p, EpiSmem<BN>&
 #pragma unroll
       for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
     }
-    if (p.epi_tma & 4) {
-      if (cc > 0 && lane == 0) {
-        bulk_wait_read0();
-        mbar_arrive_expect_tx(bar_res, TC_EPI_BUF);
-        tma_load_2d(buf, &p.epi_maps[2], bar_res, nb, row0);
-      }
-      mbar_wait(bar_res, res_phase);
-      res_phase ^= 1u;
+    if (!(p.epi_tma & 4) && p.res_f32 && row_ok) add_f32x32(v, p.res_f32 + (long long)m * p.ld_res_f32 + nb, vrf, 32);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float4 f = lds_128(rowf + (((uint32_t)j ^ swf) << 4));
-        v[4 * j] += f.x; v[4 * j + 1] += f.y; v[4 * j + 2] += f.z; v[4 * j + 3] += f.w;
-      }
-    } else if (p.res_f32 && row_ok) {
-      add_f32x32(v, p.res_f32 + (long long)m * p.ld_res_f32 + nb, vrf, 32);
-    }
-    if (p.epi_tma & 1) {
-      if (!(p.epi_tma & 4) && lane == 0) bulk_wait_read0();
-      __syncwarp();
+    for (int h = 0; h < NH; ++h) {
+      const int col = nb + h * 16;       // (NH == 1: h = 0)
+      if (p.epi_tma & 4) {
+        if (!first_box && lane == 0) {
+          bulk_wait_read0();
+          mbar_arrive_expect_tx(bar_res, BOX_BYTES);
+          tma_load_2d(buf, &p.epi_maps[2], bar_res, col, row0);
+        }
+        first_box = false;
+        mbar_wait(bar_res, res_phase);
+        res_phase ^= 1u;
 #pragma unroll
-      for (int j = 0; j < 8; ++j)
-        sts_128(rowf + (((uint32_t)j ^ swf) << 4), __float_as_uint(v[4 * j]), __float_as_uint(v[4 * j + 1]), __float_as_uint(v[4 * j + 2]),
-                __float_as_uint(v[4 * j + 3]));
-      fence_proxy_async();
-      __syncwarp();
-      if (lane == 0) {
-        tma_store_2d(&p.epi_maps[0], buf, nb, row0);
-        bulk_commit();
+        for (int j = 0; j < UNITS; ++j) {
+          const float4 f = lds_128(rowf + (((uint32_t)j ^ swf) << 4));
+          const int i = h * 16 + 4 * j;
+          v[i] += f.x; v[i + 1] += f.y; v[i + 2] += f.z; v[i + 3] += f.w;
+        }
       }
-    } else if (p.out_f32 && row_ok) {
-      store_f32x32(p.out_f32 + (long long)m * p.ld_out_f32 + nb, v, vf, 32);
+      if (p.epi_tma & 1) {
+        if (!(p.epi_tma & 4) && lane == 0) bulk_wait_read0();
+        __syncwarp();
+#pragma unroll
+        for (int j = 0; j < UNITS; ++j) {
+          const int i = h * 16 + 4 * j;
+          sts_128(rowf + (((uint32_t)j ^ swf) << 4), __float_as_uint(v[i]), __float_as_uint(v[i + 1]), __float_as_uint(v[i + 2]),
+                  __float_as_uint(v[i + 3]));
+        }
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) {
+          tma_store_2d(&p.epi_maps[0], buf, col, row0);
+          bulk_commit();
+        }
+      }
     }
+    if (!(p.epi_tma & 1) && p.out_f32 && row_ok) store_f32x32(p.out_f32 + (long long)m * p.ld_out_f32 + nb, v, vf, 32);
     if (p.epi_tma & 2) {
       if (lane == 0) bulk_wait_read0();
       __syncwarp();

@@ -339,7 +339,8 @@ __global__ void __launch_bounds__(TcGeo<BN>::THREADS, 1) tc_gemm_kernel(const __
     // prefetch alone stretched the main loop of a conv1 layer by 1.5 - 1.9 k cycles).  Sleep through the pipeline fill instead.
     if (MODE == TC_EPI_GN && p.epi_sleep_ns > 0) __nanosleep(p.epi_sleep_ns);
     int it = 0;
-    const uint32_t epi_buf = smem_base + (uint32_t)STAGES * stage_bytes + (uint32_t)ew * TC_EPI_BUF;    // TMA epilogue: behind the ring
+    const uint32_t epi_box = (p.epi_tma & 8) ? TC_EPI_BUF / 2 : TC_EPI_BUF;                         // TMA epilogue: per-warp staging buffer,
+    const uint32_t epi_buf = smem_base + (uint32_t)STAGES * stage_bytes + (uint32_t)ew * epi_box;   // behind the ring
     const uint32_t my_bar_res = smem_u32(&bar_res[ew & 15]);
     uint32_t res_phase = 0;
     for (int tile = tile_first; tile < num_tiles; tile += tile_step, ++it) {
@@ -373,7 +374,7 @@ __global__ void __launch_bounds__(TcGeo<BN>::THREADS, 1) tc_gemm_kernel(const __
     if (MODE == TC_EPI_PLAIN && (p.epi_tma & 4) && lane == 0 && n0 + c_begin * 32 < p.N) {
       // the residual box of this warp's first chunk: in flight while the main loop runs
       bulk_wait_read0();                                 // the previous tile's stores have read the buffer
-      mbar_arrive_expect_tx(my_bar_res, TC_EPI_BUF);
+      mbar_arrive_expect_tx(my_bar_res, epi_box);
       tma_load_2d(epi_buf, &p.epi_maps[2], my_bar_res, n0 + c_begin * 32, tile_m * TC_BM + quarter * 32);
     }
     GnPrefetch<MODE == TC_EPI_GN ? BN : 64> pf;
@@ -387,7 +388,8 @@ __global__ void __launch_bounds__(TcGeo<BN>::THREADS, 1) tc_gemm_kernel(const __
     if (p.dbg && threadIdx.x == 64 && it == 0) ts[5] = clock64();   // accumulators complete
     const uint32_t taddr = tmem_base + (uint32_t)buf * (uint32_t)p.acc_stride + ((uint32_t)(quarter * 32) << 16);
     if constexpr (MODE == TC_EPI_PLAIN) {
-      if (p.epi_tma) epilogue_plain_tma<BN>(p, es, taddr, m, n0, c_begin, lane, tile_m, quarter, epi_buf, my_bar_res, res_phase);
+      if (p.epi_tma & 8) epilogue_plain_tma<BN, true>(p, es, taddr, m, n0, c_begin, lane, tile_m, quarter, epi_buf, my_bar_res, res_phase);
+      else if (p.epi_tma) epilogue_plain_tma<BN, false>(p, es, taddr, m, n0, c_begin, lane, tile_m, quarter, epi_buf, my_bar_res, res_phase);
       else epilogue_plain<BN>(p, es, taddr, m, n0, c_begin, lane, tile_m, quarter);
     }
     else if constexpr (MODE == TC_EPI_GN) epilogue_gn<BN>(p, es, taddr, m, n0, c_begin, row, lane, pf);
@@ -504,7 +506,7 @@ int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t*
   return make_tmap_bf16_strided(out, base, rank, dims, strides_bytes, box, nullptr);
 }
 
-int make_tmap_epi(CUtensorMap* out, const void* base, bool f32, uint64_t cols, uint64_t rows, uint64_t ld) {
+int make_tmap_epi(CUtensorMap* out, const void* base, bool f32, uint64_t cols, uint64_t rows, uint64_t ld, int box_cols) {
   PFN_encodeTiled fn = get_encode_fn();
   LDP_CHECK(fn != nullptr, LDP_ERR_NO_DEVICE, "cuTensorMapEncodeTiled driver entry point not available");
   const uint64_t es = f32 ? 4 : 2;
@@ -512,9 +514,11 @@ int make_tmap_epi(CUtensorMap* out, const void* base, bool f32, uint64_t cols, u
             "epilogue tensor map: base / leading dimension must be 16-byte aligned, columns a multiple of 32");
   cuuint64_t gdim[2] = {cols, rows};
   cuuint64_t gstr[1] = {ld * es};
-  cuuint32_t bx[2] = {32, 32}, estr[2] = {1, 1};
+  cuuint32_t bx[2] = {(cuuint32_t)box_cols, 32}, estr[2] = {1, 1};
+  const uint64_t row_bytes = (uint64_t)box_cols * es;
+  LDP_CHECK(row_bytes == 64 || row_bytes == 128, LDP_ERR_INVALID_ARG, "epilogue tensor map: box rows must be 64 or 128 bytes");
   CUresult r = fn(out, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstr, bx,
-                  estr, CU_TENSOR_MAP_INTERLEAVE_NONE, f32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                  estr, CU_TENSOR_MAP_INTERLEAVE_NONE, row_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_last_error("cuTensorMapEncodeTiled (epilogue map) failed with CUresult " + std::to_string((int)r));
@@ -525,14 +529,16 @@ int make_tmap_epi(CUtensorMap* out, const void* base, bool f32, uint64_t cols, u
 
 // Host side of TcGemm::epi_tma: which of out_f32 / out_bf16 / res_f32 can move as 32 x 32 boxes, and their maps (the caller copies the
 // three maps to device memory and sets op->epi_maps / op->epi_tma = *bits).
-int tc_build_epi_maps(const TcGemm& op, size_t rows, CUtensorMap host[3], int* bits) {
+int tc_build_epi_maps(const TcGemm& op, size_t rows, CUtensorMap host[3], int* bits, bool half) {
   *bits = 0;
+  const int fcols = half ? 16 : 32;
   memset(host, 0, 3 * sizeof(CUtensorMap));
   if (op.mode != TC_EPI_PLAIN || op.N % 32 != 0 || op.n_acc != 1 || op.shift[0] != 0 || op.use_aux) return LDP_OK;
   auto ok = [](const void* p) { return p != nullptr && (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
-  if (ok(op.out_f32) && op.ld_out_f32 % 4 == 0) { LDP_TRY(make_tmap_epi(&host[0], op.out_f32, true, op.N, rows, op.ld_out_f32)); *bits |= 1; }
-  if (ok(op.out_bf16) && op.ld_out_bf16 % 8 == 0) { LDP_TRY(make_tmap_epi(&host[1], op.out_bf16, false, op.N, rows, op.ld_out_bf16)); *bits |= 2; }
-  if (ok(op.res_f32) && op.ld_res_f32 % 4 == 0) { LDP_TRY(make_tmap_epi(&host[2], op.res_f32, true, op.N, rows, op.ld_res_f32)); *bits |= 4; }
+  if (ok(op.out_f32) && op.ld_out_f32 % 4 == 0) { LDP_TRY(make_tmap_epi(&host[0], op.out_f32, true, op.N, rows, op.ld_out_f32, fcols)); *bits |= 1; }
+  if (ok(op.out_bf16) && op.ld_out_bf16 % 8 == 0) { LDP_TRY(make_tmap_epi(&host[1], op.out_bf16, false, op.N, rows, op.ld_out_bf16, 32)); *bits |= 2; }
+  if (ok(op.res_f32) && op.ld_res_f32 % 4 == 0) { LDP_TRY(make_tmap_epi(&host[2], op.res_f32, true, op.N, rows, op.ld_res_f32, fcols)); *bits |= 4; }
+  if (*bits && half) *bits |= 8;
   return LDP_OK;
 }
 
@@ -623,7 +629,7 @@ static int launch_tc_gemm_inst(const TcGemm& p_in, cudaStream_t s) {
 
   }
   const int stage_bytes = (PAIR ? TC_A_BYTES + p.w_max * (BN / 2) * TC_BK * 2 : tc_stage_bytes(BN, p.w_max)) + p.n_tail * TC_BK * 2;
-  const int epi_bytes = p.epi_tma ? TcGeo<BN>::EPI_WARPS * TC_EPI_BUF : 0;
+  const int epi_bytes = p.epi_tma ? TcGeo<BN>::EPI_WARPS * ((p.epi_tma & 8) ? TC_EPI_BUF / 2 : TC_EPI_BUF) : 0;
   if (p.epi_tma)
     LDP_CHECK(MODE == TC_EPI_PLAIN && p.epi_maps && p.N % 32 == 0 && p.n_acc == 1 && p.shift[0] == 0 && !p.use_aux, LDP_ERR_INVALID_ARG,
               "tc_gemm: the TMA epilogue needs the PLAIN epilogue, one accumulator and N % 32 == 0");

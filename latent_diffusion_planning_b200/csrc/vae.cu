@@ -782,7 +782,9 @@ static int vae_epi_maps(Arena& arena, TcGemm* op, size_t rows) {
   if (!on) return LDP_OK;
   CUtensorMap host[3];
   int bits = 0;
-  LDP_TRY(tc_build_epi_maps(*op, rows, host, &bits));
+  // 256-wide tiles: 2 KB staging buffers (16-column f32 boxes) buy the CTA pairs a fifth ring stage (LDP_VAE_EPI_HALF=0: 4 KB everywhere)
+  static const bool half_ok = !(getenv("LDP_VAE_EPI_HALF") && getenv("LDP_VAE_EPI_HALF")[0] == '0');
+  LDP_TRY(tc_build_epi_maps(*op, rows, host, &bits, half_ok && op->block_n == 256));
   if (!bits) return LDP_OK;
   CUtensorMap* dev;
   LDP_TRY(arena.alloc_t(&dev, 3));
