@@ -186,6 +186,13 @@ struct TcGemm {
   int tiles_m = 0, tiles_n = 0, grid_ctas = 0, acc_bufs = 1, acc_stride = 0, persistent = 0;
   unsigned epi_sleep_ns = 0;        // GN epilogue warps sleep this long before staging / prefetching (LDP_EPI_SLEEP, default 1000)
   int epi_skip = 0;                 // diagnostics (LDP_EPI_SKIP): 1 stores, 2 FiLM loads, 4 residual, 8 activation, 16 tap shuffles
+  // Tap rows shared through shared memory (persistent PLAIN kernel; the VAE's 3x3 convolutions whose tile is two whole image rows):
+  // a stage's A box holds a_rows = 256 rows - the tile's two image rows plus the row above and the row below - and its nw = 3 W tiles are
+  // the three kh taps of one (kw, channel block): tap j multiplies the 128-row window that starts a_tap_shift16 * 16 bytes (one image
+  // row pair = 8 KB, swizzle-atom aligned) further down, all into ONE accumulator.  Each activation row is fetched 4/6 as often.
+  int a_rows = 128;                 // rows of the A box of a stage (128 B each)
+  int a_tap_shift16 = 0;            // A descriptor advance per W tile of a stage, in 16-byte units
+  int taps_same_acc = 0;            // 1: the nw W tiles of a stage accumulate into accumulator 0 (with the shifted A windows)
   // TMA epilogue (PLAIN epilogue, N % 32 == 0; the VAE convolutions).  A thread of the epilogue owns one output row, so a
   // vector store of a warp touches 32 different lines: with 128 x 256 f32 tiles the LSU, not the tensor pipe, set the pace
   // of the level-1 convolutions (profiles/r2c_vae_epilogue.md).  With these bits set the warp's 32 x 32 block goes through

@@ -30,6 +30,7 @@ constexpr int TC_MAX_RUNS = 64;            // (taps x sources) + aux sources of 
 constexpr int TC_MAX_STAGES = 8;
 
 constexpr int TC_SMEM_RING = 196 * 1024;        // shared-memory budget of the TMA ring (static smem takes <= 20 KB more)
+constexpr int TC_SMEM_RING_PLAIN = 204 * 1024;  // PLAIN epilogue kernels (ring + TMA-epilogue staging): their static part is <= 19.1 KB
 
 template <int BN>
 struct TcSmem {
@@ -387,6 +388,7 @@ __device__ __forceinline__ void epilogue_plain_tma(const TcGemm& p, EpiSmem<BN>&
   const uint32_t rowb = buf + (uint32_t)lane * 64u, swb = (uint32_t)((lane >> 1) & 3);
   const uint32_t rowf = HALF ? rowb : buf + (uint32_t)lane * 128u, swf = HALF ? swb : (uint32_t)(lane & 7);
   bool first_box = true;                 // its residual was requested by the caller
+  const bool stats_early = HALF && p.gn_part && (p.epi_tma & 1) && !(p.epi_tma & 4) && !p.res_f32;
 #pragma unroll 1
   for (int cc = 0; cc < CPP; ++cc) {
     const int c = c_begin + cc;
@@ -435,6 +437,15 @@ __device__ __forceinline__ void epilogue_plain_tma(const TcGemm& p, EpiSmem<BN>&
           bulk_commit();
         }
       }
+      // HALF without a residual: v is final, so the GroupNorm sums run here - under the first box's store, whose read the second box
+      // has to wait for (the store queues behind the producer's operand loads in the TMA unit: ~1.5k cycles)
+      if (HALF && h == 0 && stats_early) {
+        float2* o = gscr + (quarter * NC + c) * 8;
+        if (p.gn_cpg == 4) chunk_group_sums<8>(v, row_ok, o, lane);
+        else if (p.gn_cpg == 8) chunk_group_sums<4>(v, row_ok, o, lane);
+        else if (p.gn_cpg == 16) chunk_group_sums<2>(v, row_ok, o, lane);
+        else chunk_group_sums<1>(v, row_ok, o, lane);
+      }
     }
     if (!(p.epi_tma & 1) && p.out_f32 && row_ok) store_f32x32(p.out_f32 + (long long)m * p.ld_out_f32 + nb, v, vf, 32);
     if (p.epi_tma & 2) {
@@ -453,7 +464,7 @@ __device__ __forceinline__ void epilogue_plain_tma(const TcGemm& p, EpiSmem<BN>&
     } else if (p.out_bf16 && row_ok) {
       store_bf16x32(p.out_bf16 + (long long)m * p.ld_out_bf16 + nb, v, vb, 32);
     }
-    if (p.gn_part) {                      // uniform
+    if (p.gn_part && !stats_early) {      // uniform
       float2* o = gscr + (quarter * NC + c) * 8;
       if (p.gn_cpg == 4) chunk_group_sums<8>(v, row_ok, o, lane);
       else if (p.gn_cpg == 8) chunk_group_sums<4>(v, row_ok, o, lane);

@@ -63,7 +63,9 @@ __global__ void __launch_bounds__(TcGeo<BN>::THREADS, 1) tc_gemm_kernel(const __
   const uint32_t cta_rank = PAIR ? cluster_ctarank() : 0u;
   const bool leader = cta_rank == 0;
   const int STAGES = p.num_stages;
-  const uint32_t stage_bytes = TC_A_BYTES + (uint32_t)p.w_max * B_BYTES + (MODE == TC_EPI_DDPM ? (uint32_t)p.n_tail * (TC_BK * 2) : 0u);
+  // A box of a stage: 128 rows, or 256 in the persistent kernel's shared-tap-row mode (TcGemm::a_rows) - a compile-time constant elsewhere
+  const uint32_t a_bytes = PERSIST ? (uint32_t)p.a_rows * (TC_BK * 2) : (uint32_t)TC_A_BYTES;
+  const uint32_t stage_bytes = a_bytes + (uint32_t)p.w_max * B_BYTES + (MODE == TC_EPI_DDPM ? (uint32_t)p.n_tail * (TC_BK * 2) : 0u);
   // DDPM: this CTA owns the widened last N tile (BN + n_tail columns)
   const bool tail_tile = MODE == TC_EPI_DDPM && p.n_tail > 0 && blockIdx.y + 1 == gridDim.y;
   __shared__ __align__(8) uint64_t bar_full[TC_MAX_STAGES];
@@ -161,7 +163,7 @@ __global__ void __launch_bounds__(TcGeo<BN>::THREADS, 1) tc_gemm_kernel(const __
         const uint32_t nw = (uint32_t)(r_src_acc >> 16) & 0xffu;
         const int d1 = (int)(short)(r_d12 & 0xffff), c2 = c2_base + (r_d12 >> 16);
         const CUtensorMap* map_a = &p.map_a[r_src_acc & 0xff];
-        const uint32_t tx = (PAIR ? 2u : 1u) * (TC_A_BYTES + nw * (uint32_t)B_BYTES) + (tail_tile ? (uint32_t)p.n_tail * (TC_BK * 2) : 0u);
+        const uint32_t tx = (PAIR ? 2u : 1u) * (a_bytes + nw * (uint32_t)B_BYTES) + (tail_tile ? (uint32_t)p.n_tail * (TC_BK * 2) : 0u);
         int c0 = r_c0, wkc = r_wk * TC_BK;
         for (int i = 0; i < r_count; ++i) {
           if (PERSIST && p.dbg) {
@@ -178,15 +180,15 @@ __global__ void __launch_bounds__(TcGeo<BN>::THREADS, 1) tc_gemm_kernel(const __
             if (leader) mbar_arrive_expect_tx(bar, tx);
             tma_load_4d_2sm(sa, map_a, bar_leader, c0, d1, c2, c3);
             for (uint32_t j = 0; j < nw; ++j)
-              tma_load_2d_2sm(sa + TC_A_BYTES + j * B_BYTES, &p.map_b, bar_leader, wkc + (int)j * TC_BK, n0 + (int)cta_rank * (BN / 2));
+              tma_load_2d_2sm(sa + a_bytes + j * B_BYTES, &p.map_b, bar_leader, wkc + (int)j * TC_BK, n0 + (int)cta_rank * (BN / 2));
           } else {
             mbar_arrive_expect_tx(bar, tx);
             tma_load_4d(sa, map_a, bar, c0, d1, c2, c3);
             if (nw == 1) {
-              tma_load_2d(sa + TC_A_BYTES, &p.map_b, bar, wkc, n0);
-              if (MODE == TC_EPI_DDPM && tail_tile) tma_load_2d(sa + TC_A_BYTES + B_BYTES, &p.map_b_tail, bar, wkc, n0 + BN);
+              tma_load_2d(sa + a_bytes, &p.map_b, bar, wkc, n0);
+              if (MODE == TC_EPI_DDPM && tail_tile) tma_load_2d(sa + a_bytes + B_BYTES, &p.map_b_tail, bar, wkc, n0 + BN);
             } else {
-              for (uint32_t j = 0; j < nw; ++j) tma_load_2d(sa + TC_A_BYTES + j * B_BYTES, &p.map_b, bar, wkc + (int)j * TC_BK, n0);
+              for (uint32_t j = 0; j < nw; ++j) tma_load_2d(sa + a_bytes + j * B_BYTES, &p.map_b, bar, wkc + (int)j * TC_BK, n0);
             }
           }
           c0 += TC_BK;
@@ -256,7 +258,7 @@ __global__ void __launch_bounds__(TcGeo<BN>::THREADS, 1) tc_gemm_kernel(const __
           }
           tc_fence_after();
           if (dbg_on && kb == 0) ts[3] = clock64();
-          const uint64_t db = da + (TC_A_BYTES >> 4);
+          const uint64_t db = da + (a_bytes >> 4);
           if (PAIR) {
             umma_bf16_ss_2sm(acc_base, da, db, idesc, accf);
             umma_bf16_ss_2sm(acc_base, da + 2, db + 2, idesc, 1u);
@@ -279,11 +281,14 @@ __global__ void __launch_bounds__(TcGeo<BN>::THREADS, 1) tc_gemm_kernel(const __
         mbar_wait(full0 + 8u * stage, phase);
         tc_fence_after();
         if (p.dbg && kb == 0) ts[3] = clock64();        // first operands landed
-        const uint32_t a_lo = a_lo0 + stage * stage_step;
-        uint32_t b_lo = a_lo + (TC_A_BYTES >> 4);
+        uint32_t a_lo = a_lo0 + stage * stage_step;
+        uint32_t b_lo = a_lo + (a_bytes >> 4);
         uint32_t d = acc_base;
-        for (uint32_t j = 0; j < nw_main; ++j, b_lo += B_STEP, d += BN) {     // the A tile is shared by the taps' accumulators
-          umma_lohi<PAIR>(d, a_lo, b_lo, DESC_HI, idesc, accf);
+        // the A tile is shared by the taps' accumulators; shared-tap-row mode (PERSIST only): one accumulator, the A window moves instead
+        const bool same_acc = PERSIST && p.taps_same_acc != 0;
+        const uint32_t a_step = same_acc ? (uint32_t)p.a_tap_shift16 : 0u, d_step = same_acc ? 0u : (uint32_t)BN;
+        for (uint32_t j = 0; j < nw_main; ++j, b_lo += B_STEP, d += d_step, a_lo += a_step) {
+          umma_lohi<PAIR>(d, a_lo, b_lo, DESC_HI, idesc, (same_acc && j > 0) ? 1u : accf);
           umma_lohi<PAIR>(d, a_lo + 2, b_lo + 2, DESC_HI, idesc, 1u);          // +16 bf16 = 32 bytes along K inside the swizzle row
           umma_lohi<PAIR>(d, a_lo + 4, b_lo + 4, DESC_HI, idesc, 1u);
           umma_lohi<PAIR>(d, a_lo + 6, b_lo + 6, DESC_HI, idesc, 1u);
@@ -299,7 +304,7 @@ __global__ void __launch_bounds__(TcGeo<BN>::THREADS, 1) tc_gemm_kernel(const __
         mbar_wait(full0 + 8u * stage, phase);
         tc_fence_after();
         const uint32_t a_lo = a_lo0 + stage * stage_step;
-        const uint32_t b_lo = a_lo + (TC_A_BYTES >> 4);
+        const uint32_t b_lo = a_lo + (a_bytes >> 4);
         umma_lohi<PAIR>(d_aux, a_lo, b_lo, DESC_HI, idesc, accf);
         umma_lohi<PAIR>(d_aux, a_lo + 2, b_lo + 2, DESC_HI, idesc, 1u);
         umma_lohi<PAIR>(d_aux, a_lo + 4, b_lo + 4, DESC_HI, idesc, 1u);
@@ -542,8 +547,12 @@ int tc_build_epi_maps(const TcGemm& op, size_t rows, CUtensorMap host[3], int* b
   return LDP_OK;
 }
 
+template <int MODE>
+static constexpr int ring_budget() { return MODE == TC_EPI_PLAIN ? TC_SMEM_RING_PLAIN : TC_SMEM_RING; }
+
 template <int BN, int MODE>
 static int set_smem_attr() {
+  constexpr int TC_SMEM_RING = ring_budget<MODE>();        // (shadows the global: every attribute below uses this kernel family's budget)
   LDP_CUDA_OK(cudaFuncSetAttribute(tc_gemm_kernel<BN, MODE, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    TC_SMEM_RING + 1024));
   constexpr bool kPairable = (MODE == TC_EPI_PLAIN || MODE == TC_EPI_GN) && BN <= 128;
@@ -597,8 +606,9 @@ int tc_gemm_geometry(TcGemm* p) {
   static int persist = -1;
   if (persist < 0) { const char* e = getenv("LDP_PERSIST"); persist = (e && e[0] == '0') ? 0 : 1; }
   // pairs + persistence (the VAE convolutions): PLAIN epilogue, BN >= 128; a paired launch that is not persistent needs BN <= 128
-  const bool persistent = persist && tiles > 148 && p->mode == TC_EPI_PLAIN && (!p->pair || bn >= 128);
-  p->grid_ctas = persistent ? 148 : tiles;
+  // (the shared-tap-row layout exists only in the persistent kernel: such a launch is persistent whatever its tile count)
+  const bool persistent = (persist && tiles > 148 && p->mode == TC_EPI_PLAIN && (!p->pair || bn >= 128)) || p->a_rows == 256;
+  p->grid_ctas = persistent ? std::min(148, tiles) : tiles;
   p->persistent = persistent ? 1 : 0;
   p->acc_stride = n_acc_total * bn + p->n_tail;
   p->acc_bufs = (persistent && 2 * p->acc_stride <= 512) ? 2 : 1;
@@ -628,12 +638,15 @@ static int launch_tc_gemm_inst(const TcGemm& p_in, cudaStream_t s) {
     p.epi_sleep_ns = (unsigned)sleep_ns;
 
   }
-  const int stage_bytes = (PAIR ? TC_A_BYTES + p.w_max * (BN / 2) * TC_BK * 2 : tc_stage_bytes(BN, p.w_max)) + p.n_tail * TC_BK * 2;
+  LDP_CHECK(p.a_rows == 128 || (PERSIST && p.a_rows == 256 && p.taps_same_acc && p.n_acc == 1), LDP_ERR_INVALID_ARG,
+            "tc_gemm: 256-row A boxes exist only in the persistent kernel's shared-tap-row mode");
+  const int a_bytes = p.a_rows * TC_BK * 2;
+  const int stage_bytes = a_bytes + p.w_max * (PAIR ? BN / 2 : BN) * TC_BK * 2 + p.n_tail * TC_BK * 2;
   const int epi_bytes = p.epi_tma ? TcGeo<BN>::EPI_WARPS * ((p.epi_tma & 8) ? TC_EPI_BUF / 2 : TC_EPI_BUF) : 0;
   if (p.epi_tma)
     LDP_CHECK(MODE == TC_EPI_PLAIN && p.epi_maps && p.N % 32 == 0 && p.n_acc == 1 && p.shift[0] == 0 && !p.use_aux, LDP_ERR_INVALID_ARG,
               "tc_gemm: the TMA epilogue needs the PLAIN epilogue, one accumulator and N % 32 == 0");
-  p.num_stages = std::min(TC_MAX_STAGES, (TC_SMEM_RING - epi_bytes) / stage_bytes);
+  p.num_stages = std::min(TC_MAX_STAGES, (ring_budget<MODE>() - epi_bytes) / stage_bytes);
   LDP_CHECK(p.num_stages >= 2, LDP_ERR_UNSUPPORTED, "tc_gemm: stage does not fit the shared-memory ring twice");
   if (MODE == TC_EPI_DDPM)
     LDP_CHECK(p.num_stages * stage_bytes >= TC_BM * (BN + p.n_tail + 1) * 4, LDP_ERR_UNSUPPORTED,

@@ -745,7 +745,9 @@ static TileGeo tile_geo(int S) {
   return g;
 }
 
-static int vae_pack(LdpVae* h, int id, const float* wgt, int k, int pad, int cin, int cout, PackedW** out) {
+// share_rows: the stage order of TcGemm::a_rows == 256 - a stage is (kw, channel block) with the three kh taps as its W tiles
+static int vae_pack(LdpVae* h, int id, const float* wgt, int k, int pad, int cin, int cout, PackedW** out, bool share_rows = false) {
+  if (share_rows) id += 1 << 20;                     // its own cache entry: the K order of the packed weights differs
   auto it = h->packed.find(id);
   if (it != h->packed.end()) {
     *out = &it->second;
@@ -754,6 +756,14 @@ static int vae_pack(LdpVae* h, int id, const float* wgt, int k, int pad, int cin
   PackedW pw;
   std::vector<TcStage> st;
   std::vector<int32_t> kmap;
+  if (share_rows) {
+    for (int dx = 0; dx < k; ++dx)
+      for (int c0 = 0; c0 < cin; c0 += 64) {
+        st.push_back(make_stage(0, 0, k, c0, dx - pad, -pad, (int)kmap.size() / 64));      // A box starts one image row above the tile
+        for (int dy = 0; dy < k; ++dy)
+          for (int i = 0; i < 64; ++i) kmap.push_back(c0 + i < cin ? (dy * k + dx) * cin + c0 + i : -1);
+      }
+  } else
   for (int dy = 0; dy < k; ++dy)
     for (int dx = 0; dx < k; ++dx)
       for (int c0 = 0; c0 < cin; c0 += 64) {
@@ -784,7 +794,7 @@ static int vae_epi_maps(Arena& arena, TcGemm* op, size_t rows) {
   int bits = 0;
   // 256-wide tiles: 2 KB staging buffers (16-column f32 boxes) buy the CTA pairs a fifth ring stage (LDP_VAE_EPI_HALF=0: 4 KB everywhere)
   static const bool half_ok = !(getenv("LDP_VAE_EPI_HALF") && getenv("LDP_VAE_EPI_HALF")[0] == '0');
-  LDP_TRY(tc_build_epi_maps(*op, rows, host, &bits, half_ok && op->block_n == 256));
+  LDP_TRY(tc_build_epi_maps(*op, rows, host, &bits, (half_ok && op->block_n == 256) || op->a_rows == 256));
   if (!bits) return LDP_OK;
   CUtensorMap* dev;
   LDP_TRY(arena.alloc_t(&dev, 3));
@@ -800,31 +810,41 @@ static int vae_conv_tc(LdpVae* h, VaeWs* w, int id, const ConvW& cw, const float
                        int stride, TcGemm* op) {
   PackedW* pw;
   const int pad = (cw.k == 3 && stride == 1) ? 1 : 0;
-  LDP_TRY(vae_pack(h, id, cw.w, cw.k, pad, cw.cin, cw.cout, &pw));
   const int S_out = S_in / stride;
   const TileGeo g = tile_geo(S_out);
-  *op = TcGemm();
-  uint64_t dims[4] = {(uint64_t)cw.cin, (uint64_t)S_in, (uint64_t)S_in, (uint64_t)w->Bc};
-  uint64_t str[3] = {(uint64_t)cw.cin * 2, (uint64_t)S_in * cw.cin * 2, (uint64_t)S_in * S_in * cw.cin * 2};
-  uint32_t box[4] = {64, (uint32_t)(g.wb * stride), (uint32_t)(g.hb * stride), (uint32_t)g.ib};
-  uint32_t es[4] = {1, (uint32_t)stride, (uint32_t)stride, 1};
-  LDP_TRY(make_tmap_bf16_strided(&op->map_a[0], in, 4, dims, str, box, es));
-  for (int i = 1; i < 4; ++i) op->map_a[i] = op->map_a[0];
   // 256-wide tiles where the channel count allows: one A tile feeds twice the MMA work (per-tap stages of 48 KB with
   // 512 cycles of MMAs instead of 32 KB with 256), which is what the latency-bound per-tap ring needs
   static const bool bn256 = !(getenv("LDP_VAE_BN256") && getenv("LDP_VAE_BN256")[0] == '0');
   const int bn = (bn256 && cw.cout % 256 == 0) ? 256 : (cw.cout > 64 ? 128 : 64);
+  static const bool pair_ok = !(getenv("LDP_VAE_PAIR") && getenv("LDP_VAE_PAIR")[0] == '0');
+  const int tiles_m = ceil_div(w->Bc * S_out * S_out, 128), tiles_n = ceil_div(cw.cout, bn);
+  const bool pair = pair_ok && bn >= 128 && tiles_m % 2 == 0 && tiles_m * tiles_n > 148;
+  // Shared tap rows (TcGemm::a_rows = 256): 3x3 stride-1 convolutions whose tile is exactly two whole rows of one image, as CTA pairs
+  // at BN = 128 (a stage is 32 KB of A + 3 x 8 KB of W; three of them fit next to 2 KB staging buffers).  LDP_VAE_SHARE_ROWS=0: per-tap stages.
+  static const bool share_ok = !(getenv("LDP_VAE_SHARE_ROWS") && getenv("LDP_VAE_SHARE_ROWS")[0] == '0');
+  const bool share_rows = share_ok && pair && bn == 128 && cw.k == 3 && stride == 1 && g.ib == 1 && g.hb == 2 && g.wb == S_out &&
+                          g.wb * g.hb == 128 && cw.cin % 64 == 0;
+  LDP_TRY(vae_pack(h, id, cw.w, cw.k, pad, cw.cin, cw.cout, &pw, share_rows));
+  *op = TcGemm();
+  uint64_t dims[4] = {(uint64_t)cw.cin, (uint64_t)S_in, (uint64_t)S_in, (uint64_t)w->Bc};
+  uint64_t str[3] = {(uint64_t)cw.cin * 2, (uint64_t)S_in * cw.cin * 2, (uint64_t)S_in * S_in * cw.cin * 2};
+  uint32_t box[4] = {64, (uint32_t)(g.wb * stride), (uint32_t)((share_rows ? g.hb + 2 : g.hb) * stride), (uint32_t)g.ib};
+  uint32_t es[4] = {1, (uint32_t)stride, (uint32_t)stride, 1};
+  LDP_TRY(make_tmap_bf16_strided(&op->map_a[0], in, 4, dims, str, box, es));
+  for (int i = 1; i < 4; ++i) op->map_a[i] = op->map_a[0];
+  if (share_rows) {
+    op->a_rows = 256;
+    op->a_tap_shift16 = (g.wb * 128) >> 4;           // one image row of the box = wb rows of 128 bytes
+    op->taps_same_acc = 1;
+  }
   uint64_t bd[2] = {(uint64_t)pw->kp, (uint64_t)pw->n_pad};
   uint64_t bs[1] = {(uint64_t)pw->kp * 2};
   // CTA pairs (cta_group::2) where the launch is persistent: the convolutions are bound by L2 -> SM operand delivery, and in a
   // pair each CTA fetches only half of every W tile (LDP_VAE_PAIR=0: single CTAs)
-  static const bool pair_ok = !(getenv("LDP_VAE_PAIR") && getenv("LDP_VAE_PAIR")[0] == '0');
-  const int tiles_m = ceil_div(w->Bc * S_out * S_out, 128), tiles_n = ceil_div(cw.cout, bn);
-  const bool pair = pair_ok && bn >= 128 && tiles_m % 2 == 0 && tiles_m * tiles_n > 148;
   uint32_t bb[2] = {64, (uint32_t)(pair ? bn / 2 : bn)};
   LDP_TRY(make_tmap_bf16(&op->map_b, pw->wt, 2, bd, bs, bb));
   op->pair = pair ? 1 : 0;
-  op->kb = pw->kb_dev; op->num_kb = pw->num_kb; op->runs = pw->runs_dev; op->num_runs = pw->num_runs; tc_set_inline_runs(op, pw->runs_host.data(), pw->num_runs); op->w_max = 1; op->k_pad = pw->kp;
+  op->kb = pw->kb_dev; op->num_kb = pw->num_kb; op->runs = pw->runs_dev; op->num_runs = pw->num_runs; tc_set_inline_runs(op, pw->runs_host.data(), pw->num_runs); op->w_max = share_rows ? cw.k : 1; op->k_pad = pw->kp;
   op->M = w->Bc * S_out * S_out; op->N = cw.cout; op->block_n = bn;
   op->tiles_per_item = g.tiles_per_img; op->rows_step = g.hb * stride; op->items_per_tile = g.ib;
   op->rows_per_item = 1;

