@@ -52,6 +52,12 @@ __device__ __forceinline__ void umma_lohi(uint32_t d_tmem, uint32_t a_lo, uint32
   }
 }
 
+}  // namespace ldp
+
+#include "tc_gemm_v1.cuh"
+
+namespace ldp {
+
 // ---- the kernel --------------------------------------------------------------------------------
 template <int BN, int MODE, bool PAIR, bool PERSIST>
 __global__ void __launch_bounds__(TcGeo<BN>::THREADS, 1) tc_gemm_kernel(const __grid_constant__ TcGemm p) {
@@ -563,6 +569,14 @@ static int set_smem_attr() {
   if (kPersistable)
     LDP_CUDA_OK(cudaFuncSetAttribute(tc_gemm_kernel<BN, MODE, false, kPersistable>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      TC_SMEM_RING + 1024));
+  LDP_CUDA_OK(cudaFuncSetAttribute(tc_gemm_kernel_v1<BN, MODE, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   TC_SMEM_RING + 1024));
+  if (kPairable)
+    LDP_CUDA_OK(cudaFuncSetAttribute(tc_gemm_kernel_v1<BN, MODE, kPairable, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     TC_SMEM_RING + 1024));
+  if (kPersistable)
+    LDP_CUDA_OK(cudaFuncSetAttribute(tc_gemm_kernel_v1<BN, MODE, false, kPersistable>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     TC_SMEM_RING + 1024));
   constexpr bool kPairPersist = MODE == TC_EPI_PLAIN && BN >= 128;
   if (kPairPersist)
     LDP_CUDA_OK(cudaFuncSetAttribute(tc_gemm_kernel<BN, MODE, kPairPersist, kPairPersist>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -692,7 +706,15 @@ static int launch_tc_gemm_inst(const TcGemm& p_in, cudaStream_t s) {
     }
     cfg.gridDim = dim3(2 * std::min(max_clusters, p.tiles_m / 2 * p.tiles_n), 1, 1);
   }
-  cudaError_t e = cudaLaunchKernelEx(&cfg, tc_gemm_kernel<BN, MODE, PAIR, PERSIST>, p);
+  // ops that use none of the later features (TMA epilogue, paired persistence, shared tap rows) run on the v1 body (tc_gemm_v1.cuh)
+  const bool v2 = p.epi_tma != 0 || (PAIR && PERSIST) || p.a_rows != 128;
+  cudaError_t e;
+  if constexpr (PAIR && PERSIST) {
+    e = cudaLaunchKernelEx(&cfg, tc_gemm_kernel<BN, MODE, PAIR, PERSIST>, p);
+  } else {
+    e = v2 ? cudaLaunchKernelEx(&cfg, tc_gemm_kernel<BN, MODE, PAIR, PERSIST>, p)
+           : cudaLaunchKernelEx(&cfg, tc_gemm_kernel_v1<BN, MODE, PAIR, PERSIST>, p);
+  }
   if (e != cudaSuccess) {
     set_last_error(std::string("tc_gemm launch failed: ") + cudaGetErrorString(e));
     return LDP_ERR_CUDA;
