@@ -621,7 +621,10 @@ int tc_gemm_geometry(TcGemm* p) {
   if (persist < 0) { const char* e = getenv("LDP_PERSIST"); persist = (e && e[0] == '0') ? 0 : 1; }
   // pairs + persistence (the VAE convolutions): PLAIN epilogue, BN >= 128; a paired launch that is not persistent needs BN <= 128
   // (the shared-tap-row layout exists only in the persistent kernel: such a launch is persistent whatever its tile count)
-  const bool persistent = (persist && tiles > 148 && p->mode == TC_EPI_PLAIN && (!p->pair || bn >= 128)) || p->a_rows == 256;
+  // ... and so is a paired 256-wide launch (no plain-grid kernel is instantiated for it): ops are built for a full chunk of images and
+  // replayed for the last, smaller one
+  const bool persistent = (persist && tiles > 148 && p->mode == TC_EPI_PLAIN && (!p->pair || bn >= 128)) || p->a_rows == 256 ||
+                          (p->pair && bn == 256 && p->mode == TC_EPI_PLAIN);
   p->grid_ctas = persistent ? std::min(148, tiles) : tiles;
   p->persistent = persistent ? 1 : 0;
   p->acc_stride = n_acc_total * bn + p->n_tail;

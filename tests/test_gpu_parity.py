@@ -417,6 +417,23 @@ def test_vae_chunking_is_invisible(H):
     assert _maxerr(whole, parts) < 1e-4
 
 
+def test_vae_last_chunk_of_a_batch_replays_the_full_chunk_ops(H):
+    """B = one full 592-image chunk + 8 images at the benchmark topology: the ops are built for 592 images (CTA pairs, 256-wide tiles,
+    shared tap rows) and replayed with 8 - a handful of tiles per launch.  (A paired 256-wide launch that fell back to a plain grid
+    had no kernel: found with the decoder, B = 1184 in chunks of 128.)  The small batch alone runs other kernels (single CTAs), so
+    the comparison is at the bf16 gate, not bit-exact."""
+    blocks = (128, 256, 512, 512)
+    p = P.init_params(P.vae_encoder_spec(blocks), seed=3, perturb=0.1)
+    vae = H.VaeEncoder(p, blocks)
+    img = _images(600, 64, seed=13).cuda()
+    whole = vae.encode(img, precision="bf16")
+    tail = vae.encode(img[592:], precision="bf16")
+    assert torch.isfinite(whole).all()
+    scale = max(1.0, float(tail.abs().max()))
+    assert _maxerr(whole[592:], tail) < 2 * TOL_BF16 * scale
+    vae.close()
+
+
 # ------------------------------------------------------------------------------------------------
 # VAE decoder (next-row N2: plan_viz)
 # ------------------------------------------------------------------------------------------------

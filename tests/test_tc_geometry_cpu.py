@@ -52,7 +52,10 @@ def test_vae_convolutions_are_persistent_pairs_with_two_accumulator_buffers(lib)
 def test_pair_rounds_odd_tile_counts_up_and_small_launches_stay_plain_grids(lib):
     g = geo(lib, 3 * 128, 128, 128, PLAIN, pair=1)
     assert g["tiles_m"] == 4 and g["persistent"] == 0 and g["grid"] == 4
-    # a paired BN = 256 launch exists only in persistent form; the same shape as single CTAs is a plain grid
+    # a paired BN = 256 launch exists only in persistent form - also when the last chunk of a batch leaves it a handful of tiles;
+    # the same shape as single CTAs is a plain grid
+    g = geo(lib, 8 * 64, 512, 256, PLAIN, pair=1)
+    assert g["persistent"] == 1 and g["grid"] == 8 and g["acc_bufs"] == 2
     g = geo(lib, 100 * 128, 256, 256, PLAIN)
     assert g["persistent"] == 0 and g["grid"] == 100 and g["acc_bufs"] == 1
 
