@@ -176,6 +176,9 @@ class Planner:
                row_offset: int = 0, n_steps: Optional[int] = None, sampler="ddpm", precision="bf16") -> torch.Tensor:
         x, c = _f32c(x_T), _f32c(global_cond)
         B, T, D = x.shape
+        if D != self.input_dim or tuple(c.shape) != (B, self.global_cond_dim):      # the C side sees pointers only
+            raise ValueError(f"shape mismatch: x_T {tuple(x.shape)}, cond {tuple(c.shape)}; expected (B,T,{self.input_dim}) and "
+                             f"(B,{self.global_cond_dim})")
         n_steps = self.n_train_steps if n_steps is None else int(n_steps)
         z = None
         if noise is not None:
@@ -277,6 +280,9 @@ class Idm:
                row_offset: int = 0, n_steps: Optional[int] = None, sampler="ddpm", precision="bf16") -> torch.Tensor:
         s, a = _f32c(s), _f32c(a_T)
         n = s.shape[0]
+        if s.dim() != 2 or s.shape[1] != 2 * self.obs_dim or tuple(a.shape) != (n, self.action_dim):   # the C side sees pointers only
+            raise ValueError(f"shape mismatch: s {tuple(s.shape)}, a_T {tuple(a.shape)}; expected (N,{2 * self.obs_dim}) and "
+                             f"(N,{self.action_dim})")
         n_steps = self.n_train_steps if n_steps is None else int(n_steps)
         z = None
         if noise is not None:

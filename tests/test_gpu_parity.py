@@ -417,6 +417,24 @@ def test_vae_chunking_is_invisible(H):
     assert _maxerr(whole, parts) < 1e-4
 
 
+def test_sampling_entry_points_reject_mismatched_shapes(H):
+    """The C ABI takes pointers and counts; the host mirror is where a wrong column count must be caught (an IDM state matrix with
+    obs_dim instead of 2 x obs_dim columns used to be read out of bounds)."""
+    D, A = 12, 3
+    idm = H.Idm(P.init_params(P.idm_spec(D, A, 64, 1, 32, (32,)), seed=0), D, A, 64, 1, 32, (32,))
+    with pytest.raises(ValueError):
+        idm.sample(torch.zeros(5, D).cuda(), torch.zeros(5, A).cuda(), n_steps=2)
+    with pytest.raises(ValueError):
+        idm.sample(torch.zeros(5, 2 * D).cuda(), torch.zeros(4, A).cuda(), n_steps=2)
+    idm.close()
+    pl = H.Planner(P.init_params(P.unet_spec(10, 6, (32, 64), 5, 32), seed=0), 10, 6, (32, 64), 32)
+    with pytest.raises(ValueError):
+        pl.sample(torch.zeros(2, 8, 9).cuda(), torch.zeros(2, 6).cuda(), n_steps=2)
+    with pytest.raises(ValueError):
+        pl.sample(torch.zeros(2, 8, 10).cuda(), torch.zeros(2, 7).cuda(), n_steps=2)
+    pl.close()
+
+
 def test_vae_last_chunk_of_a_batch_replays_the_full_chunk_ops(H):
     """B = one full 592-image chunk + 8 images at the benchmark topology: the ops are built for 592 images (CTA pairs, 256-wide tiles,
     shared tap rows) and replayed with 8 - a handful of tiles per launch.  (A paired 256-wide launch that fell back to a plain grid
