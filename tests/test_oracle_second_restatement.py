@@ -107,6 +107,42 @@ def test_vae_encoder_second_restatement():
     assert np.abs(got - ref).max() < 1e-9
 
 
+def vae_decode_loops(p, z, blocks, layers, groups):
+    """FlaxAutoencoderKL.decode restated with the loop primitives above: post_quant_conv 1x1 -> conv_in -> mid (resnet, attention,
+    resnet) -> up blocks over the REVERSED channel list with layers + 1 resnets each, nearest x2 (out[i, j] = in[i // 2, j // 2]) +
+    conv 3x3 on all but the last -> GroupNorm, swish, conv_out."""
+    p = {k: np.asarray(v, np.float64) for k, v in p.items()}
+    x = conv2d_loops(z, p["post_quant_conv/kernel"], p["post_quant_conv/bias"], pad=(0, 0, 0, 0))
+    x = conv2d_loops(x, p["decoder/conv_in/kernel"], p["decoder/conv_in/bias"])
+    x = resnet_loops(p, "decoder/mid_block/resnets_0", x, groups)
+    x = attention_loops(p, "decoder/mid_block/attentions_0", x, groups)
+    x = resnet_loops(p, "decoder/mid_block/resnets_1", x, groups)
+    for i in range(len(blocks)):
+        for j in range(layers + 1):
+            x = resnet_loops(p, f"decoder/up_blocks_{i}/resnets_{j}", x, groups)
+        if i != len(blocks) - 1:
+            B, H, W, C = x.shape
+            up = np.empty((B, 2 * H, 2 * W, C))
+            for a in range(2 * H):
+                for b in range(2 * W):
+                    up[:, a, b] = x[:, a // 2, b // 2]
+            u = f"decoder/up_blocks_{i}/upsamplers_0/conv"
+            x = conv2d_loops(up, p[f"{u}/kernel"], p[f"{u}/bias"])
+    x = swish(group_norm_loops(x, groups, p["decoder/conv_norm_out/scale"], p["decoder/conv_norm_out/bias"]))
+    return conv2d_loops(x, p["decoder/conv_out/kernel"], p["decoder/conv_out/bias"])
+
+
+def test_vae_decoder_second_restatement():
+    blocks = (8, 16)
+    p = P.init_params(P.vae_decoder_spec(blocks, 3, 4, 1), seed=12, perturb=0.1)
+    g = np.random.default_rng(3)
+    z = g.standard_normal((2, 4, 4, 4))
+    ref = O.vae_decode(p, z, blocks, 1, 4).numpy()
+    got = vae_decode_loops(p, z, blocks, 1, 4)
+    assert got.shape == ref.shape == (2, 8, 8, 3)
+    assert np.abs(got - ref).max() < 1e-9
+
+
 def test_downsample_pads_the_high_side_only():
     """The (0, 1) pad of FlaxDownsample2D: output pixel (i, j) reads input rows 2i .. 2i+2 - shifting the pad to the low side
     (PyTorch's padding=1) changes the result, so the loop version and the oracle agreeing is not vacuous."""
