@@ -354,14 +354,17 @@ __global__ void __launch_bounds__(TcGeo<BN>::THREADS, 1) tc_gemm_kernel(const __
     const uint32_t epi_buf = smem_base + (uint32_t)STAGES * stage_bytes + (uint32_t)ew * epi_box;   // behind the ring
     const uint32_t my_bar_res = smem_u32(&bar_res[ew & 15]);
     uint32_t res_phase = 0;
+    int staged_n0 = -1;
     for (int tile = tile_first; tile < num_tiles; tile += tile_step, ++it) {
     const int tile_m = PERSIST ? (PP ? 2 * (tile % tiles_m_s) + (int)cta_rank : tile % tiles_m_s) : (int)blockIdx.x;
     const int n0 = (PERSIST ? tile / tiles_m_s : (int)blockIdx.y) * BN;
     const int buf = PERSIST ? it % p.acc_bufs : 0;
     const uint32_t use = PERSIST ? (uint32_t)(it / p.acc_bufs) : 0u;
     const int m = tile_m * TC_BM + row;
-    // stage the per-column vectors while the main loop runs
-    {
+    // stage the per-column vectors while the main loop runs; the persistent kernel does it only when the N tile changes (uniform across
+    // the CTA; the barrier that ends the previous tile already separates this write from that tile's reads)
+    if (!PERSIST || n0 != staged_n0) {
+      staged_n0 = n0;
       const int et = threadIdx.x - 64;
       const bool uniform_step = p.film && p.step.rows == nullptr;
       const float* trow = uniform_step ? p.ttab + (long long)step_of(p.step, 0) * p.ld_ttab + p.film_off : nullptr;
