@@ -327,75 +327,102 @@ __global__ void __launch_bounds__(256) vae_gn_apply_img_kernel(const float* __re
 
 // One-head self-attention core over L = h*w tokens (FlaxAttentionBlock): scores = (q C^-1/4)(k C^-1/4)^T, softmax, @ v.
 // qkv: (B, L, 3C) f32 [q | k | v];  out (B, L, C) f32 and/or bf16.  One block per image; L <= 64.
-// Scores: the block walks C in chunks of 32 channels staged in shared memory (coalesced loads), every thread owns
-// a 4x4 patch of the L x L score matrix.  P V: thread = channel, loop over tokens (coalesced over channels).
+// Scores: the block walks C in chunks of 32 channels staged TRANSPOSED in shared memory ([channel][token], so that a thread's four
+// tokens are one 16-byte load), every thread owns a 4x4 patch of the L x L score matrix: 2 LDS.128 per 16 FMA (the first version read
+// eight scalars and was shared-memory-issue-bound).  Softmax: four threads per row.  P V: the probabilities are kept transposed
+// ([key][query]); a thread owns one channel pair position and 16 queries, i.e. 4 LDS.128 + 1 coalesced global load per 16 FMA.
 __global__ void __launch_bounds__(256) vae_attn_kernel(const float* __restrict__ qkv, float* __restrict__ out_f32,
                                                        __nv_bfloat16* __restrict__ out_bf16, int L, int C) {
-  __shared__ float sc[64][65];
-  __shared__ float qs[64][33], ks[64][33];           // 32-channel chunks (static shared memory stays under 48 KB)
+  __shared__ __align__(16) float sc[64][68];         // probabilities, transposed: sc[key j][query i]
+  __shared__ __align__(16) float qs[32][68], ks[32][68];   // [channel of the chunk][token]
   const long long b = blockIdx.x;
   const float* base = qkv + b * L * 3 * C;
   const float scale = rsqrtf(sqrtf((float)C));
   const float s2 = scale * scale;
   const int ti = (threadIdx.x >> 4) * 4, tj = (threadIdx.x & 15) * 4;     // 16 x 16 threads x (4 x 4) = 64 x 64
   float acc[4][4] = {};
+  // a thread stages tokens (tid >> 5) + 8 r, channel (tid & 31) of every chunk; the next chunk's 16 values are fetched into registers
+  // before the current one is consumed (one block per image and 8 warps: nothing else hides the L2 latency)
+  const int si = threadIdx.x >> 5, scn = threadIdx.x & 31;
+  float qn[8], kn[8];
+  auto fetch = [&](int c0) {
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+      const int i = si + 8 * r;
+      const bool ok = c0 + scn < C && i < L;
+      qn[r] = ok ? __ldg(base + (long long)i * 3 * C + c0 + scn) : 0.f;
+      kn[r] = ok ? __ldg(base + (long long)i * 3 * C + C + c0 + scn) : 0.f;
+    }
+  };
+  fetch(0);
   for (int c0 = 0; c0 < C; c0 += 32) {
-    for (int e = threadIdx.x; e < L * 32; e += blockDim.x) {
-      const int i = e >> 5, c = e & 31;
-      const bool ok = c0 + c < C;
-      qs[i][c] = ok ? base[(long long)i * 3 * C + c0 + c] : 0.f;
-      ks[i][c] = ok ? base[(long long)i * 3 * C + C + c0 + c] : 0.f;
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+      qs[scn][si + 8 * r] = qn[r];
+      ks[scn][si + 8 * r] = kn[r];
     }
     __syncthreads();
-    if (ti < L && tj < L) {
-      for (int c = 0; c < 32; ++c) {
-        float qa[4], kb[4];
+    if (c0 + 32 < C) fetch(c0 + 32);
+#pragma unroll 8
+    for (int c = 0; c < 32; ++c) {
+      const float4 q4 = *reinterpret_cast<const float4*>(&qs[c][ti]);
+      const float4 k4 = *reinterpret_cast<const float4*>(&ks[c][tj]);
+      const float qa[4] = {q4.x, q4.y, q4.z, q4.w}, kb[4] = {k4.x, k4.y, k4.z, k4.w};
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          qa[u] = ti + u < L ? qs[ti + u][c] : 0.f;
-          kb[u] = tj + u < L ? ks[tj + u][c] : 0.f;
-        }
+      for (int u = 0; u < 4; ++u)
 #pragma unroll
-        for (int u = 0; u < 4; ++u)
-#pragma unroll
-          for (int v = 0; v < 4; ++v) acc[u][v] = fmaf(qa[u], kb[v], acc[u][v]);
-      }
+        for (int v = 0; v < 4; ++v) acc[u][v] = fmaf(qa[u], kb[v], acc[u][v]);
     }
     __syncthreads();
   }
 #pragma unroll
   for (int u = 0; u < 4; ++u)
 #pragma unroll
-    for (int v = 0; v < 4; ++v)
-      if (ti + u < L && tj + v < L) sc[ti + u][tj + v] = acc[u][v] * s2;
+    for (int v = 0; v < 4; ++v) sc[tj + v][ti + u] = (ti + u < L && tj + v < L) ? acc[u][v] * s2 : -INFINITY;   // padded keys: weight 0
   __syncthreads();
-  for (int i = threadIdx.x; i < L; i += blockDim.x) {
+  {
+    // softmax over the keys of query i: four threads per query (adjacent lanes), 16 keys each
+    const int i = threadIdx.x >> 2, part = threadIdx.x & 3;
     float mx = -INFINITY;
-    for (int j = 0; j < L; ++j) mx = fmaxf(mx, sc[i][j]);
+    for (int j = part * 16; j < part * 16 + 16; ++j) mx = fmaxf(mx, sc[j][i]);
+    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
     float sum = 0.f;
-    for (int j = 0; j < L; ++j) {
-      const float e = expf(sc[i][j] - mx);
-      sc[i][j] = e;
+    for (int j = part * 16; j < part * 16 + 16; ++j) {
+      const float e = i < L ? expf(sc[j][i] - mx) : 0.f;       // exp(-inf - mx) = 0 for padded keys
+      sc[j][i] = e;
       sum += e;
     }
-    const float inv = 1.f / sum;
-    for (int j = 0; j < L; ++j) sc[i][j] *= inv;
+    sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+    sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+    const float inv = i < L ? 1.f / sum : 0.f;
+    for (int j = part * 16; j < part * 16 + 16; ++j) sc[j][i] *= inv;
   }
   __syncthreads();
-  for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    for (int i0 = 0; i0 < L; i0 += 8) {
-      float o[8] = {};
-      for (int j = 0; j < L; ++j) {
-        const float vv = base[(long long)j * 3 * C + 2 * C + c];
+  // out[i][c] = sum_j p[i][j] v[j][c]: thread = (channel lane, 16-query block); channels strided by 64 so that a warp reads 32 consecutive floats of v
+  const int cl = threadIdx.x & 63, qb = (threadIdx.x >> 6) * 16;
+  for (int c = cl; c < C; c += 64) {
+    float o[16] = {};
+    for (int j0 = 0; j0 < L; j0 += 8) {
+      float vv[8];                                     // eight independent loads in flight (one per iteration was a serial chain of L2 round trips)
 #pragma unroll
-        for (int u = 0; u < 8; ++u) o[u] = fmaf(sc[min(i0 + u, L - 1)][j], vv, o[u]);
-      }
+      for (int jj = 0; jj < 8; ++jj) vv[jj] = j0 + jj < L ? __ldg(base + (long long)(j0 + jj) * 3 * C + 2 * C + c) : 0.f;
 #pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        if (i0 + u < L) {
-          if (out_f32) out_f32[(b * L + i0 + u) * C + c] = o[u];
-          if (out_bf16) out_bf16[(b * L + i0 + u) * C + c] = __float2bfloat16(o[u]);
+      for (int jj = 0; jj < 8; ++jj) {
+        const int j = min(j0 + jj, 63);                // (rows beyond L hold zeros for valid queries)
+#pragma unroll
+        for (int u4 = 0; u4 < 4; ++u4) {
+          const float4 p4 = *reinterpret_cast<const float4*>(&sc[j][qb + 4 * u4]);
+          o[4 * u4] = fmaf(p4.x, vv[jj], o[4 * u4]); o[4 * u4 + 1] = fmaf(p4.y, vv[jj], o[4 * u4 + 1]);
+          o[4 * u4 + 2] = fmaf(p4.z, vv[jj], o[4 * u4 + 2]); o[4 * u4 + 3] = fmaf(p4.w, vv[jj], o[4 * u4 + 3]);
         }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 16; ++u) {
+      if (qb + u < L) {
+        if (out_f32) out_f32[(b * L + qb + u) * C + c] = o[u];
+        if (out_bf16) out_bf16[(b * L + qb + u) * C + c] = __float2bfloat16(o[u]);
       }
     }
   }
