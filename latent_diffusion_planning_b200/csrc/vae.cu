@@ -286,15 +286,29 @@ __global__ void __launch_bounds__(256) vae_gn_apply_kernel(const float* __restri
 // 47 % issue-active, 4.6 TB/s; ncu r2c); same arithmetic per element, so the results are bit-identical.  Four independent 16-byte loads
 // are in flight per thread.
 template <int ACT>
-__global__ void __launch_bounds__(256) vae_gn_apply_img_kernel(const float* __restrict__ x, const float* __restrict__ mr,
+__global__ void __launch_bounds__(256) vae_gn_apply_img_kernel(const float* __restrict__ x, const float* __restrict__ part,
                                                                const float* __restrict__ gamma, const float* __restrict__ beta,
                                                                float* __restrict__ y_f32, __nv_bfloat16* __restrict__ y_bf16, int P, int C,
-                                                               int G, int rows_per_block) {
+                                                               int G, int rows_per_block, int slabs, float inv_n, float eps) {
   const int cq = C >> 2, cpg = C / G;
   const int q = threadIdx.x % cq, rl = threadIdx.x / cq, rpb = 256 / cq;
   const int b = blockIdx.y;
   const int r_begin = blockIdx.x * rows_per_block, r_end = min(P, r_begin + rows_per_block);
-  const float2 m = __ldg(reinterpret_cast<const float2*>(mr) + (b * G + (4 * q) / cpg));
+  // (mean, rstd) of this image's groups from the per-slab partial sums, in the fixed slab order of vae_gn_final_kernel (whose launch this
+  // replaces: same values, bit for bit)
+  __shared__ float2 stat[64];
+  if (threadIdx.x < G) {
+    float a = 0.f, a2 = 0.f;
+    for (int sl = 0; sl < slabs; ++sl) {
+      const float* pp = part + (((long long)b * slabs + sl) * G + threadIdx.x) * 2;
+      a += pp[0];
+      a2 += pp[1];
+    }
+    const float mu = a * inv_n;
+    stat[threadIdx.x] = make_float2(mu, rsqrtf(fmaxf(a2 * inv_n - mu * mu, 0.f) + eps));
+  }
+  __syncthreads();
+  const float2 m = stat[(4 * q) / cpg];
   const float4 ga = __ldg(reinterpret_cast<const float4*>(gamma) + q), be = __ldg(reinterpret_cast<const float4*>(beta) + q);
   const size_t img0 = (size_t)b * P * cq;
   const float4* x4 = reinterpret_cast<const float4*>(x) + img0 + q;
@@ -661,18 +675,23 @@ static int vae_gn(LdpVae* h, VaeWs* w, const float* x, int nimg, int P, int C, c
     vae_gn_stats_kernel<<<dim3(nimg, slabs), 256, 0, s>>>(x, w->part, P, C, G);
     VAE_LAUNCH_OK("vae_gn_stats");
   }
-  vae_gn_final_kernel<<<(nimg * G + 127) / 128, 128, 0, s>>>(w->part, w->stats, nimg * G, G, slabs, 1.f / ((float)P * (C / G)), 1e-6f);
-  VAE_LAUNCH_OK("vae_gn_final");
   static const bool img_major = !(getenv("LDP_VAE_GN_IMG") && getenv("LDP_VAE_GN_IMG")[0] == '0');
   const int cq = C / 4, cpg = C / G;
-  if (img_major && cpg % 4 == 0 && nimg <= 65535 && (act == 0 || act == 1)) {
+  const float inv_n = 1.f / ((float)P * (C / G));
+  const bool fused_final = img_major && cpg % 4 == 0 && nimg <= 65535 && (act == 0 || act == 1) && G <= 64;
+  if (!fused_final) {
+    vae_gn_final_kernel<<<(nimg * G + 127) / 128, 128, 0, s>>>(w->part, w->stats, nimg * G, G, slabs, inv_n, 1e-6f);
+    VAE_LAUNCH_OK("vae_gn_final");
+  }
+  if (fused_final) {
     // ~16 float4 per thread, but enough blocks to fill the machine a few times over
     const int rpb = 256 / cq;
     int rows_per_block = rpb * 16;
     while (rows_per_block > rpb * 4 && (long long)nimg * ceil_div(P, rows_per_block) < 148 * 8) rows_per_block >>= 1;
     const dim3 grid(ceil_div(P, rows_per_block), nimg);
-    if (act == 1) vae_gn_apply_img_kernel<1><<<grid, 256, 0, s>>>(x, w->stats, gamma, beta, y_f32, y_bf16, P, C, G, rows_per_block);
-    else vae_gn_apply_img_kernel<0><<<grid, 256, 0, s>>>(x, w->stats, gamma, beta, y_f32, y_bf16, P, C, G, rows_per_block);
+    // the finalise step of the statistics (sum over slabs -> mean, rstd) runs inside the apply pass: 22 fewer launches per encoder pass
+    if (act == 1) vae_gn_apply_img_kernel<1><<<grid, 256, 0, s>>>(x, w->part, gamma, beta, y_f32, y_bf16, P, C, G, rows_per_block, slabs, inv_n, 1e-6f);
+    else vae_gn_apply_img_kernel<0><<<grid, 256, 0, s>>>(x, w->part, gamma, beta, y_f32, y_bf16, P, C, G, rows_per_block, slabs, inv_n, 1e-6f);
     VAE_LAUNCH_OK("vae_gn_apply_img");
     return LDP_OK;
   }
