@@ -18,6 +18,7 @@ struct IdmBlockW {
 
 struct IdmWs {
   int N = 0;
+  uint64_t last_use = 0;         // LRU stamp (ws_evict_lru)
   Arena arena;
   float *spre = nullptr, *h = nullptr, *hn = nullptr, *u = nullptr, *a_state = nullptr, *eps_buf = nullptr;
   int32_t* step_dev = nullptr;
@@ -92,6 +93,7 @@ struct LdpIdm {
   float* ctab_h = nullptr;   // [n_train][H]: cond(t) Wc + b0
   float* coef = nullptr;
   std::map<int, std::unique_ptr<IdmWs>> ws;
+  uint64_t use_clock = 0;
   // bf16 packed weights
   bool packed = false;
   std::vector<PackedW> pw1, pw2;
@@ -196,12 +198,14 @@ static int idm_get_ws(LdpIdm* h, int N, IdmWs** out) {
   LDP_CHECK(N > 0, LDP_ERR_BAD_SHAPE, "N must be positive");
   auto it = h->ws.find(N);
   if (it != h->ws.end()) {
+    it->second->last_use = ++h->use_clock;
     *out = it->second.get();
     return LDP_OK;
   }
+  ws_evict_lru(h->ws);
   const int H = h->cfg.hidden_dim, A = h->cfg.action_dim;
   std::unique_ptr<IdmWs> w(new IdmWs());
-  w->N = N;
+  w->N = N; w->last_use = ++h->use_clock;
   LDP_TRY(w->arena.alloc_t(&w->spre, (size_t)N * H));
   LDP_TRY(w->arena.alloc_t(&w->h, (size_t)N * H));
   LDP_TRY(w->arena.alloc_t(&w->hn, (size_t)N * H));

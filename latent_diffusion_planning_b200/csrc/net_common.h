@@ -110,6 +110,20 @@ inline int upload_stage_table(Arena& arena, const std::vector<TcStage>& st, Pack
   return LDP_OK;
 }
 
+// Per-shape workspaces (activations, tensor maps, CUDA graphs) are cached in the handles; a caller that walks through many batch sizes
+// would otherwise keep one of each alive for the life of the handle.  Keeps at most `cap` entries: the least recently used one is
+// released (after a device synchronize - its buffers may still be in flight) before a new shape is added.
+constexpr size_t LDP_MAX_CACHED_SHAPES = 8;
+template <class Map>
+inline void ws_evict_lru(Map& m, size_t cap = LDP_MAX_CACHED_SHAPES) {
+  if (m.size() < cap) return;
+  cudaDeviceSynchronize();
+  auto victim = m.begin();
+  for (auto it = m.begin(); it != m.end(); ++it)
+    if (it->second->last_use < victim->second->last_use) victim = it;
+  m.erase(victim);
+}
+
 // DDPM coefficient table [n][8] (see kernels.h DdpmStep), fp32 arithmetic in the reference's op order
 // (diffusers FlaxDDPMScheduler.step / _get_variance).
 void ddpm_schedule_host(int n, std::vector<float>& betas, std::vector<float>& alphas, std::vector<float>& acp);

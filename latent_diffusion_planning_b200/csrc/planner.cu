@@ -80,6 +80,7 @@ struct ConvPack : PackedW {
 
 struct PlanWs {
   int B = 0, T = 0;
+  uint64_t last_use = 0;         // LRU stamp (ws_evict_lru)
   Arena arena;
   float* otab = nullptr;
   float* otab_q = nullptr;       // half2 (scale, shift) pairs, quad-transposed, for the tcgen05 epilogues (film_pack_kernel)
@@ -141,6 +142,7 @@ struct LdpPlanner {
   float* wc_all = nullptr;   // [Dc][sum_c2]       observation part of every FiLM Dense
   float* coef = nullptr;     // [n_train][8]
   std::map<std::pair<int, int>, std::unique_ptr<PlanWs>> ws;
+  uint64_t use_clock = 0;
   std::map<std::pair<int, int>, ConvPack> packed;   // (op id * 2 + layout, T_in)
   PackedW pw_otab;                  // wc_all^T packed K-major in bf16 (observation part of every FiLM Dense)
   bool otab_packed = false;
@@ -312,11 +314,13 @@ static int get_ws(LdpPlanner* h, int B, int T, PlanWs** out) {
   auto key = std::make_pair(B, T);
   auto it = h->ws.find(key);
   if (it != h->ws.end()) {
+    it->second->last_use = ++h->use_clock;
     *out = it->second.get();
     return LDP_OK;
   }
+  ws_evict_lru(h->ws);
   std::unique_ptr<PlanWs> w(new PlanWs());
-  w->B = B; w->T = T;
+  w->B = B; w->T = T; w->last_use = ++h->use_clock;
   LDP_TRY(w->arena.alloc_t(&w->otab, (size_t)B * h->sum_c2));
   LDP_TRY(w->arena.alloc_t(&w->otab_q, (size_t)B * h->sum_c2));
   LDP_TRY(w->arena.alloc_t(&w->x_state, (size_t)B * T * c.input_dim));

@@ -477,6 +477,7 @@ struct VaeTcConv {
 
 struct VaeWs {
   int Bc = 0;
+  uint64_t last_use = 0;                             // LRU stamp (ws_evict_lru)
   Arena arena;
   float *S = nullptr, *Hf = nullptr, *stats = nullptr, *part = nullptr, *qkv = nullptr;
   float* Gf = nullptr;                               // fp32 path: GN output
@@ -504,6 +505,7 @@ struct LdpVae {
   ConvW aq, ak, av, ap;
   float* wqkv = nullptr; float* bqkv = nullptr;      // [C][3C], [3C] concatenated projections
   std::map<int, std::unique_ptr<VaeWs>> ws;
+  uint64_t use_clock = 0;
   std::map<int, PackedW> packed;                     // conv id -> packed weights (tc path)
   PackedW pw_in[2];                                  // conv_in as a K = 64 dense GEMM: [0] uint8 pixels (normalisation folded in), [1] float pixels
   bool pw_in_ready[2] = {false, false};
@@ -644,12 +646,14 @@ static size_t vae_max_act(const LdpVae* h) {
 static int vae_get_ws(LdpVae* h, int Bc, VaeWs** out) {
   auto it = h->ws.find(Bc);
   if (it != h->ws.end()) {
+    it->second->last_use = ++h->use_clock;
     *out = it->second.get();
     return LDP_OK;
   }
+  ws_evict_lru(h->ws);
   const LdpVaeConfig& c = h->cfg;
   std::unique_ptr<VaeWs> w(new VaeWs());
-  w->Bc = Bc;
+  w->Bc = Bc; w->last_use = ++h->use_clock;
   const size_t max_act = vae_max_act(h);
   const int S = c.image_size >> (c.n_blocks - 1);
   const int cl = c.block_out_channels[c.n_blocks - 1];

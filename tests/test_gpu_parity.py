@@ -417,6 +417,22 @@ def test_vae_chunking_is_invisible(H):
     assert _maxerr(whole, parts) < 1e-4
 
 
+def test_workspace_cache_is_bounded_and_eviction_is_invisible(H):
+    """A handle keeps at most eight per-shape workspaces (csrc/net_common.h ws_evict_lru); walking through more batch sizes than that
+    evicts the oldest - the same call afterwards rebuilds it and returns the same bits."""
+    D, Dc = 10, 6
+    pl = H.Planner(P.init_params(P.unet_spec(D, Dc, (32, 64), 5, 32), seed=0, perturb=0.1), D, Dc, (32, 64), 32)
+    g = torch.Generator().manual_seed(0)
+    x, c = torch.randn(12, 8, D, generator=g).cuda(), (torch.rand(12, Dc, generator=g) * 2 - 1).cuda()
+    first = pl.sample(x[:3], c[:3], seed=5, n_steps=4, precision="fp32").clone()
+    for B in range(1, 13):                      # 12 shapes > 8 cached
+        out = pl.sample(x[:B], c[:B], seed=5, n_steps=4, precision="fp32")
+        assert torch.isfinite(out).all()
+    again = pl.sample(x[:3], c[:3], seed=5, n_steps=4, precision="fp32")
+    assert torch.equal(first, again)
+    pl.close()
+
+
 def test_sampling_entry_points_reject_mismatched_shapes(H):
     """The C ABI takes pointers and counts; the host mirror is where a wrong column count must be caught (an IDM state matrix with
     obs_dim instead of 2 x obs_dim columns used to be read out of bounds)."""
