@@ -763,6 +763,16 @@ struct TcDense {
   struct EpiMaps { CUtensorMap m[3]; };
   std::deque<EpiMaps> epi_host;
   std::deque<TcRun> run_host;
+  // Forget every cached op and its device-side tables (called when the step's shape changes: the workspace is rebuilt then, so the
+  // pointer-keyed entries can never be hit again and would only accumulate).  The caller has synchronised the device.
+  void reset() {
+    ops.clear();
+    epi_host.clear();
+    run_host.clear();
+    arena.release();
+    kb_dev = nullptr;
+    kb_cap = 0;
+  }
   int init(int max_kb) {
     if (kb_dev && max_kb <= kb_cap) return LDP_OK;
     LDP_TRY(tc_driver_check());
@@ -1484,7 +1494,11 @@ template <typename F>
 static int run_step(LdpTrainer* h, int prec, const LdpTrainer::GraphKey& key, cudaStream_t s, F&& body) {
   if (prec != LDP_PREC_BF16 || !h->use_graph) return body(s);
   // one shape at a time: the workspace is rebuilt when the shape changes, which would leave older graphs dangling
-  if (!h->graphs.empty() && h->graphs.find(key) == h->graphs.end()) h->drop_graphs();
+  if (!h->graphs.empty() && h->graphs.find(key) == h->graphs.end()) {
+    h->drop_graphs();
+    cudaDeviceSynchronize();
+    h->tc.reset();
+  }
   LdpTrainer::GraphSlot& slot = h->graphs[key];
   if (slot.exec) {
     LDP_CUDA_OK(cudaGraphLaunch(slot.exec, s));
