@@ -377,7 +377,7 @@ def run_ours(args) -> None:
             "denoise_steps_per_sec": value * N_DIFF,
             "roofline": {"bound": "tensor", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
                          "frac": achieved_tf / peak_tf, "traffic": traffic, "traffic_source": traffic_src,
-                         "kernel": "tc_gemm_kernel<BN,EPI> (tcgen05 implicit-GEMM conv + fused GN/Mish/FiLM/DDPM epilogues)",
+                         "kernel": "tc_gemm_kernel_v1<BN,EPI,PAIR> (tcgen05 implicit-GEMM conv + fused GN/Mish/FiLM/DDPM epilogues)",
                          "launches_per_step": launches_per_step, "avg_launch_us": avg_launch_us,
                          "algorithmic_flops_per_launch": flops_step / launches_per_step,
                          "peak_source": peak_src, "isolated": per_op},
@@ -480,7 +480,7 @@ def vae_block(ctx, args, planner, x_host, c_host):
                       "B_per_gpu": VAE_B, "l2": "256 MB L2 flush between steps; inputs (50 MB) + activations exceed L2"},
            "roofline": {"bound": "tensor", "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf,
                         "algorithmic_gflop_per_image": VAE_GFLOP_PER_IMG, "launches_per_step": launches, "peak_source": peak_src,
-                        "kernel": "tc_gemm_kernel<*, PLAIN, persistent> (3x3 / 1x1 / stride-2 implicit-GEMM convolutions)"},
+                        "kernel": "tc_gemm_kernel<*, PLAIN, pair, persistent> (3x3 / 1x1 / stride-2 implicit-GEMM convolutions, TMA epilogue)"},
            "e2e": {"value": VAE_B * ctx.world / ms_e2e * 1e3, "unit": "img/s", "ms_per_step": ms_e2e,
                    "h2d_bytes_per_step": img_host.numel(), "d2h_bytes_per_step": lat_host.numel() * 4,
                    "api": "handles.VaeEncoder.encode on pinned uint8 host frames, latents copied back"}}
